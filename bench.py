@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py -- EGT attention-block forward+backward graphs/sec (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C0|C0e64|C1|C2|C3|C4|C5]
+    python bench.py --impl reference ...      # CPU arm: the oracle port of the reference TF path
+
+A "step" = one EGTBlock forward + backward over one batch of synthetic dense graphs (per GPU:
+B graphs of N nodes) plus, for N>1 ranks, the single all-reduce of the flat weight gradient.
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# per-GPU workloads
+WORKLOADS = {
+    'C0':    dict(N=128, d=64, d_e=8, h=8, B=128, note='headline: N=128, h=8, bf16, d=64, d_e=8'),
+    'C0e64': dict(N=128, d=64, d_e=64, h=8, B=128, note='headline with ZINC-like edge width'),
+    'C1':    dict(N=37, d=64, d_e=64, h=8, B=128, note='ZINC'),
+    'C2':    dict(N=75, d=64, d_e=8, h=8, B=128, note='MNIST'),
+    'C3':    dict(N=190, d=96, d_e=8, h=8, B=64, note='CLUSTER d=96'),
+    'C4':    dict(N=188, d=64, d_e=8, h=8, B=128, note='PATTERN'),
+    'C5':    dict(N=512, d=128, d_e=32, h=16, B=64, note='synthetic roofline sweep'),
+    'S64':   dict(N=64, d=64, d_e=8, h=8, B=128, note='sweep N=64'),
+    'S256':  dict(N=256, d=64, d_e=8, h=8, B=128, note='sweep N=256'),
+    'S512':  dict(N=512, d=64, d_e=8, h=8, B=64, note='sweep N=512'),
+}
+METRIC = 'EGT-layer fwd+bwd graphs/sec'
+
+
+def alg_bytes_per_graph(N, d, d_e, h, s=2):
+    """fwd+bwd algorithmic HBM bytes per graph."""
+    return s * (5 * N * N * d_e + 6 * N * d) + 16 * N * h + N
+
+
+def alg_bytes_fwd(N, d, d_e, h, s=2):
+    return s * (2 * N * N * d_e + 2 * N * d) + 8 * N * h + N
+
+
+def alg_bytes_bwd(N, d, d_e, h, s=2):
+    return s * (3 * N * N * d_e + 4 * N * d) + 8 * N * h
+
+
+def alg_flops_per_graph(N, d, d_e, h):
+    F = 2 * N * d * 3 * d + 2 * N * d * d + 4 * N * N * d + 4 * N * N * d_e * h + 2 * N * N * h * d_e
+    return 3 * F
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return dict(hbm_gbs=j['hbm_gbs'], bf16_tflops=j['bf16_tflops'], source='measured')
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, source='fallback')
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            hd = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(hd, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksEventReasonHwSlowdown: 'hw_slowdown',
+                     nv.nvmlClocksEventReasonHwThermalSlowdown: 'hw_thermal_slowdown',
+                     nv.nvmlClocksEventReasonSwThermalSlowdown: 'sw_thermal_slowdown',
+                     nv.nvmlClocksEventReasonSwPowerCap: 'sw_power_cap'}
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(hd, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(hd)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                time.sleep(0.02)
+        except Exception as ex:   # NVML missing: report that instead of inventing clocks
+            self.reasons.add(f'nvml_unavailable:{type(ex).__name__}')
+
+    def summary(self):
+        s = sorted(self.samples)
+        return dict(sm_mhz=(s[len(s) // 2] if s else None), sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons),
+                    samples=len(s))
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_reference_run(w, steps, warmup, sample_graphs=None, budget_s=20.0):
+    """Times the oracle (op-for-op CPU restatement of the reference TF path, fp32, eager, every
+    [B,N,N,h] intermediate materialised, backward by autograd) on the host cores."""
+    from oracle import egt_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    N, d, d_e, h = w['N'], w['d'], w['d_e'], w['h']
+    Bs = sample_graphs or max(1, min(w['B'], int(2.0e8 // (N * N * h * 16))))
+    cfg = O.BlockConfig(model_width=d, edge_width=d_e, num_heads=h)
+    params = {k: v.requires_grad_(True) for k, v in O.init_block_params(cfg).items()}
+    hh, ee, mask = O.synthetic_batch(Bs, N, d, d_e)
+    g = torch.Generator().manual_seed(7)
+    dh, de = torch.randn(hh.shape, generator=g), torch.randn(ee.shape, generator=g)
+
+    def step():
+        hr, er = hh.clone().requires_grad_(True), ee.clone().requires_grad_(True)
+        h2, e2 = O.egt_block(hr, er, mask, params, cfg)
+        torch.autograd.grad([h2, e2], [hr, er] + list(params.values()), [dh, de])
+
+    for _ in range(max(1, warmup)):
+        step()
+    t0 = time.perf_counter()
+    n = 0
+    while n < steps and (n < 1 or time.perf_counter() - t0 < budget_s):
+        step()
+        n += 1
+    dt = time.perf_counter() - t0
+    return dict(value=Bs * n / dt, unit='graphs/s', cores=torch.get_num_threads(), kind='port',
+                sample=f'{n} steps x {Bs} graphs of N={N} (fp32 oracle port of the reference TF path; '
+                       f'TensorFlow is not installable in this image)', ms_per_step=1e3 * dt / n, steps=n)
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    r = cpu_reference_run(w, args.steps, args.warmup)
+    line = dict(impl='reference', metric=METRIC, value=r['value'], unit='graphs/s', n_gpus=args.gpus,
+                steps=r['steps'], warmup=args.warmup, ms_per_step=r['ms_per_step'], higher_is_better=True,
+                scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+                config=dict(workload=args.workload, **{k: w[k] for k in ('N', 'd', 'd_e', 'h')},
+                            graphs_per_step=None, note=w['note']),
+                cpu_baseline=dict(value=r['value'], unit='graphs/s', cores=r['cores'], kind=r['kind'],
+                                  sample=r['sample']),
+                e2e=dict(value=r['value'], unit='graphs/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+def run_ours(args, w):
+    import torch.distributed as dist
+    import egt_b200
+    from egt_b200 import _lib as L
+    rank = int(os.environ.get('RANK', 0))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    lib = L.load()
+    N, d, d_e, h, B = w['N'], w['d'], w['d_e'], w['h'], w['B']
+    training = bool(args.random_mask_prob > 0)
+    blk = egt_b200.EGTBlock(model_width=d, edge_width=d_e, num_heads=h, scale_degree=bool(args.scale_degree),
+                            random_mask_prob=args.random_mask_prob, seed=1000 + rank).to(dev)
+    blk.train(training)
+    # synthetic inputs: per-rank seed, N(0,1) activations, dense graphs (num_nodes = N)
+    nsets = args.input_sets
+    g = torch.Generator(device='cpu').manual_seed(20240 + rank)
+    host = []
+    for _ in range(nsets):
+        hh = torch.randn(B, N, d, generator=g).bfloat16().pin_memory()
+        ee = torch.randn(B, N, N, d_e, generator=g).bfloat16().pin_memory()
+        mm = torch.ones(B, N, dtype=torch.bool).pin_memory()
+        host.append((hh, ee, mm))
+    devs = [tuple(t.to(dev) for t in s) for s in host]
+    dh = torch.randn(B, N, d, generator=g).bfloat16().to(dev)
+    de = torch.randn(B, N, N, d_e, generator=g).bfloat16().to(dev)
+    grad_host = torch.empty(blk.flat.numel(), dtype=torch.float32).pin_memory()
+
+    def step(i, inputs=None):
+        hh, ee, mm = inputs if inputs is not None else devs[i % nsets]
+        hh = hh.detach().requires_grad_(True)
+        ee = ee.detach().requires_grad_(True)
+        blk.flat.grad = None
+        h2, e2 = blk(hh, ee, mm)
+        torch.autograd.backward([h2, e2], [dh, de])
+        egt_b200.allreduce_flat_grads([blk])
+        return hh.grad, ee.grad
+
+    def timed(fn, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for i in range(max(3, args.warmup)):
+        step(i)
+    torch.cuda.synchronize()
+
+    # ---- timed region 1: inputs resident in HBM ----
+    sampler = ClockSampler(local)
+    sampler.start()
+    lib.egt_profile_enable(1)
+    l0 = lib.egt_launch_count()
+    ms = timed(step, args.steps)
+    launches = lib.egt_launch_count() - l0
+    prof = L.profile_read()
+    lib.egt_profile_enable(0)
+    path = lib.egt_last_path()
+
+    # ---- timed region 2: end to end through the public API with HOST buffers ----
+    def step_e2e(i):
+        hh, ee, mm = host[i % nsets]
+        inputs = (hh.to(dev, non_blocking=True), ee.to(dev, non_blocking=True), mm.to(dev, non_blocking=True))
+        step(i, inputs)
+        grad_host.copy_(blk.flat.grad, non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the caller consumes the step's result on the host
+
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = measured_peaks()
+    graphs = B * world * args.steps
+    value = graphs / (ms / 1e3)
+    # dominant kernel = the one with the largest total time in the profiled region
+    dom = max(prof.items(), key=lambda kv: kv[1][0]) if prof else (None, (0.0, 0))
+    total_prof_ms = sum(v[0] for v in prof.values()) or 1.0
+    kb = {'fwd': alg_bytes_fwd(N, d, d_e, h), 'bwd': alg_bytes_bwd(N, d, d_e, h)}
+    dom_name = dom[0] or ''
+    per_launch_bytes = B * (kb['fwd'] if 'fwd' in dom_name else kb['bwd'])
+    dom_avg_ms = dom[1][0] / max(1, dom[1][1])
+    achieved = per_launch_bytes / (dom_avg_ms * 1e-3) / 1e9 if dom_avg_ms > 0 else 0.0
+    step_bytes = B * alg_bytes_per_graph(N, d, d_e, h)
+    step_gbs = step_bytes * args.steps / (ms * 1e-3) / 1e9 / 1.0
+    traffic = None
+    tp = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(dom_name)
+    cpu = cpu_reference_run(w, steps=1000, warmup=1, budget_s=args.cpu_budget) if world == 1 and not args.no_cpu else None
+    line = dict(
+        metric=METRIC, value=value, unit='graphs/s', n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
+        ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16',
+        data='synthetic',
+        config=dict(workload=args.workload, N=N, d=d, d_e=d_e, h=h, graphs_per_gpu=B, global_batch=B * world,
+                    parallelism=f'dp{world}', note=w['note'], random_mask_prob=args.random_mask_prob,
+                    scale_degree=bool(args.scale_degree),
+                    l2=f'rotating {nsets} input sets per rank (working set > 126 MB L2)',
+                    path='fused-tcgen05' if path == 1 else 'staged'),
+        roofline=dict(bound='hbm', kernel=dom_name, achieved=achieved, peak=peaks['hbm_gbs'], unit='GB/s',
+                      frac=achieved / peaks['hbm_gbs'], traffic=traffic, peak_source=peaks['source'],
+                      kernel_share_of_step=dom[1][0] / total_prof_ms,
+                      step_achieved=step_gbs, step_frac=step_gbs / world / peaks['hbm_gbs'],
+                      kernels={k: dict(ms_total=v[0], launches=v[1]) for k, v in prof.items()}),
+        e2e=dict(value=graphs / (ms_e2e / 1e3), unit='graphs/s',
+                 h2d_bytes_per_step=sum(t.numel() * t.element_size() for t in host[0]),
+                 d2h_bytes_per_step=grad_host.numel() * 4, ms_per_step=ms_e2e / args.steps),
+        gpu_launches=int(launches), clocks=sampler.summary(),
+    )
+    if cpu is not None:
+        line['cpu_baseline'] = dict(value=cpu['value'], unit='graphs/s', cores=cpu['cores'], kind=cpu['kind'],
+                                    sample=cpu['sample'])
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='C0', choices=sorted(WORKLOADS))
+    ap.add_argument('--random-mask-prob', type=float, default=0.0)
+    ap.add_argument('--scale-degree', type=int, default=0)
+    ap.add_argument('--input-sets', type=int, default=4)
+    ap.add_argument('--cpu-budget', type=float, default=15.0)
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == 'reference':
+        return run_reference(args, w)
+    return run_ours(args, w)
+
+
+if __name__ == '__main__':
+    main()

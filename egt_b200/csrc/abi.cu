@@ -1,0 +1,415 @@
+// abi.cu -- extern "C" entry points of libegt_b200.so (see include/egt_b200.h).
+#include <stdarg.h>
+#include <string.h>
+#include <mutex>
+#include <vector>
+#include "common.cuh"
+#include "kernels.h"
+
+namespace egt {
+
+static thread_local char g_err[512] = "";
+static thread_local int g_last_path = 0;
+
+void set_error(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  int n = snprintf(g_err, sizeof(g_err), "egt_b200[%d]: ", code);
+  vsnprintf(g_err + n, sizeof(g_err) - n, fmt, ap);
+  va_end(ap);
+}
+
+// ---- launch counter / per-kernel event profiler -------------------------------------------
+struct ProfSlot { const char *name; double ms; long count; };
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static long g_launches = 0;
+static std::vector<ProfSlot> g_slots;
+struct Pending { int slot; cudaEvent_t e0, e1; };
+static std::vector<Pending> g_pending;
+
+LaunchScope::LaunchScope(const char *name, cudaStream_t stream) : slot(-1), st(stream), e1(nullptr) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ++g_launches;
+  if (!g_prof_on) return;
+  for (size_t i = 0; i < g_slots.size(); ++i)
+    if (!strcmp(g_slots[i].name, name)) slot = (int)i;
+  if (slot < 0) { g_slots.push_back(ProfSlot{name, 0.0, 0}); slot = (int)g_slots.size() - 1; }
+  cudaEvent_t e0;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, st);
+  g_pending.push_back(Pending{slot, e0, e1});
+}
+LaunchScope::~LaunchScope() {
+  if (e1) cudaEventRecord(e1, st);
+}
+
+static size_t esize(int dtype) { return dtype == EGT_F32 ? 4 : 2; }
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static int check_attn_cfg(const egt_attn_cfg_t *c) {
+  EGT_REQUIRE(c != nullptr, EGT_E_ARG, "cfg is NULL");
+  EGT_REQUIRE(c->B > 0 && c->N > 0 && c->h > 0 && c->dk > 0, EGT_E_SHAPE, "B,N,h,dk must be positive (got %d,%d,%d,%d)",
+              c->B, c->N, c->h, c->dk);
+  EGT_REQUIRE(c->dk <= 16, EGT_E_SHAPE, "dk=%d > 16 is not supported", c->dk);
+  EGT_REQUIRE(c->dtype == EGT_F32 || c->dtype == EGT_BF16, EGT_E_DTYPE, "dtype must be EGT_F32 or EGT_BF16");
+  // egt_layers.py:20-24
+  EGT_REQUIRE(!(c->scale_degree && !c->gate_input), EGT_E_ARG, "scale_degree requires gate_input");
+  EGT_REQUIRE(c->scaler_type == EGT_SCALER_LOG || c->scaler_type == EGT_SCALER_LINEAR, EGT_E_ARG,
+              "scaler_type must be log or linear");
+  EGT_REQUIRE(c->attn_mask >= EGT_MASK_NONE && c->attn_mask <= EGT_MASK_ADJ_U8, EGT_E_ARG, "bad attn_mask kind");
+  EGT_REQUIRE(c->random_mask_prob >= 0.f && c->random_mask_prob < 1.f, EGT_E_ARG, "random_mask_prob out of range");
+  EGT_REQUIRE(c->attn_dropout >= 0.f && c->attn_dropout < 1.f, EGT_E_ARG, "attn_dropout out of range");
+  EGT_REQUIRE(c->num_virtual_nodes >= 0 && c->num_virtual_nodes <= c->N, EGT_E_ARG, "num_virtual_nodes out of range");
+  return EGT_OK;
+}
+
+static AttnParams make_attn_params(const egt_attn_cfg_t *c) {
+  AttnParams P;
+  memset(&P, 0, sizeof(P));
+  P.B = c->B; P.N = c->N; P.h = c->h; P.dk = c->dk;
+  P.scale = 1.0f / sqrtf((float)c->dk);
+  P.has_clip = c->has_clip; P.clip_lo = c->clip_lo; P.clip_hi = c->clip_hi;
+  P.scale_degree = c->scale_degree; P.scaler_type = c->scaler_type;
+  P.num_virtual_nodes = c->num_virtual_nodes;
+  P.attn_mask = c->attn_mask;
+  P.rand_mask = c->training && c->random_mask_prob > 0.f;
+  P.dropout = c->training && c->attn_dropout > 0.f;
+  P.random_mask_prob = c->random_mask_prob; P.attn_dropout = c->attn_dropout;
+  P.seed = c->seed; P.offset = c->offset;
+  return P;
+}
+
+static int check_device() {
+  int dev = 0;
+  EGT_CHECK_CUDA(cudaGetDevice(&dev));
+  int major = 0;
+  EGT_CHECK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  EGT_REQUIRE(major == 10, EGT_E_ARCH, "libegt_b200 is built for sm_100a only (device has compute capability %d.x)", major);
+  return EGT_OK;
+}
+
+// workspace carving -------------------------------------------------------------------------
+struct BlockWs {
+  char *E, *G, *Hhat, *dHext, *dE, *dG;      // [pairs,h] dtype
+  float *row_ws;                              // [2,B,N,h]
+  char *d_v_att, *d_qkv;                      // [R,d], [R,3d] dtype
+  float *hn, *dhn;                            // [R,d] f32
+  size_t total;
+};
+static BlockWs carve(const egt_block_cfg_t *c, int backward, void *base) {
+  const egt_attn_cfg_t &a = c->attn;
+  size_t es = esize(a.dtype);
+  size_t pairs = (size_t)a.B * a.N * a.N, R = (size_t)a.B * a.N, d = (size_t)a.h * a.dk;
+  size_t off = 0;
+  char *b = (char *)base;
+  BlockWs w;
+  memset(&w, 0, sizeof(w));
+  auto take = [&](size_t bytes) { char *p = b ? b + off : nullptr; off += align_up(bytes); return p; };
+  bool edge = c->edge_channel_type != EGT_EDGE_NONE;
+  bool residual = c->edge_channel_type >= EGT_EDGE_RESIDUAL;
+  if (edge) {
+    w.E = take(pairs * a.h * es);
+    if (c->gate_attention) w.G = take(pairs * a.h * es);
+  }
+  if (residual) w.Hhat = take(pairs * a.h * es);
+  if (backward) {
+    if (residual) w.dHext = take(pairs * a.h * es);
+    if (edge) {
+      w.dE = take(pairs * a.h * es);
+      if (c->gate_attention) w.dG = take(pairs * a.h * es);
+    }
+    w.row_ws = (float *)take(2 * R * a.h * sizeof(float));
+    w.d_v_att = take(R * d * es);
+    w.d_qkv = take(R * 3 * d * es);
+    w.hn = (float *)take(R * d * sizeof(float));
+    w.dhn = (float *)take(R * d * sizeof(float));
+  }
+  w.total = off;
+  return w;
+}
+
+static int check_block_cfg(const egt_block_cfg_t *c) {
+  EGT_REQUIRE(c != nullptr, EGT_E_ARG, "cfg is NULL");
+  EGT_REQUIRE(c->edge_channel_type >= EGT_EDGE_NONE && c->edge_channel_type <= EGT_EDGE_CONSTRAINED, EGT_E_ARG,
+              "bad edge_channel_type");
+  // graph_xformer_model_base.py:46-47
+  EGT_REQUIRE(!(c->attn.scale_degree && !c->gate_attention), EGT_E_ARG, "scale_degree only works with gate_attention");
+  EGT_REQUIRE(!(c->attn.scale_degree && c->edge_channel_type == EGT_EDGE_NONE), EGT_E_ARG,
+              "scale_degree needs gates, i.e. an edge channel");
+  if (c->edge_channel_type != EGT_EDGE_NONE) {
+    EGT_REQUIRE(c->d_e > 0, EGT_E_SHAPE, "d_e must be positive");
+    EGT_REQUIRE(c->attn.h <= 16, EGT_E_SHAPE, "block path supports h <= 16 (got %d)", c->attn.h);
+  }
+  return EGT_OK;
+}
+
+static egt_attn_cfg_t derived_attn_cfg(const egt_block_cfg_t *c) {
+  egt_attn_cfg_t a = c->attn;
+  a.edge_input = c->edge_channel_type != EGT_EDGE_NONE;                       // graph_xformer_model_base.py:120
+  a.gate_input = a.edge_input && c->gate_attention;                          // :121
+  a.attn_mask = c->edge_channel_type == EGT_EDGE_CONSTRAINED ? EGT_MASK_ADJ_U8 : EGT_MASK_NONE;   // :122
+  return a;
+}
+
+static EdgeParams make_edge_params(const egt_block_cfg_t *c, const egt_block_weights_t *w) {
+  EdgeParams p;
+  memset(&p, 0, sizeof(p));
+  p.pairs = (size_t)c->attn.B * c->attn.N * c->attn.N;
+  p.d_e = c->d_e; p.h = c->attn.h;
+  p.has_ln = c->edge_channel_type >= EGT_EDGE_RESIDUAL;
+  p.ln_eps = c->ln_eps;
+  p.gated = c->gate_attention;
+  p.act = c->edge_act; p.act_alpha = c->edge_act_alpha;
+  p.ln_g = w->norm_edge_gamma; p.ln_b = w->norm_edge_beta;
+  p.w_e = w->dense_edge_b_kernel; p.b_e = w->dense_edge_b_bias;
+  p.w_g = w->attention_gates_kernel; p.b_g = w->attention_gates_bias;
+  p.w_r = w->dense_edge_r_kernel; p.b_r = w->dense_edge_r_bias;
+  return p;
+}
+
+}  // namespace egt
+
+using namespace egt;
+
+extern "C" {
+
+int egt_abi_version(void) { return EGT_ABI_VERSION; }
+const char *egt_last_error(void) { return g_err; }
+int egt_last_path(void) { return g_last_path; }
+
+float egt_rng_uniform_host(uint64_t seed, uint64_t offset, uint32_t stream_id, uint64_t idx) {
+  return rng_uniform(seed, offset, stream_id, idx);
+}
+
+long egt_launch_count(void) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  return g_launches;
+}
+
+int egt_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = on != 0;
+  if (on) { g_slots.clear(); }
+  return EGT_OK;
+}
+
+// Synchronises the device, folds pending event pairs into per-kernel totals and writes up to `max`
+// entries: names (64 bytes each, NUL padded), total milliseconds, launch counts.  Returns #entries.
+int egt_profile_read(char *names_host, double *ms_host, long *counts_host, int max) {
+  cudaDeviceSynchronize();
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto &p : g_pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess) { g_slots[p.slot].ms += ms; g_slots[p.slot].count++; }
+    cudaEventDestroy(p.e0); cudaEventDestroy(p.e1);
+  }
+  g_pending.clear();
+  int n = 0;
+  for (auto &sl : g_slots) {
+    if (n >= max) break;
+    memset(names_host + 64 * n, 0, 64);
+    strncpy(names_host + 64 * n, sl.name, 63);
+    ms_host[n] = sl.ms; counts_host[n] = sl.count;
+    ++n;
+  }
+  return n;
+}
+
+int64_t egt_block_param_layout(const egt_block_cfg_t *c, int64_t *off) {
+  if (!c) return -1;
+  int64_t d = (int64_t)c->attn.h * c->attn.dk, de = c->d_e, h = c->attn.h;
+  bool edge = c->edge_channel_type != EGT_EDGE_NONE;
+  bool residual = c->edge_channel_type >= EGT_EDGE_RESIDUAL;
+  bool gated = edge && c->gate_attention;
+  int64_t sizes[14] = {d, d, d * 3 * d, 3 * d, d * d, d,
+                       residual ? de : 0, residual ? de : 0,
+                       gated ? de * h : 0, gated ? h : 0,
+                       edge ? de * h : 0, edge ? h : 0,
+                       residual ? h * de : 0, residual ? de : 0};
+  int64_t tot = 0;
+  for (int i = 0; i < 14; ++i) {
+    if (off) off[i] = sizes[i] ? tot : -1;
+    tot += sizes[i];
+  }
+  return tot;
+}
+
+int egt_attn_fwd(const egt_attn_cfg_t *cfg, const void *qkv, const void *E, const void *G, const void *M,
+                 const uint8_t *mask, void *v_att, void *h_hat, void *a_tild, float *lse, float *deg,
+                 void *stream) {
+  int rc = check_attn_cfg(cfg);
+  if (rc) return rc;
+  if ((rc = check_device())) return rc;
+  EGT_REQUIRE(qkv && v_att && lse && deg, EGT_E_ARG, "qkv, v_att, lse, deg must be non-NULL");
+  EGT_REQUIRE(!cfg->edge_input || E, EGT_E_ARG, "edge_input set but E is NULL");
+  EGT_REQUIRE(!cfg->gate_input || G, EGT_E_ARG, "gate_input set but G is NULL");
+  EGT_REQUIRE(cfg->attn_mask == EGT_MASK_NONE || M, EGT_E_ARG, "attn_mask set but M is NULL");
+  AttnParams P = make_attn_params(cfg);
+  P.qkv = qkv; P.E = cfg->edge_input ? E : nullptr; P.G = cfg->gate_input ? G : nullptr;
+  P.M = M; P.mask = mask; P.v_att = v_att; P.h_hat = h_hat; P.a_tild = a_tild; P.lse = lse; P.deg = deg;
+  return attn_staged_fwd(P, cfg->dtype, (cudaStream_t)stream);
+}
+
+int egt_attn_bwd(const egt_attn_cfg_t *cfg, const void *qkv, const void *E, const void *G, const void *M,
+                 const uint8_t *mask, const float *lse, const float *deg, const void *d_v_att,
+                 const void *d_h_hat, void *d_qkv, void *dE, void *dG, float *row_ws, void *stream) {
+  int rc = check_attn_cfg(cfg);
+  if (rc) return rc;
+  if ((rc = check_device())) return rc;
+  EGT_REQUIRE(qkv && lse && deg && d_v_att && d_qkv && row_ws, EGT_E_ARG,
+              "qkv, lse, deg, d_v_att, d_qkv, row_ws must be non-NULL");
+  AttnParams P = make_attn_params(cfg);
+  P.qkv = qkv; P.E = cfg->edge_input ? E : nullptr; P.G = cfg->gate_input ? G : nullptr;
+  P.M = M; P.mask = mask; P.lse = (float *)lse; P.deg = (float *)deg;
+  P.d_v_att = d_v_att; P.d_h_hat = d_h_hat; P.d_qkv = d_qkv;
+  P.dE = cfg->edge_input ? dE : nullptr; P.dG = cfg->gate_input ? dG : nullptr;
+  P.row_ws = row_ws;
+  return attn_staged_bwd(P, cfg->dtype, (cudaStream_t)stream);
+}
+
+size_t egt_block_workspace_bytes(const egt_block_cfg_t *cfg, int32_t backward) {
+  if (!cfg) return 0;
+  return carve(cfg, backward, nullptr).total + 256;
+}
+
+int egt_block_fwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, const egt_block_fwd_io_t *io,
+                  void *stream) {
+  int rc = check_block_cfg(cfg);
+  if (rc) return rc;
+  egt_attn_cfg_t a = derived_attn_cfg(cfg);
+  if ((rc = check_attn_cfg(&a))) return rc;
+  if ((rc = check_device())) return rc;
+  EGT_REQUIRE(w && io, EGT_E_ARG, "weights / io is NULL");
+  EGT_REQUIRE(io->h && io->h_out && io->qkv && io->v_att && io->lse && io->deg, EGT_E_ARG,
+              "h, h_out, qkv, v_att, lse, deg must be non-NULL");
+  const bool edge = cfg->edge_channel_type != EGT_EDGE_NONE;
+  const bool residual = cfg->edge_channel_type >= EGT_EDGE_RESIDUAL;
+  EGT_REQUIRE(!edge || io->e, EGT_E_ARG, "e is NULL");
+  EGT_REQUIRE(!residual || io->e_out, EGT_E_ARG, "e_out is NULL");
+  EGT_REQUIRE(cfg->edge_channel_type != EGT_EDGE_CONSTRAINED || io->adj, EGT_E_ARG, "constrained needs adj");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int R = a.B * a.N, d = a.h * a.dk;
+
+  // node side: LN_h + QKV (graph_xformer_model_base.py:108-114)
+  LinearArgs lq;
+  memset(&lq, 0, sizeof(lq));
+  lq.x = io->h; lq.W = w->dense_qkv_kernel; lq.bias = w->dense_qkv_bias; lq.out = io->qkv;
+  lq.ln_gamma = w->norm_mha_gamma; lq.ln_beta = w->norm_mha_beta; lq.ln_eps = cfg->ln_eps;
+  lq.R = R; lq.din = d; lq.dout = 3 * d;
+  if ((rc = linear_launch(lq, a.dtype, st))) return rc;
+
+  size_t need = egt_block_workspace_bytes(cfg, 0);
+  EGT_REQUIRE(io->workspace_bytes >= need && (io->workspace || need <= 256), EGT_E_ARG,
+              "workspace too small: %zu < %zu", io->workspace_bytes, need);
+  BlockWs ws = carve(cfg, 0, io->workspace);
+  g_last_path = 0;
+
+  EdgeParams ep = make_edge_params(cfg, w);
+  if (edge) {
+    ep.e = io->e; ep.E = ws.E; ep.G = ws.G;
+    if ((rc = edge_proj_fwd_launch(ep, a.dtype, st))) return rc;
+  }
+  AttnParams P = make_attn_params(&a);
+  P.qkv = io->qkv; P.E = ws.E; P.G = a.gate_input ? ws.G : nullptr; P.M = io->adj; P.mask = io->mask;
+  P.v_att = io->v_att; P.h_hat = ws.Hhat; P.lse = io->lse; P.deg = io->deg;
+  if ((rc = attn_staged_fwd(P, a.dtype, st))) return rc;
+  if (residual) {
+    ep.h_hat = ws.Hhat; ep.e_out = io->e_out;
+    if ((rc = edge_out_fwd_launch(ep, a.dtype, st))) return rc;
+  }
+  // h' = V_att W_O + b_O + h  (graph_xformer_model_base.py:136-140)
+  LinearArgs lo;
+  memset(&lo, 0, sizeof(lo));
+  lo.x = io->v_att; lo.W = w->dense_mha_kernel; lo.bias = w->dense_mha_bias; lo.res = io->h; lo.out = io->h_out;
+  lo.R = R; lo.din = d; lo.dout = d;
+  return linear_launch(lo, a.dtype, st);
+}
+
+int egt_block_bwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, const egt_block_grads_t *g,
+                  const egt_block_bwd_io_t *io, void *stream) {
+  int rc = check_block_cfg(cfg);
+  if (rc) return rc;
+  egt_attn_cfg_t a = derived_attn_cfg(cfg);
+  if ((rc = check_attn_cfg(&a))) return rc;
+  if ((rc = check_device())) return rc;
+  EGT_REQUIRE(w && g && io, EGT_E_ARG, "weights / grads / io is NULL");
+  EGT_REQUIRE(io->h && io->qkv && io->v_att && io->lse && io->deg && io->dh_out && io->dh, EGT_E_ARG,
+              "h, qkv, v_att, lse, deg, dh_out, dh must be non-NULL");
+  const bool edge = cfg->edge_channel_type != EGT_EDGE_NONE;
+  const bool residual = cfg->edge_channel_type >= EGT_EDGE_RESIDUAL;
+  EGT_REQUIRE(!edge || (io->e && io->de), EGT_E_ARG, "e / de is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int R = a.B * a.N, d = a.h * a.dk;
+  size_t need = egt_block_workspace_bytes(cfg, 1);
+  EGT_REQUIRE(io->workspace && io->workspace_bytes >= need, EGT_E_ARG, "workspace too small: %zu < %zu",
+              io->workspace_bytes, need);
+  BlockWs ws = carve(cfg, 1, io->workspace);
+  g_last_path = 0;
+
+  // dV_att = dh' W_O^T ; dW_O += V_att^T dh' ; db_O += colsum(dh')
+  LinearArgs l1;
+  memset(&l1, 0, sizeof(l1));
+  l1.x = io->dh_out; l1.W = w->dense_mha_kernel; l1.trans = 1; l1.out = ws.d_v_att; l1.R = R; l1.din = d; l1.dout = d;
+  if ((rc = linear_launch(l1, a.dtype, st))) return rc;
+  XtyArgs x1;
+  memset(&x1, 0, sizeof(x1));
+  x1.X = io->v_att; x1.Y = io->dh_out; x1.dW = g->dense_mha_kernel; x1.db = g->dense_mha_bias; x1.R = R; x1.dx = d; x1.dy = d;
+  if ((rc = xty_launch(x1, a.dtype, st))) return rc;
+
+  EdgeParams ep = make_edge_params(cfg, w);
+  ep.g_ln_g = g->norm_edge_gamma; ep.g_ln_b = g->norm_edge_beta;
+  ep.g_w_e = g->dense_edge_b_kernel; ep.g_b_e = g->dense_edge_b_bias;
+  ep.g_w_g = g->attention_gates_kernel; ep.g_b_g = g->attention_gates_bias;
+  ep.e = io->e;
+  if (edge) {   // recompute E, G
+    ep.E = ws.E; ep.G = ws.G;
+    if ((rc = edge_proj_fwd_launch(ep, a.dtype, st))) return rc;
+  }
+  const bool have_de_out = residual && io->de_out;
+  if (have_de_out) {   // dH_ext = de' W_r^T
+    EdgeParams e1 = ep;
+    e1.de_out = io->de_out; e1.d_h_ext = ws.dHext; e1.g_w_r = nullptr; e1.g_b_r = nullptr;
+    if ((rc = edge_out_bwd_launch(e1, a.dtype, st))) return rc;
+  }
+  AttnParams P = make_attn_params(&a);
+  P.qkv = io->qkv; P.E = ws.E; P.G = a.gate_input ? ws.G : nullptr; P.M = io->adj; P.mask = io->mask;
+  P.lse = (float *)io->lse; P.deg = (float *)io->deg;
+  P.d_v_att = ws.d_v_att; P.d_h_hat = have_de_out ? ws.dHext : nullptr; P.d_qkv = ws.d_qkv;
+  P.dE = ws.dE; P.dG = a.gate_input ? ws.dG : nullptr; P.row_ws = ws.row_ws;
+  P.h_hat = have_de_out ? ws.Hhat : nullptr;     // row pass re-materialises H_hat for dW_r
+  if ((rc = attn_staged_bwd(P, a.dtype, st))) return rc;
+  if (have_de_out) {   // dW_r += H_hat^T de' ; db_r += colsum(de')
+    EdgeParams e2 = ep;
+    e2.de_out = io->de_out; e2.h_hat = ws.Hhat; e2.d_h_ext = nullptr;
+    e2.g_w_r = g->dense_edge_r_kernel; e2.g_b_r = g->dense_edge_r_bias;
+    if ((rc = edge_out_bwd_launch(e2, a.dtype, st))) return rc;
+  }
+  if (edge) {
+    ep.dE = ws.dE; ep.dG = ws.dG; ep.de = io->de; ep.de_out = io->de_out;
+    if ((rc = edge_proj_bwd_launch(ep, a.dtype, st))) return rc;
+  }
+  // node side: hn = LN(h); dW_qkv += hn^T dqkv; dhn = dqkv W_qkv^T; dh = LN_bwd(dhn) + dh'
+  LinearArgs l2;
+  memset(&l2, 0, sizeof(l2));
+  l2.x = io->h; l2.ln_gamma = w->norm_mha_gamma; l2.ln_beta = w->norm_mha_beta; l2.ln_eps = cfg->ln_eps;
+  l2.xn_out = ws.hn; l2.R = R; l2.din = d; l2.dout = 0;
+  if ((rc = linear_launch(l2, a.dtype, st))) return rc;
+  XtyArgs x2;
+  memset(&x2, 0, sizeof(x2));
+  x2.X = ws.hn; x2.x_f32 = 1; x2.Y = ws.d_qkv; x2.dW = g->dense_qkv_kernel; x2.db = g->dense_qkv_bias;
+  x2.R = R; x2.dx = d; x2.dy = 3 * d;
+  if ((rc = xty_launch(x2, a.dtype, st))) return rc;
+  LinearArgs l3;
+  memset(&l3, 0, sizeof(l3));
+  l3.x = ws.d_qkv; l3.W = w->dense_qkv_kernel; l3.trans = 1; l3.out = ws.dhn; l3.out_f32 = 1;
+  l3.R = R; l3.din = 3 * d; l3.dout = d;
+  if ((rc = linear_launch(l3, a.dtype, st))) return rc;
+  LnBwdArgs lb;
+  memset(&lb, 0, sizeof(lb));
+  lb.x = io->h; lb.dy = ws.dhn; lb.dres = io->dh_out; lb.gamma = w->norm_mha_gamma; lb.eps = cfg->ln_eps;
+  lb.dx = io->dh; lb.dgamma = g->norm_mha_gamma; lb.dbeta = g->norm_mha_beta; lb.R = R; lb.D = d;
+  return ln_bwd_launch(lb, a.dtype, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,147 @@
+"""Host-side mirror of the reference's layer interface for the hot path.
+
+``EGT``       <-> lib/models/egt_layers.py:4-217   (same constructor kwargs, same positional input list)
+``EGTBlock``  <-> edge_update_{none,bias,residual} + mha_block of
+                  lib/models/graph_xformer_model_base.py:106-223 for one layer ``tag``; owns the
+                  weights under the reference's layer names.
+"""
+import math
+from typing import Dict, Optional
+
+import torch
+from torch import nn
+
+from . import ops
+
+_KERAS_NAMES = {   # flat-buffer field -> (reference layer name stem, keras weight name)
+    'norm_mha_gamma': ('norm_mha', 'gamma'), 'norm_mha_beta': ('norm_mha', 'beta'),
+    'dense_qkv_kernel': ('dense_qkv', 'kernel'), 'dense_qkv_bias': ('dense_qkv', 'bias'),
+    'dense_mha_kernel': ('dense_mha', 'kernel'), 'dense_mha_bias': ('dense_mha', 'bias'),
+    'norm_edge_gamma': ('norm_edge', 'gamma'), 'norm_edge_beta': ('norm_edge', 'beta'),
+    'attention_gates_kernel': ('attention_gates', 'kernel'), 'attention_gates_bias': ('attention_gates', 'bias'),
+    'dense_edge_b_kernel': ('dense_edge_b', 'kernel'), 'dense_edge_b_bias': ('dense_edge_b', 'bias'),
+    'dense_edge_r_kernel': ('dense_edge_r', 'kernel'), 'dense_edge_r_bias': ('dense_edge_r', 'bias'),
+}
+
+
+class _RngState:
+    """seed/offset bookkeeping for the in-kernel counter RNG (random key mask, dropout)."""
+
+    def __init__(self, seed=0):
+        self.seed = seed
+        self.offset = 0
+
+    def next(self):
+        self.offset += 1
+        return self.seed, self.offset
+
+
+class EGT(nn.Module):
+    """Drop-in for the reference Keras layer ``EGT`` (egt_layers.py:4-40).  No weights.
+
+    ``forward([QKV, E?, G?, M?], mask=None, training=None) -> (V_att, H_hat, A_tild)``;
+    ``A_tild`` is ``None`` unless ``return_attn=True`` (only Analysis taps consume it,
+    graph_xformer_model_base.py:134)."""
+
+    def __init__(self, num_heads=8, clip_logits_value=(-5, 5), scale_degree=False, scaler_type='log',
+                 edge_input=True, gate_input=True, attn_mask=False, num_virtual_nodes=0,
+                 random_mask_prob=0., attn_dropout=0., return_attn=False, seed=0):
+        super().__init__()
+        clip = None if clip_logits_value is None else tuple(float(v) for v in clip_logits_value)
+        self.spec = ops.AttnSpec(num_heads=num_heads, clip_logits_value=clip, scale_degree=scale_degree,
+                                 scaler_type=scaler_type, edge_input=edge_input, gate_input=gate_input,
+                                 attn_mask=attn_mask, num_virtual_nodes=num_virtual_nodes,
+                                 random_mask_prob=random_mask_prob, attn_dropout=attn_dropout)
+        self.spec.validate()
+        self.return_attn = return_attn
+        self.rng = _RngState(seed)
+
+    def get_config(self):
+        """Same keys as egt_layers.py:42-55, plus ``attn_dropout`` which the reference forgets."""
+        s = self.spec
+        return dict(num_heads=s.num_heads, clip_logits_value=s.clip_logits_value, scale_degree=s.scale_degree,
+                    scaler_type=s.scaler_type, edge_input=s.edge_input, gate_input=s.gate_input,
+                    attn_mask=s.attn_mask, num_virtual_nodes=s.num_virtual_nodes,
+                    random_mask_prob=s.random_mask_prob, attn_dropout=s.attn_dropout)
+
+    def compute_mask(self, inputs, mask):                                    # egt_layers.py:215-217
+        return [mask[0] if isinstance(mask, (list, tuple)) else mask, None, None]
+
+    def forward(self, inputs, mask=None, training=None):
+        if training is None:                                                 # egt_layers.py:58-59
+            training = self.training
+        seed, offset = self.rng.next() if training else (0, 0)
+        return ops.egt_attention(inputs, mask, training, spec=self.spec, seed=seed, offset=offset,
+                                 return_attn=self.return_attn)
+
+
+class EGTBlock(nn.Module):
+    """One attention block ``(h, e, mask) -> (h', e')``.
+
+    All weights live in ONE flat float32 parameter (``self.flat``) so that data-parallel training
+    needs a single all-reduce on ``self.flat.grad``; named views follow the reference's layer names
+    (``norm_mha``, ``dense_qkv``, ``dense_mha``, ``norm_edge``, ``attention_gates``,
+    ``dense_edge_b``, ``dense_edge_r``)."""
+
+    def __init__(self, tag='00', seed=0, **kwargs):
+        super().__init__()
+        if 'clip_logits_value' in kwargs and kwargs['clip_logits_value'] is not None:
+            kwargs['clip_logits_value'] = tuple(float(v) for v in kwargs['clip_logits_value'])
+        self.spec = ops.BlockSpec(**kwargs)
+        self.spec.validate()
+        self.tag = tag
+        total, self.layout = ops.param_layout(self.spec)
+        self.flat = nn.Parameter(torch.zeros(total, dtype=torch.float32))
+        self.rng = _RngState(seed)
+        self.reset_parameters()
+
+    # -- parameters ---------------------------------------------------------------------
+    def view(self, field: str) -> torch.Tensor:
+        off, shape = self.layout[field]
+        return self.flat.data[off:off + math.prod(shape)].view(shape)
+
+    def grad_view(self, field: str) -> Optional[torch.Tensor]:
+        if self.flat.grad is None:
+            return None
+        off, shape = self.layout[field]
+        return self.flat.grad[off:off + math.prod(shape)].view(shape)
+
+    def reset_parameters(self, seed=1234):
+        """Keras defaults: Dense = glorot_uniform kernel / zero bias; LayerNormalization = ones / zeros."""
+        g = torch.Generator().manual_seed(seed)
+        for f in self.layout:
+            v = self.view(f)
+            if f.endswith('kernel'):
+                lim = math.sqrt(6.0 / (v.shape[0] + v.shape[1]))
+                v.copy_((torch.rand(v.shape, generator=g) * 2 - 1) * lim)
+            elif f.endswith('gamma'):
+                v.fill_(1.)
+            else:
+                v.zero_()
+
+    def keras_weights(self) -> Dict[str, torch.Tensor]:
+        """{'<layer>_{tag}/<weight>': tensor} with Keras layouts (Dense kernel [in,out])."""
+        return {f'{_KERAS_NAMES[f][0]}_{self.tag}/{_KERAS_NAMES[f][1]}': self.view(f).clone() for f in self.layout}
+
+    def load_keras_weights(self, weights: Dict[str, torch.Tensor], strict=True):
+        """Load by reference layer name (what ``load_weights(by_name=True)`` does,
+        lib/training/training_base.py:362).  Accepts keys with or without the ``_{tag}`` suffix."""
+        for f in self.layout:
+            stem, wn = _KERAS_NAMES[f]
+            for key in (f'{stem}_{self.tag}/{wn}', f'{stem}/{wn}'):
+                if key in weights:
+                    w = torch.as_tensor(weights[key], dtype=torch.float32)
+                    assert tuple(w.shape) == tuple(self.layout[f][1]), f'{key}: {tuple(w.shape)} != {self.layout[f][1]}'
+                    self.view(f).copy_(w)
+                    break
+            else:
+                if strict:
+                    raise KeyError(f'missing weight for {stem}_{self.tag}/{wn}')
+
+    # -- call ---------------------------------------------------------------------------
+    def forward(self, h, e, mask=None, edge_mask=None, training=None):
+        if training is None:
+            training = self.training
+        seed, offset = self.rng.next() if training else (0, 0)
+        return ops.egt_block(h, e, mask, self.flat, self.spec, self.layout, edge_mask=edge_mask,
+                             training=training, seed=seed, offset=offset)

@@ -1,0 +1,195 @@
+/* egt_b200.h -- C ABI of the B200-native EGT edge-augmented attention block.
+ *
+ * This is the drop-in boundary for ONE hot path of shamim-hussain/egt (TF2/Keras):
+ *
+ *   egt_attn_fwd / egt_attn_bwd    replace  EGT.call_gated / EGT.call_ungated
+ *                                  (lib/models/egt_layers.py:57-143, :145-213) and the
+ *                                  TF autodiff of them (driven by Model.fit,
+ *                                  lib/training/training_base.py:294)
+ *   egt_block_fwd / egt_block_bwd  replace  edge_update_{none,bias,residual} around
+ *                                  mha_block (lib/models/graph_xformer_model_base.py
+ *                                  :106-145, :149-162, :164-223; dispatch :328-339)
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no C++ or torch types cross the boundary.
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns and
+ *     allocates every buffer (inputs, outputs, saved statistics, workspace).  The library
+ *     never allocates or frees device memory and keeps no pointer after it returns.
+ *   - every entry point is stream-ordered on `stream` (a cudaStream_t passed as void*), does
+ *     not synchronise the host, and returns 0 or a negative egt_status; the message of the
+ *     last failure on the calling thread is egt_last_error().
+ *   - tensors are dense row-major with the reference's layouts (head axis innermost):
+ *       h, h_out, v_att      [B, N, d]            channel c = dd*h + hh   (egt_layers.py:73-76,139-141)
+ *       qkv                  [B, N, 3*d]          channel   = s*d + dd*h + hh,  s = 0,1,2 for Q,K,V
+ *       e, e_out             [B, N, N, d_e]
+ *       E, G, H_hat, A_tild  [B, N, N, h]         (egt_layers.py:79-80)
+ *       mask                 [B, N]  uint8, 1 = real node  (Keras mask of h; only KEYS are masked,
+ *                                                  egt_layers.py:91-94)
+ *       lse, deg             [B, N, h] float32    row statistics saved for the backward
+ *   - `dtype` selects the element type of activations / activation gradients (EGT_F32 or
+ *     EGT_BF16).  Weights, weight gradients and saved row statistics are always float32.
+ */
+#ifndef EGT_B200_H_
+#define EGT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EGT_ABI_VERSION 1
+
+typedef enum egt_status {
+  EGT_OK = 0,
+  EGT_E_SHAPE = -1,   /* unsupported / inconsistent sizes  (reference: assert at egt_layers.py:70) */
+  EGT_E_DTYPE = -2,
+  EGT_E_ALIGN = -3,
+  EGT_E_ARCH = -4,    /* not an sm_100 device */
+  EGT_E_CUDA = -5,    /* a CUDA runtime call failed */
+  EGT_E_ARG = -6      /* bad flag combination      (reference: ValueError at egt_layers.py:20-24) */
+} egt_status;
+
+enum { EGT_F32 = 0, EGT_BF16 = 1 };
+enum { EGT_SCALER_LOG = 0, EGT_SCALER_LINEAR = 1 };                 /* egt_layers.py:23-24,125-130 */
+enum { EGT_EDGE_NONE = 0, EGT_EDGE_BIAS = 1, EGT_EDGE_RESIDUAL = 2, /* graph_xformer_model_base.py:328-334 */
+       EGT_EDGE_CONSTRAINED = 3 };
+enum { EGT_ACT_NONE = 0, EGT_ACT_LRELU = 1, EGT_ACT_RELU = 2, EGT_ACT_ELU = 3,
+       EGT_ACT_TANH = 4, EGT_ACT_SIGMOID = 5 };                     /* graph_xformer_model_base.py:149-162 */
+enum { EGT_MASK_NONE = 0,
+       EGT_MASK_DENSE = 1,   /* M: [B,N,N,h] of the activation dtype, 0/1 (egt_layers.py:96-101)      */
+       EGT_MASK_ADJ_U8 = 2   /* M: [B,N,N] uint8 adjacency, broadcast over heads
+                                (what AdjMatModel.get_edge_mask tiles, graph_model_base.py:131-142)  */ };
+
+/* Constructor arguments of the reference `EGT` layer (egt_layers.py:5-16) + sizes. */
+typedef struct egt_attn_cfg {
+  int32_t B, N, h, dk;          /* d = h*dk;  dk = qkv_channels / (3*h)  (egt_layers.py:70-71) */
+  int32_t dtype;                /* EGT_F32 | EGT_BF16 */
+  int32_t edge_input;           /* E present            */
+  int32_t gate_input;           /* G present            */
+  int32_t attn_mask;            /* EGT_MASK_*           */
+  int32_t has_clip;             /* clip_logits_value is not None */
+  float clip_lo, clip_hi;
+  int32_t scale_degree;
+  int32_t scaler_type;          /* EGT_SCALER_* */
+  int32_t num_virtual_nodes;
+  int32_t training;             /* random mask / dropout only when nonzero (egt_layers.py:103,116) */
+  float random_mask_prob;
+  float attn_dropout;
+  uint64_t seed;                /* counter-based RNG (Philox4x32-10), see DESIGN.md "RNG" */
+  uint64_t offset;
+} egt_attn_cfg_t;
+
+/* Hyper-parameters of GraphTransformerBase that reach the attention block
+ * (graph_xformer_model_base.py:17-45). */
+typedef struct egt_block_cfg {
+  egt_attn_cfg_t attn;          /* attn.edge_input / gate_input / attn_mask are derived by the library */
+  int32_t d_e;                  /* edge_width */
+  int32_t edge_channel_type;    /* EGT_EDGE_* */
+  int32_t gate_attention;
+  int32_t edge_act;             /* EGT_ACT_*  */
+  float edge_act_alpha;         /* 'lreluX' -> X/10 (graph_xformer_model_base.py:150-152) */
+  float ln_eps;                 /* keras LayerNormalization default 1e-3 */
+} egt_block_cfg_t;
+
+/* float32 parameters, Keras layouts: Dense kernel [in,out]; names of SURVEY.md appendix D. */
+typedef struct egt_block_weights {
+  const float *norm_mha_gamma, *norm_mha_beta;            /* [d]            norm_mha_{tag}        */
+  const float *dense_qkv_kernel, *dense_qkv_bias;         /* [d,3d], [3d]   dense_qkv_{tag}       */
+  const float *dense_mha_kernel, *dense_mha_bias;         /* [d,d], [d]     dense_mha_{tag}       */
+  const float *norm_edge_gamma, *norm_edge_beta;          /* [d_e]          norm_edge_{tag}       */
+  const float *attention_gates_kernel, *attention_gates_bias; /* [d_e,h],[h] attention_gates_{tag} */
+  const float *dense_edge_b_kernel, *dense_edge_b_bias;   /* [d_e,h], [h]   dense_edge_b_{tag}    */
+  const float *dense_edge_r_kernel, *dense_edge_r_bias;   /* [h,d_e], [d_e] dense_edge_r_{tag}    */
+} egt_block_weights_t;
+
+/* float32 gradient accumulators (the library ADDS into them); same shapes as the weights.
+ * They may all point into one flat buffer so that data-parallel training needs a single
+ * all-reduce (MirroredStrategy semantics, lib/training/training_base.py:230-238). */
+typedef struct egt_block_grads {
+  float *norm_mha_gamma, *norm_mha_beta;
+  float *dense_qkv_kernel, *dense_qkv_bias;
+  float *dense_mha_kernel, *dense_mha_bias;
+  float *norm_edge_gamma, *norm_edge_beta;
+  float *attention_gates_kernel, *attention_gates_bias;
+  float *dense_edge_b_kernel, *dense_edge_b_bias;
+  float *dense_edge_r_kernel, *dense_edge_r_bias;
+} egt_block_grads_t;
+
+typedef struct egt_block_fwd_io {
+  const void *h;            /* [B,N,d]                     */
+  const void *e;            /* [B,N,N,d_e] (NULL for EGT_EDGE_NONE) */
+  const uint8_t *mask;      /* [B,N] or NULL               */
+  const uint8_t *adj;       /* [B,N,N] uint8, only for EGT_EDGE_CONSTRAINED */
+  void *h_out;              /* [B,N,d]                     */
+  void *e_out;              /* [B,N,N,d_e]; written only for residual/constrained */
+  /* saved for the backward (caller keeps them alive) */
+  void *qkv;                /* [B,N,3d]  activation dtype  */
+  void *v_att;              /* [B,N,d]   activation dtype  */
+  float *lse;               /* [B,N,h]                     */
+  float *deg;               /* [B,N,h]                     */
+  void *workspace;          /* egt_block_workspace_bytes() */
+  size_t workspace_bytes;
+} egt_block_fwd_io_t;
+
+typedef struct egt_block_bwd_io {
+  const void *h, *e;
+  const uint8_t *mask, *adj;
+  const void *qkv, *v_att;  /* saved by the forward */
+  const float *lse, *deg;
+  const void *dh_out;       /* [B,N,d]      upstream gradient of h_out */
+  const void *de_out;       /* [B,N,N,d_e]  upstream gradient of e_out (NULL = zero) */
+  void *dh;                 /* [B,N,d]      */
+  void *de;                 /* [B,N,N,d_e]  (NULL for EGT_EDGE_NONE) */
+  void *workspace;
+  size_t workspace_bytes;
+} egt_block_bwd_io_t;
+
+int egt_abi_version(void);
+const char *egt_last_error(void);
+
+/* Number of floats in the flat gradient buffer of one block and the offset of each tensor in it,
+ * in the order of egt_block_weights_t (absent tensors get offset -1).  offsets_host: int64[14]. */
+int64_t egt_block_param_layout(const egt_block_cfg_t *cfg, int64_t *offsets_host);
+
+/* ---- EGT layer: ([QKV, E?, G?, M?], mask) -> (V_att, H_hat, A_tild?) ------------------- */
+/* h_hat may be NULL (not materialised); a_tild NULL = skip (only Analysis taps consume it,
+ * graph_xformer_model_base.py:134). lse/deg: [B,N,h] float32, written. */
+int egt_attn_fwd(const egt_attn_cfg_t *cfg, const void *qkv, const void *E, const void *G,
+                 const void *M, const uint8_t *mask, void *v_att, void *h_hat, void *a_tild,
+                 float *lse, float *deg, void *stream);
+
+/* d_h_hat may be NULL (treated as zero).  Writes d_qkv [B,N,3d], dE, dG [B,N,N,h]
+ * (dE / dG may be NULL when the corresponding input is absent).
+ * row_ws: float32 scratch of 2*B*N*h elements (row terms shared by the row and column passes). */
+int egt_attn_bwd(const egt_attn_cfg_t *cfg, const void *qkv, const void *E, const void *G,
+                 const void *M, const uint8_t *mask, const float *lse, const float *deg,
+                 const void *d_v_att, const void *d_h_hat, void *d_qkv, void *dE, void *dG,
+                 float *row_ws, void *stream);
+
+/* ---- attention block: (h, e, mask) -> (h', e') ----------------------------------------- */
+size_t egt_block_workspace_bytes(const egt_block_cfg_t *cfg, int32_t backward);
+int egt_block_fwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w,
+                  const egt_block_fwd_io_t *io, void *stream);
+int egt_block_bwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w,
+                  const egt_block_grads_t *g, const egt_block_bwd_io_t *io, void *stream);
+
+/* Which implementation the last egt_block_fwd / egt_block_bwd on this thread dispatched to:
+ * 0 = staged kernels (any shape, fp32 or bf16), 1 = fused tcgen05 kernel. */
+int egt_last_path(void);
+
+/* Number of CUDA kernels this library has launched in this process (bench.py's gpu_launches). */
+long egt_launch_count(void);
+/* Per-kernel CUDA-event timing of every launch (bench.py's roofline leg).  enable(1) clears the table. */
+int egt_profile_enable(int on);
+int egt_profile_read(char *names_host, double *ms_host, long *counts_host, int max_entries);
+
+/* Counter-based uniform in [0,1) used for the random key mask / dropout (testing hook; host code).
+ * stream_id 0 = random mask, 1 = attention dropout.  idx = ((b*N + l)*N + m)*h + hh. */
+float egt_rng_uniform_host(uint64_t seed, uint64_t offset, uint32_t stream_id, uint64_t idx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EGT_B200_H_ */

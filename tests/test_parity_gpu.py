@@ -1,0 +1,303 @@
+"""GPU parity: every test calls the CUDA path through the C ABI (egt_b200.ops -> libegt_b200.so)
+and checks it against the CPU oracle / the golden vectors produced from the reference's source.
+
+Tolerances (BASELINE.json north_star): fp32 rtol 1e-3, bf16 rtol 1e-2; mask / index behaviour
+(which attention entries are exactly zero, scaler-1 rows, padded-key exclusion) bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import egt_oracle as O
+from tests import philox
+from tests.golden_util import layer_case, block_case
+
+pytestmark = pytest.mark.gpu
+
+DEV = 'cuda:0'
+TOL = {torch.float32: dict(rtol=1e-3, atol=2e-4), torch.bfloat16: dict(rtol=1e-2, atol=1e-2)}
+
+
+def _close(got, ref, dtype, what='', scale_atol=True):
+    got = got.detach().double().cpu()
+    ref = ref.detach().double().cpu()
+    tol = TOL[dtype]
+    atol = tol['atol'] * (max(1.0, float(ref.abs().max())) if scale_atol else 1.0)
+    err = (got - ref).abs()
+    bound = atol + tol['rtol'] * ref.abs()
+    bad = err > bound
+    assert not bad.any(), (f'{what}: {int(bad.sum())}/{bad.numel()} elements out of tolerance; '
+                           f'max err {float(err.max()):.3e} at ref {float(ref.flatten()[err.argmax()]):.3e}')
+
+
+def _round(x, dtype):
+    """The values the GPU actually sees (bf16 rounding of the inputs is shared with the oracle)."""
+    return x.to(dtype).double()
+
+
+# ------------------------------------------------------------------------------------------
+# EGT layer  (egt_attn_fwd / egt_attn_bwd)  vs golden vectors and oracle
+# ------------------------------------------------------------------------------------------
+def _run_layer(c, dtype, seed=77, offset=5, want_grads=False):
+    import egt_b200
+    flags = dict(c['flags'])
+    layer = egt_b200.EGT(return_attn=True, seed=seed, **flags)
+    layer.rng.offset = offset - 1
+    nd = 1 + int(flags['edge_input']) + int(flags['gate_input'])      # differentiable inputs (not M)
+    ins_gpu = [t.to(dtype).to(DEV).requires_grad_(want_grads and i < nd) for i, t in enumerate(c['inputs'])]
+    mask = c['mask'].to(DEV)
+    V, H, A = layer(ins_gpu, mask=mask, training=c['training'])
+    # oracle on the rounded inputs with the kernel's own RNG draws
+    B, N, _ = c['QKV'].shape
+    h = flags['num_heads']
+    ins_ref = [_round(t, dtype).requires_grad_(want_grads) for t in c['inputs']]
+    kw = {}
+    odt = torch.float64
+    if c['training'] and flags['random_mask_prob'] > 0:
+        kw['uniform_noise'] = torch.from_numpy(philox.noise_tensor(seed, offset, 0, B, N, h)).double()
+        if flags['random_mask_prob'] > 0.5:      # all-keys-masked rows: only fp32 reproduces TF (appendix B-3)
+            odt = torch.float32
+    if c['training'] and flags['attn_dropout'] > 0:
+        kw['dropout_noise'] = torch.from_numpy(philox.noise_tensor(seed, offset, 1, B, N, h)).double()
+    ins_o = [t.detach().to(odt).requires_grad_(want_grads) for t in ins_ref]
+    kw = {k: v.to(odt) for k, v in kw.items()}
+    Vr, Hr, Ar = O.egt_layer(ins_o, mask=c['mask'], training=c['training'], **flags, **kw)
+    return (V, H, A), (Vr, Hr, Ar), ins_gpu, ins_o
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('idx', range(19))
+def test_layer_forward_golden(idx, dtype, golden_dir):
+    c = layer_case(golden_dir, idx)
+    (V, H, A), (Vr, Hr, Ar), _, _ = _run_layer(c, dtype)
+    _close(V, Vr, dtype, f'layer case {idx} V_att')
+    _close(H, Hr, dtype, f'layer case {idx} H_hat')
+    _close(A, Ar, dtype, f'layer case {idx} A_tild')
+    # bit-exact mask behaviour: exactly the same entries are exactly zero
+    assert torch.equal(A.cpu() == 0, Ar == 0), f'layer case {idx}: zero pattern of A_tild differs'
+    if not c['training']:
+        # deterministic cases must also match the committed golden outputs (made from the reference source)
+        if dtype == torch.float32:
+            _close(V, c['V_att'], dtype, f'layer case {idx} V_att vs golden')
+            _close(H, c['H_hat'], dtype, f'layer case {idx} H_hat vs golden')
+            assert torch.equal(A.cpu() == 0, c['A_tild'] == 0)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('idx', [0, 1, 2, 3, 5, 7, 8, 9, 10, 11, 12, 13, 14, 16])
+def test_layer_backward(idx, dtype, golden_dir):
+    c = layer_case(golden_dir, idx)
+    (V, H, A), (Vr, Hr, Ar), ins_gpu, ins_o = _run_layer(c, dtype, want_grads=True)
+    g = torch.Generator().manual_seed(idx)
+    dV = torch.randn(V.shape, generator=g)
+    dH = torch.randn(H.shape, generator=g)
+    dVg, dHg = dV.to(dtype).to(DEV), dH.to(dtype).to(DEV)
+    nd = 1 + int(c['flags']['edge_input']) + int(c['flags']['gate_input'])
+    grads = torch.autograd.grad([V, H], ins_gpu[:nd], [dVg, dHg])
+    ref = torch.autograd.grad([Vr, Hr], ins_o[:nd], [dVg.cpu().to(Vr.dtype), dHg.cpu().to(Hr.dtype)])
+    for nm, a, b in zip(('dQKV', 'dE', 'dG'), grads, ref):
+        _close(a, b, dtype, f'layer case {idx} {nm}')
+
+
+def test_layer_errors():
+    import egt_b200
+    with pytest.raises(ValueError):
+        egt_b200.EGT(scale_degree=True, gate_input=False)           # egt_layers.py:20-21
+    with pytest.raises(ValueError):
+        egt_b200.EGT(scaler_type='sqrt')                            # egt_layers.py:23-24
+    layer = egt_b200.EGT(num_heads=8)
+    q = torch.zeros(1, 4, 3 * 8 * 2 + 1, device=DEV)
+    with pytest.raises(AssertionError):                             # egt_layers.py:70
+        layer([q, torch.zeros(1, 4, 4, 8, device=DEV), torch.zeros(1, 4, 4, 8, device=DEV)])
+    with pytest.raises(RuntimeError):                               # no CPU fallback
+        layer([torch.zeros(1, 4, 48), torch.zeros(1, 4, 4, 8), torch.zeros(1, 4, 4, 8)])
+
+
+# ------------------------------------------------------------------------------------------
+# attention block  (egt_block_fwd / egt_block_bwd)
+# ------------------------------------------------------------------------------------------
+def _spec_kwargs(cfg: O.BlockConfig):
+    return dict(model_width=cfg.model_width, edge_width=cfg.edge_width, num_heads=cfg.num_heads,
+                gate_attention=cfg.gate_attention, add_n_norm=cfg.add_n_norm,
+                clip_logits_value=cfg.clip_logits_value, edge_activation=cfg.edge_activation,
+                edge_channel_type=cfg.edge_channel_type, scale_degree=cfg.scale_degree,
+                scaler_type=cfg.scaler_type, num_virtual_nodes=cfg.num_virtual_nodes,
+                random_mask_prob=cfg.random_mask_prob, attn_dropout=cfg.attn_dropout)
+
+
+def _oracle_params(block):
+    return {k.replace('_00/', '/'): v.double() for k, v in block.keras_weights().items()}
+
+
+def _run_block(cfg, params, h, e, mask, edge_mask, training, dtype, seed=31, offset=9, grads=False, force_path=None):
+    import egt_b200
+    blk = egt_b200.EGTBlock(seed=seed, **_spec_kwargs(cfg))
+    blk.load_keras_weights({k: v for k, v in params.items() if not k.startswith('ffn')})
+    blk = blk.to(DEV)
+    blk.rng.offset = offset - 1
+    hg = h.to(dtype).to(DEV).requires_grad_(grads)
+    eg = e.to(dtype).to(DEV).requires_grad_(grads)
+    emg = None if edge_mask is None else edge_mask.to(DEV)
+    h2, e2 = blk(hg, eg, mask.to(DEV), edge_mask=emg, training=training)
+    B, N, _ = h.shape
+    noise = None
+    if training and cfg.random_mask_prob > 0:
+        noise = {'random_mask': torch.from_numpy(philox.noise_tensor(seed, offset, 0, B, N, cfg.num_heads)).double()}
+    hr = _round(h, dtype).requires_grad_(grads)
+    er = _round(e, dtype).requires_grad_(grads)
+    pr = {k: v.double().clone().requires_grad_(grads) for k, v in params.items() if not k.startswith('ffn')}
+    h2r, e2r = O.egt_block(hr, er, mask, pr, cfg, edge_mask=None if edge_mask is None else edge_mask.double(),
+                           training=training, noise=noise)
+    return blk, (hg, eg, h2, e2), (hr, er, pr, h2r, e2r)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('idx', range(16))
+def test_block_forward_golden(idx, dtype, golden_dir):
+    c = block_case(golden_dir, idx)
+    if c['cfg'].add_n_norm:
+        import egt_b200
+        with pytest.raises(NotImplementedError):
+            egt_b200.EGTBlock(**_spec_kwargs(c['cfg']))
+        return
+    blk, (hg, eg, h2, e2), (hr, er, pr, h2r, e2r) = _run_block(
+        c['cfg'], c['params'], c['h'], c['e'], c['mask'], c.get('edge_mask'), c['training'], dtype)
+    _close(h2, h2r, dtype, f"block case {idx} h'")
+    _close(e2, e2r, dtype, f"block case {idx} e'")
+    if dtype == torch.float32 and not c['training']:
+        _close(h2, c['h_out'], dtype, f"block case {idx} h' vs golden")
+        _close(e2, c['e_out'], dtype, f"block case {idx} e' vs golden")
+
+
+BWD_CASES = [
+    # (B, N, d, d_e, h, overrides)
+    (2, 9, 16, 8, 4, {}),
+    (2, 9, 16, 8, 4, dict(edge_channel_type='bias')),
+    (2, 9, 16, 8, 4, dict(edge_channel_type='none')),
+    (2, 9, 16, 8, 4, dict(edge_channel_type='constrained', scale_degree=True)),
+    (2, 9, 16, 8, 4, dict(gate_attention=False)),
+    (2, 9, 16, 8, 4, dict(scale_degree=True, scaler_type='linear', num_virtual_nodes=1)),
+    (2, 9, 16, 8, 4, dict(edge_activation='lrelu2')),
+    (2, 9, 16, 8, 4, dict(edge_activation='elu', clip_logits_value=None)),
+    (2, 9, 16, 8, 4, dict(random_mask_prob=0.2, training=True, scale_degree=True)),
+    (3, 37, 64, 64, 8, dict(scale_degree=True)),                 # ZINC-500K widths, N=37
+    (2, 13, 48, 48, 8, {}),                                      # ZINC-100K widths, dk=6
+    (2, 21, 96, 8, 8, dict(scale_degree=True)),                  # BASELINE CLUSTER d=96, dk=12
+    (2, 19, 128, 32, 16, dict(scale_degree=True)),               # C5 widths
+    (2, 75, 64, 8, 8, dict(random_mask_prob=0.1, training=True)),  # MNIST shape, shipped training flags
+    (1, 130, 64, 8, 8, {}),                                      # N just above one 128-row tile
+]
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('case', range(len(BWD_CASES)))
+def test_block_forward_backward_vs_oracle(case, dtype):
+    B, N, d, de, nh, ov = BWD_CASES[case]
+    ov = dict(ov)
+    training = ov.pop('training', False)
+    cfg = O.BlockConfig(model_width=d, edge_width=de, num_heads=nh, **ov)
+    params = O.init_block_params(cfg, seed=1234 + case, dtype=torch.float64)
+    h, e, mask = O.synthetic_batch(B, N, d, de, seed=20240 + case, ragged=True, dtype=torch.float64)
+    edge_mask = None
+    if cfg.edge_channel_type == 'constrained':
+        g = torch.Generator().manual_seed(case)
+        adj = ((torch.rand(B, N, N, generator=g) < 0.4) | torch.eye(N, dtype=torch.bool)[None]).double()
+        edge_mask = adj[..., None].repeat(1, 1, 1, nh)
+    blk, (hg, eg, h2, e2), (hr, er, pr, h2r, e2r) = _run_block(cfg, params, h, e, mask, edge_mask, training, dtype,
+                                                               grads=True)
+    _close(h2, h2r, dtype, "h'")
+    _close(e2, e2r, dtype, "e'")
+    g = torch.Generator().manual_seed(99 + case)
+    dh = torch.randn(h2.shape, generator=g).to(dtype)
+    de_ = torch.randn(e2.shape, generator=g).to(dtype)
+    residual = cfg.edge_channel_type in ('residual', 'constrained')
+    if residual:
+        gin = torch.autograd.grad([h2, e2], [hg, eg, blk.flat], [dh.to(DEV), de_.to(DEV)], allow_unused=True)
+        rin = torch.autograd.grad([h2r, e2r], [hr, er] + list(pr.values()), [dh.double(), de_.double()],
+                                  allow_unused=True)
+    else:
+        gin = torch.autograd.grad([h2], [hg, eg, blk.flat], [dh.to(DEV)], allow_unused=True)
+        rin = torch.autograd.grad([h2r], [hr, er] + list(pr.values()), [dh.double()], allow_unused=True)
+    _close(gin[0], rin[0], dtype, 'dh')
+    if cfg.edge_channel_type != 'none':
+        _close(gin[1], rin[1], dtype, 'de')
+    blk.flat.grad = gin[2]
+    for (name, _), gr in zip(pr.items(), rin[2:]):
+        field = name.replace('/', '_')
+        got = blk.grad_view(field)
+        # weight gradients are sums over B*N^2 terms: compare relative to their own scale
+        tol = 2e-3 if dtype == torch.float32 else 3e-2
+        denom = max(float(gr.abs().max()), 1e-6)
+        err = float((got.double().cpu() - gr).abs().max()) / denom
+        assert err < tol, f'grad {name}: rel-to-max err {err:.3e}'
+
+
+def test_block_mask_is_bit_exact_and_padding_is_inert():
+    """Padded KEYS never influence valid rows: perturbing padded nodes / padded edge columns leaves
+    h' and e' at valid positions bit-identical (egt_layers.py:91-94)."""
+    import egt_b200
+    torch.manual_seed(0)
+    B, N, d, de, nh = 4, 50, 64, 8, 8
+    blk = egt_b200.EGTBlock(model_width=d, edge_width=de, num_heads=nh, scale_degree=True).to(DEV)
+    nn_ = torch.tensor([50, 33, 17, 1])
+    mask = (torch.arange(N)[None] < nn_[:, None]).to(DEV)
+    h = torch.randn(B, N, d, device=DEV).bfloat16()
+    e = torch.randn(B, N, N, de, device=DEV).bfloat16()
+    h2, e2 = blk(h, e, mask)
+    hp, ep = h.clone(), e.clone()
+    for b in range(B):
+        n = int(nn_[b])
+        hp[b, n:] = torch.randn(N - n, d, device=DEV).bfloat16() * 3
+        ep[b, :, n:] = torch.randn(N, N - n, de, device=DEV).bfloat16() * 3
+    h2p, e2p = blk(hp, ep, mask)
+    for b in range(B):
+        n = int(nn_[b])
+        assert torch.equal(h2[b, :n], h2p[b, :n])
+        assert torch.equal(e2[b, :n, :n], e2p[b, :n, :n])
+    assert torch.isfinite(h2.float()).all() and torch.isfinite(e2.float()).all()   # padded rows: finite garbage
+
+
+@pytest.mark.parametrize('N,d,de,nh,B', [(128, 64, 8, 8, 16), (190, 96, 8, 8, 4), (188, 64, 8, 8, 4),
+                                         (75, 64, 8, 8, 16), (37, 64, 64, 8, 16), (512, 128, 32, 16, 2)])
+def test_block_full_size_vs_oracle_sample(N, d, de, nh, B):
+    """BASELINE.json shapes at full N: oracle on two graphs of the batch + permutation equivariance."""
+    import egt_b200
+    cfg = O.BlockConfig(model_width=d, edge_width=de, num_heads=nh, scale_degree=True)
+    params = O.init_block_params(cfg, dtype=torch.float64)
+    h, e, mask = O.synthetic_batch(B, N, d, de, ragged=True, dtype=torch.float32)
+    blk = egt_b200.EGTBlock(**_spec_kwargs(cfg))
+    blk.load_keras_weights(params)
+    blk = blk.to(DEV)
+    hg, eg = h.bfloat16().to(DEV).requires_grad_(True), e.bfloat16().to(DEV).requires_grad_(True)
+    h2, e2 = blk(hg, eg, mask.to(DEV))
+    g = torch.Generator().manual_seed(1)
+    dh, de_ = torch.randn(h2.shape, generator=g).bfloat16(), torch.randn(e2.shape, generator=g).bfloat16()
+    gh, ge = torch.autograd.grad([h2, e2], [hg, eg], [dh.to(DEV), de_.to(DEV)])
+    sel = [0, B - 1]
+    hr = _round(h[sel], torch.bfloat16).requires_grad_(True)
+    er = _round(e[sel], torch.bfloat16).requires_grad_(True)
+    h2r, e2r = O.egt_block(hr, er, mask[sel], params, cfg)
+    ghr, ger = torch.autograd.grad([h2r, e2r], [hr, er], [dh[sel].double(), de_[sel].double()])
+    _close(h2[sel], h2r, torch.bfloat16, "h'")
+    _close(e2[sel], e2r, torch.bfloat16, "e'")
+    _close(gh[sel], ghr, torch.bfloat16, 'dh')
+    _close(ge[sel], ger, torch.bfloat16, 'de')
+    # graphs are independent: permuting the batch permutes the outputs bit-exactly
+    perm = torch.randperm(B, generator=g)
+    h2p, e2p = blk(hg.detach()[perm], eg.detach()[perm], mask[perm].to(DEV))
+    assert torch.equal(h2p, h2.detach()[perm]) and torch.equal(e2p, e2.detach()[perm])
+
+
+def test_gradient_linearity():
+    """backward is linear in the upstream gradients (size-independent property)."""
+    import egt_b200
+    torch.manual_seed(1)
+    B, N, d, de, nh = 8, 64, 64, 8, 8
+    blk = egt_b200.EGTBlock(model_width=d, edge_width=de, num_heads=nh).to(DEV)
+    h = torch.randn(B, N, d, device=DEV, requires_grad=True)
+    e = torch.randn(B, N, N, de, device=DEV, requires_grad=True)
+    h2, e2 = blk(h, e, None)
+    a, b = torch.randn_like(h2), torch.randn_like(e2)
+    g1 = torch.autograd.grad([h2, e2], [h, e, blk.flat], [a, b], retain_graph=True)
+    g2 = torch.autograd.grad([h2, e2], [h, e, blk.flat], [2 * a, 2 * b], retain_graph=True)
+    for x, y in zip(g1, g2):
+        torch.testing.assert_close(2 * x, y, rtol=1e-4, atol=1e-4)
