@@ -112,11 +112,13 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(AttnParams P) {
     for (int dd = 0; dd < DKMAX; ++dd)
       if (dd < P.dk) o[dd] += a * ldf(vrow + dd * P.h + hh);
   }
-  float lse = mrun + __logf(sum);
+  const float lsum = __logf(sum);          // (row max, log row sum) are kept apart: a fused lse would
+  const float lse = mrun;                  // absorb log(sum) when every key is masked (mrun = -1e9)
   float inv = 1.f / sum;
   float s = scaler_of(P, l, deg);
   size_t ps = ((size_t)b * P.N + l) * P.h + hh;
-  P.lse[ps] = lse;
+  P.lse[ps] = mrun;
+  P.lse[(size_t)P.B * P.N * P.h + ps] = lsum;
   P.deg[ps] = deg;
   T *vo = (T *)P.v_att + ((size_t)b * P.N + l) * d;
 #pragma unroll
@@ -131,7 +133,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(AttnParams P) {
         if (dd < P.dk) k[dd] = ldf(krow + dd * P.h + hh);
       float S_raw, x, gin, keep;
       ctx.eval(l, m, q, k, S_raw, x, gin, keep);
-      float p = __expf(x - lse);
+      float p = __expf((x - lse) - lsum);
       float g = P.G ? sigmoid_f(gin) : 1.f;
       size_t pe = (((size_t)b * P.N + l) * P.N + m) * P.h + hh;
       stf((T *)P.a_tild + pe, p * g * keep);
@@ -162,6 +164,7 @@ __global__ void __launch_bounds__(128) attn_bwd_row_kernel(AttnParams P) {
   }
   size_t ps = ((size_t)b * P.N + l) * P.h + hh;
   const float lse = P.lse[ps];
+  const float lsum = P.lse[(size_t)P.B * P.N * P.h + ps];
   const float deg = P.deg[ps];
   const float s = scaler_of(P, l, deg);
   LogitCtx<T> ctx(P, b, hh);
@@ -180,7 +183,7 @@ __global__ void __launch_bounds__(128) attn_bwd_row_kernel(AttnParams P) {
       }
     float S_raw, x, gin, keep;
     ctx.eval(l, m, q, k, S_raw, x, gin, keep);
-    float p = __expf(x - lse);
+    float p = __expf((x - lse) - lsum);
     float g = P.G ? sigmoid_f(gin) : 1.f;
     ds += p * g * keep * dAp;
   }
@@ -204,7 +207,7 @@ __global__ void __launch_bounds__(128) attn_bwd_row_kernel(AttnParams P) {
       }
     float S_raw, x, gin, keep;
     float Hh = ctx.eval(l, m, q, k, S_raw, x, gin, keep);
-    float p = __expf(x - lse);
+    float p = __expf((x - lse) - lsum);
     float g = P.G ? sigmoid_f(gin) : 1.f;
     float dA = s * dAp * keep;
     float dP = dA * g;
@@ -254,6 +257,7 @@ __global__ void __launch_bounds__(128) attn_bwd_col_kernel(AttnParams P) {
   for (int l = 0; l < P.N; ++l) {
     size_t ps = ((size_t)b * P.N + l) * P.h + hh;
     const float lse = P.lse[ps];
+    const float lsum = P.lse[rs + ps];
     const float D = P.row_ws[ps];
     const float s = P.row_ws[rs + ps];
     const T *qrow = qkv + ((size_t)b * P.N + l) * 3 * d;
@@ -269,7 +273,7 @@ __global__ void __launch_bounds__(128) attn_bwd_col_kernel(AttnParams P) {
     }
     float S_raw, x, gin, keep;
     ctx.eval(l, m, q, k, S_raw, x, gin, keep);
-    float p = __expf(x - lse);
+    float p = __expf((x - lse) - lsum);
     float g = P.G ? sigmoid_f(gin) : 1.f;
     float a_d = p * g * keep;
     float dA = s * dAp * keep;

@@ -102,7 +102,7 @@ class _EGTAttnFn(torch.autograd.Function):
         v_att = torch.empty(B, N, d, dtype=qkv.dtype, device=qkv.device)
         h_hat = torch.empty(B, N, N, h, dtype=qkv.dtype, device=qkv.device)
         a_tild = torch.empty(B, N, N, h, dtype=qkv.dtype, device=qkv.device) if want_attn else None
-        lse = torch.empty(B, N, h, dtype=torch.float32, device=qkv.device)
+        lse = torch.empty(2, B, N, h, dtype=torch.float32, device=qkv.device)
         deg = torch.empty(B, N, h, dtype=torch.float32, device=qkv.device)
         L.check(lib.egt_attn_fwd(C.byref(cfg), _ptr(qkv), _ptr(E), _ptr(G), _ptr(M), _ptr(mask_u8),
                                  _ptr(v_att), _ptr(h_hat), _ptr(a_tild), _ptr(lse), _ptr(deg), _stream()))
@@ -270,7 +270,7 @@ class _EGTBlockFn(torch.autograd.Function):
         e_out = torch.empty_like(e) if spec.is_residual else None
         qkv = torch.empty(B, N, 3 * d, dtype=h.dtype, device=dev)
         v_att = torch.empty(B, N, d, dtype=h.dtype, device=dev)
-        lse = torch.empty(B, N, spec.num_heads, dtype=torch.float32, device=dev)
+        lse = torch.empty(2, B, N, spec.num_heads, dtype=torch.float32, device=dev)
         deg = torch.empty(B, N, spec.num_heads, dtype=torch.float32, device=dev)
         nbytes = lib.egt_block_workspace_bytes(C.byref(cfg), 0)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)

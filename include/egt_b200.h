@@ -25,7 +25,9 @@
  *       E, G, H_hat, A_tild  [B, N, N, h]         (egt_layers.py:79-80)
  *       mask                 [B, N]  uint8, 1 = real node  (Keras mask of h; only KEYS are masked,
  *                                                  egt_layers.py:91-94)
- *       lse, deg             [B, N, h] float32    row statistics saved for the backward
+ *       lse                  [2, B, N, h] float32   row max and log row-sum of the masked logits (kept
+ *                                                  apart so an all-keys-masked row at -1e9 stays exact)
+ *       deg                  [B, N, h] float32      gate sum (centrality)
  *   - `dtype` selects the element type of activations / activation gradients (EGT_F32 or
  *     EGT_BF16).  Weights, weight gradients and saved row statistics are always float32.
  */
@@ -127,7 +129,7 @@ typedef struct egt_block_fwd_io {
   /* saved for the backward (caller keeps them alive) */
   void *qkv;                /* [B,N,3d]  activation dtype  */
   void *v_att;              /* [B,N,d]   activation dtype  */
-  float *lse;               /* [B,N,h]                     */
+  float *lse;               /* [2,B,N,h]                   */
   float *deg;               /* [B,N,h]                     */
   void *workspace;          /* egt_block_workspace_bytes() */
   size_t workspace_bytes;
@@ -155,7 +157,7 @@ int64_t egt_block_param_layout(const egt_block_cfg_t *cfg, int64_t *offsets_host
 
 /* ---- EGT layer: ([QKV, E?, G?, M?], mask) -> (V_att, H_hat, A_tild?) ------------------- */
 /* h_hat may be NULL (not materialised); a_tild NULL = skip (only Analysis taps consume it,
- * graph_xformer_model_base.py:134). lse/deg: [B,N,h] float32, written. */
+ * graph_xformer_model_base.py:134). lse: [2,B,N,h], deg: [B,N,h] float32, written. */
 int egt_attn_fwd(const egt_attn_cfg_t *cfg, const void *qkv, const void *E, const void *G,
                  const void *M, const uint8_t *mask, void *v_att, void *h_hat, void *a_tild,
                  float *lse, float *deg, void *stream);
