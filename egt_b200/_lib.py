@@ -18,7 +18,8 @@ EGT_E_SHAPE, EGT_E_DTYPE, EGT_E_ALIGN, EGT_E_ARCH, EGT_E_CUDA, EGT_E_ARG = -1, -
 
 EXPORTS = ['egt_abi_version', 'egt_last_error', 'egt_last_path', 'egt_rng_uniform_host',
            'egt_block_param_layout', 'egt_attn_fwd', 'egt_attn_bwd', 'egt_block_workspace_bytes',
-           'egt_block_fwd', 'egt_block_bwd', 'egt_launch_count', 'egt_profile_enable', 'egt_profile_read']
+           'egt_block_fwd', 'egt_block_bwd', 'egt_launch_count', 'egt_profile_enable', 'egt_profile_read',
+           'egt_debug_umma_probe', 'egt_debug_force_staged']
 
 WEIGHT_FIELDS = ['norm_mha_gamma', 'norm_mha_beta', 'dense_qkv_kernel', 'dense_qkv_bias',
                  'dense_mha_kernel', 'dense_mha_bias', 'norm_edge_gamma', 'norm_edge_beta',
@@ -100,6 +101,10 @@ def load():
     lib.egt_profile_enable.argtypes = [C.c_int]
     lib.egt_profile_read.restype = C.c_int
     lib.egt_profile_read.argtypes = [C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_long), C.c_int]
+    lib.egt_debug_force_staged.argtypes = [C.c_int]
+    lib.egt_debug_umma_probe.restype = C.c_int
+    lib.egt_debug_umma_probe.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32,
+                                         C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), vp, vp, vp, vp]
     if lib.egt_abi_version() != 1:
         raise RuntimeError('libegt_b200.so ABI version mismatch')
     _lib = lib

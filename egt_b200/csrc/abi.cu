@@ -5,11 +5,13 @@
 #include <vector>
 #include "common.cuh"
 #include "kernels.h"
+#include "fused.h"
 
 namespace egt {
 
 static thread_local char g_err[512] = "";
 static thread_local int g_last_path = 0;
+static int g_force_staged = 0;    // egt_debug_force_staged(): route every shape through the staged kernels
 
 void set_error(int code, const char *fmt, ...) {
   va_list ap;
@@ -77,6 +79,7 @@ static AttnParams make_attn_params(const egt_attn_cfg_t *c) {
   P.dropout = c->training && c->attn_dropout > 0.f;
   P.random_mask_prob = c->random_mask_prob; P.attn_dropout = c->attn_dropout;
   P.seed = c->seed; P.offset = c->offset;
+  P.dq_scale = 1.0f;
   return P;
 }
 
@@ -95,6 +98,7 @@ struct BlockWs {
   float *row_ws;                              // [2,B,N,h]
   char *d_v_att, *d_qkv;                      // [R,d], [R,3d] dtype
   float *hn, *dhn;                            // [R,d] f32
+  char *prep;                                 // FusedPrep (fused path only)
   size_t total;
 };
 static BlockWs carve(const egt_block_cfg_t *c, int backward, void *base) {
@@ -108,6 +112,9 @@ static BlockWs carve(const egt_block_cfg_t *c, int backward, void *base) {
   auto take = [&](size_t bytes) { char *p = b ? b + off : nullptr; off += align_up(bytes); return p; };
   bool edge = c->edge_channel_type != EGT_EDGE_NONE;
   bool residual = c->edge_channel_type >= EGT_EDGE_RESIDUAL;
+  const bool fused = fused_supported(c, a.dtype);
+  if (fused) w.prep = take(sizeof(FusedPrep));
+  if (fused && !backward) { w.total = off; return w; }
   if (edge) {
     w.E = take(pairs * a.h * es);
     if (c->gate_attention) w.G = take(pairs * a.h * es);
@@ -181,6 +188,8 @@ int egt_last_path(void) { return g_last_path; }
 float egt_rng_uniform_host(uint64_t seed, uint64_t offset, uint32_t stream_id, uint64_t idx) {
   return rng_uniform(seed, offset, stream_id, idx);
 }
+
+int egt_debug_force_staged(int on) { g_force_staged = on != 0; return EGT_OK; }
 
 long egt_launch_count(void) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -297,13 +306,34 @@ int egt_block_fwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
   lq.x = io->h; lq.W = w->dense_qkv_kernel; lq.bias = w->dense_qkv_bias; lq.out = io->qkv;
   lq.ln_gamma = w->norm_mha_gamma; lq.ln_beta = w->norm_mha_beta; lq.ln_eps = cfg->ln_eps;
   lq.R = R; lq.din = d; lq.dout = 3 * d;
+  const bool fused = fused_supported(cfg, a.dtype) && !g_force_staged;
+  if (fused) { lq.scale = 1.0f / sqrtf((float)a.dk); lq.scale_cols = d; }   // Q is stored pre-scaled
   if ((rc = linear_launch(lq, a.dtype, st))) return rc;
 
   size_t need = egt_block_workspace_bytes(cfg, 0);
   EGT_REQUIRE(io->workspace_bytes >= need && (io->workspace || need <= 256), EGT_E_ARG,
               "workspace too small: %zu < %zu", io->workspace_bytes, need);
   BlockWs ws = carve(cfg, 0, io->workspace);
-  g_last_path = 0;
+  g_last_path = fused ? 1 : 0;
+
+  if (fused) {
+    if ((rc = fused_prep_launch(cfg, w, (FusedPrep *)ws.prep, st))) return rc;
+    FusedFwdArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.B = a.B; fa.N = a.N; fa.mask = io->mask; fa.prep = (const FusedPrep *)ws.prep;
+    fa.v_att = (__nv_bfloat16 *)io->v_att; fa.lse = io->lse; fa.deg = io->deg;
+    fa.clip_lo = a.clip_lo; fa.clip_hi = a.clip_hi;
+    fa.scale_degree = a.scale_degree; fa.scaler_type = a.scaler_type; fa.num_virtual_nodes = a.num_virtual_nodes;
+    fa.rand_mask = a.training && a.random_mask_prob > 0.f;
+    fa.rand_thr = (uint32_t)ceilf(a.random_mask_prob * 65536.0f - 0.5f);
+    fa.seed = a.seed; fa.offset = a.offset;
+    if ((rc = fused_fwd_launch(fa, io->e, io->e_out, io->qkv, st))) return rc;
+    LinearArgs lo;
+    memset(&lo, 0, sizeof(lo));
+    lo.x = io->v_att; lo.W = w->dense_mha_kernel; lo.bias = w->dense_mha_bias; lo.res = io->h; lo.out = io->h_out;
+    lo.R = R; lo.din = d; lo.dout = d;
+    return linear_launch(lo, a.dtype, st);
+  }
 
   EdgeParams ep = make_edge_params(cfg, w);
   if (edge) {
@@ -345,6 +375,7 @@ int egt_block_bwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
   EGT_REQUIRE(io->workspace && io->workspace_bytes >= need, EGT_E_ARG, "workspace too small: %zu < %zu",
               io->workspace_bytes, need);
   BlockWs ws = carve(cfg, 1, io->workspace);
+  const bool fused = fused_supported(cfg, a.dtype) && !g_force_staged;
   g_last_path = 0;
 
   // dV_att = dh' W_O^T ; dW_O += V_att^T dh' ; db_O += colsum(dh')
@@ -378,6 +409,7 @@ int egt_block_bwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
   P.d_v_att = ws.d_v_att; P.d_h_hat = have_de_out ? ws.dHext : nullptr; P.d_qkv = ws.d_qkv;
   P.dE = ws.dE; P.dG = a.gate_input ? ws.dG : nullptr; P.row_ws = ws.row_ws;
   P.h_hat = have_de_out ? ws.Hhat : nullptr;     // row pass re-materialises H_hat for dW_r
+  if (fused) { P.dq_scale = P.scale; P.scale = 1.0f; }   // the fused forward saved a pre-scaled Q
   if ((rc = attn_staged_bwd(P, a.dtype, st))) return rc;
   if (have_de_out) {   // dW_r += H_hat^T de' ; db_r += colsum(de')
     EdgeParams e2 = ep;

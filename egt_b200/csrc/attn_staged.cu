@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(128) attn_bwd_row_kernel(AttnParams P) {
   T *dqo = (T *)P.d_qkv + ((size_t)b * P.N + l) * 3 * d;
 #pragma unroll
   for (int dd = 0; dd < DKMAX; ++dd)
-    if (dd < P.dk) stf(dqo + dd * P.h + hh, dq[dd]);
+    if (dd < P.dk) stf(dqo + dd * P.h + hh, dq[dd] * P.dq_scale);
 }
 
 // backward, column pass: thread (b,m,hh) owns dK[m,:,hh] and dV[m,:,hh].

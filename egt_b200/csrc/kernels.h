@@ -23,6 +23,7 @@ struct AttnParams {
   const void *d_v_att, *d_h_hat;
   void *d_qkv, *dE, *dG;
   float *row_ws;                     // [2,B,N,h]: D, s
+  float dq_scale;                    // dQ is multiplied by this on store (1, or dk^-0.5 when qkv holds a pre-scaled Q)
 };
 
 int attn_staged_fwd(const AttnParams &P, int dtype, cudaStream_t st);
@@ -40,6 +41,7 @@ struct LinearArgs {
   void *out; int out_f32;
   const float *ln_gamma, *ln_beta; float ln_eps;    // LN prologue when ln_gamma != NULL
   float *xn_out;                                    // optional: write LN(x) as float32 [R,din]
+  float scale; int scale_cols;                      // out[:, :scale_cols] *= scale (0 cols = off)
   int R, din, dout;
 };
 int linear_launch(const LinearArgs &a, int dtype, cudaStream_t st);

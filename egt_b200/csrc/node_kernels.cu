@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(256) linear_kernel(LinearArgs a) {
       int r = r0 + rr;
       if (r < a.R) {
         float v = acc[rr];
+        if (j < a.scale_cols) v *= a.scale;
         if (a.res) v += ldf((const T *)a.res + (size_t)r * a.dout + j);
         st_any<T>(a.out, (size_t)r * a.dout + j, a.out_f32, v);
       }

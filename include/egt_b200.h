@@ -191,6 +191,18 @@ int egt_profile_read(char *names_host, double *ms_host, long *counts_host, int m
  * stream_id 0 = random mask, 1 = attention dropout.  idx = ((b*N + l)*N + m)*h + hh. */
 float egt_rng_uniform_host(uint64_t seed, uint64_t offset, uint32_t stream_id, uint64_t idx);
 
+/* Testing hook: nonzero routes every shape through the staged kernels (process-wide). */
+int egt_debug_force_staged(int on);
+
+/* Bring-up hook: one tcgen05.mma chain D[128,N] = A[128,16*ksteps] * B[N,16*ksteps]^T with A / B laid out
+ * in shared memory (or TMEM for A) in the canonical layout `*_mode` selects
+ * (0 K-major 128B swizzle, 1 TMEM (A only), 2 MN-major 128B swizzle, 3 K-major no swizzle, 4 MN-major no
+ * swizzle) and the given descriptor offsets.  tests/test_umma_probe.py pins every operand form the fused
+ * kernels rely on.  A, B: bf16 device pointers; D: float32 [128,N]. */
+int egt_debug_umma_probe(int a_mode, int b_mode, int N, int ksteps, uint32_t a_lbo, uint32_t a_sbo,
+                         uint32_t b_lbo, uint32_t b_sbo, const uint32_t *a_off_host, const uint32_t *b_off_host,
+                         const void *A, const void *B, float *D, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -254,9 +254,10 @@ def test_block_forward_backward_vs_oracle(case, dtype):
         # weight gradients are sums over B*N^2 terms: compare relative to their own scale
         tol = 2e-3 if dtype == torch.float32 else 3e-2
         # a bias gradient can be analytically ~0 (e.g. dense_edge_b/bias in 'bias' mode: softmax is
-        # shift-invariant), so its error is measured against the scale of its kernel's gradient
+        # shift-invariant), so its error is measured against the scale of its kernel's gradient (a sum of
+        # B*N^2 bf16-rounded terms carries the same absolute noise as the kernel's gradient does)
         kname = name.rsplit('/', 1)[0] + '/kernel'
-        floor = 1e-2 * float(dict(zip(pr, rin[2:]))[kname].abs().max()) if name.endswith('bias') and kname in pr else 0.
+        floor = 1e-1 * float(dict(zip(pr, rin[2:]))[kname].abs().max()) if name.endswith('bias') and kname in pr else 0.
         denom = max(float(gr.abs().max()), floor, 1e-6)
         err = float((got.double().cpu() - gr).abs().max()) / denom
         assert err < tol, f'grad {name}: rel-to-max err {err:.3e}'
@@ -366,3 +367,39 @@ def test_all_masked_rows(gated, dtype):
     gr = torch.autograd.grad([Vr, Hr], ins_o[:nd], [dV.float(), dH.float()])
     for a, b, nm in zip(gg, gr, ('dQKV', 'dE', 'dG')):
         _close(a, b, dtype, nm)
+
+
+@pytest.mark.parametrize('training,rmp', [(False, 0.), (True, 0.1)])
+@pytest.mark.parametrize('N,B', [(128, 6), (75, 5), (37, 7), (190, 3), (9, 4), (1, 3), (257, 2)])
+def test_fused_path_matches_staged_and_oracle(N, B, training, rmp):
+    """Shapes of the reference's MNIST/CLUSTER/PATTERN configs (d=64, d_e=8, h=8) dispatch to the fused
+    tcgen05 kernels; they must agree with the staged kernels and the oracle (incl. the same random key mask)."""
+    import egt_b200
+    from egt_b200 import _lib as L
+    lib = L.load()
+    d, de, nh = 64, 8, 8
+    cfg = O.BlockConfig(model_width=d, edge_width=de, num_heads=nh, scale_degree=True, random_mask_prob=rmp)
+    params = O.init_block_params(cfg, seed=5, dtype=torch.float64)
+    h, e, mask = O.synthetic_batch(B, N, d, de, seed=11, ragged=True, dtype=torch.float64)
+    outs = {}
+    for force in (0, 1):
+        lib.egt_debug_force_staged(force)
+        try:
+            blk, (hg, eg, h2, e2), (hr, er, pr, h2r, e2r) = _run_block(cfg, params, h, e, mask, None, training,
+                                                                       torch.bfloat16, grads=True)
+            assert lib.egt_last_path() == (0 if force else 1)
+            g = torch.Generator().manual_seed(3)
+            dh = torch.randn(h2.shape, generator=g).bfloat16()
+            de_ = torch.randn(e2.shape, generator=g).bfloat16()
+            gin = torch.autograd.grad([h2, e2], [hg, eg, blk.flat], [dh.to(DEV), de_.to(DEV)])
+            rin = torch.autograd.grad([h2r, e2r], [hr, er], [dh.double(), de_.double()])
+        finally:
+            lib.egt_debug_force_staged(0)
+        _close(h2, h2r, torch.bfloat16, f"h' force_staged={force}")
+        _close(e2, e2r, torch.bfloat16, f"e' force_staged={force}")
+        _close(gin[0], rin[0], torch.bfloat16, f'dh force_staged={force}')
+        _close(gin[1], rin[1], torch.bfloat16, f'de force_staged={force}')
+        outs[force] = (h2, e2, gin)
+    # weight gradients of the two paths agree to bf16 accumulation noise
+    wa, wb = outs[0][2][2], outs[1][2][2]
+    assert float((wa - wb).abs().max()) <= 3e-2 * float(wb.abs().max())
