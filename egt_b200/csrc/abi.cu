@@ -112,7 +112,7 @@ static BlockWs carve(const egt_block_cfg_t *c, int backward, void *base) {
   auto take = [&](size_t bytes) { char *p = b ? b + off : nullptr; off += align_up(bytes); return p; };
   bool edge = c->edge_channel_type != EGT_EDGE_NONE;
   bool residual = c->edge_channel_type >= EGT_EDGE_RESIDUAL;
-  const bool fused = fused_supported(c, a.dtype);
+  const bool fused = fused_supported(c, a.dtype) && !g_force_staged;
   if (fused) w.prep = take(sizeof(FusedPrep));
   if (fused && !backward) { w.total = off; return w; }
   if (edge) {
