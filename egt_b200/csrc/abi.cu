@@ -99,9 +99,10 @@ struct BlockWs {
   char *d_v_att, *d_qkv;                      // [R,d], [R,3d] dtype
   float *hn, *dhn;                            // [R,d] f32
   char *prep;                                 // FusedPrep (fused path only)
+  float *d_qkv_f32, *partials;                // fused backward: [R,3d] f32, [ctas,FPART] f32
   size_t total;
 };
-static BlockWs carve(const egt_block_cfg_t *c, int backward, void *base) {
+static BlockWs carve(const egt_block_cfg_t *c, int backward, void *base, bool has_de_out = true) {
   const egt_attn_cfg_t &a = c->attn;
   size_t es = esize(a.dtype);
   size_t pairs = (size_t)a.B * a.N * a.N, R = (size_t)a.B * a.N, d = (size_t)a.h * a.dk;
@@ -115,6 +116,15 @@ static BlockWs carve(const egt_block_cfg_t *c, int backward, void *base) {
   const bool fused = fused_supported(c, a.dtype) && !g_force_staged;
   if (fused) w.prep = take(sizeof(FusedPrep));
   if (fused && !backward) { w.total = off; return w; }
+  if (fused && backward && has_de_out) {      // fused backward: nothing of shape [pairs,h] is materialised
+    w.d_v_att = take(R * d * es);
+    w.d_qkv_f32 = (float *)take(R * 3 * d * sizeof(float));
+    w.partials = (float *)take((size_t)a.B * ((a.N + 127) / 128) * FPART * sizeof(float));
+    w.hn = (float *)take(R * d * sizeof(float));
+    w.dhn = (float *)take(R * d * sizeof(float));
+    w.total = off;
+    return w;
+  }
   if (edge) {
     w.E = take(pairs * a.h * es);
     if (c->gate_attention) w.G = take(pairs * a.h * es);
@@ -279,7 +289,8 @@ int egt_attn_bwd(const egt_attn_cfg_t *cfg, const void *qkv, const void *E, cons
 
 size_t egt_block_workspace_bytes(const egt_block_cfg_t *cfg, int32_t backward) {
   if (!cfg) return 0;
-  return carve(cfg, backward, nullptr).total + 256;
+  size_t a = carve(cfg, backward, nullptr, true).total, b = carve(cfg, backward, nullptr, false).total;
+  return (a > b ? a : b) + 256;
 }
 
 int egt_block_fwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, const egt_block_fwd_io_t *io,
@@ -374,9 +385,11 @@ int egt_block_bwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
   size_t need = egt_block_workspace_bytes(cfg, 1);
   EGT_REQUIRE(io->workspace && io->workspace_bytes >= need, EGT_E_ARG, "workspace too small: %zu < %zu",
               io->workspace_bytes, need);
-  BlockWs ws = carve(cfg, 1, io->workspace);
+  const bool have_de = io->de_out != nullptr;
+  BlockWs ws = carve(cfg, 1, io->workspace, have_de);
   const bool fused = fused_supported(cfg, a.dtype) && !g_force_staged;
-  g_last_path = 0;
+  const bool fused_bwd = fused && have_de;
+  g_last_path = fused_bwd ? 1 : 0;
 
   // dV_att = dh' W_O^T ; dW_O += V_att^T dh' ; db_O += colsum(dh')
   LinearArgs l1;
@@ -387,6 +400,46 @@ int egt_block_bwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
   memset(&x1, 0, sizeof(x1));
   x1.X = io->v_att; x1.Y = io->dh_out; x1.dW = g->dense_mha_kernel; x1.db = g->dense_mha_bias; x1.R = R; x1.dx = d; x1.dy = d;
   if ((rc = xty_launch(x1, a.dtype, st))) return rc;
+
+  if (fused_bwd) {
+    // N x N part in one kernel (fused_bwd.cu): de, dQ|dK|dV and the edge-side weight-gradient partial sums
+    if ((rc = fused_prep_launch(cfg, w, (FusedPrep *)ws.prep, st))) return rc;
+    const int tiles = (a.N + 127) / 128;
+    if (tiles > 1) EGT_CHECK_CUDA(cudaMemsetAsync(ws.d_qkv_f32, 0, (size_t)R * 3 * d * sizeof(float), st));
+    FusedBwdArgs fb;
+    memset(&fb, 0, sizeof(fb));
+    fb.B = a.B; fb.N = a.N; fb.mask = io->mask; fb.prep = (const FusedPrep *)ws.prep;
+    fb.v_att = (const __nv_bfloat16 *)io->v_att; fb.d_v_att = (const __nv_bfloat16 *)ws.d_v_att;
+    fb.lse = io->lse; fb.deg = io->deg; fb.d_qkv = ws.d_qkv_f32; fb.partials = ws.partials;
+    fb.clip_lo = a.clip_lo; fb.clip_hi = a.clip_hi; fb.dq_scale = 1.0f / sqrtf((float)a.dk);
+    fb.scale_degree = a.scale_degree; fb.scaler_type = a.scaler_type; fb.num_virtual_nodes = a.num_virtual_nodes;
+    fb.rand_mask = a.training && a.random_mask_prob > 0.f;
+    fb.rand_thr = (uint32_t)ceilf(a.random_mask_prob * 65536.0f - 0.5f);
+    fb.seed = a.seed; fb.offset = a.offset;
+    if ((rc = fused_bwd_launch(fb, io->e, io->de_out, io->de, io->qkv, st))) return rc;
+    if ((rc = fused_bwd_finalize_launch(ws.partials, a.B * tiles, w, g, st))) return rc;
+    // node side: hn = LN(h); dW_qkv += hn^T dqkv; dhn = dqkv W_qkv^T; dh = LN_bwd(dhn) + dh'
+    LinearArgs l2;
+    memset(&l2, 0, sizeof(l2));
+    l2.x = io->h; l2.ln_gamma = w->norm_mha_gamma; l2.ln_beta = w->norm_mha_beta; l2.ln_eps = cfg->ln_eps;
+    l2.xn_out = ws.hn; l2.R = R; l2.din = d; l2.dout = 0;
+    if ((rc = linear_launch(l2, a.dtype, st))) return rc;
+    XtyArgs x2;
+    memset(&x2, 0, sizeof(x2));
+    x2.X = ws.hn; x2.x_f32 = 1; x2.Y = ws.d_qkv_f32; x2.y_f32 = 1; x2.dW = g->dense_qkv_kernel; x2.db = g->dense_qkv_bias;
+    x2.R = R; x2.dx = d; x2.dy = 3 * d;
+    if ((rc = xty_launch(x2, a.dtype, st))) return rc;
+    LinearArgs l3;
+    memset(&l3, 0, sizeof(l3));
+    l3.x = ws.d_qkv_f32; l3.x_f32 = 1; l3.W = w->dense_qkv_kernel; l3.trans = 1; l3.out = ws.dhn; l3.out_f32 = 1;
+    l3.R = R; l3.din = 3 * d; l3.dout = d;
+    if ((rc = linear_launch(l3, a.dtype, st))) return rc;
+    LnBwdArgs lb;
+    memset(&lb, 0, sizeof(lb));
+    lb.x = io->h; lb.dy = ws.dhn; lb.dres = io->dh_out; lb.gamma = w->norm_mha_gamma; lb.eps = cfg->ln_eps;
+    lb.dx = io->dh; lb.dgamma = g->norm_mha_gamma; lb.dbeta = g->norm_mha_beta; lb.R = R; lb.D = d;
+    return ln_bwd_launch(lb, a.dtype, st);
+  }
 
   EdgeParams ep = make_edge_params(cfg, w);
   ep.g_ln_g = g->norm_edge_gamma; ep.g_ln_b = g->norm_edge_beta;

@@ -25,6 +25,11 @@ struct FusedPrep {
   __nv_bfloat16 wrblk[2 * 16 * 8];    // edge write-back of a key pair:    N = 16, K = 16
   __nv_bfloat16 wtblk[4 * 16 * 8];    // backward d e^ = dZ W'^T:          N = 16, K = 32
   __nv_bfloat16 wrtblk[2 * 16 * 8];   // backward dH_ext = de' W_r^T:      N = 16, K = 16
+  // backward images; output columns are ordered by head GROUP g = hh / 4 (fused_bwd.cu: warps 0-3 own heads
+  // 0-3, warps 4-7 heads 4-7), hh4 = hh % 4, for a key pair (key, key' in {0,1}):
+  __nv_bfloat16 b_eg[2 * 32 * 8];     // [E|G] projection: N = 32 (g,key,eg,hh4), K = 16 (key',c): W'_eg[c,hh]
+  __nv_bfloat16 b_hx[2 * 16 * 8];     // dH_ext = de' W_r^T: N = 16 (g,key,hh4), K = 16 (key',c): W_r[hh,c]
+  __nv_bfloat16 b_de[2][2 * 16 * 8];  // d x^ = dZ W'^T, one image per g: N = 16 (key',c), K = 16 (key,eg,hh4)
   float uE[FH], vE[FH], uG[FH], vG[FH], br[FDE];
   float wp[2][FDE][FH];               // W'_E, W'_G as rounded to bf16 (for the weight-gradient epilogue)
   float bound;                        // sup |masked logit| over all inputs given these weights
@@ -42,12 +47,37 @@ struct FusedFwdArgs {
   uint64_t seed, offset;
 };
 
+// Partial weight-gradient sums one backward CTA writes (fused_bwd_finalize_kernel folds them):
+//   M[c][j] = sum x^_c dZ_j (j = eg*8 + hh) | sZ[j] = sum dZ_j | Wr[hh][c] = sum H^_hh de'_c | dbr[c] = sum de'_c
+constexpr int FPART = 8 * 16 + 16 + 64 + 8;
+
+struct FusedBwdArgs {
+  int B, N;
+  const uint8_t *mask;                // [B,N] or NULL
+  const FusedPrep *prep;
+  const __nv_bfloat16 *v_att, *d_v_att;   // [B,N,64] saved forward output / its upstream gradient
+  const float *lse, *deg;             // [2,B,N,8] (only the log row-sum half is read), [B,N,8]
+  float *d_qkv;                       // [B,N,192] float32: dQ | dK | dV
+  float *partials;                    // [gridDim.x * gridDim.y][FPART]
+  float clip_lo, clip_hi, dq_scale;
+  int scale_degree, scaler_type, num_virtual_nodes;
+  int rand_mask; uint32_t rand_thr;
+  uint64_t seed, offset;
+};
+
 struct FusedTensorMaps { CUtensorMap e, e_out, q, kv; };
 
 bool fused_supported(const egt_block_cfg_t *cfg, int dtype);
 int fused_prep_launch(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, FusedPrep *prep, cudaStream_t st);
 // qkv: [B,N,192] bf16 with the Q third pre-multiplied by dk^-0.5
 int fused_fwd_launch(const FusedFwdArgs &a, const void *e, void *e_out, const void *qkv, cudaStream_t st);
+
+// e, de_out -> de (all [B,N,N,8] bf16); d_qkv must be zero-filled by the caller when N > 128 (dK/dV are
+// accumulated with atomics across the row tiles of a graph).
+int fused_bwd_launch(const FusedBwdArgs &a, const void *e, const void *de_out, void *de, const void *qkv,
+                     cudaStream_t st);
+int fused_bwd_finalize_launch(const float *partials, int nparts, const egt_block_weights_t *w,
+                              const egt_block_grads_t *g, cudaStream_t st);
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda at link time)
 int encode_tmap_3d(CUtensorMap *out, const void *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,

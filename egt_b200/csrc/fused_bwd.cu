@@ -1,0 +1,628 @@
+// fused_bwd.cu -- fused backward of the EGT attention block's N x N part on sm_100a tensor cores.
+//
+//   reference: TF autodiff of EGT.call_gated (lib/models/egt_layers.py:57-143) together with the edge
+//   projections, LayerNorm on e and the residual edge write-back of edge_update_residual
+//   (lib/models/graph_xformer_model_base.py:192-218), as derived in SURVEY.md 3.4.  Nothing of shape
+//   [B,N,N,h] touches HBM: e and de' stream in once by TMA, de streams out once by TMA, everything
+//   else (E, G, H_hat, P, g, dE, dG, dS) is recomputed / consumed on chip.
+//
+// One CTA = one graph b and 128 query rows.  Thread t of warps 0-3 and of warps 4-7 both own query row
+// l0+t == TMEM lane t; warps 0-3 ("group 0") handle heads 0-3, warps 4-7 heads 4-7, so every SM
+// sub-partition has two resident compute warps.  Warp 8 issues TMA and tcgen05.mma.
+//
+// Keys are processed in PAIRS.  For pair p the tensor core produces, in TMEM (columns ordered (g,key,hh4)):
+//     S   [128x16] = Qs   [128x64] * Kexp^T       Kexp[(g,key,hh4), c] = K[key,c] * [c % 8 == hh]
+//     dA  [128x16] = dO   [128x64] * Vexp^T       dO = dV_att (.) scaler,  Vexp likewise from V
+//     EG  [128x32] = e    [128x16] * Wblk         raw edge channels of the two keys x folded-LN weights
+//     dHx [128x16] = de'  [128x16] * Wr^T blk     gradient arriving through the edge write-back
+// The row's threads recompute p, g, H_hat from the saved row statistics and form
+//     dP = dA g ; dH = p (dP - D) + dHx ; dG = (dA p + ddeg) g (1-g) ; dS = dH [lo <= S <= hi]
+// which go back to TMEM as bf16 A-operands of
+//     dQ  [128x64] += dS [128x16] * Kexp                      (accumulated over all keys)
+//     dx^ [128x16]  = [dE|dG] [128x32] * W'^T blk             (then LayerNorm backward + residual -> de)
+// and, transposed through shared memory (MN-major A, K = query row), once per 16 keys of
+//     dKexp [(key,hh) x 64] = dS^T * Qs ;  dVexp [(key,hh) x 64] = A~^T * dO
+// whose block diagonal (c % 8 == hh) is dK / dV.  Weight-gradient sums are kept in registers
+// (packed fp32x2 FMAs) and folded by fused_bwd_finalize_kernel.
+//
+// All warps run in lock step, one __syncthreads per key pair; every tensor-core / TMA operation is issued
+// two pairs ahead of its consumer and observed through an mbarrier.
+#include "common.cuh"
+#include "fused.h"
+#include "umma.cuh"
+
+namespace egt {
+using namespace umma;
+
+namespace {
+
+constexpr int NS = 3;                                  // input stages of 8 keys: e | de' | K rows | V rows
+constexpr uint32_t SM_Q = 0;                           // [128 x 128B] swizzled, Q pre-scaled by dk^-0.5
+constexpr uint32_t SM_DO = 16384;                      // [128 x 128B] swizzled, dV_att (.) scaler
+constexpr uint32_t SM_STAGE = 32768;
+constexpr uint32_t ST_E = 0, ST_DE = 16384, ST_K = 32768, ST_V = 33792, STAGE_BYTES = 34816;
+constexpr uint32_t SM_KVX = SM_STAGE + NS * STAGE_BYTES;       // 4 slots x (Kexp 2048 | Vexp 2048)
+constexpr uint32_t SM_TR = SM_KVX + 4 * 4096;                  // dS^T 32768 | A~^T 32768  (16 keys x 128 rows)
+constexpr uint32_t SM_W = SM_TR + 65536;                       // b_eg 1024 | b_hx 512 | b_de 2 x 512
+constexpr uint32_t SM_CONST = SM_W + 2560;                     // uE vE uG vG (32 floats)
+constexpr uint32_t SM_BAR = SM_CONST + 256;
+constexpr uint32_t SM_TOTAL = SM_BAR + 256;
+static_assert(SM_TOTAL + 1024 <= 232448, "shared memory budget");
+
+constexpr uint32_t TM_DQ = 0, TM_DK = 64, TM_DV = 128;
+constexpr uint32_t TM_IN = 192, TM_IN_COLS = 80;               // 3 buffers: S 16 | dA 16 | EG 32 | dHx 16
+constexpr uint32_t IN_S = 0, IN_DA = 16, IN_EG = 32, IN_HX = 64;
+constexpr uint32_t TM_OUT = 432, TM_OUT_COLS = 32;             // 2 buffers: dS 8 | dZ 16 (bf16 A operands)
+
+constexpr uint32_t ID_N16 = idesc_bf16(128, 16, 0, 0);
+constexpr uint32_t ID_N32 = idesc_bf16(128, 32, 0, 0);
+constexpr uint32_t ID_DQ = idesc_bf16(128, 64, 0, 1);
+constexpr uint32_t ID_T = idesc_bf16(128, 64, 1, 1);
+
+struct Bars { uint64_t q_full, e_full[NS], mma1[3], mma2[3], tbar; uint32_t tmem_base; };
+
+__device__ __forceinline__ float sel8(const uint32_t *o, int hh) {
+  const uint32_t a0 = (hh & 1) ? o[1] : o[0], a1 = (hh & 1) ? o[3] : o[2];
+  const uint32_t a2 = (hh & 1) ? o[5] : o[4], a3 = (hh & 1) ? o[7] : o[6];
+  const uint32_t b0 = (hh & 2) ? a1 : a0, b1 = (hh & 2) ? a3 : a2;
+  return __uint_as_float((hh & 4) ? b1 : b0);
+}
+
+}  // namespace
+
+template <bool RAND>
+__global__ void __launch_bounds__(384, 1)
+fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant__ CUtensorMap tm_dei,
+                 const __grid_constant__ CUtensorMap tm_de, const __grid_constant__ CUtensorMap tm_q,
+                 const __grid_constant__ CUtensorMap tm_kv, const FusedBwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  Bars *bars = (Bars *)(smem + SM_BAR);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y, l0 = blockIdx.x * 128;
+  const int N = a.N;
+  const int NT = (N + 7) / 8, NP = (N + 1) / 2;       // 8-key tiles, key pairs
+
+  if (warp == 8) {
+    if (lane == 0) {
+      mbar_init(smem_u32(&bars->q_full), 1);
+      for (int i = 0; i < NS; ++i) mbar_init(smem_u32(&bars->e_full[i]), 1);
+      for (int i = 0; i < 3; ++i) { mbar_init(smem_u32(&bars->mma1[i]), 1); mbar_init(smem_u32(&bars->mma2[i]), 1); }
+      mbar_init(smem_u32(&bars->tbar), 1);
+      mbar_fence_init();
+      tma_prefetch_desc(&tm_e); tma_prefetch_desc(&tm_dei); tma_prefetch_desc(&tm_de);
+      tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_kv);
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(&bars->tmem_base), 512);
+  } else {
+    if (tid < 160) ((uint4 *)(smem + SM_W))[tid] = ((const uint4 *)a.prep->b_eg)[tid];   // b_eg | b_hx | b_de
+    if (tid < 32) ((float *)(smem + SM_CONST))[tid] = a.prep->uE[tid];                  // uE vE uG vG
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp >= 8) {
+    // ====================== issuer warpgroup (warp 8 issues; warps 9-11 only keep the barriers) ======
+    reg_dealloc<40>();
+    const bool leader = warp == 8 && lane == 0;
+    auto load_tile = [&](int T) {
+      const int st = T % NS;
+      const uint32_t bar = smem_u32(&bars->e_full[st]);
+      const uint32_t dst = sbase + SM_STAGE + st * STAGE_BYTES;
+      mbar_expect_tx(bar, STAGE_BYTES);
+      tma_load_3d(dst + ST_E, &tm_e, bar, T * 64, l0, b);
+      tma_load_3d(dst + ST_DE, &tm_dei, bar, T * 64, l0, b);
+      tma_load_3d(dst + ST_K, &tm_kv, bar, FD, T * 8, b);
+      tma_load_3d(dst + ST_V, &tm_kv, bar, 2 * FD, T * 8, b);
+    };
+    auto issue_mma1 = [&](int p) {
+      const int T = p >> 2, j = p & 3, st = T % NS, buf = p % 3, slot = p & 3;
+      mbar_wait(smem_u32(&bars->e_full[st]), (T / NS) & 1);
+      tc_fence_after();
+      const uint32_t es = sbase + SM_STAGE + st * STAGE_BYTES;
+      const uint32_t kx = sbase + SM_KVX + slot * 4096, vx = kx + 2048;
+      const uint32_t d = tmem + TM_IN + buf * TM_IN_COLS;
+#pragma unroll
+      for (int s = 0; s < 4; ++s)
+        mma_ss(d + IN_S, smem_desc(sbase + SM_Q + 32 * s, 16, 1024, LAYOUT_SW128),
+               smem_desc(kx + 32 * s, 16, 1024, LAYOUT_SW128), ID_N16, s > 0);
+#pragma unroll
+      for (int s = 0; s < 4; ++s)
+        mma_ss(d + IN_DA, smem_desc(sbase + SM_DO + 32 * s, 16, 1024, LAYOUT_SW128),
+               smem_desc(vx + 32 * s, 16, 1024, LAYOUT_SW128), ID_N16, s > 0);
+      mma_ss(d + IN_EG, smem_desc(es + ST_E + 32 * j, 16, 1024, LAYOUT_SW128),
+             smem_desc(sbase + SM_W, 512, 128, LAYOUT_NONE), ID_N32, 0);
+      mma_ss(d + IN_HX, smem_desc(es + ST_DE + 32 * j, 16, 1024, LAYOUT_SW128),
+             smem_desc(sbase + SM_W + 1024, 256, 128, LAYOUT_NONE), ID_N16, 0);
+      mma_commit(smem_u32(&bars->mma1[buf]));
+    };
+    auto issue_mma2 = [&](int p) {
+      const int buf = p % 3, ob = p & 1, slot = p & 3;
+      const uint32_t kx = sbase + SM_KVX + slot * 4096;
+      const uint32_t ao = tmem + TM_OUT + ob * TM_OUT_COLS;
+      mma_ts(tmem + TM_DQ, ao, smem_desc(kx, 2048, 1024, LAYOUT_SW128), ID_DQ, p > 0);
+      const uint32_t dd = tmem + TM_IN + buf * TM_IN_COLS + IN_EG;
+      mma_ts(dd, ao + 8, smem_desc(sbase + SM_W + 1536, 256, 128, LAYOUT_NONE), ID_N16, 0);
+      mma_ts(dd, ao + 16, smem_desc(sbase + SM_W + 2048, 256, 128, LAYOUT_NONE), ID_N16, 1);
+      mma_commit(smem_u32(&bars->mma2[buf]));
+      if ((p & 7) == 7 || p == NP - 1) {                // a 16-key block of dS^T / A~^T is complete
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+          mma_ss(tmem + TM_DK, smem_desc(sbase + SM_TR + 2048 * s, 16384, 1024, LAYOUT_SW128),
+                 smem_desc(sbase + SM_Q + 2048 * s, 16384, 1024, LAYOUT_SW128), ID_T, s > 0);
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+          mma_ss(tmem + TM_DV, smem_desc(sbase + SM_TR + 32768 + 2048 * s, 16384, 1024, LAYOUT_SW128),
+                 smem_desc(sbase + SM_DO + 2048 * s, 16384, 1024, LAYOUT_SW128), ID_T, s > 0);
+        mma_commit(smem_u32(&bars->tbar));
+      }
+    };
+    if (leader) {
+      mbar_expect_tx(smem_u32(&bars->q_full), 16384);
+      tma_load_3d(sbase + SM_Q, &tm_q, smem_u32(&bars->q_full), 0, l0, b);
+      for (int T = 0; T < NT && T < NS; ++T) load_tile(T);
+    }
+    __syncthreads();                                   // sync #0: dO tile, Kexp/Vexp of pairs 0,1 are built
+    if (leader) {
+      tc_fence_after();
+      mbar_wait(smem_u32(&bars->q_full), 0);
+      issue_mma1(0);
+      if (NP > 1) issue_mma1(1);
+    }
+    for (int it = 0; it < NP; ++it) {
+      __syncthreads();                                 // sync #(it+1)
+      if (leader) {
+        tc_fence_after();
+        issue_mma2(it);
+        if (it + 2 < NP) issue_mma1(it + 2);
+        if (it >= 2 && ((it - 2) & 3) == 3) {          // tile stored at the previous sync: recycle its stage
+          const int T = (it - 2) >> 2;
+          tma_store_wait_read<0>();
+          if (T + NS < NT) load_tile(T + NS);
+        }
+        if (it >= 1 && ((it - 1) & 3) == 3) {          // phase B of tile T's last pair ran: de is complete in place
+          const int T = (it - 1) >> 2;
+          tma_store_3d(&tm_de, sbase + SM_STAGE + (T % NS) * STAGE_BYTES + ST_DE, T * 64, l0, b);
+          tma_store_commit();
+        }
+      }
+      __syncwarp();
+    }
+    __syncthreads();                                   // sync #(NP+1): phase B of the last pair is done
+    if (leader) {
+      const int T = NT - 1;
+      tma_store_3d(&tm_de, sbase + SM_STAGE + (T % NS) * STAGE_BYTES + ST_DE, T * 64, l0, b);
+      tma_store_commit();
+      tma_store_wait_all<0>();
+    }
+    __syncwarp();
+    __syncthreads();                                   // reduction scratch zeroed
+    __syncthreads();                                   // partial sums complete
+    __syncthreads();                                   // final
+    if (warp == 8) tmem_dealloc(tmem, 512);
+    return;
+  }
+
+  // ================================= compute threads (warps 0-7) =================================
+  reg_alloc<232>();
+  const int g = tid >> 7, t = tid & 127;
+  const int l = l0 + t;
+  const bool rowvalid = l < N;
+  const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  const float *cst = (const float *)(smem + SM_CONST);
+  const uint8_t *maskb = a.mask ? a.mask + (size_t)b * N : nullptr;
+  const float lo = a.clip_lo, hi = a.clip_hi;
+
+  // ---- per-row quantities: D = sum_dd dV_att * V_att, scaler s, ddeg, log2 row sum; dO tile ---------
+  float Dr[4], ddeg[4], l2[4];
+  {
+    float s8[8], deg8[8];
+    const size_t ps = ((size_t)b * N + (rowvalid ? l : 0)) * FH, rs = (size_t)a.B * N * FH;
+#pragma unroll
+    for (int hh = 0; hh < 8; ++hh) {
+      deg8[hh] = a.deg[ps + hh];
+      float s = 1.f;
+      if (a.scale_degree && l >= a.num_virtual_nodes)                        // egt_layers.py:123-135
+        s = a.scaler_type == EGT_SCALER_LOG ? log1pf(deg8[hh]) : deg8[hh];
+      s8[hh] = s;
+    }
+    const uint4 *dvp = (const uint4 *)(a.d_v_att + ((size_t)b * N + (rowvalid ? l : 0)) * FD);
+    const uint4 *vp = (const uint4 *)(a.v_att + ((size_t)b * N + (rowvalid ? l : 0)) * FD);
+    float Dacc[8];
+#pragma unroll
+    for (int hh = 0; hh < 8; ++hh) Dacc[hh] = 0.f;
+#pragma unroll
+    for (int dd = 0; dd < 8; ++dd) {
+      uint4 dv = dvp[dd], vv = vp[dd];
+      if (!rowvalid) { dv = make_uint4(0, 0, 0, 0); vv = dv; }
+      const float d8[8] = {bf16_lo(dv.x), bf16_hi(dv.x), bf16_lo(dv.y), bf16_hi(dv.y),
+                           bf16_lo(dv.z), bf16_hi(dv.z), bf16_lo(dv.w), bf16_hi(dv.w)};
+      const float v8[8] = {bf16_lo(vv.x), bf16_hi(vv.x), bf16_lo(vv.y), bf16_hi(vv.y),
+                           bf16_lo(vv.z), bf16_hi(vv.z), bf16_lo(vv.w), bf16_hi(vv.w)};
+#pragma unroll
+      for (int hh = 0; hh < 8; ++hh) Dacc[hh] = fmaf(d8[hh], v8[hh], Dacc[hh]);
+      if ((dd >> 2) == g) {                                                  // this thread stages chunks 4g..4g+3
+        uint4 o;
+        o.x = pack_bf16(d8[0] * s8[0], d8[1] * s8[1]); o.y = pack_bf16(d8[2] * s8[2], d8[3] * s8[3]);
+        o.z = pack_bf16(d8[4] * s8[4], d8[5] * s8[5]); o.w = pack_bf16(d8[6] * s8[6], d8[7] * s8[7]);
+        *(uint4 *)(smem + SM_DO + sw128_off(t, dd * 8)) = o;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int hh = 4 * g + i;
+      // D = s * ds with ds = sum_dd dV_att * O (O = V_att / s, the un-scaled attention output)
+      float D = 0.f, dg = 0.f, lsum = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) if (q == hh) { D = Dacc[q]; }
+      float s = 1.f, dgv = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) if (q == hh) { s = s8[q]; dgv = deg8[q]; }
+      if (a.scale_degree && l >= a.num_virtual_nodes) {
+        const float ds = s != 0.f ? D / s : 0.f;
+        dg = a.scaler_type == EGT_SCALER_LOG ? ds / (1.f + dgv) : ds;
+      }
+      if (rowvalid) lsum = a.lse[rs + ps + hh];
+      Dr[i] = rowvalid ? D : 0.f;
+      ddeg[i] = rowvalid ? dg : 0.f;
+      l2[i] = lsum * kLog2e;
+    }
+  }
+
+  // ---- weight-gradient partial sums (registers) ---------------------------------------------------
+  float2 ME[8][2], MG[8][2], WR[4][4], sE[2], sG[2];
+  float dbr[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    ME[c][0] = ME[c][1] = MG[c][0] = MG[c][1] = make_float2(0.f, 0.f);
+    dbr[c] = 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) WR[i][q] = make_float2(0.f, 0.f);
+  sE[0] = sE[1] = sG[0] = sG[1] = make_float2(0.f, 0.f);
+
+  auto build = [&](int p2) {    // expanded K / V operands of pair p2 into slot p2 & 3 (one 16-byte chunk per thread)
+    const int T2 = p2 >> 2, j2 = p2 & 3, st = T2 % NS;
+    const int which = tid >> 7, rem = tid & 127, n = rem >> 3, dd = rem & 7;
+    const int hh = 4 * (n >> 3) + (n & 3), ks = 2 * j2 + ((n >> 2) & 1);
+    const uint8_t *rows = smem + SM_STAGE + st * STAGE_BYTES + (which ? ST_V : ST_K);
+    const uint32_t val = *(const uint16_t *)(rows + ks * 128 + (dd * 8 + hh) * 2);
+    const uint32_t wv = val << ((hh & 1) * 16);
+    uint4 ch;
+    ch.x = (hh >> 1) == 0 ? wv : 0u; ch.y = (hh >> 1) == 1 ? wv : 0u;
+    ch.z = (hh >> 1) == 2 ? wv : 0u; ch.w = (hh >> 1) == 3 ? wv : 0u;
+    *(uint4 *)(smem + SM_KVX + (p2 & 3) * 4096 + which * 2048 + n * 128 + (((dd ^ n) & 7) << 4)) = ch;
+  };
+
+  auto ln_stats = [&](const uint4 ev, float *x, float &r, float &nrm) {
+    x[0] = bf16_lo(ev.x); x[1] = bf16_hi(ev.x); x[2] = bf16_lo(ev.y); x[3] = bf16_hi(ev.y);
+    x[4] = bf16_lo(ev.z); x[5] = bf16_hi(ev.z); x[6] = bf16_lo(ev.w); x[7] = bf16_hi(ev.w);
+    float mu = ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
+    mu *= 0.125f;
+    float var = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { const float dlt = x[c] - mu; var = fmaf(dlt, dlt, var); }
+    r = rsqrtf(fmaf(var, 0.125f, 1e-3f));
+    nrm = -r * mu;
+  };
+
+  // ---- phase A: pair p, this thread's 4 heads of both keys ------------------------------------------
+  auto phase_a = [&](int p) {
+    const int T = p >> 2, j = p & 3, st = T % NS, buf = p % 3, ob = p & 1;
+    const uint8_t *es = smem + SM_STAGE + st * STAGE_BYTES;
+    const uint32_t tin = tlane + TM_IN + buf * TM_IN_COLS;
+    const uint32_t tout = tlane + TM_OUT + ob * TM_OUT_COLS;
+    uint32_t dsp[4], dzp[8];
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      const int ks = 2 * j + kk, m = 8 * T + ks;
+      uint32_t sreg[4], dareg[4], egreg[8], hxreg[4];
+      tmem_ld4(tin + IN_S + g * 8 + kk * 4, sreg);
+      tmem_ld4(tin + IN_DA + g * 8 + kk * 4, dareg);
+      tmem_ld8(tin + IN_EG + g * 16 + kk * 8, egreg);
+      tmem_ld4(tin + IN_HX + g * 8 + kk * 4, hxreg);
+      const uint32_t eoff = sw128_off(t, ks * 8);
+      float x[8], r, nrm;
+      ln_stats(*(const uint4 *)(es + ST_E + eoff), x, r, nrm);
+      const uint4 dev = *(const uint4 *)(es + ST_DE + eoff);
+      bool kvalid = rowvalid && m < N;
+      if (maskb && m < N) kvalid = kvalid && maskb[m] != 0;
+      uint32_t rb0 = 0u, rb1 = 0u;
+      if (RAND) {
+        const uint64_t qd = ((uint64_t)b * N + (uint64_t)l) * N + (uint64_t)m;
+        Philox4 ph = philox4x32_10((uint32_t)qd, (uint32_t)(qd >> 32), (uint32_t)a.offset,
+                                   (uint32_t)(a.offset >> 32), (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+        rb0 = g ? ph.z : ph.x; rb1 = g ? ph.w : ph.y;      // heads 4g..4g+3 use words 2g, 2g+1
+      }
+      tmem_ld_wait();
+      float dS[4], At[4], dH[4], dGv[4], Hh[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int hh = 4 * g + i;
+        const float S = __uint_as_float(sreg[i]), dA = __uint_as_float(dareg[i]);
+        const float E = fmaf(r, __uint_as_float(egreg[i]), fmaf(nrm, cst[hh], cst[8 + hh]));
+        const float G = fmaf(r, __uint_as_float(egreg[4 + i]), fmaf(nrm, cst[16 + hh], cst[24 + hh]));
+        const float Sc = fminf(fmaxf(S, lo), hi);                          // egt_layers.py:81-82
+        const bool inr = S == Sc;                                          // clip passes gradient inside [lo,hi]
+        Hh[i] = Sc + E;                                                    // :85-86
+        bool live = kvalid;
+        if (RAND) {
+          const uint32_t w = i < 2 ? rb0 : rb1;
+          const uint32_t bits = (i & 1) ? (w >> 16) : (w & 0xFFFFu);
+          live = live && !(bits < a.rand_thr);                             // :103-108
+        }
+        const float pr = live ? ex2_approx(fmaf(Hh[i], kLog2e, -l2[i])) : 0.f;          // softmax probability
+        const float gg = live ? rcp_approx(1.f + ex2_approx(-G * kLog2e)) : 0.f;        // gate
+        At[i] = pr * gg;
+        const float dP = dA * gg;
+        dH[i] = fmaf(pr, dP - Dr[i], __uint_as_float(hxreg[i]));
+        const float dg = fmaf(dA, pr, ddeg[i]);
+        dGv[i] = dg * fmaf(-gg, gg, gg);
+        dS[i] = inr ? dH[i] : 0.f;
+      }
+      dsp[kk * 2 + 0] = pack_bf16(dS[0], dS[1]); dsp[kk * 2 + 1] = pack_bf16(dS[2], dS[3]);
+      dzp[kk * 4 + 0] = pack_bf16(dH[0], dH[1]); dzp[kk * 4 + 1] = pack_bf16(dH[2], dH[3]);
+      dzp[kk * 4 + 2] = pack_bf16(dGv[0], dGv[1]); dzp[kk * 4 + 3] = pack_bf16(dGv[2], dGv[3]);
+      {   // transposed operands: row = query t (K index), 16-byte chunk = key, bytes 8g.. = heads 4g..4g+3
+        const int k16 = m & 15;
+        if (k16 == 0 && m > 0) mbar_wait(smem_u32(&bars->tbar), ((m >> 4) - 1) & 1);   // previous block consumed
+        const uint32_t off = (uint32_t)(k16 >> 3) * 16384u + (uint32_t)(t >> 3) * 1024u + (uint32_t)(t & 7) * 128u +
+                             ((uint32_t)((k16 ^ t) & 7) << 4) + (uint32_t)g * 8u;
+        *(uint2 *)(smem + SM_TR + off) = make_uint2(dsp[kk * 2], dsp[kk * 2 + 1]);
+        *(uint2 *)(smem + SM_TR + 32768 + off) = make_uint2(pack_bf16(At[0], At[1]), pack_bf16(At[2], At[3]));
+      }
+      {   // weight-gradient sums: M += x^ (x) [dE|dG] ; sZ += [dE|dG] ; Wr += H^ (x) de'
+        const float2 dE0 = make_float2(dH[0], dH[1]), dE1 = make_float2(dH[2], dH[3]);
+        const float2 dG0 = make_float2(dGv[0], dGv[1]), dG1 = make_float2(dGv[2], dGv[3]);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float xh = fmaf(r, x[c], nrm);
+          const float2 xx = make_float2(xh, xh);
+          ffma2(ME[c][0], xx, dE0); ffma2(ME[c][1], xx, dE1);
+          ffma2(MG[c][0], xx, dG0); ffma2(MG[c][1], xx, dG1);
+        }
+        fadd2(sE[0], dE0); fadd2(sE[1], dE1); fadd2(sG[0], dG0); fadd2(sG[1], dG1);
+        const float2 dp[4] = {make_float2(bf16_lo(dev.x), bf16_hi(dev.x)), make_float2(bf16_lo(dev.y), bf16_hi(dev.y)),
+                              make_float2(bf16_lo(dev.z), bf16_hi(dev.z)), make_float2(bf16_lo(dev.w), bf16_hi(dev.w))};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 h2 = make_float2(Hh[i], Hh[i]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) ffma2(WR[i][q], h2, dp[q]);
+        }
+      }
+    }
+    tmem_st4(tout + g * 4, dsp);
+    tmem_st8(tout + 8 + g * 8, dzp);
+  };
+
+  // ---- phase B: LayerNorm backward + residual for key g of pair p -> de, in place over de' -----------
+  auto phase_b = [&](int p) {
+    const int T = p >> 2, j = p & 3, st = T % NS, buf = p % 3;
+    uint8_t *es = smem + SM_STAGE + st * STAGE_BYTES;
+    const int ks = 2 * j + g;
+    uint32_t dr[8];
+    tmem_ld8(tlane + TM_IN + buf * TM_IN_COLS + IN_EG + g * 8, dr);
+    const uint32_t eoff = sw128_off(t, ks * 8);
+    float x[8], r, nrm;
+    ln_stats(*(const uint4 *)(es + ST_E + eoff), x, r, nrm);
+    const uint4 dev = *(const uint4 *)(es + ST_DE + eoff);
+    const float dp[8] = {bf16_lo(dev.x), bf16_hi(dev.x), bf16_lo(dev.y), bf16_hi(dev.y),
+                         bf16_lo(dev.z), bf16_hi(dev.z), bf16_lo(dev.w), bf16_hi(dev.w)};
+    tmem_ld_wait();
+    float xh[8], m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      xh[c] = fmaf(r, x[c], nrm);
+      const float dxh = __uint_as_float(dr[c]);
+      m1 += dxh;
+      m2 = fmaf(dxh, xh[c], m2);
+    }
+    m1 *= 0.125f; m2 *= 0.125f;
+    float o[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float dxh = __uint_as_float(dr[c]);
+      o[c] = fmaf(r, dxh - fmaf(xh[c], m2, m1), dp[c]);
+      dbr[c] += dp[c];
+    }
+    uint4 ov;
+    ov.x = pack_bf16(o[0], o[1]); ov.y = pack_bf16(o[2], o[3]);
+    ov.z = pack_bf16(o[4], o[5]); ov.w = pack_bf16(o[6], o[7]);
+    *(uint4 *)(es + ST_DE + eoff) = ov;
+  };
+
+  // ---- dK / dV of the 16-key block kb: lane t = (key, hh) picks the block diagonal --------------------
+  const bool single_tile = gridDim.x == 1;
+  auto t_epilogue = [&](int kb) {
+    const int m = 16 * kb + (t >> 3), hh = t & 7;
+    float *dst = a.d_qkv + ((size_t)b * N + (m < N ? m : 0)) * (3 * FD) + FD + hh;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t o[32];
+        tmem_ld32(tlane + (which ? TM_DV : TM_DK) + 32 * half, o);
+        tmem_ld_wait();
+        if (m < N) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float v = sel8(o + 8 * q, hh);
+            float *pd = dst + which * FD + (half * 4 + q) * 8;
+            if (single_tile) *pd = v;
+            else atomicAdd(pd, v);
+          }
+        }
+      }
+    }
+  };
+
+  // ---- pipeline ------------------------------------------------------------------------------------
+  mbar_wait(smem_u32(&bars->e_full[0]), 0);
+  build(0);
+  if (NP > 1) build(1);
+  fence_proxy_async_smem();
+  __syncthreads();                                     // sync #0
+  for (int it = 0; it < NP; ++it) {
+    mbar_wait(smem_u32(&bars->mma1[it % 3]), (it / 3) & 1);
+    tc_fence_after();
+    phase_a(it);
+    if (it >= 1) {
+      mbar_wait(smem_u32(&bars->mma2[(it - 1) % 3]), ((it - 1) / 3) & 1);
+      tc_fence_after();
+      phase_b(it - 1);
+      if (((it - 1) & 7) == 7) {                       // dS^T / A~^T block (it-1)/8 went through the tensor core
+        const int kb = (it - 1) >> 3;
+        if ((kb & 1) == g) {
+          mbar_wait(smem_u32(&bars->tbar), kb & 1);
+          tc_fence_after();
+          t_epilogue(kb);
+        }
+      }
+    }
+    if (it + 2 < NP) {
+      const int T2 = (it + 2) >> 2;
+      mbar_wait(smem_u32(&bars->e_full[T2 % NS]), (T2 / NS) & 1);
+      build(it + 2);
+    }
+    tmem_st_wait();
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();                                   // sync #(it+1)
+  }
+  mbar_wait(smem_u32(&bars->mma2[(NP - 1) % 3]), ((NP - 1) / 3) & 1);
+  tc_fence_after();
+  phase_b(NP - 1);
+  fence_proxy_async_smem();
+  __syncthreads();                                     // sync #(NP+1)
+  {
+    const int kb = (NP - 1) >> 3;                      // last (possibly partial) 16-key block
+    mbar_wait(smem_u32(&bars->tbar), kb & 1);
+    tc_fence_after();
+    if ((kb & 1) == g) t_epilogue(kb);
+  }
+  // dQ: all tcgen05.mma of this CTA have completed (tbar was committed last)
+  {
+    uint32_t o[32];
+    tmem_ld32(tlane + TM_DQ + g * 32, o);              // warp-collective: never inside a divergent branch
+    tmem_ld_wait();
+    if (rowvalid) {
+      float4 *dq = (float4 *)(a.d_qkv + ((size_t)b * N + l) * (3 * FD) + g * 32);
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        dq[q] = make_float4(__uint_as_float(o[4 * q]) * a.dq_scale, __uint_as_float(o[4 * q + 1]) * a.dq_scale,
+                            __uint_as_float(o[4 * q + 2]) * a.dq_scale, __uint_as_float(o[4 * q + 3]) * a.dq_scale);
+    }
+  }
+
+  // ---- weight-gradient partial sums: warp shuffle -> shared atomics -> one row per CTA ----------------
+  float *red = (float *)(smem + SM_TR);                // the transposed-operand buffers are idle now
+  if (tid < FPART) red[tid] = 0.f;
+  __syncthreads();                                     // reduction scratch zeroed
+  {
+    auto put = [&](int idx, float v) {
+      v = warp_sum(v);
+      if (lane == 0) atomicAdd(red + idx, v);
+    };
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      put(c * 16 + 4 * g + 0, ME[c][0].x); put(c * 16 + 4 * g + 1, ME[c][0].y);
+      put(c * 16 + 4 * g + 2, ME[c][1].x); put(c * 16 + 4 * g + 3, ME[c][1].y);
+      put(c * 16 + 8 + 4 * g + 0, MG[c][0].x); put(c * 16 + 8 + 4 * g + 1, MG[c][0].y);
+      put(c * 16 + 8 + 4 * g + 2, MG[c][1].x); put(c * 16 + 8 + 4 * g + 3, MG[c][1].y);
+      put(208 + c, dbr[c]);
+    }
+    put(128 + 4 * g + 0, sE[0].x); put(128 + 4 * g + 1, sE[0].y); put(128 + 4 * g + 2, sE[1].x); put(128 + 4 * g + 3, sE[1].y);
+    put(136 + 4 * g + 0, sG[0].x); put(136 + 4 * g + 1, sG[0].y); put(136 + 4 * g + 2, sG[1].x); put(136 + 4 * g + 3, sG[1].y);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        put(144 + (4 * g + i) * 8 + 2 * q, WR[i][q].x);
+        put(144 + (4 * g + i) * 8 + 2 * q + 1, WR[i][q].y);
+      }
+  }
+  __syncthreads();                                     // partial sums complete
+  if (tid < FPART) a.partials[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * FPART + tid] = red[tid];
+  tc_fence_before();
+  __syncthreads();                                     // final
+}
+
+// Folds the per-CTA partial sums into the weight gradients (the library ADDS into them).
+//   e^ = gamma (.) x^ + beta ;  [E|G] = e^ W + b ;  e' = e + H^ W_r + b_r
+__global__ void __launch_bounds__(256) fused_bwd_finalize_kernel(const float *partials, int nparts, egt_block_weights_t w,
+                                                                 egt_block_grads_t g) {
+  __shared__ float s[FPART];
+  const int tid = threadIdx.x;
+  if (tid < FPART) {
+    float acc = 0.f;
+    for (int i = 0; i < nparts; ++i) acc += partials[(size_t)i * FPART + tid];
+    s[tid] = acc;
+  }
+  __syncthreads();
+  const float *M = s, *sZ = s + 128, *Wr = s + 144, *dbr = s + 208;
+  if (tid < 128) {                        // dW_E, dW_G
+    const int c = tid / 16, j = tid % 16, eg = j / 8, hh = j % 8;
+    float *dst = eg ? g.attention_gates_kernel : g.dense_edge_b_kernel;
+    dst[c * FH + hh] += w.norm_edge_gamma[c] * M[c * 16 + j] + w.norm_edge_beta[c] * sZ[j];
+  } else if (tid < 144) {                 // db_E, db_G
+    const int j = tid - 128, eg = j / 8, hh = j % 8;
+    (eg ? g.attention_gates_bias : g.dense_edge_b_bias)[hh] += sZ[j];
+  } else if (tid < 208) {                 // dW_r
+    g.dense_edge_r_kernel[tid - 144] += Wr[tid - 144];
+  } else if (tid < 216) {                 // db_r
+    g.dense_edge_r_bias[tid - 208] += dbr[tid - 208];
+  } else if (tid < 224) {                 // dgamma_e, dbeta_e
+    const int c = tid - 216;
+    float dg = 0.f, db = 0.f;
+    for (int hh = 0; hh < FH; ++hh) {
+      const float we = w.dense_edge_b_kernel[c * FH + hh], wg = w.attention_gates_kernel[c * FH + hh];
+      dg += we * M[c * 16 + hh] + wg * M[c * 16 + 8 + hh];
+      db += we * sZ[hh] + wg * sZ[8 + hh];
+    }
+    g.norm_edge_gamma[c] += dg;
+    g.norm_edge_beta[c] += db;
+  }
+}
+
+int fused_bwd_launch(const FusedBwdArgs &a, const void *e, const void *de_out, void *de, const void *qkv,
+                     cudaStream_t st) {
+  CUtensorMap tm_e, tm_dei, tm_de, tm_q, tm_kv;
+  const uint64_t N = a.N, B = a.B;
+  int rc;
+  if ((rc = encode_tmap_3d(&tm_e, e, N * FDE, N, B, N * FDE * 2, N * N * FDE * 2, 64, 128, 1, 1))) return rc;
+  if ((rc = encode_tmap_3d(&tm_dei, de_out, N * FDE, N, B, N * FDE * 2, N * N * FDE * 2, 64, 128, 1, 1))) return rc;
+  if ((rc = encode_tmap_3d(&tm_de, de, N * FDE, N, B, N * FDE * 2, N * N * FDE * 2, 64, 128, 1, 1))) return rc;
+  if ((rc = encode_tmap_3d(&tm_q, qkv, 3 * FD, N, B, 3 * FD * 2, N * 3 * FD * 2, 64, 128, 1, 1))) return rc;
+  if ((rc = encode_tmap_3d(&tm_kv, qkv, 3 * FD, N, B, 3 * FD * 2, N * 3 * FD * 2, 64, 8, 1, 0))) return rc;
+  const int smem = SM_TOTAL + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    EGT_CHECK_CUDA(cudaFuncSetAttribute(fused_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    EGT_CHECK_CUDA(cudaFuncSetAttribute(fused_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  dim3 grid((a.N + 127) / 128, a.B);
+  LaunchScope _ls("fused_bwd_kernel", st);
+  if (a.rand_mask) fused_bwd_kernel<true><<<grid, 384, smem, st>>>(tm_e, tm_dei, tm_de, tm_q, tm_kv, a);
+  else fused_bwd_kernel<false><<<grid, 384, smem, st>>>(tm_e, tm_dei, tm_de, tm_q, tm_kv, a);
+  EGT_CHECK_CUDA(cudaGetLastError());
+  return EGT_OK;
+}
+
+int fused_bwd_finalize_launch(const float *partials, int nparts, const egt_block_weights_t *w,
+                              const egt_block_grads_t *g, cudaStream_t st) {
+  LaunchScope _ls("fused_bwd_finalize_kernel", st);
+  fused_bwd_finalize_kernel<<<1, 256, 0, st>>>(partials, nparts, *w, *g);
+  EGT_CHECK_CUDA(cudaGetLastError());
+  return EGT_OK;
+}
+
+}  // namespace egt

@@ -66,6 +66,24 @@ __global__ void __launch_bounds__(128) fused_prep_kernel(egt_block_weights_t w, 
     out->wrtblk[(k / 8) * (16 * 8) + n * 8 + (k % 8)] =
         __float2bfloat16_rn(key == key2 ? w.dense_edge_r_kernel[a * FDE + b] : 0.f);
   }
+  // backward images (head-group ordered, fused.h)
+  for (int i = tid; i < 32 * 16; i += 128) {      // b_eg
+    int n = i / 16, k = i % 16;
+    int g = n / 16, key = (n / 8) % 2, eg = (n / 4) % 2, hh = 4 * g + n % 4, key2 = k / 8, c = k % 8;
+    out->b_eg[(k / 8) * (32 * 8) + n * 8 + (k % 8)] = __float2bfloat16_rn(key == key2 ? wp[eg][c][hh] : 0.f);
+  }
+  for (int i = tid; i < 16 * 16; i += 128) {      // b_hx, b_de[g]
+    int n = i / 16, k = i % 16;
+    {
+      int g = n / 8, key = (n / 4) % 2, hh = 4 * g + n % 4, key2 = k / 8, c = k % 8;
+      out->b_hx[(k / 8) * (16 * 8) + n * 8 + (k % 8)] =
+          __float2bfloat16_rn(key == key2 ? w.dense_edge_r_kernel[hh * FDE + c] : 0.f);
+    }
+    for (int g = 0; g < 2; ++g) {
+      int key2 = n / 8, c = n % 8, key = k / 8, eg = (k / 4) % 2, hh = 4 * g + k % 4;
+      out->b_de[g][(k / 8) * (16 * 8) + n * 8 + (k % 8)] = __float2bfloat16_rn(key == key2 ? wp[eg][c][hh] : 0.f);
+    }
+  }
   // wtblk: n = key*8 + c ; k = key'*16 + eg*8 + hh           (N = 16, K = 32)   value W'_eg[c][hh]
   for (int i = tid; i < 16 * 32; i += 128) {
     int n = i / 32, k = i % 32;

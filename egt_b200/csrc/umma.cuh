@@ -35,12 +35,13 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
-// Bounded wait: a wrong phase must never hang the GPU box.  After ~2^28 failed probes (seconds) the
-// kernel traps (the launch then reports cudaErrorLaunchFailed instead of hanging).
+// Bounded wait: a wrong phase must never hang the GPU box.  After ~2 s without completion the kernel
+// traps (the launch then reports cudaErrorLaunchFailed instead of hanging).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 28)) __trap();
+    if (clock64() - t0 > 4000000000ll) __trap();
   }
 }
 
@@ -73,6 +74,12 @@ template <int N>
 __device__ __forceinline__ void tma_store_wait_all() {
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
+
+// ---- register rebalancing between warpgroups (all 4 warps of a warpgroup execute the same one) ----
+template <int R>
+__device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R>
+__device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
 
 // ---- TMEM ------------------------------------------------------------------------------------
 // One full warp calls alloc / dealloc.  ncols: power of two in [32, 512].
@@ -163,6 +170,43 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t *r) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t *r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t *r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, const uint32_t *r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(r[0]), "r"(r[1]) : "memory");
+}
+
+// ---- fast math (MUFU) and packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2) -----------------------
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void ffma2(float2 &acc, const float2 a, const float2 b) {   // acc += a * b (lane-wise)
+  unsigned long long &c = reinterpret_cast<unsigned long long &>(acc);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;"
+      : "+l"(c)
+      : "l"(reinterpret_cast<const unsigned long long &>(a)), "l"(reinterpret_cast<const unsigned long long &>(b)));
+}
+__device__ __forceinline__ void fadd2(float2 &acc, const float2 a) {
+  unsigned long long &c = reinterpret_cast<unsigned long long &>(acc);
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(c) : "l"(reinterpret_cast<const unsigned long long &>(a)));
+}
 
 // ---- small helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {   // element 2j in the low half
