@@ -312,14 +312,18 @@ int egt_block_fwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
   const int R = a.B * a.N, d = a.h * a.dk;
 
   // node side: LN_h + QKV (graph_xformer_model_base.py:108-114)
-  LinearArgs lq;
-  memset(&lq, 0, sizeof(lq));
-  lq.x = io->h; lq.W = w->dense_qkv_kernel; lq.bias = w->dense_qkv_bias; lq.out = io->qkv;
-  lq.ln_gamma = w->norm_mha_gamma; lq.ln_beta = w->norm_mha_beta; lq.ln_eps = cfg->ln_eps;
-  lq.R = R; lq.din = d; lq.dout = 3 * d;
   const bool fused = fused_supported(cfg, a.dtype) && !g_force_staged;
-  if (fused) { lq.scale = 1.0f / sqrtf((float)a.dk); lq.scale_cols = d; }   // Q is stored pre-scaled
-  if ((rc = linear_launch(lq, a.dtype, st))) return rc;
+  if (fused) {   // Q is stored pre-scaled by dk^-0.5
+    if ((rc = node_qkv_launch(io->h, w->norm_mha_gamma, w->norm_mha_beta, cfg->ln_eps, w->dense_qkv_kernel,
+                              w->dense_qkv_bias, 1.0f / sqrtf((float)a.dk), io->qkv, R, st))) return rc;
+  } else {
+    LinearArgs lq;
+    memset(&lq, 0, sizeof(lq));
+    lq.x = io->h; lq.W = w->dense_qkv_kernel; lq.bias = w->dense_qkv_bias; lq.out = io->qkv;
+    lq.ln_gamma = w->norm_mha_gamma; lq.ln_beta = w->norm_mha_beta; lq.ln_eps = cfg->ln_eps;
+    lq.R = R; lq.din = d; lq.dout = 3 * d;
+    if ((rc = linear_launch(lq, a.dtype, st))) return rc;
+  }
 
   size_t need = egt_block_workspace_bytes(cfg, 0);
   EGT_REQUIRE(io->workspace_bytes >= need && (io->workspace || need <= 256), EGT_E_ARG,
@@ -339,11 +343,7 @@ int egt_block_fwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
     fa.rand_thr = (uint32_t)ceilf(a.random_mask_prob * 65536.0f - 0.5f);
     fa.seed = a.seed; fa.offset = a.offset;
     if ((rc = fused_fwd_launch(fa, io->e, io->e_out, io->qkv, st))) return rc;
-    LinearArgs lo;
-    memset(&lo, 0, sizeof(lo));
-    lo.x = io->v_att; lo.W = w->dense_mha_kernel; lo.bias = w->dense_mha_bias; lo.res = io->h; lo.out = io->h_out;
-    lo.R = R; lo.din = d; lo.dout = d;
-    return linear_launch(lo, a.dtype, st);
+    return node_out_launch(io->v_att, io->h, w->dense_mha_kernel, w->dense_mha_bias, io->h_out, R, st);
   }
 
   EdgeParams ep = make_edge_params(cfg, w);
@@ -391,17 +391,9 @@ int egt_block_bwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
   const bool fused_bwd = fused && have_de;
   g_last_path = fused_bwd ? 1 : 0;
 
-  // dV_att = dh' W_O^T ; dW_O += V_att^T dh' ; db_O += colsum(dh')
-  LinearArgs l1;
-  memset(&l1, 0, sizeof(l1));
-  l1.x = io->dh_out; l1.W = w->dense_mha_kernel; l1.trans = 1; l1.out = ws.d_v_att; l1.R = R; l1.din = d; l1.dout = d;
-  if ((rc = linear_launch(l1, a.dtype, st))) return rc;
-  XtyArgs x1;
-  memset(&x1, 0, sizeof(x1));
-  x1.X = io->v_att; x1.Y = io->dh_out; x1.dW = g->dense_mha_kernel; x1.db = g->dense_mha_bias; x1.R = R; x1.dx = d; x1.dy = d;
-  if ((rc = xty_launch(x1, a.dtype, st))) return rc;
-
   if (fused_bwd) {
+    if ((rc = node_bwd1_launch(io->dh_out, io->v_att, w->dense_mha_kernel, ws.d_v_att, g->dense_mha_kernel,
+                               g->dense_mha_bias, R, st))) return rc;
     // N x N part in one kernel (fused_bwd.cu): de, dQ|dK|dV and the edge-side weight-gradient partial sums
     if ((rc = fused_prep_launch(cfg, w, (FusedPrep *)ws.prep, st))) return rc;
     const int tiles = (a.N + 127) / 128;
@@ -418,28 +410,20 @@ int egt_block_bwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
     fb.seed = a.seed; fb.offset = a.offset;
     if ((rc = fused_bwd_launch(fb, io->e, io->de_out, io->de, io->qkv, st))) return rc;
     if ((rc = fused_bwd_finalize_launch(ws.partials, a.B * tiles, w, g, st))) return rc;
-    // node side: hn = LN(h); dW_qkv += hn^T dqkv; dhn = dqkv W_qkv^T; dh = LN_bwd(dhn) + dh'
-    LinearArgs l2;
-    memset(&l2, 0, sizeof(l2));
-    l2.x = io->h; l2.ln_gamma = w->norm_mha_gamma; l2.ln_beta = w->norm_mha_beta; l2.ln_eps = cfg->ln_eps;
-    l2.xn_out = ws.hn; l2.R = R; l2.din = d; l2.dout = 0;
-    if ((rc = linear_launch(l2, a.dtype, st))) return rc;
-    XtyArgs x2;
-    memset(&x2, 0, sizeof(x2));
-    x2.X = ws.hn; x2.x_f32 = 1; x2.Y = ws.d_qkv_f32; x2.y_f32 = 1; x2.dW = g->dense_qkv_kernel; x2.db = g->dense_qkv_bias;
-    x2.R = R; x2.dx = d; x2.dy = 3 * d;
-    if ((rc = xty_launch(x2, a.dtype, st))) return rc;
-    LinearArgs l3;
-    memset(&l3, 0, sizeof(l3));
-    l3.x = ws.d_qkv_f32; l3.x_f32 = 1; l3.W = w->dense_qkv_kernel; l3.trans = 1; l3.out = ws.dhn; l3.out_f32 = 1;
-    l3.R = R; l3.din = 3 * d; l3.dout = d;
-    if ((rc = linear_launch(l3, a.dtype, st))) return rc;
-    LnBwdArgs lb;
-    memset(&lb, 0, sizeof(lb));
-    lb.x = io->h; lb.dy = ws.dhn; lb.dres = io->dh_out; lb.gamma = w->norm_mha_gamma; lb.eps = cfg->ln_eps;
-    lb.dx = io->dh; lb.dgamma = g->norm_mha_gamma; lb.dbeta = g->norm_mha_beta; lb.R = R; lb.D = d;
-    return ln_bwd_launch(lb, a.dtype, st);
+    return node_bwd2_launch(io->h, io->dh_out, ws.d_qkv_f32, w->norm_mha_gamma, w->norm_mha_beta, cfg->ln_eps,
+                            w->dense_qkv_kernel, io->dh, g->dense_qkv_kernel, g->dense_qkv_bias, g->norm_mha_gamma,
+                            g->norm_mha_beta, R, st);
   }
+
+  // dV_att = dh' W_O^T ; dW_O += V_att^T dh' ; db_O += colsum(dh')
+  LinearArgs l1;
+  memset(&l1, 0, sizeof(l1));
+  l1.x = io->dh_out; l1.W = w->dense_mha_kernel; l1.trans = 1; l1.out = ws.d_v_att; l1.R = R; l1.din = d; l1.dout = d;
+  if ((rc = linear_launch(l1, a.dtype, st))) return rc;
+  XtyArgs x1;
+  memset(&x1, 0, sizeof(x1));
+  x1.X = io->v_att; x1.Y = io->dh_out; x1.dW = g->dense_mha_kernel; x1.db = g->dense_mha_bias; x1.R = R; x1.dx = d; x1.dy = d;
+  if ((rc = xty_launch(x1, a.dtype, st))) return rc;
 
   EdgeParams ep = make_edge_params(cfg, w);
   ep.g_ln_g = g->norm_edge_gamma; ep.g_ln_b = g->norm_edge_beta;

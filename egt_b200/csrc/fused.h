@@ -79,6 +79,17 @@ int fused_bwd_launch(const FusedBwdArgs &a, const void *e, const void *de_out, v
 int fused_bwd_finalize_launch(const float *partials, int nparts, const egt_block_weights_t *w,
                               const egt_block_grads_t *g, cudaStream_t st);
 
+// node side on tensor cores (node_tc.cu); bf16 activations, d = 64
+int node_qkv_launch(const void *h, const float *gamma, const float *beta, float eps, const float *W, const float *bias,
+                    float qscale, void *qkv, int R, cudaStream_t st);
+int node_out_launch(const void *v_att, const void *h, const float *W, const float *bias, void *h_out, int R,
+                    cudaStream_t st);
+int node_bwd1_launch(const void *dh_out, const void *v_att, const float *W, void *d_v_att, float *dW, float *db, int R,
+                     cudaStream_t st);
+int node_bwd2_launch(const void *h, const void *dh_out, const float *dqkv, const float *gamma, const float *beta,
+                     float eps, const float *W, void *dh, float *dW, float *db, float *dgamma, float *dbeta, int R,
+                     cudaStream_t st);
+
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda at link time)
 int encode_tmap_3d(CUtensorMap *out, const void *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
                    uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2, int swizzle128);

@@ -56,7 +56,7 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
                  const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                  const FusedFwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
   const uint32_t sbase = smem_u32(smem);
   Bars *bars = (Bars *)(smem + SM_BAR);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;

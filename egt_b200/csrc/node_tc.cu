@@ -1,0 +1,542 @@
+// node_tc.cu -- node-channel side of the block on sm_100a tensor cores (bf16 activations, d = 64, h = 8):
+//
+//   node_qkv_kernel    qkv  = LN(h) W_qkv + b_qkv, Q third pre-scaled     (graph_xformer_model_base.py:107-114)
+//   node_out_kernel    h'   = h + V_att W_O + b_O                         (:136-140)
+//   node_bwd1_kernel   dV_att = dh' W_O^T ; dW_O += V_att^T dh' ; db_O += colsum(dh')
+//   node_bwd2_kernel   dhn = dqkv W_qkv^T ; dh = LN_bwd(dhn) + dh' ; dgamma, dbeta ;
+//                      dW_qkv += LN(h)^T dqkv ; db_qkv += colsum(dqkv)
+//
+// One CTA = 128 rows of the flattened [B*N, d] node tensor per iteration (grid-stride), thread = row =
+// TMEM lane.  Row tiles are written to shared memory as 128B-swizzled tcgen05 operands; the weights
+// are converted to bf16 operand images once per CTA.  The row-contracted products (X^T Y, needed for the
+// weight gradients) use the tile itself as an MN-major A operand next to a tile of ones, so rows 0-63 of
+// the accumulator hold dW and row 64 holds the column sum (the bias gradient); they accumulate in TMEM
+// over the CTA's tiles and are flushed once with atomics.
+#include "common.cuh"
+#include "fused.h"
+#include "umma.cuh"
+
+namespace egt {
+using namespace umma;
+
+namespace {
+
+constexpr int ND = 64;            // model width served by these kernels
+constexpr uint32_t TILE = 16384;  // [128 rows x 128 B] swizzled tile
+
+struct NodeBars { uint64_t bar; uint32_t tmem_base; uint32_t pad; };
+
+// thread t's row of 64 bf16 (8 x 16 B) -> swizzled tile
+__device__ __forceinline__ void put_row(uint8_t *tile, int t, const uint4 *v) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) *(uint4 *)(tile + sw128_off(t, 8 * j)) = v[j];
+}
+__device__ __forceinline__ void unpack8(const uint4 v, float *x) {
+  x[0] = bf16_lo(v.x); x[1] = bf16_hi(v.x); x[2] = bf16_lo(v.y); x[3] = bf16_hi(v.y);
+  x[4] = bf16_lo(v.z); x[5] = bf16_hi(v.z); x[6] = bf16_lo(v.w); x[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ uint4 pack8(const float *x) {
+  uint4 v;
+  v.x = pack_bf16(x[0], x[1]); v.y = pack_bf16(x[2], x[3]); v.z = pack_bf16(x[4], x[5]); v.w = pack_bf16(x[6], x[7]);
+  return v;
+}
+// B operand images from a float32 Keras kernel W[kdim][ndim] (row-major, "x @ W"):
+//   MN-major (n contiguous), 128B swizzle, atoms of 64 n: used for x @ W       (contraction over W's rows)
+__device__ __forceinline__ void build_w_mn(uint8_t *img, const float *W, int kdim, int ndim, int tid, int nthr) {
+  for (int i = tid; i < kdim * ndim; i += nthr) {
+    const int k = i / ndim, n = i % ndim;
+    const uint32_t off = (uint32_t)(n >> 6) * (uint32_t)(kdim * 128) + (uint32_t)(k >> 3) * 1024u + (uint32_t)(k & 7) * 128u +
+                         ((uint32_t)((((n & 63) >> 3) ^ k) & 7) << 4) + (uint32_t)(n & 7) * 2u;
+    *(__nv_bfloat16 *)(img + off) = __float2bfloat16_rn(W[i]);
+  }
+}
+//   K-major image of W^T, i.e. B[n = row of W][k = column of W]: used for x @ W^T (contraction over W's columns)
+__device__ __forceinline__ void build_wt_k(uint8_t *img, const float *W, int nrows, int kcols, int tid, int nthr) {
+  for (int i = tid; i < nrows * kcols; i += nthr) {
+    const int n = i / kcols, k = i % kcols;
+    *(__nv_bfloat16 *)(img + (uint32_t)(k >> 6) * (uint32_t)(nrows * 128) + sw128_off(n, k & 63)) = __float2bfloat16_rn(W[i]);
+  }
+}
+__device__ __forceinline__ void fill_ones(uint8_t *tile, int tid, int nthr) {
+  for (int i = tid; i < (int)(TILE / 16); i += nthr) ((uint4 *)tile)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+}
+
+__device__ __forceinline__ void node_setup(NodeBars *bars, int tid, uint32_t cols) {
+  if (tid < 32) {
+    if (tid == 0) { mbar_init(smem_u32(&bars->bar), 1); mbar_fence_init(); }
+    __syncwarp();
+    tmem_alloc(smem_u32(&bars->tmem_base), cols);
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+struct NodeQkvArgs {
+  const __nv_bfloat16 *h; const float *gamma, *beta; float eps;
+  const float *W, *bias; float qscale;
+  __nv_bfloat16 *qkv; int R;
+};
+
+__global__ void __launch_bounds__(128) node_qkv_kernel(const NodeQkvArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t *sA = smem, *sW = smem + TILE;                     // A 16 KB | W image 3 x 8 KB
+  float *sgb = (float *)(smem + TILE + 24576);               // gamma, beta, bias(192)
+  NodeBars *bars = (NodeBars *)(smem + TILE + 24576 + 1536);
+  const int t = threadIdx.x;
+  node_setup(bars, t, 256);
+  build_w_mn(sW, a.W, ND, 3 * ND, t, 128);
+  if (t < ND) { sgb[t] = a.gamma[t]; sgb[ND + t] = a.beta[t]; }
+  for (int i = t; i < 3 * ND; i += 128) sgb[2 * ND + i] = a.bias[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+  const uint32_t tlane = tmem + ((uint32_t)((t >> 5) * 32) << 16);
+  constexpr uint32_t IDESC = idesc_bf16(128, 192, 0, 1);
+  uint32_t phase = 0;
+  for (int tile = blockIdx.x; tile * 128 < a.R; tile += gridDim.x) {
+    const int r = tile * 128 + t;
+    {   // LayerNorm of this thread's row -> bf16 A tile
+      uint4 v[8];
+      float x[64];
+      const uint4 *src = (const uint4 *)(a.h + (size_t)(r < a.R ? r : 0) * ND);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { v[j] = r < a.R ? src[j] : make_uint4(0, 0, 0, 0); unpack8(v[j], x + 8 * j); }
+      float mu = 0.f;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) mu += x[c];
+      mu *= (1.f / 64.f);
+      float var = 0.f;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) { const float dlt = x[c] - mu; var = fmaf(dlt, dlt, var); }
+      const float rs = rsqrtf(var * (1.f / 64.f) + a.eps);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float y[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) y[c] = fmaf((x[8 * j + c] - mu) * rs, sgb[8 * j + c], sgb[ND + 8 * j + c]);
+        *(uint4 *)(sA + sw128_off(t, 8 * j)) = pack8(y);
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (t == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int s = 0; s < 4; ++s)
+        mma_ss(tmem, smem_desc(smem_u32(sA) + 32 * s, 16, 1024, LAYOUT_SW128),
+               smem_desc(smem_u32(sW) + 2048 * s, ND * 128, 1024, LAYOUT_SW128), IDESC, s > 0);
+      mma_commit(smem_u32(&bars->bar));
+    }
+    mbar_wait(smem_u32(&bars->bar), phase);
+    phase ^= 1;
+    tc_fence_after();
+#pragma unroll 1
+    for (int ch = 0; ch < 6; ++ch) {
+      uint32_t o[32];
+      tmem_ld32(tlane + 32 * ch, o);
+      tmem_ld_wait();
+      if (r < a.R) {
+        const float sc = ch < 2 ? a.qscale : 1.f;
+        uint4 *dst = (uint4 *)(a.qkv + (size_t)r * (3 * ND) + 32 * ch);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float y[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) y[c] = (__uint_as_float(o[8 * q + c]) + sgb[2 * ND + 32 * ch + 8 * q + c]) * sc;
+          dst[q] = pack8(y);
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  if (t < 32) tmem_dealloc(tmem, 256);
+}
+
+// ------------------------------------------------------------------------------------------------
+struct NodeOutArgs {
+  const __nv_bfloat16 *v_att, *h; const float *W, *bias;
+  __nv_bfloat16 *h_out; int R;
+};
+
+__global__ void __launch_bounds__(128) node_out_kernel(const NodeOutArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t *sA = smem, *sW = smem + TILE;                     // A 16 KB | W_O image 8 KB
+  float *sb = (float *)(smem + TILE + 8192);
+  NodeBars *bars = (NodeBars *)(smem + TILE + 8192 + 256);
+  const int t = threadIdx.x;
+  node_setup(bars, t, 64);
+  build_w_mn(sW, a.W, ND, ND, t, 128);
+  if (t < ND) sb[t] = a.bias[t];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+  const uint32_t tlane = tmem + ((uint32_t)((t >> 5) * 32) << 16);
+  constexpr uint32_t IDESC = idesc_bf16(128, 64, 0, 1);
+  uint32_t phase = 0;
+  for (int tile = blockIdx.x; tile * 128 < a.R; tile += gridDim.x) {
+    const int r = tile * 128 + t;
+    {
+      uint4 v[8];
+      const uint4 *src = (const uint4 *)(a.v_att + (size_t)(r < a.R ? r : 0) * ND);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = r < a.R ? src[j] : make_uint4(0, 0, 0, 0);
+      put_row(sA, t, v);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (t == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int s = 0; s < 4; ++s)
+        mma_ss(tmem, smem_desc(smem_u32(sA) + 32 * s, 16, 1024, LAYOUT_SW128),
+               smem_desc(smem_u32(sW) + 2048 * s, ND * 128, 1024, LAYOUT_SW128), IDESC, s > 0);
+      mma_commit(smem_u32(&bars->bar));
+    }
+    mbar_wait(smem_u32(&bars->bar), phase);
+    phase ^= 1;
+    tc_fence_after();
+#pragma unroll 1
+    for (int ch = 0; ch < 2; ++ch) {
+      uint32_t o[32];
+      tmem_ld32(tlane + 32 * ch, o);
+      tmem_ld_wait();
+      if (r < a.R) {
+        const uint4 *res = (const uint4 *)(a.h + (size_t)r * ND + 32 * ch);
+        uint4 *dst = (uint4 *)(a.h_out + (size_t)r * ND + 32 * ch);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float y[8], hr[8];
+          unpack8(res[q], hr);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) y[c] = __uint_as_float(o[8 * q + c]) + sb[32 * ch + 8 * q + c] + hr[c];
+          dst[q] = pack8(y);
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  if (t < 32) tmem_dealloc(tmem, 64);
+}
+
+// ------------------------------------------------------------------------------------------------
+struct NodeBwd1Args {
+  const __nv_bfloat16 *dh_out, *v_att; const float *W;       // W_O [64,64]
+  __nv_bfloat16 *d_v_att; float *dW, *db; int R;
+};
+
+__global__ void __launch_bounds__(128) node_bwd1_kernel(const NodeBwd1Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t *sX = smem, *sOnes = smem + TILE, *sY = smem + 2 * TILE, *sW = smem + 3 * TILE;   // X | 1 | Y | W_O^T image 8 KB
+  NodeBars *bars = (NodeBars *)(smem + 3 * TILE + 8192);
+  const int t = threadIdx.x;
+  node_setup(bars, t, 128);
+  build_wt_k(sW, a.W, ND, ND, t, 128);
+  fill_ones(sOnes, t, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+  const uint32_t tlane = tmem + ((uint32_t)((t >> 5) * 32) << 16);
+  constexpr uint32_t ID_MAIN = idesc_bf16(128, 64, 0, 0), ID_T = idesc_bf16(128, 64, 1, 1);
+  constexpr uint32_t TM_D1 = 0, TM_D2 = 64;
+  uint32_t phase = 0;
+  bool first = true;
+  for (int tile = blockIdx.x; tile * 128 < a.R; tile += gridDim.x) {
+    const int r = tile * 128 + t;
+    {
+      uint4 v[8];
+      const uint4 *sx = (const uint4 *)(a.v_att + (size_t)(r < a.R ? r : 0) * ND);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = r < a.R ? sx[j] : make_uint4(0, 0, 0, 0);
+      put_row(sX, t, v);
+      const uint4 *sy = (const uint4 *)(a.dh_out + (size_t)(r < a.R ? r : 0) * ND);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = r < a.R ? sy[j] : make_uint4(0, 0, 0, 0);
+      put_row(sY, t, v);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (t == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int s = 0; s < 4; ++s)      // dV_att = dh' W_O^T
+        mma_ss(tmem + TM_D1, smem_desc(smem_u32(sY) + 32 * s, 16, 1024, LAYOUT_SW128),
+               smem_desc(smem_u32(sW) + 32 * s, 16, 1024, LAYOUT_SW128), ID_MAIN, s > 0);
+#pragma unroll
+      for (int s = 0; s < 8; ++s)      // [V_att | 1]^T dh'
+        mma_ss(tmem + TM_D2, smem_desc(smem_u32(sX) + 2048 * s, TILE, 1024, LAYOUT_SW128),
+               smem_desc(smem_u32(sY) + 2048 * s, TILE, 1024, LAYOUT_SW128), ID_T, !(first && s == 0));
+      mma_commit(smem_u32(&bars->bar));
+    }
+    first = false;
+    mbar_wait(smem_u32(&bars->bar), phase);
+    phase ^= 1;
+    tc_fence_after();
+#pragma unroll 1
+    for (int ch = 0; ch < 2; ++ch) {
+      uint32_t o[32];
+      tmem_ld32(tlane + TM_D1 + 32 * ch, o);
+      tmem_ld_wait();
+      if (r < a.R) {
+        uint4 *dst = (uint4 *)(a.d_v_att + (size_t)r * ND + 32 * ch);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float y[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) y[c] = __uint_as_float(o[8 * q + c]);
+          dst[q] = pack8(y);
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  if (!first) {   // flush dW_O (rows 0-63) and db_O (row 64)
+#pragma unroll 1
+    for (int ch = 0; ch < 2; ++ch) {
+      uint32_t o[32];
+      tmem_ld32(tlane + TM_D2 + 32 * ch, o);
+      tmem_ld_wait();
+      if (t <= ND) {
+        float *dst = t < ND ? a.dW + (size_t)t * ND + 32 * ch : a.db + 32 * ch;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) atomicAdd(dst + c, __uint_as_float(o[c]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (t < 32) tmem_dealloc(tmem, 128);
+}
+
+// ------------------------------------------------------------------------------------------------
+struct NodeBwd2Args {
+  const __nv_bfloat16 *h, *dh_out; const float *dqkv;       // dqkv [R,192] float32
+  const float *gamma, *beta; float eps;
+  const float *W;                                            // W_qkv [64,192]
+  __nv_bfloat16 *dh; float *dW, *db, *dgamma, *dbeta; int R;
+};
+
+__global__ void __launch_bounds__(128) node_bwd2_kernel(const NodeBwd2Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t *sX = smem, *sOnes = smem + TILE, *sY = smem + 2 * TILE;   // LN(h) | 1 | dqkv (3 tiles)
+  uint8_t *sW = smem + 5 * TILE;                                      // W_qkv^T image: 3 k-atoms x 8 KB
+  float *sred = (float *)(smem + 5 * TILE + 24576);                   // [128][65] float32 transpose scratch
+  float *sgb = sred + 128 * 65;                                       // gamma, beta
+  NodeBars *bars = (NodeBars *)(sgb + 2 * ND);
+  const int t = threadIdx.x;
+  node_setup(bars, t, 256);
+  build_wt_k(sW, a.W, ND, 3 * ND, t, 128);
+  fill_ones(sOnes, t, 128);
+  if (t < ND) { sgb[t] = a.gamma[t]; sgb[ND + t] = a.beta[t]; }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+  const uint32_t tlane = tmem + ((uint32_t)((t >> 5) * 32) << 16);
+  constexpr uint32_t ID_MAIN = idesc_bf16(128, 64, 0, 0), ID_T = idesc_bf16(128, 192, 1, 1);
+  constexpr uint32_t TM_D1 = 0, TM_D2 = 64;
+  uint32_t phase = 0;
+  bool first = true;
+  float dg_acc = 0.f, db_acc = 0.f;     // thread c < 64: dgamma[c]; thread 64 + c: dbeta[c]
+  for (int tile = blockIdx.x; tile * 128 < a.R; tile += gridDim.x) {
+    const int r = tile * 128 + t;
+    const bool valid = r < a.R;
+    float xh[64], rs;
+    {   // x^ = (h - mu) rstd ; LN(h) -> X tile
+      const uint4 *src = (const uint4 *)(a.h + (size_t)(valid ? r : 0) * ND);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) unpack8(valid ? src[j] : make_uint4(0, 0, 0, 0), xh + 8 * j);
+      float mu = 0.f;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) mu += xh[c];
+      mu *= (1.f / 64.f);
+      float var = 0.f;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) { xh[c] -= mu; var = fmaf(xh[c], xh[c], var); }
+      rs = rsqrtf(var * (1.f / 64.f) + a.eps);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float y[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          xh[8 * j + c] *= rs;
+          y[c] = valid ? fmaf(xh[8 * j + c], sgb[8 * j + c], sgb[ND + 8 * j + c]) : 0.f;
+        }
+        *(uint4 *)(sX + sw128_off(t, 8 * j)) = pack8(y);
+      }
+      // dqkv row (float32) -> three bf16 tiles
+      const float4 *sq = (const float4 *)(a.dqkv + (size_t)(valid ? r : 0) * (3 * ND));
+#pragma unroll 4
+      for (int j = 0; j < 24; ++j) {
+        float y[8];
+        const float4 p0 = valid ? sq[2 * j] : make_float4(0, 0, 0, 0), p1 = valid ? sq[2 * j + 1] : make_float4(0, 0, 0, 0);
+        y[0] = p0.x; y[1] = p0.y; y[2] = p0.z; y[3] = p0.w; y[4] = p1.x; y[5] = p1.y; y[6] = p1.z; y[7] = p1.w;
+        *(uint4 *)(sY + (uint32_t)(j >> 3) * TILE + sw128_off(t, 8 * (j & 7))) = pack8(y);
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (t == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int s = 0; s < 12; ++s)     // dhn = dqkv W_qkv^T   (K = 192)
+        mma_ss(tmem + TM_D1, smem_desc(smem_u32(sY) + (uint32_t)(s >> 2) * TILE + 32 * (s & 3), 16, 1024, LAYOUT_SW128),
+               smem_desc(smem_u32(sW) + (uint32_t)(s >> 2) * 8192 + 32 * (s & 3), 16, 1024, LAYOUT_SW128), ID_MAIN, s > 0);
+#pragma unroll
+      for (int s = 0; s < 8; ++s)      // [LN(h) | 1]^T dqkv
+        mma_ss(tmem + TM_D2, smem_desc(smem_u32(sX) + 2048 * s, TILE, 1024, LAYOUT_SW128),
+               smem_desc(smem_u32(sY) + 2048 * s, TILE, 1024, LAYOUT_SW128), ID_T, !(first && s == 0));
+      mma_commit(smem_u32(&bars->bar));
+    }
+    first = false;
+    mbar_wait(smem_u32(&bars->bar), phase);
+    phase ^= 1;
+    tc_fence_after();
+    {   // LayerNorm backward + residual for this thread's row
+      float dy[64];
+      uint32_t o[32];
+      tmem_ld32(tlane + TM_D1, o);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 32; ++c) dy[c] = __uint_as_float(o[c]);
+      tmem_ld32(tlane + TM_D1 + 32, o);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 32; ++c) dy[32 + c] = __uint_as_float(o[c]);
+      float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) {
+        const float dxh = dy[c] * sgb[c];
+        m1 += dxh;
+        m2 = fmaf(dxh, xh[c], m2);
+        sred[t * 65 + c] = dy[c] * xh[c];          // -> dgamma (column sums below)
+      }
+      m1 *= (1.f / 64.f); m2 *= (1.f / 64.f);
+      if (valid) {
+        const uint4 *res = (const uint4 *)(a.dh_out + (size_t)r * ND);
+        uint4 *dst = (uint4 *)(a.dh + (size_t)r * ND);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float y[8], hr[8];
+          unpack8(res[j], hr);
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            y[c] = fmaf(rs, fmaf(dy[8 * j + c], sgb[8 * j + c], -fmaf(xh[8 * j + c], m2, m1)), hr[c]);
+          dst[j] = pack8(y);
+        }
+      }
+      __syncthreads();
+      if (t < ND) {
+        float s = 0.f;
+#pragma unroll 8
+        for (int rr = 0; rr < 128; ++rr) s += sred[rr * 65 + t];
+        dg_acc += s;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int c = 0; c < 64; ++c) sred[t * 65 + c] = dy[c];   // -> dbeta
+      __syncthreads();
+      if (t >= ND) {
+        float s = 0.f;
+#pragma unroll 8
+        for (int rr = 0; rr < 128; ++rr) s += sred[rr * 65 + (t - ND)];
+        db_acc += s;
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  if (!first) {
+    if (t < ND) atomicAdd(a.dgamma + t, dg_acc);
+    else atomicAdd(a.dbeta + (t - ND), db_acc);
+#pragma unroll 1
+    for (int ch = 0; ch < 6; ++ch) {   // dW_qkv (rows 0-63), db_qkv (row 64)
+      uint32_t o[32];
+      tmem_ld32(tlane + TM_D2 + 32 * ch, o);
+      tmem_ld_wait();
+      if (t <= ND) {
+        float *dst = t < ND ? a.dW + (size_t)t * (3 * ND) + 32 * ch : a.db + 32 * ch;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) atomicAdd(dst + c, __uint_as_float(o[c]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (t < 32) tmem_dealloc(tmem, 256);
+}
+
+// ------------------------------------------------------------------------------------------------
+static int node_grid(int R) {
+  int tiles = (R + 127) / 128;
+  return tiles < 148 ? tiles : 148;
+}
+template <typename K>
+static int set_smem(K kernel, int bytes) {
+  EGT_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return EGT_OK;
+}
+
+int node_qkv_launch(const void *h, const float *gamma, const float *beta, float eps, const float *W, const float *bias,
+                    float qscale, void *qkv, int R, cudaStream_t st) {
+  NodeQkvArgs a{(const __nv_bfloat16 *)h, gamma, beta, eps, W, bias, qscale, (__nv_bfloat16 *)qkv, R};
+  const int smem = TILE + 24576 + 1536 + 64 + 1024;
+  static bool once = false;
+  if (!once) { int rc = set_smem(node_qkv_kernel, smem); if (rc) return rc; once = true; }
+  LaunchScope _ls("node_qkv_kernel", st);
+  node_qkv_kernel<<<node_grid(R), 128, smem, st>>>(a);
+  EGT_CHECK_CUDA(cudaGetLastError());
+  return EGT_OK;
+}
+
+int node_out_launch(const void *v_att, const void *h, const float *W, const float *bias, void *h_out, int R,
+                    cudaStream_t st) {
+  NodeOutArgs a{(const __nv_bfloat16 *)v_att, (const __nv_bfloat16 *)h, W, bias, (__nv_bfloat16 *)h_out, R};
+  const int smem = TILE + 8192 + 256 + 64 + 1024;
+  LaunchScope _ls("node_out_kernel", st);
+  node_out_kernel<<<node_grid(R), 128, smem, st>>>(a);
+  EGT_CHECK_CUDA(cudaGetLastError());
+  return EGT_OK;
+}
+
+int node_bwd1_launch(const void *dh_out, const void *v_att, const float *W, void *d_v_att, float *dW, float *db, int R,
+                     cudaStream_t st) {
+  NodeBwd1Args a{(const __nv_bfloat16 *)dh_out, (const __nv_bfloat16 *)v_att, W, (__nv_bfloat16 *)d_v_att, dW, db, R};
+  const int smem = 3 * TILE + 8192 + 64 + 1024;
+  static bool once = false;
+  if (!once) { int rc = set_smem(node_bwd1_kernel, smem); if (rc) return rc; once = true; }
+  LaunchScope _ls("node_bwd1_kernel", st);
+  node_bwd1_kernel<<<node_grid(R), 128, smem, st>>>(a);
+  EGT_CHECK_CUDA(cudaGetLastError());
+  return EGT_OK;
+}
+
+int node_bwd2_launch(const void *h, const void *dh_out, const float *dqkv, const float *gamma, const float *beta,
+                     float eps, const float *W, void *dh, float *dW, float *db, float *dgamma, float *dbeta, int R,
+                     cudaStream_t st) {
+  NodeBwd2Args a{(const __nv_bfloat16 *)h, (const __nv_bfloat16 *)dh_out, dqkv, gamma, beta, eps, W,
+                 (__nv_bfloat16 *)dh, dW, db, dgamma, dbeta, R};
+  const int smem = 5 * TILE + 24576 + 128 * 65 * 4 + 2 * ND * 4 + 64 + 1024;
+  static bool once = false;
+  if (!once) { int rc = set_smem(node_bwd2_kernel, smem); if (rc) return rc; once = true; }
+  LaunchScope _ls("node_bwd2_kernel", st);
+  node_bwd2_kernel<<<node_grid(R), 128, smem, st>>>(a);
+  EGT_CHECK_CUDA(cudaGetLastError());
+  return EGT_OK;
+}
+
+}  // namespace egt
