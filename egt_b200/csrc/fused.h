@@ -30,6 +30,7 @@ struct FusedPrep {
   __nv_bfloat16 b_eg[2 * 32 * 8];     // [E|G] projection: N = 32 (g,key,eg,hh4), K = 16 (key',c): W'_eg[c,hh]
   __nv_bfloat16 b_hx[2 * 16 * 8];     // dH_ext = de' W_r^T: N = 16 (g,key,hh4), K = 16 (key',c): W_r[hh,c]
   __nv_bfloat16 b_de[2][2 * 16 * 8];  // d x^ = dZ W'^T, one image per g: N = 16 (key',c), K = 16 (key,eg,hh4)
+  __nv_bfloat16 b_wr[2 * 16 * 8];     // forward edge write-back H^ W_r: N = 16 (key',c), K = 16 (g,key,hh4): W_r[hh,c]
   float uE[FH], vE[FH], uG[FH], vG[FH], br[FDE];
   float wp[2][FDE][FH];               // W'_E, W'_G as rounded to bf16 (for the weight-gradient epilogue)
   float bound;                        // sup |masked logit| over all inputs given these weights

@@ -5,20 +5,25 @@
 //   (lib/models/graph_xformer_model_base.py:192-218).  The [B,N,N,h] tensors E, G, H_hat, A~ never
 //   leave the SM: e is streamed in once by TMA, e' streamed out once by TMA.
 //
-// One CTA = one graph b and 128 query rows; thread t of warps 0-3 owns query row l0+t == TMEM lane t.
-// Keys are processed in sub-tiles of 4 (two key PAIRS).  Per key pair the tensor core produces, in TMEM,
-//     S  [128 x 16]  = Q[128x64] * Kexp^T      Kexp[(key,hh), c] = K[key,c] * [c % 8 == hh]
-//     EG [128 x 32]  = e_tile[128 x 16] * Wblk (raw edge channels of the two keys x folded-LN weights)
-// (the per-head dot product is a block-diagonal contraction over the head-innermost channel axis, so it
-// is a plain GEMM against an expanded K).  The row's thread then applies LN statistics, clip, masks,
-// exp / sigmoid, accumulates the softmax denominator and the gate sum, and writes A~ and H_hat back
-// to TMEM as bf16 A-operands of
-//     O  [128 x 64] += A~[128 x 16] * Vexp     Vexp[(key,hh), c] = V[key,c] * [c % 8 == hh]
-//     De [128 x 16]  = H_hat[128 x 16] * Wrblk (edge write-back of the two keys)
-// Softmax runs without max subtraction: logits are bounded by clip + |E| <= FusedPrep::bound.
+// One CTA = one graph b and 128 query rows.  Thread t of warps 0-3 and of warps 4-7 both own query row
+// l0+t == TMEM lane t; warps 0-3 ("group 0") handle heads 0-3, warps 4-7 heads 4-7, so every SM
+// sub-partition has two resident compute warps.  Warp 8 issues TMA and tcgen05.mma (warps 9-11 complete its
+// warpgroup so that setmaxnreg can move registers to the compute warps).
 //
-// Warp 4 issues TMA and tcgen05.mma; all ordering is __syncthreads + completion mbarriers, every async
-// operation is issued two sub-tiles ahead of its consumer.
+// Keys are processed in PAIRS.  For pair p the tensor core produces, in TMEM (columns ordered (g,key,hh4)):
+//     S  [128x16] = Qs [128x64] * Kexp^T      Kexp[(g,key,hh4), c] = K[key,c] * [c % 8 == hh]
+//     EG [128x32] = e  [128x16] * Wblk        raw edge channels of the two keys x folded-LN weights
+// (the per-head dot product is a block-diagonal contraction over the head-innermost channel axis, so it is a
+// plain GEMM against an expanded K).  The row's threads apply the LN statistics, clip, masks, exp / sigmoid,
+// accumulate the softmax denominator and the gate sum, and write A~ and H_hat back to TMEM as bf16
+// A-operands of
+//     O  [128x64] += A~ [128x16] * Vexp       Vexp[(g,key,hh4), c] = V[key,c] * [c % 8 == hh]
+//     De [128x16]  = H_hat [128x16] * Wr blk  edge write-back of the two keys
+// e' = e + De + b_r is formed in place over the e stage and leaves by TMA store.
+// Softmax runs without max subtraction: logits are bounded by clip + |E| (FusedPrep::bound).
+//
+// All warps run in lock step, one __syncthreads per key pair; every tensor-core / TMA operation is issued
+// two pairs ahead of its consumer and observed through an mbarrier (same skeleton as fused_bwd.cu).
 #include "common.cuh"
 #include "fused.h"
 #include "umma.cuh"
@@ -28,43 +33,44 @@ using namespace umma;
 
 namespace {
 
-constexpr int NS = 4;                                  // e-tile stages (8 keys each)
-constexpr uint32_t SM_Q = 0;                           // [128 x 128B] swizzled
-constexpr uint32_t SM_STAGE = 16384;                   // NS x (16384 e + 1024 K rows + 1024 V rows)
-constexpr uint32_t STAGE_BYTES = 18432;
-constexpr uint32_t SM_OST = SM_STAGE + NS * STAGE_BYTES;        // 2 x 16384 e' staging
-constexpr uint32_t SM_KVX = SM_OST + 2 * 16384;                 // 4 x 8192: Kexp(2 pairs) | Vexp(2 pairs)
-constexpr uint32_t SM_WBLK = SM_KVX + 4 * 8192;                 // 1024
-constexpr uint32_t SM_WRBLK = SM_WBLK + 1024;                   // 512
-constexpr uint32_t SM_CONST = SM_WRBLK + 512;                   // 40 floats
-constexpr uint32_t SM_BAR = SM_CONST + 256;                     // mbarriers
+constexpr int NS = 4;                                  // input stages of 8 keys: e | K rows | V rows
+constexpr uint32_t SM_Q = 0;                           // [128 x 128B] swizzled, Q pre-scaled by dk^-0.5
+constexpr uint32_t SM_STAGE = 16384;
+constexpr uint32_t ST_E = 0, ST_K = 16384, ST_V = 17408, STAGE_BYTES = 18432;
+constexpr uint32_t SM_KVX = SM_STAGE + NS * STAGE_BYTES;       // 4 slots x (Kexp 2048 | Vexp 2048)
+constexpr uint32_t SM_W = SM_KVX + 4 * 4096;                   // b_eg 1024 | b_wr 512
+constexpr uint32_t SM_CONST = SM_W + 1536;                     // uE vE uG vG br (40 floats)
+constexpr uint32_t SM_BAR = SM_CONST + 256;
 constexpr uint32_t SM_TOTAL = SM_BAR + 256;
-constexpr uint32_t TM_O = 0, TM_BUF = 64, TM_BUF_COLS = 96, TM_PAIR_COLS = 48;
 
-constexpr uint32_t ID_S = idesc_bf16(128, 16, 0, 0);
-constexpr uint32_t ID_EG = idesc_bf16(128, 32, 0, 0);
+constexpr uint32_t TM_O = 0;
+constexpr uint32_t TM_IN = 64, TM_IN_COLS = 48;                // 3 buffers: S 16 | EG 32
+constexpr uint32_t IN_S = 0, IN_EG = 16;
+constexpr uint32_t TM_OUT = 208, TM_OUT_COLS = 16;             // 2 buffers: A~ 8 | H_hat 8 (bf16 A operands)
+
+constexpr uint32_t ID_N16 = idesc_bf16(128, 16, 0, 0);
+constexpr uint32_t ID_N32 = idesc_bf16(128, 32, 0, 0);
 constexpr uint32_t ID_PV = idesc_bf16(128, 64, 0, 1);
-constexpr uint32_t ID_WR = idesc_bf16(128, 16, 0, 0);
 
 struct Bars { uint64_t q_full, e_full[NS], mma1[3], mma2[3]; uint32_t tmem_base; };
 
 }  // namespace
 
 template <bool RAND>
-__global__ void __launch_bounds__(160, 1)
+__global__ void __launch_bounds__(384, 1)
 fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant__ CUtensorMap tm_eo,
                  const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                  const FusedFwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // shared address space is kept
   const uint32_t sbase = smem_u32(smem);
   Bars *bars = (Bars *)(smem + SM_BAR);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y, l0 = blockIdx.x * 128;
   const int N = a.N;
-  const int NT = (N + 7) / 8, NSUB = 2 * NT;
+  const int NT = (N + 7) / 8, NP = (N + 1) / 2;       // 8-key tiles, key pairs
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       mbar_init(smem_u32(&bars->q_full), 1);
       for (int i = 0; i < NS; ++i) mbar_init(smem_u32(&bars->e_full[i]), 1);
@@ -73,13 +79,11 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
       tma_prefetch_desc(&tm_e); tma_prefetch_desc(&tm_eo); tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_kv);
     }
     __syncwarp();
-    tmem_alloc(smem_u32(&bars->tmem_base), 512);
-  } else {
-    // derived weights -> smem (generic proxy writes; made visible to the tensor core by the fence below)
-    const uint4 *src = (const uint4 *)a.prep->wblk;
-    if (tid < 64) ((uint4 *)(smem + SM_WBLK))[tid] = src[tid];
-    if (tid < 32) ((uint4 *)(smem + SM_WRBLK))[tid] = ((const uint4 *)a.prep->wrblk)[tid];
-    if (tid < 40) ((float *)(smem + SM_CONST))[tid] = a.prep->uE[tid];   // uE,vE,uG,vG,br are contiguous
+    tmem_alloc(smem_u32(&bars->tmem_base), 256);
+  } else if (warp < 8) {
+    if (tid < 64) ((uint4 *)(smem + SM_W))[tid] = ((const uint4 *)a.prep->b_eg)[tid];            // b_eg
+    else if (tid < 96) ((uint4 *)(smem + SM_W + 1024))[tid - 64] = ((const uint4 *)a.prep->b_wr)[tid - 64];
+    if (tid < 40) ((float *)(smem + SM_CONST))[tid] = a.prep->uE[tid];                            // uE vE uG vG br
     fence_proxy_async_smem();
   }
   tc_fence_before();
@@ -87,275 +91,266 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
-  auto load_tile = [&](int T) {     // issuer lane 0
-    const int st = T % NS;
-    const uint32_t bar = smem_u32(&bars->e_full[st]);
-    const uint32_t dst = sbase + SM_STAGE + st * STAGE_BYTES;
-    mbar_expect_tx(bar, STAGE_BYTES);
-    tma_load_3d(dst, &tm_e, bar, T * 64, l0, b);
-    tma_load_3d(dst + 16384, &tm_kv, bar, FD, T * 8, b);
-    tma_load_3d(dst + 17408, &tm_kv, bar, 2 * FD, T * 8, b);
-  };
-
-  if (warp == 4) {
-    // =============================== issuer warp ===============================================
-    if (lane == 0) {
+  if (warp >= 8) {
+    // ====================== issuer warpgroup (warp 8 issues; warps 9-11 only keep the barriers) ======
+    reg_dealloc<40>();
+    const bool leader = warp == 8 && lane == 0;
+    auto load_tile = [&](int T) {
+      const int st = T % NS;
+      const uint32_t bar = smem_u32(&bars->e_full[st]);
+      const uint32_t dst = sbase + SM_STAGE + st * STAGE_BYTES;
+      mbar_expect_tx(bar, STAGE_BYTES);
+      tma_load_3d(dst + ST_E, &tm_e, bar, T * 64, l0, b);
+      tma_load_3d(dst + ST_K, &tm_kv, bar, FD, T * 8, b);
+      tma_load_3d(dst + ST_V, &tm_kv, bar, 2 * FD, T * 8, b);
+    };
+    auto issue_mma1 = [&](int p) {
+      const int T = p >> 2, j = p & 3, st = T % NS, buf = p % 3, slot = p & 3;
+      mbar_wait(smem_u32(&bars->e_full[st]), (T / NS) & 1);
+      tc_fence_after();
+      const uint32_t es = sbase + SM_STAGE + st * STAGE_BYTES;
+      const uint32_t kx = sbase + SM_KVX + slot * 4096;
+      const uint32_t d = tmem + TM_IN + buf * TM_IN_COLS;
+#pragma unroll
+      for (int s = 0; s < 4; ++s)
+        mma_ss(d + IN_S, smem_desc(sbase + SM_Q + 32 * s, 16, 1024, LAYOUT_SW128),
+               smem_desc(kx + 32 * s, 16, 1024, LAYOUT_SW128), ID_N16, s > 0);
+      mma_ss(d + IN_EG, smem_desc(es + ST_E + 32 * j, 16, 1024, LAYOUT_SW128),
+             smem_desc(sbase + SM_W, 512, 128, LAYOUT_NONE), ID_N32, 0);
+      mma_commit(smem_u32(&bars->mma1[buf]));
+    };
+    auto issue_mma2 = [&](int p) {
+      const int buf = p % 3, ob = p & 1, slot = p & 3;
+      const uint32_t vx = sbase + SM_KVX + slot * 4096 + 2048;
+      const uint32_t ao = tmem + TM_OUT + ob * TM_OUT_COLS;
+      mma_ts(tmem + TM_O, ao, smem_desc(vx, 2048, 1024, LAYOUT_SW128), ID_PV, p > 0);
+      mma_ts(tmem + TM_IN + buf * TM_IN_COLS + IN_EG, ao + 8, smem_desc(sbase + SM_W + 1024, 256, 128, LAYOUT_NONE),
+             ID_N16, 0);
+      mma_commit(smem_u32(&bars->mma2[buf]));
+    };
+    if (leader) {
       mbar_expect_tx(smem_u32(&bars->q_full), 16384);
       tma_load_3d(sbase + SM_Q, &tm_q, smem_u32(&bars->q_full), 0, l0, b);
       for (int T = 0; T < NT && T < NS; ++T) load_tile(T);
     }
-    auto issue_mma1 = [&](int t) {
-      const int T = t >> 1, half = t & 1, st = T % NS, buf = t % 3, slot = t & 3;
-      mbar_wait(smem_u32(&bars->e_full[st]), (T / NS) & 1);
-      tc_fence_after();
-      const uint32_t es = sbase + SM_STAGE + st * STAGE_BYTES;
-      const uint32_t kx = sbase + SM_KVX + slot * 8192;
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const uint32_t d = tmem + TM_BUF + buf * TM_BUF_COLS + j * TM_PAIR_COLS;
-#pragma unroll
-        for (int s = 0; s < 4; ++s)
-          mma_ss(d, smem_desc(sbase + SM_Q + 32 * s, 16, 1024, LAYOUT_SW128),
-                 smem_desc(kx + j * 2048 + 32 * s, 16, 1024, LAYOUT_SW128), ID_S, s > 0);
-        mma_ss(d + 16, smem_desc(es + 32 * (half * 2 + j), 16, 1024, LAYOUT_SW128),
-               smem_desc(sbase + SM_WBLK, 512, 128, LAYOUT_NONE), ID_EG, 0);
-      }
-      mma_commit(smem_u32(&bars->mma1[buf]));
-    };
-    auto issue_mma2 = [&](int t) {
-      const int buf = t % 3, slot = t & 3;
-      const uint32_t vx = sbase + SM_KVX + slot * 8192 + 4096;
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const uint32_t d = tmem + TM_BUF + buf * TM_BUF_COLS + j * TM_PAIR_COLS;
-        mma_ts(tmem + TM_O, d, smem_desc(vx + j * 2048, 2048, 1024, LAYOUT_SW128), ID_PV, (t > 0 || j > 0));
-        mma_ts(d + 16, d + 8, smem_desc(sbase + SM_WRBLK, 256, 128, LAYOUT_NONE), ID_WR, 0);
-      }
-      mma_commit(smem_u32(&bars->mma2[buf]));
-    };
-    __syncthreads();                                   // sync #0: Kexp/Vexp of sub-tiles 0,1 are built
-    if (lane == 0) {
+    __syncthreads();                                   // sync #0: Kexp/Vexp of pairs 0,1 are built
+    if (leader) {
       tc_fence_after();
       mbar_wait(smem_u32(&bars->q_full), 0);
       issue_mma1(0);
-      if (NSUB > 1) issue_mma1(1);
+      if (NP > 1) issue_mma1(1);
     }
-    bool store_pending = false;
-    for (int t = 0; t < NSUB; ++t) {
-      __syncthreads();                                 // sync #(t+1)
-      if (lane == 0) {
+    for (int it = 0; it < NP; ++it) {
+      __syncthreads();                                 // sync #(it+1)
+      if (leader) {
         tc_fence_after();
-        if (store_pending) { tma_store_wait_read<0>(); store_pending = false; }
-        issue_mma2(t);
-        if (t + 2 < NSUB) issue_mma1(t + 2);
-        if (t >= 1 && ((t - 1) & 1)) {                 // tile T is complete: store e', refill its stage
-          const int T = (t - 1) >> 1;
-          tma_store_3d(&tm_eo, sbase + SM_OST + (T & 1) * 16384, T * 64, l0, b);
-          tma_store_commit();
-          store_pending = true;
+        issue_mma2(it);
+        if (it + 2 < NP) issue_mma1(it + 2);
+        if (it >= 2 && ((it - 2) & 3) == 3) {          // tile stored at the previous sync: recycle its stage
+          const int T = (it - 2) >> 2;
+          tma_store_wait_read<0>();
           if (T + NS < NT) load_tile(T + NS);
+        }
+        if (it >= 1 && ((it - 1) & 3) == 3) {          // phase B of tile T's last pair ran: e' is complete in place
+          const int T = (it - 1) >> 2;
+          tma_store_3d(&tm_eo, sbase + SM_STAGE + (T % NS) * STAGE_BYTES + ST_E, T * 64, l0, b);
+          tma_store_commit();
         }
       }
       __syncwarp();
     }
-    __syncthreads();                                   // sync #(NSUB+1): last tile staged
-    if (lane == 0) {
+    __syncthreads();                                   // sync #(NP+1): phase B of the last pair is done
+    if (leader) {
       const int T = NT - 1;
-      tma_store_3d(&tm_eo, sbase + SM_OST + (T & 1) * 16384, T * 64, l0, b);
+      tma_store_3d(&tm_eo, sbase + SM_STAGE + (T % NS) * STAGE_BYTES + ST_E, T * 64, l0, b);
       tma_store_commit();
       tma_store_wait_all<0>();
     }
     __syncwarp();
     __syncthreads();                                   // final
-    tmem_dealloc(tmem, 512);
+    if (warp == 8) tmem_dealloc(tmem, 256);
     return;
   }
 
-  // ================================= row threads (warps 0-3) =====================================
-  const int l = l0 + tid;
-  const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+  // ================================= compute threads (warps 0-7) =================================
+  reg_alloc<232>();
+  const int g = tid >> 7, t = tid & 127;
+  const int l = l0 + t;
+  const bool rowvalid = l < N;
+  const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   const float *cst = (const float *)(smem + SM_CONST);
-  float uE[8], vE[8], uG[8], vG[8], br[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { uE[i] = cst[i]; vE[i] = cst[8 + i]; uG[i] = cst[16 + i]; vG[i] = cst[24 + i]; br[i] = cst[32 + i]; }
-  float psum[8], gsum[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { psum[i] = 0.f; gsum[i] = 0.f; }
   const uint8_t *maskb = a.mask ? a.mask + (size_t)b * N : nullptr;
-
-  auto build = [&](int t2) {    // expanded K / V operands of sub-tile t2 into slot t2 & 3
-    const int T2 = t2 >> 1, half2 = t2 & 1, st = T2 % NS;
-    const uint8_t *rows = smem + SM_STAGE + st * STAGE_BYTES + 16384;
-    uint8_t *kx = smem + SM_KVX + (t2 & 3) * 8192;
+  const float lo = a.clip_lo, hi = a.clip_hi;
+  float psum[4], gsum[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int idx = tid + 128 * q;
-      const int which = idx >> 8, rem = idx & 255, pair = rem >> 7, row = (rem >> 3) & 15, dd = rem & 7;
-      const int key = row >> 3, hh = row & 7, ks = half2 * 4 + pair * 2 + key;
-      const uint32_t val = *(const uint16_t *)(rows + which * 1024 + ks * 128 + (dd * 8 + hh) * 2);
-      const uint32_t wv = val << ((hh & 1) * 16);
-      uint4 ch;
-      ch.x = (hh >> 1) == 0 ? wv : 0u; ch.y = (hh >> 1) == 1 ? wv : 0u;
-      ch.z = (hh >> 1) == 2 ? wv : 0u; ch.w = (hh >> 1) == 3 ? wv : 0u;
-      *(uint4 *)(kx + which * 4096 + pair * 2048 + row * 128 + (((dd ^ row) & 7) << 4)) = ch;
-    }
+  for (int i = 0; i < 4; ++i) { psum[i] = 0.f; gsum[i] = 0.f; }
+  const uint32_t trow = (uint32_t)t * 128u, tx7 = (uint32_t)(t & 7);
+
+  auto build = [&](int p2) {    // expanded K / V operands of pair p2 into slot p2 & 3 (one 16-byte chunk per thread)
+    const int T2 = p2 >> 2, j2 = p2 & 3, st = T2 % NS;
+    const int which = tid >> 7, rem = tid & 127, n = rem >> 3, dd = rem & 7;
+    const int hh = 4 * (n >> 3) + (n & 3), ks = 2 * j2 + ((n >> 2) & 1);
+    const uint8_t *rows = smem + SM_STAGE + st * STAGE_BYTES + (which ? ST_V : ST_K);
+    const uint32_t val = *(const uint16_t *)(rows + ks * 128 + (dd * 8 + hh) * 2);
+    const uint32_t wv = val << ((hh & 1) * 16);
+    uint4 ch;
+    ch.x = (hh >> 1) == 0 ? wv : 0u; ch.y = (hh >> 1) == 1 ? wv : 0u;
+    ch.z = (hh >> 1) == 2 ? wv : 0u; ch.w = (hh >> 1) == 3 ? wv : 0u;
+    *(uint4 *)(smem + SM_KVX + (p2 & 3) * 4096 + which * 2048 + n * 128 + (((dd ^ n) & 7) << 4)) = ch;
   };
 
-  auto phase_a = [&](int t) {
-    const int T = t >> 1, half = t & 1, st = T % NS, buf = t % 3;
+  // ---- phase A: pair p, this thread's 4 heads of both keys ------------------------------------------
+  auto phase_a = [&](int p) {
+    const int T = p >> 2, j = p & 3, st = T % NS, buf = p % 3, ob = p & 1;
     const uint8_t *es = smem + SM_STAGE + st * STAGE_BYTES;
-    const uint32_t tb = tlane + TM_BUF + buf * TM_BUF_COLS;
+    const uint32_t tin = tlane + TM_IN + buf * TM_IN_COLS;
+    const uint32_t tout = tlane + TM_OUT + ob * TM_OUT_COLS;
+    uint32_t sreg[8], egreg[16];
+    tmem_ld8(tin + IN_S + g * 8, sreg);
+    tmem_ld16(tin + IN_EG + g * 16, egreg);
+    float r[2], nrm[2];
+    bool kvalid[2];
+    uint32_t rb[2][2];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      uint32_t sreg[16], egreg[32], apack[8], hpack[8];
-      tmem_ld16(tb + j * TM_PAIR_COLS, sreg);
-      tmem_ld32(tb + j * TM_PAIR_COLS + 16, egreg);
-      tmem_ld_wait();
-      float av[16], hv[16];
+    for (int kk = 0; kk < 2; ++kk) {
+      const int ks = 2 * j + kk, m = 8 * T + ks;
+      const uint4 ev = *(const uint4 *)(es + ST_E + trow + (((uint32_t)ks ^ tx7) << 4));
+      const float x[8] = {bf16_lo(ev.x), bf16_hi(ev.x), bf16_lo(ev.y), bf16_hi(ev.y),
+                          bf16_lo(ev.z), bf16_hi(ev.z), bf16_lo(ev.w), bf16_hi(ev.w)};
+      float mu = ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
+      mu *= 0.125f;
+      float var = 0.f;
 #pragma unroll
-      for (int kk = 0; kk < 2; ++kk) {
-        const int ks = half * 4 + j * 2 + kk;
-        const int m = T * 8 + ks;
-        const uint4 ev = *(const uint4 *)(es + sw128_off(tid, ks * 8));
-        float x[8] = {bf16_lo(ev.x), bf16_hi(ev.x), bf16_lo(ev.y), bf16_hi(ev.y),
-                      bf16_lo(ev.z), bf16_hi(ev.z), bf16_lo(ev.w), bf16_hi(ev.w)};
-        float mu = 0.f;
+      for (int c = 0; c < 8; ++c) { const float dlt = x[c] - mu; var = fmaf(dlt, dlt, var); }
+      r[kk] = rsqrtf(fmaf(var, 0.125f, 1e-3f));
+      nrm[kk] = -r[kk] * mu;
+      kvalid[kk] = m < N;
+      if (maskb && m < N) kvalid[kk] = maskb[m] != 0;
+      rb[kk][0] = rb[kk][1] = 0u;
+      if (RAND) {
+        const uint64_t qd = ((uint64_t)b * N + (uint64_t)l) * N + (uint64_t)m;
+        Philox4 ph = philox4x32_10((uint32_t)qd, (uint32_t)(qd >> 32), (uint32_t)a.offset,
+                                   (uint32_t)(a.offset >> 32), (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+        rb[kk][0] = g ? ph.z : ph.x; rb[kk][1] = g ? ph.w : ph.y;      // heads 4g..4g+3 use words 2g, 2g+1
+      }
+    }
+    tmem_ld_wait();
+    uint32_t apack[4], hpack[4];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) mu += x[c];
-        mu *= 0.125f;
-        float var = 0.f;
+    for (int kk = 0; kk < 2; ++kk) {
+      float av[4], hv[4];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) { float dlt = x[c] - mu; var = fmaf(dlt, dlt, var); }
-        const float r = rsqrtf(fmaf(var, 0.125f, 1e-3f));
-        const float nrm = -r * mu;
-        bool kvalid = m < N;
-        if (maskb && kvalid) kvalid = maskb[m] != 0;
-        uint32_t rbits[4] = {0u, 0u, 0u, 0u};
+      for (int i = 0; i < 4; ++i) {
+        const int hh = 4 * g + i;
+        const float S = __uint_as_float(sreg[kk * 4 + i]);
+        const float E = fmaf(r[kk], __uint_as_float(egreg[kk * 8 + i]), fmaf(nrm[kk], cst[hh], cst[8 + hh]));
+        const float G = fmaf(r[kk], __uint_as_float(egreg[kk * 8 + 4 + i]), fmaf(nrm[kk], cst[16 + hh], cst[24 + hh]));
+        const float Hh = fminf(fmaxf(S, lo), hi) + E;                      // egt_layers.py:79-86
+        bool live = kvalid[kk];
         if (RAND) {
-          const uint64_t qd = ((uint64_t)b * N + (uint64_t)l) * N + (uint64_t)m;
-          Philox4 ph = philox4x32_10((uint32_t)qd, (uint32_t)(qd >> 32), (uint32_t)a.offset,
-                                     (uint32_t)(a.offset >> 32), (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
-          rbits[0] = ph.x; rbits[1] = ph.y; rbits[2] = ph.z; rbits[3] = ph.w;
+          const uint32_t w = rb[kk][i >> 1];
+          const uint32_t bits = (i & 1) ? (w >> 16) : (w & 0xFFFFu);
+          live = live && !(bits < a.rand_thr);                             // :103-108
         }
-#pragma unroll
-        for (int hh = 0; hh < 8; ++hh) {
-          const float S = __uint_as_float(sreg[kk * 8 + hh]);
-          const float aE = __uint_as_float(egreg[kk * 16 + hh]);
-          const float aG = __uint_as_float(egreg[kk * 16 + 8 + hh]);
-          const float E = fmaf(r, aE, fmaf(nrm, uE[hh], vE[hh]));
-          const float G = fmaf(r, aG, fmaf(nrm, uG[hh], vG[hh]));
-          const float Hh = fminf(fmaxf(S, a.clip_lo), a.clip_hi) + E;      // egt_layers.py:79-86
-          bool live = kvalid;
-          if (RAND) {
-            const uint32_t bits = (hh & 1) ? (rbits[hh >> 1] >> 16) : (rbits[hh >> 1] & 0xFFFFu);
-            live = live && !(bits < a.rand_thr);                           // :103-108
-          }
-          const float p = live ? exp2f(Hh * kLog2e) : 0.f;                 // :111 (unnormalised)
-          const float g = live ? __fdividef(1.f, 1.f + exp2f(-G * kLog2e)) : 0.f;   // :112
-          psum[hh] += p;
-          gsum[hh] += g;
-          av[kk * 8 + hh] = p * g;                                         // :113
-          hv[kk * 8 + hh] = Hh;
-        }
+        const float pr = live ? ex2_approx(Hh * kLog2e) : 0.f;             // :111 (unnormalised)
+        const float gg = live ? rcp_approx(1.f + ex2_approx(-G * kLog2e)) : 0.f;   // :112
+        psum[i] += pr;
+        gsum[i] += gg;
+        av[i] = pr * gg;                                                   // :113
+        hv[i] = Hh;
       }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { apack[i] = pack_bf16(av[2 * i], av[2 * i + 1]); hpack[i] = pack_bf16(hv[2 * i], hv[2 * i + 1]); }
-      tmem_st8(tb + j * TM_PAIR_COLS, apack);
-      tmem_st8(tb + j * TM_PAIR_COLS + 8, hpack);
+      apack[kk * 2 + 0] = pack_bf16(av[0], av[1]); apack[kk * 2 + 1] = pack_bf16(av[2], av[3]);
+      hpack[kk * 2 + 0] = pack_bf16(hv[0], hv[1]); hpack[kk * 2 + 1] = pack_bf16(hv[2], hv[3]);
     }
+    tmem_st4(tout + g * 4, apack);
+    tmem_st4(tout + 8 + g * 4, hpack);
   };
 
-  auto phase_b = [&](int t) {   // e' = e + H_hat W_r + b_r for the 4 keys of sub-tile t -> staging
-    const int T = t >> 1, half = t & 1, st = T % NS, buf = t % 3;
-    const uint8_t *es = smem + SM_STAGE + st * STAGE_BYTES;
-    uint8_t *os = smem + SM_OST + (T & 1) * 16384;
-    const uint32_t tb = tlane + TM_BUF + buf * TM_BUF_COLS;
+  // ---- phase B: e' = e + H_hat W_r + b_r for key g of pair p, in place over the e stage ---------------
+  auto phase_b = [&](int p) {
+    const int T = p >> 2, j = p & 3, st = T % NS, buf = p % 3;
+    uint8_t *es = smem + SM_STAGE + st * STAGE_BYTES;
+    const int ks = 2 * j + g;
+    uint32_t dr[8];
+    tmem_ld8(tlane + TM_IN + buf * TM_IN_COLS + IN_EG + g * 8, dr);
+    uint4 *pe = (uint4 *)(es + ST_E + trow + (((uint32_t)ks ^ tx7) << 4));
+    const uint4 ev = *pe;
+    const float x[8] = {bf16_lo(ev.x), bf16_hi(ev.x), bf16_lo(ev.y), bf16_hi(ev.y),
+                        bf16_lo(ev.z), bf16_hi(ev.z), bf16_lo(ev.w), bf16_hi(ev.w)};
+    tmem_ld_wait();
+    float o[8];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      uint32_t dreg[16];
-      tmem_ld16(tb + j * TM_PAIR_COLS + 16, dreg);
-      tmem_ld_wait();
-#pragma unroll
-      for (int kk = 0; kk < 2; ++kk) {
-        const int ks = half * 4 + j * 2 + kk;
-        const uint32_t off = sw128_off(tid, ks * 8);
-        const uint4 ev = *(const uint4 *)(es + off);
-        const float x[8] = {bf16_lo(ev.x), bf16_hi(ev.x), bf16_lo(ev.y), bf16_hi(ev.y),
-                            bf16_lo(ev.z), bf16_hi(ev.z), bf16_lo(ev.w), bf16_hi(ev.w)};
-        float o[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) o[c] = x[c] + (__uint_as_float(dreg[kk * 8 + c]) + br[c]);
-        uint4 ov;
-        ov.x = pack_bf16(o[0], o[1]); ov.y = pack_bf16(o[2], o[3]);
-        ov.z = pack_bf16(o[4], o[5]); ov.w = pack_bf16(o[6], o[7]);
-        *(uint4 *)(os + off) = ov;
-      }
-    }
+    for (int c = 0; c < 8; ++c) o[c] = x[c] + (__uint_as_float(dr[c]) + cst[32 + c]);
+    uint4 ov;
+    ov.x = pack_bf16(o[0], o[1]); ov.y = pack_bf16(o[2], o[3]);
+    ov.z = pack_bf16(o[4], o[5]); ov.w = pack_bf16(o[6], o[7]);
+    *pe = ov;
   };
 
-  // ---- pipeline ------------------------------------------------------------------------------
+  // ---- pipeline ------------------------------------------------------------------------------------
   mbar_wait(smem_u32(&bars->e_full[0]), 0);
   build(0);
-  if (NSUB > 1) build(1);
+  if (NP > 1) build(1);
   fence_proxy_async_smem();
   __syncthreads();                                     // sync #0
-  for (int t = 0; t < NSUB; ++t) {
-    mbar_wait(smem_u32(&bars->mma1[t % 3]), (t / 3) & 1);
+  for (int it = 0; it < NP; ++it) {
+    mbar_wait(smem_u32(&bars->mma1[it % 3]), (it / 3) & 1);
     tc_fence_after();
-    phase_a(t);
-    if (t >= 1) {
-      mbar_wait(smem_u32(&bars->mma2[(t - 1) % 3]), ((t - 1) / 3) & 1);
+    phase_a(it);
+    if (it >= 1) {
+      mbar_wait(smem_u32(&bars->mma2[(it - 1) % 3]), ((it - 1) / 3) & 1);
       tc_fence_after();
-      phase_b(t - 1);
+      phase_b(it - 1);
     }
-    if (t + 2 < NSUB) {
-      const int T2 = (t + 2) >> 1;
+    if (it + 2 < NP) {
+      const int T2 = (it + 2) >> 2;
       mbar_wait(smem_u32(&bars->e_full[T2 % NS]), (T2 / NS) & 1);
-      build(t + 2);
+      build(it + 2);
     }
     tmem_st_wait();
     fence_proxy_async_smem();
     tc_fence_before();
-    __syncthreads();                                   // sync #(t+1)
+    __syncthreads();                                   // sync #(it+1)
   }
-  mbar_wait(smem_u32(&bars->mma2[(NSUB - 1) % 3]), ((NSUB - 1) / 3) & 1);
+  mbar_wait(smem_u32(&bars->mma2[(NP - 1) % 3]), ((NP - 1) / 3) & 1);
   tc_fence_after();
-  phase_b(NSUB - 1);
+  phase_b(NP - 1);
   fence_proxy_async_smem();
-  __syncthreads();                                     // sync #(NSUB+1)
+  __syncthreads();                                     // sync #(NP+1)
 
   // ---- row epilogue: normalise, centrality scaler, V_att, saved statistics ----------------------
   {
-    float f[8];
+    float f[4];
 #pragma unroll
-    for (int hh = 0; hh < 8; ++hh) {
-      const float inv = psum[hh] > 0.f ? __fdividef(1.f, psum[hh]) : 0.f;
+    for (int i = 0; i < 4; ++i) {
+      const float inv = psum[i] > 0.f ? __fdividef(1.f, psum[i]) : 0.f;
       float s = 1.f;
       if (a.scale_degree && l >= a.num_virtual_nodes)                      // egt_layers.py:123-135
-        s = a.scaler_type == EGT_SCALER_LOG ? log1pf(gsum[hh]) : gsum[hh];
-      f[hh] = inv * s;
+        s = a.scaler_type == EGT_SCALER_LOG ? log1pf(gsum[i]) : gsum[i];
+      f[i] = inv * s;
     }
     uint32_t o[64];
     tmem_ld32(tlane + TM_O, o);
     tmem_ld32(tlane + TM_O + 32, o + 32);
     tmem_ld_wait();
-    if (l < N) {
-      uint4 *dst = (uint4 *)(a.v_att + ((size_t)b * N + l) * FD);
+    if (rowvalid) {
+      uint2 *dst = (uint2 *)(a.v_att + ((size_t)b * N + l) * FD + 4 * g);
 #pragma unroll
       for (int dd = 0; dd < 8; ++dd) {
-        uint4 v;
-        v.x = pack_bf16(__uint_as_float(o[dd * 8 + 0]) * f[0], __uint_as_float(o[dd * 8 + 1]) * f[1]);
-        v.y = pack_bf16(__uint_as_float(o[dd * 8 + 2]) * f[2], __uint_as_float(o[dd * 8 + 3]) * f[3]);
-        v.z = pack_bf16(__uint_as_float(o[dd * 8 + 4]) * f[4], __uint_as_float(o[dd * 8 + 5]) * f[5]);
-        v.w = pack_bf16(__uint_as_float(o[dd * 8 + 6]) * f[6], __uint_as_float(o[dd * 8 + 7]) * f[7]);
-        dst[dd] = v;
-      }
-      const size_t ps = ((size_t)b * N + l) * FH, rs = (size_t)a.B * N * FH;
+        float v[4];
 #pragma unroll
-      for (int hh = 0; hh < 8; ++hh) {
-        a.lse[ps + hh] = 0.f;                                              // reference point of the exponent
-        a.lse[rs + ps + hh] = psum[hh] > 0.f ? __logf(psum[hh]) : 0.f;
-        a.deg[ps + hh] = gsum[hh];
+        for (int i = 0; i < 4; ++i) {
+          const float lo4 = __uint_as_float(o[dd * 8 + i]), hi4 = __uint_as_float(o[dd * 8 + 4 + i]);
+          v[i] = (g ? hi4 : lo4) * f[i];
+        }
+        dst[dd * 2] = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));   // channels dd*8 + 4g .. +3
+      }
+      const size_t ps = ((size_t)b * N + l) * FH + 4 * g, rs = (size_t)a.B * N * FH;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        a.lse[ps + i] = 0.f;                                               // reference point of the exponent
+        a.lse[rs + ps + i] = psum[i] > 0.f ? __logf(psum[i]) : 0.f;
+        a.deg[ps + i] = gsum[i];
       }
     }
   }
@@ -380,8 +375,8 @@ int fused_fwd_launch(const FusedFwdArgs &a, const void *e, void *e_out, const vo
   }
   dim3 grid((a.N + 127) / 128, a.B);
   LaunchScope _ls("fused_fwd_kernel", st);
-  if (a.rand_mask) fused_fwd_kernel<true><<<grid, 160, smem, st>>>(tm_e, tm_eo, tm_q, tm_kv, a);
-  else fused_fwd_kernel<false><<<grid, 160, smem, st>>>(tm_e, tm_eo, tm_q, tm_kv, a);
+  if (a.rand_mask) fused_fwd_kernel<true><<<grid, 384, smem, st>>>(tm_e, tm_eo, tm_q, tm_kv, a);
+  else fused_fwd_kernel<false><<<grid, 384, smem, st>>>(tm_e, tm_eo, tm_q, tm_kv, a);
   EGT_CHECK_CUDA(cudaGetLastError());
   return EGT_OK;
 }

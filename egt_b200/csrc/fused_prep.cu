@@ -79,6 +79,11 @@ __global__ void __launch_bounds__(128) fused_prep_kernel(egt_block_weights_t w, 
       out->b_hx[(k / 8) * (16 * 8) + n * 8 + (k % 8)] =
           __float2bfloat16_rn(key == key2 ? w.dense_edge_r_kernel[hh * FDE + c] : 0.f);
     }
+    {
+      int key2 = n / 8, c = n % 8, g = k / 8, key = (k / 4) % 2, hh = 4 * g + k % 4;
+      out->b_wr[(k / 8) * (16 * 8) + n * 8 + (k % 8)] =
+          __float2bfloat16_rn(key == key2 ? w.dense_edge_r_kernel[hh * FDE + c] : 0.f);
+    }
     for (int g = 0; g < 2; ++g) {
       int key2 = n / 8, c = n % 8, key = k / 8, eg = (k / 4) % 2, hh = 4 * g + k % 4;
       out->b_de[g][(k / 8) * (16 * 8) + n * 8 + (k % 8)] = __float2bfloat16_rn(key == key2 ? wp[eg][c][hh] : 0.f);
