@@ -85,7 +85,7 @@ class ClockSampler(threading.Thread):
                 for bit, nm in names.items():
                     if r & bit:
                         self.reasons.add(nm)
-                time.sleep(0.02)
+                time.sleep(0.002)
         except Exception as ex:   # NVML missing: report that instead of inventing clocks
             self.reasons.add(f'nvml_unavailable:{type(ex).__name__}')
 
@@ -207,28 +207,119 @@ def run_ours(args, w):
         step(i)
     torch.cuda.synchronize()
 
+    # One step = one forward + backward (+ all-reduce) of the block.  The launch sequence of a step is fixed,
+    # so each of the rotating input sets is captured once into a CUDA graph and the timed region replays
+    # the graphs (one replay = one step); --no-graphs times the eager launches instead.
+    graphs, static_out, use_graphs = [], [], not args.no_graphs
+    launches_per_step = None
+    if use_graphs:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for i in range(2):
+                    step(i)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            for i in range(nsets):
+                g_ = torch.cuda.CUDAGraph()
+                l0 = lib.egt_launch_count()
+                with torch.cuda.graph(g_):
+                    out = step(i)
+                launches_per_step = lib.egt_launch_count() - l0
+                graphs.append(g_)
+                static_out.append((out, blk.flat.grad))
+            torch.cuda.synchronize()
+        except Exception as ex:   # capture not possible: measure the eager path and say so
+            print(f'[bench] CUDA graph capture failed ({type(ex).__name__}: {ex}); timing eager launches', file=sys.stderr)
+            graphs, static_out, use_graphs = [], [], False
+            torch.cuda.synchronize()
+
+    def run_step(i):
+        if use_graphs:
+            graphs[i % nsets].replay()
+        else:
+            step(i)
+
+    for i in range(3):
+        run_step(i)
+
     # ---- timed region 1: inputs resident in HBM ----
     sampler = ClockSampler(local)
     sampler.start()
-    lib.egt_profile_enable(1)
     l0 = lib.egt_launch_count()
-    ms = timed(step, args.steps)
-    launches = lib.egt_launch_count() - l0
+    ms = timed(run_step, args.steps)
+    launches = (launches_per_step * args.steps) if use_graphs else lib.egt_launch_count() - l0
+
+    # ---- per-kernel CUDA-event times of the same steps, launched eagerly (events cannot bracket graph nodes) ----
+    lib.egt_profile_enable(1)
+    timed(step, args.steps)
     prof = L.profile_read()
     lib.egt_profile_enable(0)
     path = lib.egt_last_path()
 
     # ---- timed region 2: end to end through the public API with HOST buffers ----
-    def step_e2e(i):
-        hh, ee, mm = host[i % nsets]
-        inputs = (hh.to(dev, non_blocking=True), ee.to(dev, non_blocking=True), mm.to(dev, non_blocking=True))
-        step(i, inputs)
-        grad_host.copy_(blk.flat.grad, non_blocking=True)
-        torch.cuda.current_stream().synchronize()      # the caller consumes the step's result on the host
+    # Every step copies its inputs from pinned host memory (on a copy stream, one step ahead of the compute
+    # stream, into one of two device buffer sets) and reads the step's flat weight gradient back to the host.
+    cur = torch.cuda.current_stream()
+    copy_stream = torch.cuda.Stream()
+    bufs = [tuple(torch.empty_like(t, device=dev) for t in host[0]) for _ in range(2)]
+    e2e_graphs = []
+    if use_graphs:
+        for k in range(2):
+            g_ = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_):
+                step(0, bufs[k])
+            e2e_graphs.append((g_, blk.flat.grad))
+    ev_copied = [torch.cuda.Event() for _ in range(2)]
+    ev_done = [torch.cuda.Event() for _ in range(2)]
 
-    for i in range(2):
-        step_e2e(i)
-    ms_e2e = timed(step_e2e, args.steps)
+    def prefetch(i):
+        k = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_done[k])
+            for dst, src in zip(bufs[k], host[i % nsets]):
+                dst.copy_(src, non_blocking=True)
+            ev_copied[k].record(copy_stream)
+
+    def e2e_loop(steps):
+        for k in range(2):
+            ev_done[k].record(cur)
+        prefetch(0)
+        for i in range(steps):
+            k = i % 2
+            if i + 1 < steps:
+                prefetch(i + 1)
+            cur.wait_event(ev_copied[k])
+            if use_graphs:
+                e2e_graphs[k][0].replay()
+                grad = e2e_graphs[k][1]
+            else:
+                step(i, bufs[k])
+                grad = blk.flat.grad
+            ev_done[k].record(cur)
+            grad_host.copy_(grad, non_blocking=True)
+            cur.synchronize()                          # the caller consumes the step's result on the host
+
+    e2e_loop(3)
+
+    def timed_e2e(steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        e2e_loop(steps)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms_e2e = timed_e2e(args.steps)
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -262,7 +353,8 @@ def run_ours(args, w):
                     parallelism=f'dp{world}', note=w['note'], random_mask_prob=args.random_mask_prob,
                     scale_degree=bool(args.scale_degree),
                     l2=f'rotating {nsets} input sets per rank (working set > 126 MB L2)',
-                    path='fused-tcgen05' if path == 1 else 'staged'),
+                    path='fused-tcgen05' if path == 1 else 'staged', cuda_graphs=bool(use_graphs),
+                    e2e='H2D of h,e,mask on a copy stream one step ahead (2 device buffer sets); D2H of the flat weight gradient + host sync every step'),
         roofline=dict(bound='hbm', kernel=dom_name, achieved=achieved, peak=peaks['hbm_gbs'], unit='GB/s',
                       frac=achieved / peaks['hbm_gbs'], traffic=traffic, peak_source=peaks['source'],
                       kernel_share_of_step=dom[1][0] / total_prof_ms,
@@ -293,6 +385,7 @@ def main():
     ap.add_argument('--input-sets', type=int, default=4)
     ap.add_argument('--cpu-budget', type=float, default=15.0)
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-graphs', action='store_true')
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == 'reference':

@@ -313,9 +313,14 @@ int egt_block_fwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
 
   // node side: LN_h + QKV (graph_xformer_model_base.py:108-114)
   const bool fused = fused_supported(cfg, a.dtype) && !g_force_staged;
-  if (fused) {   // Q is stored pre-scaled by dk^-0.5
+  size_t need = egt_block_workspace_bytes(cfg, 0);
+  EGT_REQUIRE(io->workspace_bytes >= need && (io->workspace || need <= 256), EGT_E_ARG,
+              "workspace too small: %zu < %zu", io->workspace_bytes, need);
+  BlockWs ws = carve(cfg, 0, io->workspace);
+  if (fused) {   // Q is stored pre-scaled by dk^-0.5; the kernel's extra CTA writes the derived weights
     if ((rc = node_qkv_launch(io->h, w->norm_mha_gamma, w->norm_mha_beta, cfg->ln_eps, w->dense_qkv_kernel,
-                              w->dense_qkv_bias, 1.0f / sqrtf((float)a.dk), io->qkv, R, st))) return rc;
+                              w->dense_qkv_bias, 1.0f / sqrtf((float)a.dk), io->qkv, R, w, a.clip_lo, a.clip_hi,
+                              (FusedPrep *)ws.prep, st))) return rc;
   } else {
     LinearArgs lq;
     memset(&lq, 0, sizeof(lq));
@@ -325,14 +330,9 @@ int egt_block_fwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
     if ((rc = linear_launch(lq, a.dtype, st))) return rc;
   }
 
-  size_t need = egt_block_workspace_bytes(cfg, 0);
-  EGT_REQUIRE(io->workspace_bytes >= need && (io->workspace || need <= 256), EGT_E_ARG,
-              "workspace too small: %zu < %zu", io->workspace_bytes, need);
-  BlockWs ws = carve(cfg, 0, io->workspace);
   g_last_path = fused ? 1 : 0;
 
   if (fused) {
-    if ((rc = fused_prep_launch(cfg, w, (FusedPrep *)ws.prep, st))) return rc;
     FusedFwdArgs fa;
     memset(&fa, 0, sizeof(fa));
     fa.B = a.B; fa.N = a.N; fa.mask = io->mask; fa.prep = (const FusedPrep *)ws.prep;
@@ -393,9 +393,8 @@ int egt_block_bwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
 
   if (fused_bwd) {
     if ((rc = node_bwd1_launch(io->dh_out, io->v_att, w->dense_mha_kernel, ws.d_v_att, g->dense_mha_kernel,
-                               g->dense_mha_bias, R, st))) return rc;
+                               g->dense_mha_bias, R, w, a.clip_lo, a.clip_hi, (FusedPrep *)ws.prep, st))) return rc;
     // N x N part in one kernel (fused_bwd.cu): de, dQ|dK|dV and the edge-side weight-gradient partial sums
-    if ((rc = fused_prep_launch(cfg, w, (FusedPrep *)ws.prep, st))) return rc;
     const int tiles = (a.N + 127) / 128;
     if (tiles > 1) EGT_CHECK_CUDA(cudaMemsetAsync(ws.d_qkv_f32, 0, (size_t)R * 3 * d * sizeof(float), st));
     FusedBwdArgs fb;

@@ -81,12 +81,14 @@ int fused_bwd_finalize_launch(const float *partials, int nparts, const egt_block
                               const egt_block_grads_t *g, cudaStream_t st);
 
 // node side on tensor cores (node_tc.cu); bf16 activations, d = 64
+// prep_out != NULL: one extra CTA of the kernel writes the FusedPrep (saves the fused_prep_kernel launch)
 int node_qkv_launch(const void *h, const float *gamma, const float *beta, float eps, const float *W, const float *bias,
-                    float qscale, void *qkv, int R, cudaStream_t st);
+                    float qscale, void *qkv, int R, const egt_block_weights_t *w, float clip_lo, float clip_hi,
+                    FusedPrep *prep_out, cudaStream_t st);
 int node_out_launch(const void *v_att, const void *h, const float *W, const float *bias, void *h_out, int R,
                     cudaStream_t st);
 int node_bwd1_launch(const void *dh_out, const void *v_att, const float *W, void *d_v_att, float *dW, float *db, int R,
-                     cudaStream_t st);
+                     const egt_block_weights_t *w, float clip_lo, float clip_hi, FusedPrep *prep_out, cudaStream_t st);
 int node_bwd2_launch(const void *h, const void *dh_out, const float *dqkv, const float *gamma, const float *beta,
                      float eps, const float *W, void *dh, float *dW, float *db, float *dgamma, float *dbeta, int R,
                      cudaStream_t st);

@@ -320,6 +320,10 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     const uint32_t tin = tlane + TM_IN + buf * TM_IN_COLS;
     const uint32_t tout = tlane + TM_OUT + ob * TM_OUT_COLS;
     uint32_t dsp[4], dzp[8];
+    const float4 uE4 = *(const float4 *)(cst + 4 * g), vE4 = *(const float4 *)(cst + 8 + 4 * g);
+    const float4 uG4 = *(const float4 *)(cst + 16 + 4 * g), vG4 = *(const float4 *)(cst + 24 + 4 * g);
+    const float uE[4] = {uE4.x, uE4.y, uE4.z, uE4.w}, vE[4] = {vE4.x, vE4.y, vE4.z, vE4.w};
+    const float uG[4] = {uG4.x, uG4.y, uG4.z, uG4.w}, vG[4] = {vG4.x, vG4.y, vG4.z, vG4.w};
 #pragma unroll
     for (int kk = 0; kk < 2; ++kk) {
       const int ks = 2 * j + kk, m = 8 * T + ks;
@@ -345,10 +349,9 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
       float dS[4], At[4], dH[4], dGv[4], Hh[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int hh = 4 * g + i;
         const float S = __uint_as_float(sreg[i]), dA = __uint_as_float(dareg[i]);
-        const float E = fmaf(r, __uint_as_float(egreg[i]), fmaf(nrm, cst[hh], cst[8 + hh]));
-        const float G = fmaf(r, __uint_as_float(egreg[4 + i]), fmaf(nrm, cst[16 + hh], cst[24 + hh]));
+        const float E = fmaf(r, __uint_as_float(egreg[i]), fmaf(nrm, uE[i], vE[i]));
+        const float G = fmaf(r, __uint_as_float(egreg[4 + i]), fmaf(nrm, uG[i], vG[i]));
         const float Sc = fminf(fmaxf(S, lo), hi);                          // egt_layers.py:81-82
         const bool inr = S == Sc;                                          // clip passes gradient inside [lo,hi]
         Hh[i] = Sc + E;                                                    // :85-86
@@ -359,7 +362,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
           live = live && !(bits < a.rand_thr);                             // :103-108
         }
         const float pr = live ? ex2_approx(fmaf(Hh[i], kLog2e, -l2[i])) : 0.f;          // softmax probability
-        const float gg = live ? rcp_approx(1.f + ex2_approx(-G * kLog2e)) : 0.f;        // gate
+        const float gg = live ? sigmoid_fast(G) : 0.f;                                  // gate
         At[i] = pr * gg;
         const float dP = dA * gg;
         dH[i] = fmaf(pr, dP - Dr[i], __uint_as_float(hxreg[i]));
@@ -489,7 +492,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     }
     if (it + 2 < NP) {
       const int T2 = (it + 2) >> 2;
-      mbar_wait(smem_u32(&bars->e_full[T2 % NS]), (T2 / NS) & 1);
+      if (((it + 2) & 3) == 0) mbar_wait(smem_u32(&bars->e_full[T2 % NS]), (T2 / NS) & 1);   // first pair of a tile
       build(it + 2);
     }
     tmem_st_wait();
@@ -562,9 +565,15 @@ __global__ void __launch_bounds__(256) fused_bwd_finalize_kernel(const float *pa
   __shared__ float s[FPART];
   const int tid = threadIdx.x;
   if (tid < FPART) {
-    float acc = 0.f;
-    for (int i = 0; i < nparts; ++i) acc += partials[(size_t)i * FPART + tid];
-    s[tid] = acc;
+    float acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+    int i = 0;
+    for (; i + 8 <= nparts; i += 8)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] += partials[(size_t)(i + q) * FPART + tid];
+    for (; i < nparts; ++i) acc[0] += partials[(size_t)i * FPART + tid];
+    s[tid] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
   }
   __syncthreads();
   const float *M = s, *sZ = s + 128, *Wr = s + 144, *dbr = s + 208;

@@ -234,6 +234,10 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
         rb[kk][0] = g ? ph.z : ph.x; rb[kk][1] = g ? ph.w : ph.y;      // heads 4g..4g+3 use words 2g, 2g+1
       }
     }
+    const float4 uE4 = *(const float4 *)(cst + 4 * g), vE4 = *(const float4 *)(cst + 8 + 4 * g);
+    const float4 uG4 = *(const float4 *)(cst + 16 + 4 * g), vG4 = *(const float4 *)(cst + 24 + 4 * g);
+    const float uE[4] = {uE4.x, uE4.y, uE4.z, uE4.w}, vE[4] = {vE4.x, vE4.y, vE4.z, vE4.w};
+    const float uG[4] = {uG4.x, uG4.y, uG4.z, uG4.w}, vG[4] = {vG4.x, vG4.y, vG4.z, vG4.w};
     tmem_ld_wait();
     uint32_t apack[4], hpack[4];
 #pragma unroll
@@ -241,10 +245,9 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
       float av[4], hv[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int hh = 4 * g + i;
         const float S = __uint_as_float(sreg[kk * 4 + i]);
-        const float E = fmaf(r[kk], __uint_as_float(egreg[kk * 8 + i]), fmaf(nrm[kk], cst[hh], cst[8 + hh]));
-        const float G = fmaf(r[kk], __uint_as_float(egreg[kk * 8 + 4 + i]), fmaf(nrm[kk], cst[16 + hh], cst[24 + hh]));
+        const float E = fmaf(r[kk], __uint_as_float(egreg[kk * 8 + i]), fmaf(nrm[kk], uE[i], vE[i]));
+        const float G = fmaf(r[kk], __uint_as_float(egreg[kk * 8 + 4 + i]), fmaf(nrm[kk], uG[i], vG[i]));
         const float Hh = fminf(fmaxf(S, lo), hi) + E;                      // egt_layers.py:79-86
         bool live = kvalid[kk];
         if (RAND) {
@@ -253,7 +256,7 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
           live = live && !(bits < a.rand_thr);                             // :103-108
         }
         const float pr = live ? ex2_approx(Hh * kLog2e) : 0.f;             // :111 (unnormalised)
-        const float gg = live ? rcp_approx(1.f + ex2_approx(-G * kLog2e)) : 0.f;   // :112
+        const float gg = live ? sigmoid_fast(G) : 0.f;                     // :112
         psum[i] += pr;
         gsum[i] += gg;
         av[i] = pr * gg;                                                   // :113
@@ -304,7 +307,7 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     }
     if (it + 2 < NP) {
       const int T2 = (it + 2) >> 2;
-      mbar_wait(smem_u32(&bars->e_full[T2 % NS]), (T2 / NS) & 1);
+      if (((it + 2) & 3) == 0) mbar_wait(smem_u32(&bars->e_full[T2 % NS]), (T2 / NS) & 1);   // first pair of a tile
       build(it + 2);
     }
     tmem_st_wait();

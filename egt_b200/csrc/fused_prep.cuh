@@ -1,0 +1,92 @@
+// fused_prep.cuh -- device body of the per-call derived-weight preparation of the fused tcgen05 path.
+// It runs either as its own one-CTA kernel (fused_prep_kernel) or as an extra CTA of the node-side
+// kernel that precedes the fused kernel on the stream (node_tc.cu), which saves a launch per pass.
+#pragma once
+#include "common.cuh"
+#include "fused.h"
+
+namespace egt {
+
+// One CTA of 128 threads.  B-operand images are K-major without swizzle: element (n, k) of an [N x K]
+// matrix lives at  (k/8) * (N*16) + n*16 + (k%8)*2  bytes (8x16-byte core matrices, LBO = N*16, SBO = 128).
+__device__ __forceinline__ void fused_prep_body(const egt_block_weights_t &w, float clip_lo, float clip_hi,
+                                                FusedPrep *out, const int tid) {
+  __shared__ float wp[2][FDE][FH];   // W' rounded to bf16
+  {
+    int eg = tid / 64, c = (tid / 8) % 8, hh = tid % 8;
+    const float *W = eg ? w.attention_gates_kernel : w.dense_edge_b_kernel;
+    float v = __bfloat162float(__float2bfloat16_rn(w.norm_edge_gamma[c] * W[c * FH + hh]));
+    wp[eg][c][hh] = v;
+    out->wp[eg][c][hh] = v;
+  }
+  __syncthreads();
+  if (tid < 16) {
+    int eg = tid / 8, hh = tid % 8;
+    const float *W = eg ? w.attention_gates_kernel : w.dense_edge_b_kernel;
+    const float *bias = eg ? w.attention_gates_bias : w.dense_edge_b_bias;
+    float u = 0.f, v = bias[hh], n2 = 0.f;
+    for (int c = 0; c < FDE; ++c) {
+      u += wp[eg][c][hh];
+      v += w.norm_edge_beta[c] * W[c * FH + hh];
+      n2 += wp[eg][c][hh] * wp[eg][c][hh];
+    }
+    (eg ? out->uG : out->uE)[hh] = u;
+    (eg ? out->vG : out->vE)[hh] = v;
+    if (eg == 0) {
+      // |LN(e)_c| has l2 norm <= sqrt(d_e)  =>  |E| <= sqrt(d_e) * ||W'[:,hh]|| + |v|
+      float bnd = fmaxf(fabsf(clip_lo), fabsf(clip_hi)) + sqrtf((float)FDE * n2) + fabsf(v);
+      for (int o = 4; o > 0; o >>= 1) bnd = fmaxf(bnd, __shfl_xor_sync(0xffu, bnd, o));
+      if (hh == 0) out->bound = bnd;
+    }
+  }
+  if (tid < FDE) out->br[tid] = w.dense_edge_r_bias[tid];
+  // wblk: n = key*16 + eg*8 + hh ; k = key'*8 + c            (N = 32, K = 16)
+  for (int i = tid; i < 32 * 16; i += 128) {
+    int n = i / 16, k = i % 16;
+    int key = n / 16, eg = (n / 8) % 2, hh = n % 8, key2 = k / 8, c = k % 8;
+    float v = key == key2 ? wp[eg][c][hh] : 0.f;
+    out->wblk[(k / 8) * (32 * 8) + n * 8 + (k % 8)] = __float2bfloat16_rn(v);
+  }
+  // wrblk: n = key*8 + c ; k = key'*8 + hh                   (N = 16, K = 16)   value W_r[hh][c]
+  // wrtblk: n = key*8 + hh ; k = key'*8 + c                  (N = 16, K = 16)   value W_r[hh][c]
+  for (int i = tid; i < 16 * 16; i += 128) {
+    int n = i / 16, k = i % 16;
+    int key = n / 8, a = n % 8, key2 = k / 8, b = k % 8;
+    out->wrblk[(k / 8) * (16 * 8) + n * 8 + (k % 8)] =
+        __float2bfloat16_rn(key == key2 ? w.dense_edge_r_kernel[b * FDE + a] : 0.f);
+    out->wrtblk[(k / 8) * (16 * 8) + n * 8 + (k % 8)] =
+        __float2bfloat16_rn(key == key2 ? w.dense_edge_r_kernel[a * FDE + b] : 0.f);
+  }
+  // backward images (head-group ordered, fused.h)
+  for (int i = tid; i < 32 * 16; i += 128) {      // b_eg
+    int n = i / 16, k = i % 16;
+    int g = n / 16, key = (n / 8) % 2, eg = (n / 4) % 2, hh = 4 * g + n % 4, key2 = k / 8, c = k % 8;
+    out->b_eg[(k / 8) * (32 * 8) + n * 8 + (k % 8)] = __float2bfloat16_rn(key == key2 ? wp[eg][c][hh] : 0.f);
+  }
+  for (int i = tid; i < 16 * 16; i += 128) {      // b_hx, b_de[g]
+    int n = i / 16, k = i % 16;
+    {
+      int g = n / 8, key = (n / 4) % 2, hh = 4 * g + n % 4, key2 = k / 8, c = k % 8;
+      out->b_hx[(k / 8) * (16 * 8) + n * 8 + (k % 8)] =
+          __float2bfloat16_rn(key == key2 ? w.dense_edge_r_kernel[hh * FDE + c] : 0.f);
+    }
+    {
+      int key2 = n / 8, c = n % 8, g = k / 8, key = (k / 4) % 2, hh = 4 * g + k % 4;
+      out->b_wr[(k / 8) * (16 * 8) + n * 8 + (k % 8)] =
+          __float2bfloat16_rn(key == key2 ? w.dense_edge_r_kernel[hh * FDE + c] : 0.f);
+    }
+    for (int g = 0; g < 2; ++g) {
+      int key2 = n / 8, c = n % 8, key = k / 8, eg = (k / 4) % 2, hh = 4 * g + k % 4;
+      out->b_de[g][(k / 8) * (16 * 8) + n * 8 + (k % 8)] = __float2bfloat16_rn(key == key2 ? wp[eg][c][hh] : 0.f);
+    }
+  }
+  // wtblk: n = key*8 + c ; k = key'*16 + eg*8 + hh           (N = 16, K = 32)   value W'_eg[c][hh]
+  for (int i = tid; i < 16 * 32; i += 128) {
+    int n = i / 32, k = i % 32;
+    int key = n / 8, c = n % 8, key2 = k / 16, eg = (k / 8) % 2, hh = k % 8;
+    out->wtblk[(k / 8) * (16 * 8) + n * 8 + (k % 8)] = __float2bfloat16_rn(key == key2 ? wp[eg][c][hh] : 0.f);
+  }
+}
+
+
+}  // namespace egt

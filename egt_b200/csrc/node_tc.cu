@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "fused.h"
 #include "umma.cuh"
+#include "fused_prep.cuh"
 
 namespace egt {
 using namespace umma;
@@ -40,22 +41,33 @@ __device__ __forceinline__ uint4 pack8(const float *x) {
   v.x = pack_bf16(x[0], x[1]); v.y = pack_bf16(x[2], x[3]); v.z = pack_bf16(x[4], x[5]); v.w = pack_bf16(x[6], x[7]);
   return v;
 }
-// B operand images from a float32 Keras kernel W[kdim][ndim] (row-major, "x @ W"):
+// B operand images from a float32 Keras kernel W[kdim][ndim] (row-major, "x @ W"); each step converts 8
+// consecutive floats of a row of W into one 16-byte chunk of the image.
 //   MN-major (n contiguous), 128B swizzle, atoms of 64 n: used for x @ W       (contraction over W's rows)
 __device__ __forceinline__ void build_w_mn(uint8_t *img, const float *W, int kdim, int ndim, int tid, int nthr) {
-  for (int i = tid; i < kdim * ndim; i += nthr) {
-    const int k = i / ndim, n = i % ndim;
+  const int nch = ndim >> 3;
+  for (int i = tid; i < kdim * nch; i += nthr) {
+    const int k = i / nch, n = (i % nch) << 3;
+    const float4 a = *(const float4 *)(W + (size_t)k * ndim + n), b = *(const float4 *)(W + (size_t)k * ndim + n + 4);
+    const float y[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
     const uint32_t off = (uint32_t)(n >> 6) * (uint32_t)(kdim * 128) + (uint32_t)(k >> 3) * 1024u + (uint32_t)(k & 7) * 128u +
-                         ((uint32_t)((((n & 63) >> 3) ^ k) & 7) << 4) + (uint32_t)(n & 7) * 2u;
-    *(__nv_bfloat16 *)(img + off) = __float2bfloat16_rn(W[i]);
+                         ((uint32_t)((((n & 63) >> 3) ^ k) & 7) << 4);
+    *(uint4 *)(img + off) = pack8(y);
   }
 }
 //   K-major image of W^T, i.e. B[n = row of W][k = column of W]: used for x @ W^T (contraction over W's columns)
 __device__ __forceinline__ void build_wt_k(uint8_t *img, const float *W, int nrows, int kcols, int tid, int nthr) {
-  for (int i = tid; i < nrows * kcols; i += nthr) {
-    const int n = i / kcols, k = i % kcols;
-    *(__nv_bfloat16 *)(img + (uint32_t)(k >> 6) * (uint32_t)(nrows * 128) + sw128_off(n, k & 63)) = __float2bfloat16_rn(W[i]);
+  const int kch = kcols >> 3;
+  for (int i = tid; i < nrows * kch; i += nthr) {
+    const int n = i / kch, k = (i % kch) << 3;
+    const float4 a = *(const float4 *)(W + (size_t)n * kcols + k), b = *(const float4 *)(W + (size_t)n * kcols + k + 4);
+    const float y[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    *(uint4 *)(img + (uint32_t)(k >> 6) * (uint32_t)(nrows * 128) + sw128_off(n, k & 63)) = pack8(y);
   }
+}
+// 16-byte vector reduction into global memory (sm_90+)
+__device__ __forceinline__ void red_add_v4(float *dst, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 __device__ __forceinline__ void fill_ones(uint8_t *tile, int tid, int nthr) {
   for (int i = tid; i < (int)(TILE / 16); i += nthr) ((uint4 *)tile)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
@@ -76,6 +88,7 @@ struct NodeQkvArgs {
   const __nv_bfloat16 *h; const float *gamma, *beta; float eps;
   const float *W, *bias; float qscale;
   __nv_bfloat16 *qkv; int R;
+  egt_block_weights_t w; float clip_lo, clip_hi; FusedPrep *prep_out;   // extra CTA: fused_prep_body (NULL = off)
 };
 
 __global__ void __launch_bounds__(128) node_qkv_kernel(const NodeQkvArgs a) {
@@ -85,6 +98,8 @@ __global__ void __launch_bounds__(128) node_qkv_kernel(const NodeQkvArgs a) {
   float *sgb = (float *)(smem + TILE + 24576);               // gamma, beta, bias(192)
   NodeBars *bars = (NodeBars *)(smem + TILE + 24576 + 1536);
   const int t = threadIdx.x;
+  const int nwork = a.prep_out ? gridDim.x - 1 : gridDim.x;
+  if ((int)blockIdx.x == nwork) { fused_prep_body(a.w, a.clip_lo, a.clip_hi, a.prep_out, t); return; }
   node_setup(bars, t, 256);
   build_w_mn(sW, a.W, ND, 3 * ND, t, 128);
   if (t < ND) { sgb[t] = a.gamma[t]; sgb[ND + t] = a.beta[t]; }
@@ -96,7 +111,7 @@ __global__ void __launch_bounds__(128) node_qkv_kernel(const NodeQkvArgs a) {
   const uint32_t tlane = tmem + ((uint32_t)((t >> 5) * 32) << 16);
   constexpr uint32_t IDESC = idesc_bf16(128, 192, 0, 1);
   uint32_t phase = 0;
-  for (int tile = blockIdx.x; tile * 128 < a.R; tile += gridDim.x) {
+  for (int tile = blockIdx.x; tile * 128 < a.R; tile += nwork) {
     const int r = tile * 128 + t;
     {   // LayerNorm of this thread's row -> bf16 A tile
       uint4 v[8];
@@ -231,6 +246,7 @@ __global__ void __launch_bounds__(128) node_out_kernel(const NodeOutArgs a) {
 struct NodeBwd1Args {
   const __nv_bfloat16 *dh_out, *v_att; const float *W;       // W_O [64,64]
   __nv_bfloat16 *d_v_att; float *dW, *db; int R;
+  egt_block_weights_t w; float clip_lo, clip_hi; FusedPrep *prep_out;   // extra CTA: fused_prep_body (NULL = off)
 };
 
 __global__ void __launch_bounds__(128) node_bwd1_kernel(const NodeBwd1Args a) {
@@ -239,6 +255,8 @@ __global__ void __launch_bounds__(128) node_bwd1_kernel(const NodeBwd1Args a) {
   uint8_t *sX = smem, *sOnes = smem + TILE, *sY = smem + 2 * TILE, *sW = smem + 3 * TILE;   // X | 1 | Y | W_O^T image 8 KB
   NodeBars *bars = (NodeBars *)(smem + 3 * TILE + 8192);
   const int t = threadIdx.x;
+  const int nwork = a.prep_out ? gridDim.x - 1 : gridDim.x;
+  if ((int)blockIdx.x == nwork) { fused_prep_body(a.w, a.clip_lo, a.clip_hi, a.prep_out, t); return; }
   node_setup(bars, t, 128);
   build_wt_k(sW, a.W, ND, ND, t, 128);
   fill_ones(sOnes, t, 128);
@@ -251,7 +269,7 @@ __global__ void __launch_bounds__(128) node_bwd1_kernel(const NodeBwd1Args a) {
   constexpr uint32_t TM_D1 = 0, TM_D2 = 64;
   uint32_t phase = 0;
   bool first = true;
-  for (int tile = blockIdx.x; tile * 128 < a.R; tile += gridDim.x) {
+  for (int tile = blockIdx.x; tile * 128 < a.R; tile += nwork) {
     const int r = tile * 128 + t;
     {
       uint4 v[8];
@@ -311,7 +329,8 @@ __global__ void __launch_bounds__(128) node_bwd1_kernel(const NodeBwd1Args a) {
       if (t <= ND) {
         float *dst = t < ND ? a.dW + (size_t)t * ND + 32 * ch : a.db + 32 * ch;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) atomicAdd(dst + c, __uint_as_float(o[c]));
+        for (int c = 0; c < 32; c += 4)
+          red_add_v4(dst + c, __uint_as_float(o[c]), __uint_as_float(o[c + 1]), __uint_as_float(o[c + 2]), __uint_as_float(o[c + 3]));
       }
     }
   }
@@ -377,14 +396,22 @@ __global__ void __launch_bounds__(128) node_bwd2_kernel(const NodeBwd2Args a) {
         }
         *(uint4 *)(sX + sw128_off(t, 8 * j)) = pack8(y);
       }
-      // dqkv row (float32) -> three bf16 tiles
-      const float4 *sq = (const float4 *)(a.dqkv + (size_t)(valid ? r : 0) * (3 * ND));
+    }
+    {   // dqkv tile (float32 [128,192], rows contiguous) -> three bf16 tiles; coalesced: 24 threads per row
+      const float *base = a.dqkv + (size_t)tile * 128 * (3 * ND);
+      const int rows_here = a.R - tile * 128 < 128 ? a.R - tile * 128 : 128;
 #pragma unroll 4
-      for (int j = 0; j < 24; ++j) {
+      for (int i = t; i < 128 * 24; i += 128) {
+        const int rr = i / 24, j = i % 24;
         float y[8];
-        const float4 p0 = valid ? sq[2 * j] : make_float4(0, 0, 0, 0), p1 = valid ? sq[2 * j + 1] : make_float4(0, 0, 0, 0);
-        y[0] = p0.x; y[1] = p0.y; y[2] = p0.z; y[3] = p0.w; y[4] = p1.x; y[5] = p1.y; y[6] = p1.z; y[7] = p1.w;
-        *(uint4 *)(sY + (uint32_t)(j >> 3) * TILE + sw128_off(t, 8 * (j & 7))) = pack8(y);
+        if (rr < rows_here) {
+          const float4 p0 = *(const float4 *)(base + (size_t)rr * (3 * ND) + 8 * j), p1 = *(const float4 *)(base + (size_t)rr * (3 * ND) + 8 * j + 4);
+          y[0] = p0.x; y[1] = p0.y; y[2] = p0.z; y[3] = p0.w; y[4] = p1.x; y[5] = p1.y; y[6] = p1.z; y[7] = p1.w;
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) y[c] = 0.f;
+        }
+        *(uint4 *)(sY + (uint32_t)(j >> 3) * TILE + sw128_off(rr, 8 * (j & 7))) = pack8(y);
       }
     }
     fence_proxy_async_smem();
@@ -471,7 +498,8 @@ __global__ void __launch_bounds__(128) node_bwd2_kernel(const NodeBwd2Args a) {
       if (t <= ND) {
         float *dst = t < ND ? a.dW + (size_t)t * (3 * ND) + 32 * ch : a.db + 32 * ch;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) atomicAdd(dst + c, __uint_as_float(o[c]));
+        for (int c = 0; c < 32; c += 4)
+          red_add_v4(dst + c, __uint_as_float(o[c]), __uint_as_float(o[c + 1]), __uint_as_float(o[c + 2]), __uint_as_float(o[c + 3]));
       }
     }
   }
@@ -492,13 +520,14 @@ static int set_smem(K kernel, int bytes) {
 }
 
 int node_qkv_launch(const void *h, const float *gamma, const float *beta, float eps, const float *W, const float *bias,
-                    float qscale, void *qkv, int R, cudaStream_t st) {
-  NodeQkvArgs a{(const __nv_bfloat16 *)h, gamma, beta, eps, W, bias, qscale, (__nv_bfloat16 *)qkv, R};
+                    float qscale, void *qkv, int R, const egt_block_weights_t *w, float clip_lo, float clip_hi,
+                    FusedPrep *prep_out, cudaStream_t st) {
+  NodeQkvArgs a{(const __nv_bfloat16 *)h, gamma, beta, eps, W, bias, qscale, (__nv_bfloat16 *)qkv, R, *w, clip_lo, clip_hi, prep_out};
   const int smem = TILE + 24576 + 1536 + 64 + 1024;
   static bool once = false;
   if (!once) { int rc = set_smem(node_qkv_kernel, smem); if (rc) return rc; once = true; }
   LaunchScope _ls("node_qkv_kernel", st);
-  node_qkv_kernel<<<node_grid(R), 128, smem, st>>>(a);
+  node_qkv_kernel<<<node_grid(R) + (prep_out ? 1 : 0), 128, smem, st>>>(a);
   EGT_CHECK_CUDA(cudaGetLastError());
   return EGT_OK;
 }
@@ -514,13 +543,13 @@ int node_out_launch(const void *v_att, const void *h, const float *W, const floa
 }
 
 int node_bwd1_launch(const void *dh_out, const void *v_att, const float *W, void *d_v_att, float *dW, float *db, int R,
-                     cudaStream_t st) {
-  NodeBwd1Args a{(const __nv_bfloat16 *)dh_out, (const __nv_bfloat16 *)v_att, W, (__nv_bfloat16 *)d_v_att, dW, db, R};
+                     const egt_block_weights_t *w, float clip_lo, float clip_hi, FusedPrep *prep_out, cudaStream_t st) {
+  NodeBwd1Args a{(const __nv_bfloat16 *)dh_out, (const __nv_bfloat16 *)v_att, W, (__nv_bfloat16 *)d_v_att, dW, db, R, *w, clip_lo, clip_hi, prep_out};
   const int smem = 3 * TILE + 8192 + 64 + 1024;
   static bool once = false;
   if (!once) { int rc = set_smem(node_bwd1_kernel, smem); if (rc) return rc; once = true; }
   LaunchScope _ls("node_bwd1_kernel", st);
-  node_bwd1_kernel<<<node_grid(R), 128, smem, st>>>(a);
+  node_bwd1_kernel<<<node_grid(R) + (prep_out ? 1 : 0), 128, smem, st>>>(a);
   EGT_CHECK_CUDA(cudaGetLastError());
   return EGT_OK;
 }
