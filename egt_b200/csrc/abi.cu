@@ -408,10 +408,9 @@ int egt_block_bwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
     fb.rand_thr = (uint32_t)ceilf(a.random_mask_prob * 65536.0f - 0.5f);
     fb.seed = a.seed; fb.offset = a.offset;
     if ((rc = fused_bwd_launch(fb, io->e, io->de_out, io->de, io->qkv, st))) return rc;
-    if ((rc = fused_bwd_finalize_launch(ws.partials, a.B * tiles, w, g, st))) return rc;
     return node_bwd2_launch(io->h, io->dh_out, ws.d_qkv_f32, w->norm_mha_gamma, w->norm_mha_beta, cfg->ln_eps,
                             w->dense_qkv_kernel, io->dh, g->dense_qkv_kernel, g->dense_qkv_bias, g->norm_mha_gamma,
-                            g->norm_mha_beta, R, st);
+                            g->norm_mha_beta, R, ws.partials, a.B * tiles, w, g, st);
   }
 
   // dV_att = dh' W_O^T ; dW_O += V_att^T dh' ; db_O += colsum(dh')

@@ -30,6 +30,7 @@
 #include "common.cuh"
 #include "fused.h"
 #include "umma.cuh"
+#include "fused_prep.cuh"
 
 namespace egt {
 using namespace umma;
@@ -46,7 +47,8 @@ constexpr uint32_t SM_TR = SM_KVX + 4 * 4096;                  // dS^T 32768 | A
 constexpr uint32_t SM_W = SM_TR + 65536;                       // b_eg 1024 | b_hx 512 | b_de 2 x 512
 constexpr uint32_t SM_CONST = SM_W + 2560;                     // uE vE uG vG (32 floats)
 constexpr uint32_t SM_BAR = SM_CONST + 256;
-constexpr uint32_t SM_TOTAL = SM_BAR + 256;
+constexpr uint32_t SM_MASK = SM_BAR + 256;                       // key-valid bytes, zero padded (N <= 4096)
+constexpr uint32_t SM_TOTAL = SM_MASK + 4096 + 16;
 static_assert(SM_TOTAL + 1024 <= 232448, "shared memory budget");
 
 constexpr uint32_t TM_DQ = 0, TM_DK = 64, TM_DV = 128;
@@ -99,6 +101,8 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
   } else {
     if (tid < 160) ((uint4 *)(smem + SM_W))[tid] = ((const uint4 *)a.prep->b_eg)[tid];   // b_eg | b_hx | b_de
     if (tid < 32) ((float *)(smem + SM_CONST))[tid] = a.prep->uE[tid];                  // uE vE uG vG
+    for (int i = tid; i < 2 * ((N + 1) / 2); i += 256)                                   // key-valid bytes
+      smem[SM_MASK + i] = i < N ? (a.mask ? (uint8_t)(a.mask[(size_t)blockIdx.y * N + i] != 0) : (uint8_t)1) : (uint8_t)0;
     fence_proxy_async_smem();
   }
   tc_fence_before();
@@ -215,8 +219,12 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
   const bool rowvalid = l < N;
   const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   const float *cst = (const float *)(smem + SM_CONST);
-  const uint8_t *maskb = a.mask ? a.mask + (size_t)b * N : nullptr;
+  const uint8_t *smask = smem + SM_MASK;
   const float lo = a.clip_lo, hi = a.clip_hi;
+  const uint32_t trow = (uint32_t)t * 128u, tx7 = (uint32_t)(t & 7);
+  const uint32_t trbase = (uint32_t)(t >> 3) * 1024u + tx7 * 128u + (uint32_t)g * 8u;
+  const uint32_t bar_mma1 = smem_u32(&bars->mma1[0]), bar_mma2 = smem_u32(&bars->mma2[0]);
+  const uint32_t bar_e = smem_u32(&bars->e_full[0]), bar_t = smem_u32(&bars->tbar);
 
   // ---- per-row quantities: D = sum_dd dV_att * V_att, scaler s, ddeg, log2 row sum; dO tile ---------
   float Dr[4], ddeg[4], l2[4];
@@ -250,7 +258,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
         uint4 o;
         o.x = pack_bf16(d8[0] * s8[0], d8[1] * s8[1]); o.y = pack_bf16(d8[2] * s8[2], d8[3] * s8[3]);
         o.z = pack_bf16(d8[4] * s8[4], d8[5] * s8[5]); o.w = pack_bf16(d8[6] * s8[6], d8[7] * s8[7]);
-        *(uint4 *)(smem + SM_DO + sw128_off(t, dd * 8)) = o;
+        *(uint4 *)(smem + SM_DO + trow + (((uint32_t)dd ^ tx7) << 4)) = o;
       }
     }
 #pragma unroll
@@ -288,17 +296,17 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     for (int q = 0; q < 4; ++q) WR[i][q] = make_float2(0.f, 0.f);
   sE[0] = sE[1] = sG[0] = sG[1] = make_float2(0.f, 0.f);
 
-  auto build = [&](int p2) {    // expanded K / V operands of pair p2 into slot p2 & 3 (one 16-byte chunk per thread)
-    const int T2 = p2 >> 2, j2 = p2 & 3, st = T2 % NS;
-    const int which = tid >> 7, rem = tid & 127, n = rem >> 3, dd = rem & 7;
-    const int hh = 4 * (n >> 3) + (n & 3), ks = 2 * j2 + ((n >> 2) & 1);
-    const uint8_t *rows = smem + SM_STAGE + st * STAGE_BYTES + (which ? ST_V : ST_K);
-    const uint32_t val = *(const uint16_t *)(rows + ks * 128 + (dd * 8 + hh) * 2);
-    const uint32_t wv = val << ((hh & 1) * 16);
+  // expanded K / V operands of pair p2 (stage st2) into slot p2 & 3: one 16-byte chunk per thread
+  const int b_n = (tid & 127) >> 3, b_dd = tid & 7, b_hh = 4 * (b_n >> 3) + (b_n & 3);
+  const uint32_t b_src = (uint32_t)(g ? ST_V : ST_K) + (uint32_t)((b_n >> 2) & 1) * 128u + (uint32_t)(b_dd * 8 + b_hh) * 2u;
+  const uint32_t b_dst = SM_KVX + (uint32_t)g * 2048u + (uint32_t)b_n * 128u + ((uint32_t)((b_dd ^ b_n) & 7) << 4);
+  auto build = [&](int p2, int st2) {
+    const uint32_t val = *(const uint16_t *)(smem + SM_STAGE + st2 * STAGE_BYTES + b_src + (p2 & 3) * 256);
+    const uint32_t wv = val << ((b_hh & 1) * 16);
     uint4 ch;
-    ch.x = (hh >> 1) == 0 ? wv : 0u; ch.y = (hh >> 1) == 1 ? wv : 0u;
-    ch.z = (hh >> 1) == 2 ? wv : 0u; ch.w = (hh >> 1) == 3 ? wv : 0u;
-    *(uint4 *)(smem + SM_KVX + (p2 & 3) * 4096 + which * 2048 + n * 128 + (((dd ^ n) & 7) << 4)) = ch;
+    ch.x = (b_hh >> 1) == 0 ? wv : 0u; ch.y = (b_hh >> 1) == 1 ? wv : 0u;
+    ch.z = (b_hh >> 1) == 2 ? wv : 0u; ch.w = (b_hh >> 1) == 3 ? wv : 0u;
+    *(uint4 *)(smem + b_dst + (p2 & 3) * 4096) = ch;
   };
 
   auto ln_stats = [&](const uint4 ev, float *x, float &r, float &nrm) {
@@ -314,8 +322,9 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
   };
 
   // ---- phase A: pair p, this thread's 4 heads of both keys ------------------------------------------
-  auto phase_a = [&](int p) {
-    const int T = p >> 2, j = p & 3, st = T % NS, buf = p % 3, ob = p & 1;
+  float cur_r = 0.f, cur_nrm = 0.f, prev_r = 0.f, prev_nrm = 0.f;   // LN statistics of key g of the current / previous pair
+  auto phase_a = [&](int p, int st, int buf) {
+    const int j = p & 3, ob = p & 1;
     const uint8_t *es = smem + SM_STAGE + st * STAGE_BYTES;
     const uint32_t tin = tlane + TM_IN + buf * TM_IN_COLS;
     const uint32_t tout = tlane + TM_OUT + ob * TM_OUT_COLS;
@@ -326,18 +335,18 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     const float uG[4] = {uG4.x, uG4.y, uG4.z, uG4.w}, vG[4] = {vG4.x, vG4.y, vG4.z, vG4.w};
 #pragma unroll
     for (int kk = 0; kk < 2; ++kk) {
-      const int ks = 2 * j + kk, m = 8 * T + ks;
+      const int ks = 2 * j + kk, m = 2 * p + kk;
       uint32_t sreg[4], dareg[4], egreg[8], hxreg[4];
       tmem_ld4(tin + IN_S + g * 8 + kk * 4, sreg);
       tmem_ld4(tin + IN_DA + g * 8 + kk * 4, dareg);
       tmem_ld8(tin + IN_EG + g * 16 + kk * 8, egreg);
       tmem_ld4(tin + IN_HX + g * 8 + kk * 4, hxreg);
-      const uint32_t eoff = sw128_off(t, ks * 8);
+      const uint32_t eoff = trow + (((uint32_t)ks ^ tx7) << 4);
       float x[8], r, nrm;
       ln_stats(*(const uint4 *)(es + ST_E + eoff), x, r, nrm);
+      if (kk == g) { cur_r = r; cur_nrm = nrm; }
       const uint4 dev = *(const uint4 *)(es + ST_DE + eoff);
-      bool kvalid = rowvalid && m < N;
-      if (maskb && m < N) kvalid = kvalid && maskb[m] != 0;
+      const bool kvalid = rowvalid && smask[m] != 0;
       uint32_t rb0 = 0u, rb1 = 0u;
       if (RAND) {
         const uint64_t qd = ((uint64_t)b * N + (uint64_t)l) * N + (uint64_t)m;
@@ -374,10 +383,9 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
       dzp[kk * 4 + 0] = pack_bf16(dH[0], dH[1]); dzp[kk * 4 + 1] = pack_bf16(dH[2], dH[3]);
       dzp[kk * 4 + 2] = pack_bf16(dGv[0], dGv[1]); dzp[kk * 4 + 3] = pack_bf16(dGv[2], dGv[3]);
       {   // transposed operands: row = query t (K index), 16-byte chunk = key, bytes 8g.. = heads 4g..4g+3
-        const int k16 = m & 15;
-        if (k16 == 0 && m > 0) mbar_wait(smem_u32(&bars->tbar), ((m >> 4) - 1) & 1);   // previous block consumed
-        const uint32_t off = (uint32_t)(k16 >> 3) * 16384u + (uint32_t)(t >> 3) * 1024u + (uint32_t)(t & 7) * 128u +
-                             ((uint32_t)((k16 ^ t) & 7) << 4) + (uint32_t)g * 8u;
+        const uint32_t k16 = (uint32_t)m & 15u;
+        if (k16 == 0 && m > 0) mbar_wait(bar_t, ((m >> 4) - 1) & 1);   // previous block consumed
+        const uint32_t off = trbase + (k16 >> 3) * 16384u + (((k16 ^ tx7) & 7u) << 4);
         *(uint2 *)(smem + SM_TR + off) = make_uint2(dsp[kk * 2], dsp[kk * 2 + 1]);
         *(uint2 *)(smem + SM_TR + 32768 + off) = make_uint2(pack_bf16(At[0], At[1]), pack_bf16(At[2], At[3]));
       }
@@ -407,15 +415,16 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
   };
 
   // ---- phase B: LayerNorm backward + residual for key g of pair p -> de, in place over de' -----------
-  auto phase_b = [&](int p) {
-    const int T = p >> 2, j = p & 3, st = T % NS, buf = p % 3;
+  auto phase_b = [&](int p, int st, int buf, const float r, const float nrm) {
+    const int j = p & 3;
     uint8_t *es = smem + SM_STAGE + st * STAGE_BYTES;
     const int ks = 2 * j + g;
     uint32_t dr[8];
     tmem_ld8(tlane + TM_IN + buf * TM_IN_COLS + IN_EG + g * 8, dr);
-    const uint32_t eoff = sw128_off(t, ks * 8);
-    float x[8], r, nrm;
-    ln_stats(*(const uint4 *)(es + ST_E + eoff), x, r, nrm);
+    const uint32_t eoff = trow + (((uint32_t)ks ^ tx7) << 4);
+    const uint4 ev = *(const uint4 *)(es + ST_E + eoff);
+    const float x[8] = {bf16_lo(ev.x), bf16_hi(ev.x), bf16_lo(ev.y), bf16_hi(ev.y),
+                        bf16_lo(ev.z), bf16_hi(ev.z), bf16_lo(ev.w), bf16_hi(ev.w)};
     const uint4 dev = *(const uint4 *)(es + ST_DE + eoff);
     const float dp[8] = {bf16_lo(dev.x), bf16_hi(dev.x), bf16_lo(dev.y), bf16_hi(dev.y),
                          bf16_lo(dev.z), bf16_hi(dev.z), bf16_lo(dev.w), bf16_hi(dev.w)};
@@ -468,46 +477,57 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
   };
 
   // ---- pipeline ------------------------------------------------------------------------------------
-  mbar_wait(smem_u32(&bars->e_full[0]), 0);
-  build(0);
-  if (NP > 1) build(1);
+  // running indices instead of divisions: pair it -> (stage st_a, TMEM buffer buf_a, parity par_a)
+  mbar_wait(bar_e, 0);
+  build(0, 0);
+  if (NP > 1) build(1, 0);
   fence_proxy_async_smem();
   __syncthreads();                                     // sync #0
+  int st_a = 0, buf_a = 0, par_a = 0;                  // pair it
+  int st_p = 0, buf_p = 0, par_p = 0;                  // pair it - 1
+  int st_n = 0, par_n = 0;                             // pair it + 2 (its tile's stage / load parity)
   for (int it = 0; it < NP; ++it) {
-    mbar_wait(smem_u32(&bars->mma1[it % 3]), (it / 3) & 1);
+    if (((it + 2) & 3) == 0 || it == 0) {              // pair it+2 sits in tile (it+2)>>2
+      const int T2 = (it + 2) >> 2;
+      st_n = T2 % NS; par_n = (T2 / NS) & 1;
+    }
+    mbar_wait(bar_mma1 + 8 * buf_a, par_a);
     tc_fence_after();
-    phase_a(it);
+    phase_a(it, st_a, buf_a);
     if (it >= 1) {
-      mbar_wait(smem_u32(&bars->mma2[(it - 1) % 3]), ((it - 1) / 3) & 1);
+      mbar_wait(bar_mma2 + 8 * buf_p, par_p);
       tc_fence_after();
-      phase_b(it - 1);
+      phase_b(it - 1, st_p, buf_p, prev_r, prev_nrm);
       if (((it - 1) & 7) == 7) {                       // dS^T / A~^T block (it-1)/8 went through the tensor core
         const int kb = (it - 1) >> 3;
         if ((kb & 1) == g) {
-          mbar_wait(smem_u32(&bars->tbar), kb & 1);
+          mbar_wait(bar_t, kb & 1);
           tc_fence_after();
           t_epilogue(kb);
         }
       }
     }
+    prev_r = cur_r; prev_nrm = cur_nrm;
     if (it + 2 < NP) {
-      const int T2 = (it + 2) >> 2;
-      if (((it + 2) & 3) == 0) mbar_wait(smem_u32(&bars->e_full[T2 % NS]), (T2 / NS) & 1);   // first pair of a tile
-      build(it + 2);
+      if (((it + 2) & 3) == 0) mbar_wait(bar_e + 8 * st_n, par_n);   // first pair of a tile
+      build(it + 2, st_n);
     }
     tmem_st_wait();
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();                                   // sync #(it+1)
+    st_p = st_a; buf_p = buf_a; par_p = par_a;
+    if (++buf_a == 3) { buf_a = 0; par_a ^= 1; }
+    if (((it + 1) & 3) == 0) { if (++st_a == NS) st_a = 0; }
   }
-  mbar_wait(smem_u32(&bars->mma2[(NP - 1) % 3]), ((NP - 1) / 3) & 1);
+  mbar_wait(bar_mma2 + 8 * buf_p, par_p);
   tc_fence_after();
-  phase_b(NP - 1);
+  phase_b(NP - 1, st_p, buf_p, prev_r, prev_nrm);
   fence_proxy_async_smem();
   __syncthreads();                                     // sync #(NP+1)
   {
     const int kb = (NP - 1) >> 3;                      // last (possibly partial) 16-key block
-    mbar_wait(smem_u32(&bars->tbar), kb & 1);
+    mbar_wait(bar_t, kb & 1);
     tc_fence_after();
     if ((kb & 1) == g) t_epilogue(kb);
   }
@@ -558,47 +578,9 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
   __syncthreads();                                     // final
 }
 
-// Folds the per-CTA partial sums into the weight gradients (the library ADDS into them).
-//   e^ = gamma (.) x^ + beta ;  [E|G] = e^ W + b ;  e' = e + H^ W_r + b_r
 __global__ void __launch_bounds__(256) fused_bwd_finalize_kernel(const float *partials, int nparts, egt_block_weights_t w,
                                                                  egt_block_grads_t g) {
-  __shared__ float s[FPART];
-  const int tid = threadIdx.x;
-  if (tid < FPART) {
-    float acc[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-    int i = 0;
-    for (; i + 8 <= nparts; i += 8)
-#pragma unroll
-      for (int q = 0; q < 8; ++q) acc[q] += partials[(size_t)(i + q) * FPART + tid];
-    for (; i < nparts; ++i) acc[0] += partials[(size_t)i * FPART + tid];
-    s[tid] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
-  }
-  __syncthreads();
-  const float *M = s, *sZ = s + 128, *Wr = s + 144, *dbr = s + 208;
-  if (tid < 128) {                        // dW_E, dW_G
-    const int c = tid / 16, j = tid % 16, eg = j / 8, hh = j % 8;
-    float *dst = eg ? g.attention_gates_kernel : g.dense_edge_b_kernel;
-    dst[c * FH + hh] += w.norm_edge_gamma[c] * M[c * 16 + j] + w.norm_edge_beta[c] * sZ[j];
-  } else if (tid < 144) {                 // db_E, db_G
-    const int j = tid - 128, eg = j / 8, hh = j % 8;
-    (eg ? g.attention_gates_bias : g.dense_edge_b_bias)[hh] += sZ[j];
-  } else if (tid < 208) {                 // dW_r
-    g.dense_edge_r_kernel[tid - 144] += Wr[tid - 144];
-  } else if (tid < 216) {                 // db_r
-    g.dense_edge_r_bias[tid - 208] += dbr[tid - 208];
-  } else if (tid < 224) {                 // dgamma_e, dbeta_e
-    const int c = tid - 216;
-    float dg = 0.f, db = 0.f;
-    for (int hh = 0; hh < FH; ++hh) {
-      const float we = w.dense_edge_b_kernel[c * FH + hh], wg = w.attention_gates_kernel[c * FH + hh];
-      dg += we * M[c * 16 + hh] + wg * M[c * 16 + 8 + hh];
-      db += we * sZ[hh] + wg * sZ[8 + hh];
-    }
-    g.norm_edge_gamma[c] += dg;
-    g.norm_edge_beta[c] += db;
-  }
+  fused_bwd_finalize_body(partials, nparts, w, g, threadIdx.x, blockDim.x);
 }
 
 int fused_bwd_launch(const FusedBwdArgs &a, const void *e, const void *de_out, void *de, const void *qkv,

@@ -41,7 +41,8 @@ constexpr uint32_t SM_KVX = SM_STAGE + NS * STAGE_BYTES;       // 4 slots x (Kex
 constexpr uint32_t SM_W = SM_KVX + 4 * 4096;                   // b_eg 1024 | b_wr 512
 constexpr uint32_t SM_CONST = SM_W + 1536;                     // uE vE uG vG br (40 floats)
 constexpr uint32_t SM_BAR = SM_CONST + 256;
-constexpr uint32_t SM_TOTAL = SM_BAR + 256;
+constexpr uint32_t SM_MASK = SM_BAR + 256;                       // key-valid bytes, zero padded (N <= 4096)
+constexpr uint32_t SM_TOTAL = SM_MASK + 4096 + 16;
 
 constexpr uint32_t TM_O = 0;
 constexpr uint32_t TM_IN = 64, TM_IN_COLS = 48;                // 3 buffers: S 16 | EG 32
@@ -84,6 +85,8 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     if (tid < 64) ((uint4 *)(smem + SM_W))[tid] = ((const uint4 *)a.prep->b_eg)[tid];            // b_eg
     else if (tid < 96) ((uint4 *)(smem + SM_W + 1024))[tid - 64] = ((const uint4 *)a.prep->b_wr)[tid - 64];
     if (tid < 40) ((float *)(smem + SM_CONST))[tid] = a.prep->uE[tid];                            // uE vE uG vG br
+    for (int i = tid; i < 2 * ((N + 1) / 2); i += 256)                                             // key-valid bytes
+      smem[SM_MASK + i] = i < N ? (a.mask ? (uint8_t)(a.mask[(size_t)blockIdx.y * N + i] != 0) : (uint8_t)1) : (uint8_t)0;
     fence_proxy_async_smem();
   }
   tc_fence_before();
@@ -179,29 +182,31 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
   const bool rowvalid = l < N;
   const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   const float *cst = (const float *)(smem + SM_CONST);
-  const uint8_t *maskb = a.mask ? a.mask + (size_t)b * N : nullptr;
+  const uint8_t *smask = smem + SM_MASK;
+  const uint32_t bar_mma1 = smem_u32(&bars->mma1[0]), bar_mma2 = smem_u32(&bars->mma2[0]);
+  const uint32_t bar_e = smem_u32(&bars->e_full[0]);
   const float lo = a.clip_lo, hi = a.clip_hi;
   float psum[4], gsum[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) { psum[i] = 0.f; gsum[i] = 0.f; }
   const uint32_t trow = (uint32_t)t * 128u, tx7 = (uint32_t)(t & 7);
 
-  auto build = [&](int p2) {    // expanded K / V operands of pair p2 into slot p2 & 3 (one 16-byte chunk per thread)
-    const int T2 = p2 >> 2, j2 = p2 & 3, st = T2 % NS;
-    const int which = tid >> 7, rem = tid & 127, n = rem >> 3, dd = rem & 7;
-    const int hh = 4 * (n >> 3) + (n & 3), ks = 2 * j2 + ((n >> 2) & 1);
-    const uint8_t *rows = smem + SM_STAGE + st * STAGE_BYTES + (which ? ST_V : ST_K);
-    const uint32_t val = *(const uint16_t *)(rows + ks * 128 + (dd * 8 + hh) * 2);
-    const uint32_t wv = val << ((hh & 1) * 16);
+  // expanded K / V operands of pair p2 (stage st2) into slot p2 & 3: one 16-byte chunk per thread
+  const int b_n = (tid & 127) >> 3, b_dd = tid & 7, b_hh = 4 * (b_n >> 3) + (b_n & 3);
+  const uint32_t b_src = (uint32_t)(g ? ST_V : ST_K) + (uint32_t)((b_n >> 2) & 1) * 128u + (uint32_t)(b_dd * 8 + b_hh) * 2u;
+  const uint32_t b_dst = SM_KVX + (uint32_t)g * 2048u + (uint32_t)b_n * 128u + ((uint32_t)((b_dd ^ b_n) & 7) << 4);
+  auto build = [&](int p2, int st2) {
+    const uint32_t val = *(const uint16_t *)(smem + SM_STAGE + st2 * STAGE_BYTES + b_src + (p2 & 3) * 256);
+    const uint32_t wv = val << ((b_hh & 1) * 16);
     uint4 ch;
-    ch.x = (hh >> 1) == 0 ? wv : 0u; ch.y = (hh >> 1) == 1 ? wv : 0u;
-    ch.z = (hh >> 1) == 2 ? wv : 0u; ch.w = (hh >> 1) == 3 ? wv : 0u;
-    *(uint4 *)(smem + SM_KVX + (p2 & 3) * 4096 + which * 2048 + n * 128 + (((dd ^ n) & 7) << 4)) = ch;
+    ch.x = (b_hh >> 1) == 0 ? wv : 0u; ch.y = (b_hh >> 1) == 1 ? wv : 0u;
+    ch.z = (b_hh >> 1) == 2 ? wv : 0u; ch.w = (b_hh >> 1) == 3 ? wv : 0u;
+    *(uint4 *)(smem + b_dst + (p2 & 3) * 4096) = ch;
   };
 
   // ---- phase A: pair p, this thread's 4 heads of both keys ------------------------------------------
-  auto phase_a = [&](int p) {
-    const int T = p >> 2, j = p & 3, st = T % NS, buf = p % 3, ob = p & 1;
+  auto phase_a = [&](int p, int st, int buf) {
+    const int j = p & 3, ob = p & 1;
     const uint8_t *es = smem + SM_STAGE + st * STAGE_BYTES;
     const uint32_t tin = tlane + TM_IN + buf * TM_IN_COLS;
     const uint32_t tout = tlane + TM_OUT + ob * TM_OUT_COLS;
@@ -213,7 +218,7 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     uint32_t rb[2][2];
 #pragma unroll
     for (int kk = 0; kk < 2; ++kk) {
-      const int ks = 2 * j + kk, m = 8 * T + ks;
+      const int ks = 2 * j + kk, m = 2 * p + kk;
       const uint4 ev = *(const uint4 *)(es + ST_E + trow + (((uint32_t)ks ^ tx7) << 4));
       const float x[8] = {bf16_lo(ev.x), bf16_hi(ev.x), bf16_lo(ev.y), bf16_hi(ev.y),
                           bf16_lo(ev.z), bf16_hi(ev.z), bf16_lo(ev.w), bf16_hi(ev.w)};
@@ -224,8 +229,7 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
       for (int c = 0; c < 8; ++c) { const float dlt = x[c] - mu; var = fmaf(dlt, dlt, var); }
       r[kk] = rsqrtf(fmaf(var, 0.125f, 1e-3f));
       nrm[kk] = -r[kk] * mu;
-      kvalid[kk] = m < N;
-      if (maskb && m < N) kvalid[kk] = maskb[m] != 0;
+      kvalid[kk] = smask[m] != 0;
       rb[kk][0] = rb[kk][1] = 0u;
       if (RAND) {
         const uint64_t qd = ((uint64_t)b * N + (uint64_t)l) * N + (uint64_t)m;
@@ -270,8 +274,8 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
   };
 
   // ---- phase B: e' = e + H_hat W_r + b_r for key g of pair p, in place over the e stage ---------------
-  auto phase_b = [&](int p) {
-    const int T = p >> 2, j = p & 3, st = T % NS, buf = p % 3;
+  auto phase_b = [&](int p, int st, int buf) {
+    const int j = p & 3;
     uint8_t *es = smem + SM_STAGE + st * STAGE_BYTES;
     const int ks = 2 * j + g;
     uint32_t dr[8];
@@ -291,33 +295,43 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
   };
 
   // ---- pipeline ------------------------------------------------------------------------------------
-  mbar_wait(smem_u32(&bars->e_full[0]), 0);
-  build(0);
-  if (NP > 1) build(1);
+  // running indices instead of divisions: pair it -> (stage st_a, TMEM buffer buf_a, parity par_a)
+  mbar_wait(bar_e, 0);
+  build(0, 0);
+  if (NP > 1) build(1, 0);
   fence_proxy_async_smem();
   __syncthreads();                                     // sync #0
+  int st_a = 0, buf_a = 0, par_a = 0;                  // pair it
+  int st_p = 0, buf_p = 0, par_p = 0;                  // pair it - 1
+  int st_n = 0, par_n = 0;                             // pair it + 2 (its tile's stage / load parity)
   for (int it = 0; it < NP; ++it) {
-    mbar_wait(smem_u32(&bars->mma1[it % 3]), (it / 3) & 1);
+    if (((it + 2) & 3) == 0 || it == 0) {
+      const int T2 = (it + 2) >> 2;
+      st_n = T2 % NS; par_n = (T2 / NS) & 1;
+    }
+    mbar_wait(bar_mma1 + 8 * buf_a, par_a);
     tc_fence_after();
-    phase_a(it);
+    phase_a(it, st_a, buf_a);
     if (it >= 1) {
-      mbar_wait(smem_u32(&bars->mma2[(it - 1) % 3]), ((it - 1) / 3) & 1);
+      mbar_wait(bar_mma2 + 8 * buf_p, par_p);
       tc_fence_after();
-      phase_b(it - 1);
+      phase_b(it - 1, st_p, buf_p);
     }
     if (it + 2 < NP) {
-      const int T2 = (it + 2) >> 2;
-      if (((it + 2) & 3) == 0) mbar_wait(smem_u32(&bars->e_full[T2 % NS]), (T2 / NS) & 1);   // first pair of a tile
-      build(it + 2);
+      if (((it + 2) & 3) == 0) mbar_wait(bar_e + 8 * st_n, par_n);   // first pair of a tile
+      build(it + 2, st_n);
     }
     tmem_st_wait();
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();                                   // sync #(it+1)
+    st_p = st_a; buf_p = buf_a; par_p = par_a;
+    if (++buf_a == 3) { buf_a = 0; par_a ^= 1; }
+    if (((it + 1) & 3) == 0) { if (++st_a == NS) st_a = 0; }
   }
-  mbar_wait(smem_u32(&bars->mma2[(NP - 1) % 3]), ((NP - 1) / 3) & 1);
+  mbar_wait(bar_mma2 + 8 * buf_p, par_p);
   tc_fence_after();
-  phase_b(NP - 1);
+  phase_b(NP - 1, st_p, buf_p);
   fence_proxy_async_smem();
   __syncthreads();                                     // sync #(NP+1)
 

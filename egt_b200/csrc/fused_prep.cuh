@@ -89,4 +89,49 @@ __device__ __forceinline__ void fused_prep_body(const egt_block_weights_t &w, fl
 }
 
 
+// Folds the per-CTA partial sums of fused_bwd_kernel into the weight gradients (the library ADDS into them).
+//   e^ = gamma (.) x^ + beta ;  [E|G] = e^ W + b ;  e' = e + H^ W_r + b_r
+// One CTA of nthr >= 32 threads; runs as its own kernel or as an extra CTA of node_bwd2_kernel.
+__device__ __forceinline__ void fused_bwd_finalize_body(const float *partials, int nparts, const egt_block_weights_t &w,
+                                                        const egt_block_grads_t &g, const int tid, const int nthr) {
+  __shared__ float s[FPART];
+  for (int col = tid; col < FPART; col += nthr) {
+    float acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+    int i = 0;
+    for (; i + 8 <= nparts; i += 8)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] += partials[(size_t)(i + q) * FPART + col];
+    for (; i < nparts; ++i) acc[0] += partials[(size_t)i * FPART + col];
+    s[col] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+  }
+  __syncthreads();
+  const float *M = s, *sZ = s + 128, *Wr = s + 144, *dbr = s + 208;
+  for (int idx = tid; idx < 224; idx += nthr) {
+    if (idx < 128) {                        // dW_E, dW_G
+      const int c = idx / 16, j = idx % 16, eg = j / 8, hh = j % 8;
+      float *dst = eg ? g.attention_gates_kernel : g.dense_edge_b_kernel;
+      dst[c * FH + hh] += w.norm_edge_gamma[c] * M[c * 16 + j] + w.norm_edge_beta[c] * sZ[j];
+    } else if (idx < 144) {                 // db_E, db_G
+      const int j = idx - 128, eg = j / 8, hh = j % 8;
+      (eg ? g.attention_gates_bias : g.dense_edge_b_bias)[hh] += sZ[j];
+    } else if (idx < 208) {                 // dW_r
+      g.dense_edge_r_kernel[idx - 144] += Wr[idx - 144];
+    } else if (idx < 216) {                 // db_r
+      g.dense_edge_r_bias[idx - 208] += dbr[idx - 208];
+    } else {                                // dgamma_e, dbeta_e
+      const int c = idx - 216;
+      float dg = 0.f, db = 0.f;
+      for (int hh = 0; hh < FH; ++hh) {
+        const float we = w.dense_edge_b_kernel[c * FH + hh], wg = w.attention_gates_kernel[c * FH + hh];
+        dg += we * M[c * 16 + hh] + wg * M[c * 16 + 8 + hh];
+        db += we * sZ[hh] + wg * sZ[8 + hh];
+      }
+      g.norm_edge_gamma[c] += dg;
+      g.norm_edge_beta[c] += db;
+    }
+  }
+}
+
 }  // namespace egt

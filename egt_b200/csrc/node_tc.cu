@@ -345,6 +345,7 @@ struct NodeBwd2Args {
   const float *gamma, *beta; float eps;
   const float *W;                                            // W_qkv [64,192]
   __nv_bfloat16 *dh; float *dW, *db, *dgamma, *dbeta; int R;
+  const float *partials; int nparts; egt_block_weights_t w; egt_block_grads_t g;   // extra CTA: finalize (NULL = off)
 };
 
 __global__ void __launch_bounds__(128) node_bwd2_kernel(const NodeBwd2Args a) {
@@ -356,6 +357,8 @@ __global__ void __launch_bounds__(128) node_bwd2_kernel(const NodeBwd2Args a) {
   float *sgb = sred + 128 * 65;                                       // gamma, beta
   NodeBars *bars = (NodeBars *)(sgb + 2 * ND);
   const int t = threadIdx.x;
+  const int nwork = a.partials ? gridDim.x - 1 : gridDim.x;
+  if ((int)blockIdx.x == nwork) { fused_bwd_finalize_body(a.partials, a.nparts, a.w, a.g, t, 128); return; }
   node_setup(bars, t, 256);
   build_wt_k(sW, a.W, ND, 3 * ND, t, 128);
   fill_ones(sOnes, t, 128);
@@ -370,7 +373,7 @@ __global__ void __launch_bounds__(128) node_bwd2_kernel(const NodeBwd2Args a) {
   uint32_t phase = 0;
   bool first = true;
   float dg_acc = 0.f, db_acc = 0.f;     // thread c < 64: dgamma[c]; thread 64 + c: dbeta[c]
-  for (int tile = blockIdx.x; tile * 128 < a.R; tile += gridDim.x) {
+  for (int tile = blockIdx.x; tile * 128 < a.R; tile += nwork) {
     const int r = tile * 128 + t;
     const bool valid = r < a.R;
     float xh[64], rs;
@@ -556,14 +559,15 @@ int node_bwd1_launch(const void *dh_out, const void *v_att, const float *W, void
 
 int node_bwd2_launch(const void *h, const void *dh_out, const float *dqkv, const float *gamma, const float *beta,
                      float eps, const float *W, void *dh, float *dW, float *db, float *dgamma, float *dbeta, int R,
+                     const float *partials, int nparts, const egt_block_weights_t *w, const egt_block_grads_t *g,
                      cudaStream_t st) {
   NodeBwd2Args a{(const __nv_bfloat16 *)h, (const __nv_bfloat16 *)dh_out, dqkv, gamma, beta, eps, W,
-                 (__nv_bfloat16 *)dh, dW, db, dgamma, dbeta, R};
+                 (__nv_bfloat16 *)dh, dW, db, dgamma, dbeta, R, partials, nparts, *w, *g};
   const int smem = 5 * TILE + 24576 + 128 * 65 * 4 + 2 * ND * 4 + 64 + 1024;
   static bool once = false;
   if (!once) { int rc = set_smem(node_bwd2_kernel, smem); if (rc) return rc; once = true; }
   LaunchScope _ls("node_bwd2_kernel", st);
-  node_bwd2_kernel<<<node_grid(R), 128, smem, st>>>(a);
+  node_bwd2_kernel<<<node_grid(R) + (partials ? 1 : 0), 128, smem, st>>>(a);
   EGT_CHECK_CUDA(cudaGetLastError());
   return EGT_OK;
 }
