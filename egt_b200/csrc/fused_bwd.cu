@@ -328,7 +328,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     const uint8_t *es = smem + SM_STAGE + st * STAGE_BYTES;
     const uint32_t tin = tlane + TM_IN + buf * TM_IN_COLS;
     const uint32_t tout = tlane + TM_OUT + ob * TM_OUT_COLS;
-    uint32_t dsp[4], dzp[8];
+    uint32_t dsp[4], dzp[8], atp[4];
     const float4 uE4 = *(const float4 *)(cst + 4 * g), vE4 = *(const float4 *)(cst + 8 + 4 * g);
     const float4 uG4 = *(const float4 *)(cst + 16 + 4 * g), vG4 = *(const float4 *)(cst + 24 + 4 * g);
     const float uE[4] = {uE4.x, uE4.y, uE4.z, uE4.w}, vE[4] = {vE4.x, vE4.y, vE4.z, vE4.w};
@@ -382,13 +382,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
       dsp[kk * 2 + 0] = pack_bf16(dS[0], dS[1]); dsp[kk * 2 + 1] = pack_bf16(dS[2], dS[3]);
       dzp[kk * 4 + 0] = pack_bf16(dH[0], dH[1]); dzp[kk * 4 + 1] = pack_bf16(dH[2], dH[3]);
       dzp[kk * 4 + 2] = pack_bf16(dGv[0], dGv[1]); dzp[kk * 4 + 3] = pack_bf16(dGv[2], dGv[3]);
-      {   // transposed operands: row = query t (K index), 16-byte chunk = key, bytes 8g.. = heads 4g..4g+3
-        const uint32_t k16 = (uint32_t)m & 15u;
-        if (k16 == 0 && m > 0) mbar_wait(bar_t, ((m >> 4) - 1) & 1);   // previous block consumed
-        const uint32_t off = trbase + (k16 >> 3) * 16384u + (((k16 ^ tx7) & 7u) << 4);
-        *(uint2 *)(smem + SM_TR + off) = make_uint2(dsp[kk * 2], dsp[kk * 2 + 1]);
-        *(uint2 *)(smem + SM_TR + 32768 + off) = make_uint2(pack_bf16(At[0], At[1]), pack_bf16(At[2], At[3]));
-      }
+      atp[kk * 2 + 0] = pack_bf16(At[0], At[1]); atp[kk * 2 + 1] = pack_bf16(At[2], At[3]);
       {   // weight-gradient sums: M += x^ (x) [dE|dG] ; sZ += [dE|dG] ; Wr += H^ (x) de'
         const float2 dE0 = make_float2(dH[0], dH[1]), dE1 = make_float2(dH[2], dH[3]);
         const float2 dG0 = make_float2(dGv[0], dGv[1]), dG1 = make_float2(dGv[2], dGv[3]);
@@ -412,6 +406,17 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     }
     tmem_st4(tout + g * 4, dsp);
     tmem_st8(tout + 8 + g * 8, dzp);
+    // transposed operands last (the previous 16-key block has long left the tensor core by now):
+    // row = query t (K index), 16-byte chunk = key, bytes 8g.. = heads 4g..4g+3
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      const int m = 2 * p + kk;
+      const uint32_t k16 = (uint32_t)m & 15u;
+      if (k16 == 0 && m > 0) mbar_wait(bar_t, ((m >> 4) - 1) & 1);   // previous block consumed
+      const uint32_t off = trbase + (k16 >> 3) * 16384u + (((k16 ^ tx7) & 7u) << 4);
+      *(uint2 *)(smem + SM_TR + off) = make_uint2(dsp[kk * 2], dsp[kk * 2 + 1]);
+      *(uint2 *)(smem + SM_TR + 32768 + off) = make_uint2(atp[kk * 2], atp[kk * 2 + 1]);
+    }
   };
 
   // ---- phase B: LayerNorm backward + residual for key g of pair p -> de, in place over de' -----------

@@ -5,12 +5,13 @@
 //   (lib/models/graph_xformer_model_base.py:192-218).  The [B,N,N,h] tensors E, G, H_hat, A~ never
 //   leave the SM: e is streamed in once by TMA, e' streamed out once by TMA.
 //
-// One CTA = one graph b and 128 query rows.  Thread t of warps 0-3 and of warps 4-7 both own query row
-// l0+t == TMEM lane t; warps 0-3 ("group 0") handle heads 0-3, warps 4-7 heads 4-7, so every SM
-// sub-partition has two resident compute warps.  Warp 8 issues TMA and tcgen05.mma (warps 9-11 complete its
-// warpgroup so that setmaxnreg can move registers to the compute warps).
+// One CTA = one graph b and 128 query rows, 16 compute warps: thread (kq, g, t) owns query row l0+t ==
+// TMEM lane t, heads 4g..4g+3, and the key pairs p with p % 2 == kq -- four resident compute warps per SM
+// sub-partition.  Warp 16 issues TMA and tcgen05.mma (warps 17-19 complete its warpgroup so that setmaxnreg
+// can move registers to the compute warps).
 //
-// Keys are processed in PAIRS.  For pair p the tensor core produces, in TMEM (columns ordered (g,key,hh4)):
+// Keys are processed in PAIRS, two pairs (one per kq) per pipeline step.  For pair p the tensor core
+// produces, in TMEM (columns ordered (g,key,hh4)):
 //     S  [128x16] = Qs [128x64] * Kexp^T      Kexp[(g,key,hh4), c] = K[key,c] * [c % 8 == hh]
 //     EG [128x32] = e  [128x16] * Wblk        raw edge channels of the two keys x folded-LN weights
 // (the per-head dot product is a block-diagonal contraction over the head-innermost channel axis, so it is a
@@ -22,8 +23,8 @@
 // e' = e + De + b_r is formed in place over the e stage and leaves by TMA store.
 // Softmax runs without max subtraction: logits are bounded by clip + |E| (FusedPrep::bound).
 //
-// All warps run in lock step, one __syncthreads per key pair; every tensor-core / TMA operation is issued
-// two pairs ahead of its consumer and observed through an mbarrier (same skeleton as fused_bwd.cu).
+// All warps run in lock step, one __syncthreads per step (4 keys); every tensor-core / TMA operation is
+// issued two steps ahead of its consumer and observed through an mbarrier (same skeleton as fused_bwd.cu).
 #include "common.cuh"
 #include "fused.h"
 #include "umma.cuh"
@@ -37,17 +38,17 @@ constexpr int NS = 4;                                  // input stages of 8 keys
 constexpr uint32_t SM_Q = 0;                           // [128 x 128B] swizzled, Q pre-scaled by dk^-0.5
 constexpr uint32_t SM_STAGE = 16384;
 constexpr uint32_t ST_E = 0, ST_K = 16384, ST_V = 17408, STAGE_BYTES = 18432;
-constexpr uint32_t SM_KVX = SM_STAGE + NS * STAGE_BYTES;       // 4 slots x (Kexp 2048 | Vexp 2048)
-constexpr uint32_t SM_W = SM_KVX + 4 * 4096;                   // b_eg 1024 | b_wr 512
+constexpr uint32_t SM_KVX = SM_STAGE + NS * STAGE_BYTES;       // 8 slots (pair p & 7) x (Kexp 2048 | Vexp 2048)
+constexpr uint32_t SM_W = SM_KVX + 8 * 4096;                   // b_eg 1024 | b_wr 512
 constexpr uint32_t SM_CONST = SM_W + 1536;                     // uE vE uG vG br (40 floats)
 constexpr uint32_t SM_BAR = SM_CONST + 256;
 constexpr uint32_t SM_MASK = SM_BAR + 256;                       // key-valid bytes, zero padded (N <= 4096)
 constexpr uint32_t SM_TOTAL = SM_MASK + 4096 + 16;
 
 constexpr uint32_t TM_O = 0;
-constexpr uint32_t TM_IN = 64, TM_IN_COLS = 48;                // 3 buffers: S 16 | EG 32
+constexpr uint32_t TM_IN = 64, TM_IN_COLS = 96, TM_PAIR = 48;  // 3 buffers x 2 pairs: S 16 | EG 32
 constexpr uint32_t IN_S = 0, IN_EG = 16;
-constexpr uint32_t TM_OUT = 208, TM_OUT_COLS = 16;             // 2 buffers: A~ 8 | H_hat 8 (bf16 A operands)
+constexpr uint32_t TM_OUT = 352, TM_OUT_COLS = 32, TM_OPAIR = 16;   // 2 buffers x 2 pairs: A~ 8 | H_hat 8 (bf16 A operands)
 
 constexpr uint32_t ID_N16 = idesc_bf16(128, 16, 0, 0);
 constexpr uint32_t ID_N32 = idesc_bf16(128, 32, 0, 0);
@@ -58,7 +59,7 @@ struct Bars { uint64_t q_full, e_full[NS], mma1[3], mma2[3]; uint32_t tmem_base;
 }  // namespace
 
 template <bool RAND>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(640, 1)
 fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant__ CUtensorMap tm_eo,
                  const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                  const FusedFwdArgs a) {
@@ -69,9 +70,9 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y, l0 = blockIdx.x * 128;
   const int N = a.N;
-  const int NT = (N + 7) / 8, NP = (N + 1) / 2;       // 8-key tiles, key pairs
+  const int NT = (N + 7) / 8, NQ = (N + 3) / 4;       // 8-key tiles, pipeline steps of 4 keys (two pairs)
 
-  if (warp == 8) {
+  if (warp == 16) {
     if (lane == 0) {
       mbar_init(smem_u32(&bars->q_full), 1);
       for (int i = 0; i < NS; ++i) mbar_init(smem_u32(&bars->e_full[i]), 1);
@@ -80,12 +81,12 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
       tma_prefetch_desc(&tm_e); tma_prefetch_desc(&tm_eo); tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_kv);
     }
     __syncwarp();
-    tmem_alloc(smem_u32(&bars->tmem_base), 256);
-  } else if (warp < 8) {
+    tmem_alloc(smem_u32(&bars->tmem_base), 512);
+  } else if (warp < 16) {
     if (tid < 64) ((uint4 *)(smem + SM_W))[tid] = ((const uint4 *)a.prep->b_eg)[tid];            // b_eg
     else if (tid < 96) ((uint4 *)(smem + SM_W + 1024))[tid - 64] = ((const uint4 *)a.prep->b_wr)[tid - 64];
     if (tid < 40) ((float *)(smem + SM_CONST))[tid] = a.prep->uE[tid];                            // uE vE uG vG br
-    for (int i = tid; i < 2 * ((N + 1) / 2); i += 256)                                             // key-valid bytes
+    for (int i = tid; i < 4 * NQ; i += 512)                                                        // key-valid bytes
       smem[SM_MASK + i] = i < N ? (a.mask ? (uint8_t)(a.mask[(size_t)blockIdx.y * N + i] != 0) : (uint8_t)1) : (uint8_t)0;
     fence_proxy_async_smem();
   }
@@ -94,10 +95,10 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
-  if (warp >= 8) {
-    // ====================== issuer warpgroup (warp 8 issues; warps 9-11 only keep the barriers) ======
-    reg_dealloc<40>();
-    const bool leader = warp == 8 && lane == 0;
+  if (warp >= 16) {
+    // ====================== issuer warpgroup (warp 16 issues; warps 17-19 only keep the barriers) ======
+    reg_dealloc<32>();   // 512 x 112 + 128 x 32 == 640 x 96: setmaxnreg only moves registers inside the CTA's launch allocation
+    const bool leader = warp == 16 && lane == 0;
     auto load_tile = [&](int T) {
       const int st = T % NS;
       const uint32_t bar = smem_u32(&bars->e_full[st]);
@@ -107,28 +108,37 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
       tma_load_3d(dst + ST_K, &tm_kv, bar, FD, T * 8, b);
       tma_load_3d(dst + ST_V, &tm_kv, bar, 2 * FD, T * 8, b);
     };
-    auto issue_mma1 = [&](int p) {
-      const int T = p >> 2, j = p & 3, st = T % NS, buf = p % 3, slot = p & 3;
-      mbar_wait(smem_u32(&bars->e_full[st]), (T / NS) & 1);
-      tc_fence_after();
+    auto issue_mma1_pair = [&](int p, int buf) {
+      const int T = p >> 2, j = p & 3, st = T % NS, slot = p & 7;
       const uint32_t es = sbase + SM_STAGE + st * STAGE_BYTES;
       const uint32_t kx = sbase + SM_KVX + slot * 4096;
-      const uint32_t d = tmem + TM_IN + buf * TM_IN_COLS;
+      const uint32_t d = tmem + TM_IN + buf * TM_IN_COLS + (p & 1) * TM_PAIR;
 #pragma unroll
       for (int s = 0; s < 4; ++s)
         mma_ss(d + IN_S, smem_desc(sbase + SM_Q + 32 * s, 16, 1024, LAYOUT_SW128),
                smem_desc(kx + 32 * s, 16, 1024, LAYOUT_SW128), ID_N16, s > 0);
       mma_ss(d + IN_EG, smem_desc(es + ST_E + 32 * j, 16, 1024, LAYOUT_SW128),
              smem_desc(sbase + SM_W, 512, 128, LAYOUT_NONE), ID_N32, 0);
+    };
+    auto issue_mma1 = [&](int q) {                     // both pairs of step q
+      const int T = q >> 1, buf = q % 3;
+      mbar_wait(smem_u32(&bars->e_full[T % NS]), (T / NS) & 1);
+      tc_fence_after();
+      issue_mma1_pair(2 * q, buf);
+      issue_mma1_pair(2 * q + 1, buf);
       mma_commit(smem_u32(&bars->mma1[buf]));
     };
-    auto issue_mma2 = [&](int p) {
-      const int buf = p % 3, ob = p & 1, slot = p & 3;
-      const uint32_t vx = sbase + SM_KVX + slot * 4096 + 2048;
-      const uint32_t ao = tmem + TM_OUT + ob * TM_OUT_COLS;
-      mma_ts(tmem + TM_O, ao, smem_desc(vx, 2048, 1024, LAYOUT_SW128), ID_PV, p > 0);
-      mma_ts(tmem + TM_IN + buf * TM_IN_COLS + IN_EG, ao + 8, smem_desc(sbase + SM_W + 1024, 256, 128, LAYOUT_NONE),
-             ID_N16, 0);
+    auto issue_mma2 = [&](int q) {
+      const int buf = q % 3, ob = q & 1;
+#pragma unroll
+      for (int kq = 0; kq < 2; ++kq) {
+        const int p = 2 * q + kq;
+        const uint32_t vx = sbase + SM_KVX + (p & 7) * 4096 + 2048;
+        const uint32_t ao = tmem + TM_OUT + ob * TM_OUT_COLS + kq * TM_OPAIR;
+        mma_ts(tmem + TM_O, ao, smem_desc(vx, 2048, 1024, LAYOUT_SW128), ID_PV, p > 0);
+        mma_ts(tmem + TM_IN + buf * TM_IN_COLS + kq * TM_PAIR + IN_EG, ao + 8,
+               smem_desc(sbase + SM_W + 1024, 256, 128, LAYOUT_NONE), ID_N16, 0);
+      }
       mma_commit(smem_u32(&bars->mma2[buf]));
     };
     if (leader) {
@@ -136,33 +146,33 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
       tma_load_3d(sbase + SM_Q, &tm_q, smem_u32(&bars->q_full), 0, l0, b);
       for (int T = 0; T < NT && T < NS; ++T) load_tile(T);
     }
-    __syncthreads();                                   // sync #0: Kexp/Vexp of pairs 0,1 are built
+    __syncthreads();                                   // sync #0: Kexp/Vexp of steps 0,1 are built
     if (leader) {
       tc_fence_after();
       mbar_wait(smem_u32(&bars->q_full), 0);
       issue_mma1(0);
-      if (NP > 1) issue_mma1(1);
+      if (NQ > 1) issue_mma1(1);
     }
-    for (int it = 0; it < NP; ++it) {
+    for (int it = 0; it < NQ; ++it) {
       __syncthreads();                                 // sync #(it+1)
       if (leader) {
         tc_fence_after();
         issue_mma2(it);
-        if (it + 2 < NP) issue_mma1(it + 2);
-        if (it >= 2 && ((it - 2) & 3) == 3) {          // tile stored at the previous sync: recycle its stage
-          const int T = (it - 2) >> 2;
+        if (it + 2 < NQ) issue_mma1(it + 2);
+        if (it >= 3 && (it & 1) == 1) {                // tile stored at the previous sync: recycle its stage
+          const int T = (it - 3) >> 1;
           tma_store_wait_read<0>();
           if (T + NS < NT) load_tile(T + NS);
         }
-        if (it >= 1 && ((it - 1) & 3) == 3) {          // phase B of tile T's last pair ran: e' is complete in place
-          const int T = (it - 1) >> 2;
+        if (it >= 2 && (it & 1) == 0) {                // phase B of tile T's second step ran: e' is complete in place
+          const int T = (it - 2) >> 1;
           tma_store_3d(&tm_eo, sbase + SM_STAGE + (T % NS) * STAGE_BYTES + ST_E, T * 64, l0, b);
           tma_store_commit();
         }
       }
       __syncwarp();
     }
-    __syncthreads();                                   // sync #(NP+1): phase B of the last pair is done
+    __syncthreads();                                   // sync #(NQ+1): phase B of the last step is done
     if (leader) {
       const int T = NT - 1;
       tma_store_3d(&tm_eo, sbase + SM_STAGE + (T % NS) * STAGE_BYTES + ST_E, T * 64, l0, b);
@@ -170,14 +180,15 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
       tma_store_wait_all<0>();
     }
     __syncwarp();
+    __syncthreads();                                   // partial row sums exchanged
     __syncthreads();                                   // final
-    if (warp == 8) tmem_dealloc(tmem, 256);
+    if (warp == 16) tmem_dealloc(tmem, 512);
     return;
   }
 
-  // ================================= compute threads (warps 0-7) =================================
-  reg_alloc<232>();
-  const int g = tid >> 7, t = tid & 127;
+  // ================================= compute threads (warps 0-15) ================================
+  reg_alloc<112>();
+  const int kq = tid >> 8, g = (tid >> 7) & 1, t = tid & 127;
   const int l = l0 + t;
   const bool rowvalid = l < N;
   const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
@@ -192,6 +203,7 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
   const uint32_t trow = (uint32_t)t * 128u, tx7 = (uint32_t)(t & 7);
 
   // expanded K / V operands of pair p2 (stage st2) into slot p2 & 3: one 16-byte chunk per thread
+  // (thread (kq, g, .) builds the K (g = 0) / V (g = 1) chunk of pair 2q + kq)
   const int b_n = (tid & 127) >> 3, b_dd = tid & 7, b_hh = 4 * (b_n >> 3) + (b_n & 3);
   const uint32_t b_src = (uint32_t)(g ? ST_V : ST_K) + (uint32_t)((b_n >> 2) & 1) * 128u + (uint32_t)(b_dd * 8 + b_hh) * 2u;
   const uint32_t b_dst = SM_KVX + (uint32_t)g * 2048u + (uint32_t)b_n * 128u + ((uint32_t)((b_dd ^ b_n) & 7) << 4);
@@ -201,15 +213,15 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     uint4 ch;
     ch.x = (b_hh >> 1) == 0 ? wv : 0u; ch.y = (b_hh >> 1) == 1 ? wv : 0u;
     ch.z = (b_hh >> 1) == 2 ? wv : 0u; ch.w = (b_hh >> 1) == 3 ? wv : 0u;
-    *(uint4 *)(smem + b_dst + (p2 & 3) * 4096) = ch;
+    *(uint4 *)(smem + b_dst + (p2 & 7) * 4096) = ch;
   };
 
   // ---- phase A: pair p, this thread's 4 heads of both keys ------------------------------------------
   auto phase_a = [&](int p, int st, int buf) {
-    const int j = p & 3, ob = p & 1;
+    const int j = p & 3, ob = (p >> 1) & 1;
     const uint8_t *es = smem + SM_STAGE + st * STAGE_BYTES;
-    const uint32_t tin = tlane + TM_IN + buf * TM_IN_COLS;
-    const uint32_t tout = tlane + TM_OUT + ob * TM_OUT_COLS;
+    const uint32_t tin = tlane + TM_IN + buf * TM_IN_COLS + kq * TM_PAIR;
+    const uint32_t tout = tlane + TM_OUT + ob * TM_OUT_COLS + kq * TM_OPAIR;
     uint32_t sreg[8], egreg[16];
     tmem_ld8(tin + IN_S + g * 8, sreg);
     tmem_ld16(tin + IN_EG + g * 16, egreg);
@@ -279,7 +291,7 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     uint8_t *es = smem + SM_STAGE + st * STAGE_BYTES;
     const int ks = 2 * j + g;
     uint32_t dr[8];
-    tmem_ld8(tlane + TM_IN + buf * TM_IN_COLS + IN_EG + g * 8, dr);
+    tmem_ld8(tlane + TM_IN + buf * TM_IN_COLS + kq * TM_PAIR + IN_EG + g * 8, dr);
     uint4 *pe = (uint4 *)(es + ST_E + trow + (((uint32_t)ks ^ tx7) << 4));
     const uint4 ev = *pe;
     const float x[8] = {bf16_lo(ev.x), bf16_hi(ev.x), bf16_lo(ev.y), bf16_hi(ev.y),
@@ -295,31 +307,28 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
   };
 
   // ---- pipeline ------------------------------------------------------------------------------------
-  // running indices instead of divisions: pair it -> (stage st_a, TMEM buffer buf_a, parity par_a)
+  // step it covers pairs 2*it (kq = 0) and 2*it + 1 (kq = 1), both in tile it >> 1; running indices
+  // instead of divisions: step it -> (stage st_a, TMEM buffer buf_a, parity par_a)
   mbar_wait(bar_e, 0);
-  build(0, 0);
-  if (NP > 1) build(1, 0);
+  build(kq, 0);
+  if (NQ > 1) build(2 + kq, 0);
   fence_proxy_async_smem();
   __syncthreads();                                     // sync #0
-  int st_a = 0, buf_a = 0, par_a = 0;                  // pair it
-  int st_p = 0, buf_p = 0, par_p = 0;                  // pair it - 1
-  int st_n = 0, par_n = 0;                             // pair it + 2 (its tile's stage / load parity)
-  for (int it = 0; it < NP; ++it) {
-    if (((it + 2) & 3) == 0 || it == 0) {
-      const int T2 = (it + 2) >> 2;
-      st_n = T2 % NS; par_n = (T2 / NS) & 1;
-    }
+  int st_a = 0, buf_a = 0, par_a = 0;                  // step it
+  int st_p = 0, buf_p = 0, par_p = 0;                  // step it - 1
+  int st_n = 1 % NS, par_n = 0;                        // step it + 2 (its tile's stage / load parity)
+  for (int it = 0; it < NQ; ++it) {
     mbar_wait(bar_mma1 + 8 * buf_a, par_a);
     tc_fence_after();
-    phase_a(it, st_a, buf_a);
+    phase_a(2 * it + kq, st_a, buf_a);
     if (it >= 1) {
       mbar_wait(bar_mma2 + 8 * buf_p, par_p);
       tc_fence_after();
-      phase_b(it - 1, st_p, buf_p);
+      phase_b(2 * (it - 1) + kq, st_p, buf_p);
     }
-    if (it + 2 < NP) {
-      if (((it + 2) & 3) == 0) mbar_wait(bar_e + 8 * st_n, par_n);   // first pair of a tile
-      build(it + 2, st_n);
+    if (it + 2 < NQ) {
+      if ((it & 1) == 0) mbar_wait(bar_e + 8 * st_n, par_n);        // first step of tile (it+2)>>1
+      build(2 * (it + 2) + kq, st_n);
     }
     tmem_st_wait();
     fence_proxy_async_smem();
@@ -327,16 +336,30 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     __syncthreads();                                   // sync #(it+1)
     st_p = st_a; buf_p = buf_a; par_p = par_a;
     if (++buf_a == 3) { buf_a = 0; par_a ^= 1; }
-    if (((it + 1) & 3) == 0) { if (++st_a == NS) st_a = 0; }
+    if (it & 1) {                                      // steps it+1 and it+3 open new tiles
+      if (++st_a == NS) st_a = 0;
+      if (++st_n == NS) { st_n = 0; par_n ^= 1; }
+    }
   }
   mbar_wait(bar_mma2 + 8 * buf_p, par_p);
   tc_fence_after();
-  phase_b(NP - 1, st_p, buf_p);
+  phase_b(2 * (NQ - 1) + kq, st_p, buf_p);
   fence_proxy_async_smem();
-  __syncthreads();                                     // sync #(NP+1)
+  __syncthreads();                                     // sync #(NQ+1)
 
   // ---- row epilogue: normalise, centrality scaler, V_att, saved statistics ----------------------
   {
+    // all tcgen05.mma have completed (the last mma2 commit was waited for): the Kexp/Vexp slots are free
+    float *xch = (float *)(smem + SM_KVX) + ((kq * 2 + g) * 128 + t) * 8;
+    *(float4 *)xch = make_float4(psum[0], psum[1], psum[2], psum[3]);
+    *(float4 *)(xch + 4) = make_float4(gsum[0], gsum[1], gsum[2], gsum[3]);
+    __syncthreads();                                   // partial row sums exchanged
+    {
+      const float *oth = (const float *)(smem + SM_KVX) + (((kq ^ 1) * 2 + g) * 128 + t) * 8;
+      const float4 p4 = *(const float4 *)oth, g4 = *(const float4 *)(oth + 4);
+      psum[0] += p4.x; psum[1] += p4.y; psum[2] += p4.z; psum[3] += p4.w;
+      gsum[0] += g4.x; gsum[1] += g4.y; gsum[2] += g4.z; gsum[3] += g4.w;
+    }
     float f[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -346,14 +369,13 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
         s = a.scaler_type == EGT_SCALER_LOG ? log1pf(gsum[i]) : gsum[i];
       f[i] = inv * s;
     }
-    uint32_t o[64];
-    tmem_ld32(tlane + TM_O, o);
-    tmem_ld32(tlane + TM_O + 32, o + 32);
+    uint32_t o[32];
+    tmem_ld32(tlane + TM_O + 32 * kq, o);              // this thread stores channel groups dd = 4kq .. 4kq+3
     tmem_ld_wait();
     if (rowvalid) {
-      uint2 *dst = (uint2 *)(a.v_att + ((size_t)b * N + l) * FD + 4 * g);
+      uint2 *dst = (uint2 *)(a.v_att + ((size_t)b * N + l) * FD + 32 * kq + 4 * g);
 #pragma unroll
-      for (int dd = 0; dd < 8; ++dd) {
+      for (int dd = 0; dd < 4; ++dd) {
         float v[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -362,12 +384,14 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
         }
         dst[dd * 2] = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));   // channels dd*8 + 4g .. +3
       }
-      const size_t ps = ((size_t)b * N + l) * FH + 4 * g, rs = (size_t)a.B * N * FH;
+      if (kq == 0) {
+        const size_t ps = ((size_t)b * N + l) * FH + 4 * g, rs = (size_t)a.B * N * FH;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        a.lse[ps + i] = 0.f;                                               // reference point of the exponent
-        a.lse[rs + ps + i] = psum[i] > 0.f ? __logf(psum[i]) : 0.f;
-        a.deg[ps + i] = gsum[i];
+        for (int i = 0; i < 4; ++i) {
+          a.lse[ps + i] = 0.f;                                             // reference point of the exponent
+          a.lse[rs + ps + i] = psum[i] > 0.f ? __logf(psum[i]) : 0.f;
+          a.deg[ps + i] = gsum[i];
+        }
       }
     }
   }
@@ -392,8 +416,8 @@ int fused_fwd_launch(const FusedFwdArgs &a, const void *e, void *e_out, const vo
   }
   dim3 grid((a.N + 127) / 128, a.B);
   LaunchScope _ls("fused_fwd_kernel", st);
-  if (a.rand_mask) fused_fwd_kernel<true><<<grid, 384, smem, st>>>(tm_e, tm_eo, tm_q, tm_kv, a);
-  else fused_fwd_kernel<false><<<grid, 384, smem, st>>>(tm_e, tm_eo, tm_q, tm_kv, a);
+  if (a.rand_mask) fused_fwd_kernel<true><<<grid, 640, smem, st>>>(tm_e, tm_eo, tm_q, tm_kv, a);
+  else fused_fwd_kernel<false><<<grid, 640, smem, st>>>(tm_e, tm_eo, tm_q, tm_kv, a);
   EGT_CHECK_CUDA(cudaGetLastError());
   return EGT_OK;
 }
