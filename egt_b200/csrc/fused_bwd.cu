@@ -25,8 +25,9 @@
 // whose block diagonal (c % 8 == hh) is dK / dV.  Weight-gradient sums are kept in registers
 // (packed fp32x2 FMAs) and folded by fused_bwd_finalize_kernel.
 //
-// All warps run in lock step, one __syncthreads per key pair; every tensor-core / TMA operation is issued
-// two pairs ahead of its consumer and observed through an mbarrier.
+// There is no CTA-wide barrier in the main loop: compute threads arrive on an mbarrier when their part of a
+// key pair is done, the issuer waits for it, and every tensor-core / TMA operation is issued two pairs ahead
+// of its consumer and observed through an mbarrier, so warps drift apart and fill each other's stalls.
 #include "common.cuh"
 #include "fused.h"
 #include "umma.cuh"
@@ -61,7 +62,7 @@ constexpr uint32_t ID_N32 = idesc_bf16(128, 32, 0, 0);
 constexpr uint32_t ID_DQ = idesc_bf16(128, 64, 0, 1);
 constexpr uint32_t ID_T = idesc_bf16(128, 64, 1, 1);
 
-struct Bars { uint64_t q_full, e_full[NS], mma1[3], mma2[3], tbar; uint32_t tmem_base; };
+struct Bars { uint64_t q_full, e_full[NS], mma1[3], mma2[3], tbar, step; uint32_t tmem_base; };
 
 __device__ __forceinline__ float sel8(const uint32_t *o, int hh) {
   const uint32_t a0 = (hh & 1) ? o[1] : o[0], a1 = (hh & 1) ? o[3] : o[2];
@@ -92,6 +93,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
       for (int i = 0; i < NS; ++i) mbar_init(smem_u32(&bars->e_full[i]), 1);
       for (int i = 0; i < 3; ++i) { mbar_init(smem_u32(&bars->mma1[i]), 1); mbar_init(smem_u32(&bars->mma2[i]), 1); }
       mbar_init(smem_u32(&bars->tbar), 1);
+      mbar_init(smem_u32(&bars->step), 256);          // every compute thread arrives once per key pair
       mbar_fence_init();
       tma_prefetch_desc(&tm_e); tma_prefetch_desc(&tm_dei); tma_prefetch_desc(&tm_de);
       tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_kv);
@@ -178,10 +180,10 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
       issue_mma1(0);
       if (NP > 1) issue_mma1(1);
     }
-    for (int it = 0; it < NP; ++it) {
-      __syncthreads();                                 // sync #(it+1)
+    for (int it = 0; it < NP && warp == 8; ++it) {     // warps 9-11 go straight to the tail barrier
       if (leader) {
-        tc_fence_after();
+        mbar_wait(smem_u32(&bars->step), it & 1);      // all compute threads finished pair it (no CTA-wide barrier:
+        tc_fence_after();                              //  fast warps run ahead into pair it+1 meanwhile)
         issue_mma2(it);
         if (it + 2 < NP) issue_mma1(it + 2);
         if (it >= 2 && ((it - 2) & 3) == 3) {          // tile stored at the previous sync: recycle its stage
@@ -224,7 +226,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
   const uint32_t trow = (uint32_t)t * 128u, tx7 = (uint32_t)(t & 7);
   const uint32_t trbase = (uint32_t)(t >> 3) * 1024u + tx7 * 128u + (uint32_t)g * 8u;
   const uint32_t bar_mma1 = smem_u32(&bars->mma1[0]), bar_mma2 = smem_u32(&bars->mma2[0]);
-  const uint32_t bar_e = smem_u32(&bars->e_full[0]), bar_t = smem_u32(&bars->tbar);
+  const uint32_t bar_e = smem_u32(&bars->e_full[0]), bar_t = smem_u32(&bars->tbar), bar_step = smem_u32(&bars->step);
 
   // ---- per-row quantities: D = sum_dd dV_att * V_att, scaler s, ddeg, log2 row sum; dO tile ---------
   float Dr[4], ddeg[4], l2[4];
@@ -520,7 +522,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     tmem_st_wait();
     fence_proxy_async_smem();
     tc_fence_before();
-    __syncthreads();                                   // sync #(it+1)
+    mbar_arrive(bar_step);                             // pair it done by this thread
     st_p = st_a; buf_p = buf_a; par_p = par_a;
     if (++buf_a == 3) { buf_a = 0; par_a ^= 1; }
     if (((it + 1) & 3) == 0) { if (++st_a == NS) st_a = 0; }

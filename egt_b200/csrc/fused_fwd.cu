@@ -23,8 +23,9 @@
 // e' = e + De + b_r is formed in place over the e stage and leaves by TMA store.
 // Softmax runs without max subtraction: logits are bounded by clip + |E| (FusedPrep::bound).
 //
-// All warps run in lock step, one __syncthreads per step (4 keys); every tensor-core / TMA operation is
-// issued two steps ahead of its consumer and observed through an mbarrier (same skeleton as fused_bwd.cu).
+// There is no CTA-wide barrier in the main loop: compute threads arrive on an mbarrier when their part of a
+// step (4 keys) is done, the issuer waits for it, and every tensor-core / TMA operation is issued two steps
+// ahead of its consumer and observed through an mbarrier, so warps drift apart and fill each other's stalls.
 #include "common.cuh"
 #include "fused.h"
 #include "umma.cuh"
@@ -54,7 +55,7 @@ constexpr uint32_t ID_N16 = idesc_bf16(128, 16, 0, 0);
 constexpr uint32_t ID_N32 = idesc_bf16(128, 32, 0, 0);
 constexpr uint32_t ID_PV = idesc_bf16(128, 64, 0, 1);
 
-struct Bars { uint64_t q_full, e_full[NS], mma1[3], mma2[3]; uint32_t tmem_base; };
+struct Bars { uint64_t q_full, e_full[NS], mma1[3], mma2[3], step; uint32_t tmem_base; };
 
 }  // namespace
 
@@ -77,6 +78,7 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
       mbar_init(smem_u32(&bars->q_full), 1);
       for (int i = 0; i < NS; ++i) mbar_init(smem_u32(&bars->e_full[i]), 1);
       for (int i = 0; i < 3; ++i) { mbar_init(smem_u32(&bars->mma1[i]), 1); mbar_init(smem_u32(&bars->mma2[i]), 1); }
+      mbar_init(smem_u32(&bars->step), 512);          // every compute thread arrives once per step
       mbar_fence_init();
       tma_prefetch_desc(&tm_e); tma_prefetch_desc(&tm_eo); tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_kv);
     }
@@ -153,10 +155,10 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
       issue_mma1(0);
       if (NQ > 1) issue_mma1(1);
     }
-    for (int it = 0; it < NQ; ++it) {
-      __syncthreads();                                 // sync #(it+1)
+    for (int it = 0; it < NQ && warp == 16; ++it) {    // warps 17-19 go straight to the tail barrier
       if (leader) {
-        tc_fence_after();
+        mbar_wait(smem_u32(&bars->step), it & 1);      // all compute threads finished step it (no CTA-wide barrier:
+        tc_fence_after();                              //  fast warps run ahead into step it+1 meanwhile)
         issue_mma2(it);
         if (it + 2 < NQ) issue_mma1(it + 2);
         if (it >= 3 && (it & 1) == 1) {                // tile stored at the previous sync: recycle its stage
@@ -195,7 +197,7 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
   const float *cst = (const float *)(smem + SM_CONST);
   const uint8_t *smask = smem + SM_MASK;
   const uint32_t bar_mma1 = smem_u32(&bars->mma1[0]), bar_mma2 = smem_u32(&bars->mma2[0]);
-  const uint32_t bar_e = smem_u32(&bars->e_full[0]);
+  const uint32_t bar_e = smem_u32(&bars->e_full[0]), bar_step = smem_u32(&bars->step);
   const float lo = a.clip_lo, hi = a.clip_hi;
   float psum[4], gsum[4];
 #pragma unroll
@@ -333,7 +335,7 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     tmem_st_wait();
     fence_proxy_async_smem();
     tc_fence_before();
-    __syncthreads();                                   // sync #(it+1)
+    mbar_arrive(bar_step);                             // step it done by this thread
     st_p = st_a; buf_p = buf_a; par_p = par_a;
     if (++buf_a == 3) { buf_a = 0; par_a ^= 1; }
     if (it & 1) {                                      // steps it+1 and it+3 open new tiles
