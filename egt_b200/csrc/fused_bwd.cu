@@ -126,45 +126,48 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
       tma_load_3d(dst + ST_K, &tm_kv, bar, FD, T * 8, b);
       tma_load_3d(dst + ST_V, &tm_kv, bar, 2 * FD, T * 8, b);
     };
-    auto issue_mma1 = [&](int p) {
-      const int T = p >> 2, j = p & 3, st = T % NS, buf = p % 3, slot = p & 3;
-      mbar_wait(smem_u32(&bars->e_full[st]), (T / NS) & 1);
+    // descriptor low words (address | LBO); the high words are compile-time constants
+    constexpr uint32_t HI_SW = desc_hi(1024, LAYOUT_SW128), HI_NONE = desc_hi(128, LAYOUT_NONE);
+    const uint32_t loQ = desc_lo(sbase + SM_Q, 16), loDO = desc_lo(sbase + SM_DO, 16);
+    const uint32_t loK = desc_lo(sbase + SM_KVX, 16), loV = desc_lo(sbase + SM_KVX + 2048, 16);
+    const uint32_t loKmn = desc_lo(sbase + SM_KVX, 2048);
+    const uint32_t loE = desc_lo(sbase + SM_STAGE + ST_E, 16), loDE = desc_lo(sbase + SM_STAGE + ST_DE, 16);
+    const uint32_t loWeg = desc_lo(sbase + SM_W, 512), loWhx = desc_lo(sbase + SM_W + 1024, 256);
+    const uint32_t loWde = desc_lo(sbase + SM_W + 1536, 256);
+    const uint32_t bar_e0 = smem_u32(&bars->e_full[0]), bar_m1 = smem_u32(&bars->mma1[0]), bar_m2 = smem_u32(&bars->mma2[0]);
+    auto issue_mma1 = [&](int p, int buf) {
+      const int T = p >> 2, j = p & 3, st = T % NS, slot = p & 3;
+      mbar_wait(bar_e0 + 8 * st, (T / NS) & 1);
       tc_fence_after();
-      const uint32_t es = sbase + SM_STAGE + st * STAGE_BYTES;
-      const uint32_t kx = sbase + SM_KVX + slot * 4096, vx = kx + 2048;
       const uint32_t d = tmem + TM_IN + buf * TM_IN_COLS;
+      const uint32_t k0 = loK + slot * 256, v0 = loV + slot * 256, e0 = st * (STAGE_BYTES / 16) + 2 * j;
 #pragma unroll
       for (int s = 0; s < 4; ++s)
-        mma_ss(d + IN_S, smem_desc(sbase + SM_Q + 32 * s, 16, 1024, LAYOUT_SW128),
-               smem_desc(kx + 32 * s, 16, 1024, LAYOUT_SW128), ID_N16, s > 0);
+        mma_ss(d + IN_S, mkdesc(loQ + 2 * s, HI_SW), mkdesc(k0 + 2 * s, HI_SW), ID_N16, s > 0);
 #pragma unroll
       for (int s = 0; s < 4; ++s)
-        mma_ss(d + IN_DA, smem_desc(sbase + SM_DO + 32 * s, 16, 1024, LAYOUT_SW128),
-               smem_desc(vx + 32 * s, 16, 1024, LAYOUT_SW128), ID_N16, s > 0);
-      mma_ss(d + IN_EG, smem_desc(es + ST_E + 32 * j, 16, 1024, LAYOUT_SW128),
-             smem_desc(sbase + SM_W, 512, 128, LAYOUT_NONE), ID_N32, 0);
-      mma_ss(d + IN_HX, smem_desc(es + ST_DE + 32 * j, 16, 1024, LAYOUT_SW128),
-             smem_desc(sbase + SM_W + 1024, 256, 128, LAYOUT_NONE), ID_N16, 0);
-      mma_commit(smem_u32(&bars->mma1[buf]));
+        mma_ss(d + IN_DA, mkdesc(loDO + 2 * s, HI_SW), mkdesc(v0 + 2 * s, HI_SW), ID_N16, s > 0);
+      mma_ss(d + IN_EG, mkdesc(loE + e0, HI_SW), mkdesc(loWeg, HI_NONE), ID_N32, 0);
+      mma_ss(d + IN_HX, mkdesc(loDE + e0, HI_SW), mkdesc(loWhx, HI_NONE), ID_N16, 0);
+      mma_commit(bar_m1 + 8 * buf);
     };
-    auto issue_mma2 = [&](int p) {
-      const int buf = p % 3, ob = p & 1, slot = p & 3;
-      const uint32_t kx = sbase + SM_KVX + slot * 4096;
+    auto issue_mma2 = [&](int p, int buf) {
+      const int ob = p & 1, slot = p & 3;
       const uint32_t ao = tmem + TM_OUT + ob * TM_OUT_COLS;
-      mma_ts(tmem + TM_DQ, ao, smem_desc(kx, 2048, 1024, LAYOUT_SW128), ID_DQ, p > 0);
+      mma_ts(tmem + TM_DQ, ao, mkdesc(loKmn + slot * 256, HI_SW), ID_DQ, p > 0);
       const uint32_t dd = tmem + TM_IN + buf * TM_IN_COLS + IN_EG;
-      mma_ts(dd, ao + 8, smem_desc(sbase + SM_W + 1536, 256, 128, LAYOUT_NONE), ID_N16, 0);
-      mma_ts(dd, ao + 16, smem_desc(sbase + SM_W + 2048, 256, 128, LAYOUT_NONE), ID_N16, 1);
-      mma_commit(smem_u32(&bars->mma2[buf]));
+      mma_ts(dd, ao + 8, mkdesc(loWde, HI_NONE), ID_N16, 0);
+      mma_ts(dd, ao + 16, mkdesc(loWde + 32, HI_NONE), ID_N16, 1);
+      mma_commit(bar_m2 + 8 * buf);
       if ((p & 7) == 7 || p == NP - 1) {                // a 16-key block of dS^T / A~^T is complete
+        const uint32_t loT = desc_lo(sbase + SM_TR, 16384), loQm = desc_lo(sbase + SM_Q, 16384);
+        const uint32_t loDOm = desc_lo(sbase + SM_DO, 16384);
 #pragma unroll
         for (int s = 0; s < 8; ++s)
-          mma_ss(tmem + TM_DK, smem_desc(sbase + SM_TR + 2048 * s, 16384, 1024, LAYOUT_SW128),
-                 smem_desc(sbase + SM_Q + 2048 * s, 16384, 1024, LAYOUT_SW128), ID_T, s > 0);
+          mma_ss(tmem + TM_DK, mkdesc(loT + 128 * s, HI_SW), mkdesc(loQm + 128 * s, HI_SW), ID_T, s > 0);
 #pragma unroll
         for (int s = 0; s < 8; ++s)
-          mma_ss(tmem + TM_DV, smem_desc(sbase + SM_TR + 32768 + 2048 * s, 16384, 1024, LAYOUT_SW128),
-                 smem_desc(sbase + SM_DO + 2048 * s, 16384, 1024, LAYOUT_SW128), ID_T, s > 0);
+          mma_ss(tmem + TM_DV, mkdesc(loT + 2048 + 128 * s, HI_SW), mkdesc(loDOm + 128 * s, HI_SW), ID_T, s > 0);
         mma_commit(smem_u32(&bars->tbar));
       }
     };
@@ -177,15 +180,17 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     if (leader) {
       tc_fence_after();
       mbar_wait(smem_u32(&bars->q_full), 0);
-      issue_mma1(0);
-      if (NP > 1) issue_mma1(1);
+      issue_mma1(0, 0);
+      if (NP > 1) issue_mma1(1, 1);
     }
+    const uint32_t bar_step = smem_u32(&bars->step);
+    int ibuf = 0;                                      // it % 3
     for (int it = 0; it < NP && warp == 8; ++it) {     // warps 9-11 go straight to the tail barrier
       if (leader) {
-        mbar_wait(smem_u32(&bars->step), it & 1);      // all compute threads finished pair it (no CTA-wide barrier:
+        mbar_wait(bar_step, it & 1);                   // all compute threads finished pair it (no CTA-wide barrier:
         tc_fence_after();                              //  fast warps run ahead into pair it+1 meanwhile)
-        issue_mma2(it);
-        if (it + 2 < NP) issue_mma1(it + 2);
+        issue_mma2(it, ibuf);
+        if (it + 2 < NP) issue_mma1(it + 2, ibuf == 0 ? 2 : ibuf - 1);
         if (it >= 2 && ((it - 2) & 3) == 3) {          // tile stored at the previous sync: recycle its stage
           const int T = (it - 2) >> 2;
           tma_store_wait_read<0>();
@@ -197,6 +202,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
           tma_store_commit();
         }
       }
+      if (++ibuf == 3) ibuf = 0;
       __syncwarp();
     }
     __syncthreads();                                   // sync #(NP+1): phase B of the last pair is done

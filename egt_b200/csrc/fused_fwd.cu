@@ -110,38 +110,39 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
       tma_load_3d(dst + ST_K, &tm_kv, bar, FD, T * 8, b);
       tma_load_3d(dst + ST_V, &tm_kv, bar, 2 * FD, T * 8, b);
     };
-    auto issue_mma1_pair = [&](int p, int buf) {
-      const int T = p >> 2, j = p & 3, st = T % NS, slot = p & 7;
-      const uint32_t es = sbase + SM_STAGE + st * STAGE_BYTES;
-      const uint32_t kx = sbase + SM_KVX + slot * 4096;
+    // descriptor low words (address | LBO); the high words are compile-time constants
+    constexpr uint32_t HI_SW = desc_hi(1024, LAYOUT_SW128), HI_NONE = desc_hi(128, LAYOUT_NONE);
+    const uint32_t loQ = desc_lo(sbase + SM_Q, 16), loK = desc_lo(sbase + SM_KVX, 16);
+    const uint32_t loV = desc_lo(sbase + SM_KVX + 2048, 2048), loE = desc_lo(sbase + SM_STAGE + ST_E, 16);
+    const uint32_t loWeg = desc_lo(sbase + SM_W, 512), loWr = desc_lo(sbase + SM_W + 1024, 256);
+    auto issue_mma1_pair = [&](int p, int st, int buf) {
+      const int j = p & 3, slot = p & 7;
       const uint32_t d = tmem + TM_IN + buf * TM_IN_COLS + (p & 1) * TM_PAIR;
+      const uint32_t k0 = loK + slot * 256;            // 4096 B per slot
 #pragma unroll
       for (int s = 0; s < 4; ++s)
-        mma_ss(d + IN_S, smem_desc(sbase + SM_Q + 32 * s, 16, 1024, LAYOUT_SW128),
-               smem_desc(kx + 32 * s, 16, 1024, LAYOUT_SW128), ID_N16, s > 0);
-      mma_ss(d + IN_EG, smem_desc(es + ST_E + 32 * j, 16, 1024, LAYOUT_SW128),
-             smem_desc(sbase + SM_W, 512, 128, LAYOUT_NONE), ID_N32, 0);
+        mma_ss(d + IN_S, mkdesc(loQ + 2 * s, HI_SW), mkdesc(k0 + 2 * s, HI_SW), ID_N16, s > 0);
+      mma_ss(d + IN_EG, mkdesc(loE + st * (STAGE_BYTES / 16) + 2 * j, HI_SW), mkdesc(loWeg, HI_NONE), ID_N32, 0);
     };
-    auto issue_mma1 = [&](int q) {                     // both pairs of step q
-      const int T = q >> 1, buf = q % 3;
-      mbar_wait(smem_u32(&bars->e_full[T % NS]), (T / NS) & 1);
+    const uint32_t bar_e0 = smem_u32(&bars->e_full[0]), bar_m1 = smem_u32(&bars->mma1[0]), bar_m2 = smem_u32(&bars->mma2[0]);
+    auto issue_mma1 = [&](int q, int buf) {            // both pairs of step q
+      const int T = q >> 1, st = T % NS;
+      mbar_wait(bar_e0 + 8 * st, (T / NS) & 1);
       tc_fence_after();
-      issue_mma1_pair(2 * q, buf);
-      issue_mma1_pair(2 * q + 1, buf);
-      mma_commit(smem_u32(&bars->mma1[buf]));
+      issue_mma1_pair(2 * q, st, buf);
+      issue_mma1_pair(2 * q + 1, st, buf);
+      mma_commit(bar_m1 + 8 * buf);
     };
-    auto issue_mma2 = [&](int q) {
-      const int buf = q % 3, ob = q & 1;
+    auto issue_mma2 = [&](int q, int buf) {
+      const int ob = q & 1;
 #pragma unroll
       for (int kq = 0; kq < 2; ++kq) {
         const int p = 2 * q + kq;
-        const uint32_t vx = sbase + SM_KVX + (p & 7) * 4096 + 2048;
         const uint32_t ao = tmem + TM_OUT + ob * TM_OUT_COLS + kq * TM_OPAIR;
-        mma_ts(tmem + TM_O, ao, smem_desc(vx, 2048, 1024, LAYOUT_SW128), ID_PV, p > 0);
-        mma_ts(tmem + TM_IN + buf * TM_IN_COLS + kq * TM_PAIR + IN_EG, ao + 8,
-               smem_desc(sbase + SM_W + 1024, 256, 128, LAYOUT_NONE), ID_N16, 0);
+        mma_ts(tmem + TM_O, ao, mkdesc(loV + (p & 7) * 256, HI_SW), ID_PV, p > 0);
+        mma_ts(tmem + TM_IN + buf * TM_IN_COLS + kq * TM_PAIR + IN_EG, ao + 8, mkdesc(loWr, HI_NONE), ID_N16, 0);
       }
-      mma_commit(smem_u32(&bars->mma2[buf]));
+      mma_commit(bar_m2 + 8 * buf);
     };
     if (leader) {
       mbar_expect_tx(smem_u32(&bars->q_full), 16384);
@@ -152,15 +153,17 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     if (leader) {
       tc_fence_after();
       mbar_wait(smem_u32(&bars->q_full), 0);
-      issue_mma1(0);
-      if (NQ > 1) issue_mma1(1);
+      issue_mma1(0, 0);
+      if (NQ > 1) issue_mma1(1, 1);
     }
+    const uint32_t bar_step = smem_u32(&bars->step);
+    int ibuf = 0;                                      // it % 3
     for (int it = 0; it < NQ && warp == 16; ++it) {    // warps 17-19 go straight to the tail barrier
       if (leader) {
-        mbar_wait(smem_u32(&bars->step), it & 1);      // all compute threads finished step it (no CTA-wide barrier:
+        mbar_wait(bar_step, it & 1);                   // all compute threads finished step it (no CTA-wide barrier:
         tc_fence_after();                              //  fast warps run ahead into step it+1 meanwhile)
-        issue_mma2(it);
-        if (it + 2 < NQ) issue_mma1(it + 2);
+        issue_mma2(it, ibuf);
+        if (it + 2 < NQ) issue_mma1(it + 2, ibuf == 0 ? 2 : ibuf - 1);
         if (it >= 3 && (it & 1) == 1) {                // tile stored at the previous sync: recycle its stage
           const int T = (it - 3) >> 1;
           tma_store_wait_read<0>();
@@ -172,6 +175,7 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
           tma_store_commit();
         }
       }
+      if (++ibuf == 3) ibuf = 0;
       __syncwarp();
     }
     __syncthreads();                                   // sync #(NQ+1): phase B of the last step is done

@@ -101,6 +101,16 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
   uint32_t hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
   return ((uint64_t)hi << 32) | lo;
 }
+// The same descriptor split into its two words: the high word depends only on (SBO, layout) and is a
+// compile-time constant at every call site; the low word is (address | LBO) and advances by bytes >> 4.
+__host__ __device__ constexpr uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t addr, uint32_t lbo_bytes) {
+  return ((addr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint64_t mkdesc(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+
 // kind::f16 instruction descriptor: bf16 x bf16 -> f32.
 //   [4,6) D format (1 = f32)  [7,10) A format (1 = bf16)  [10,13) B format  [15] A major (1 = MN)
 //   [16] B major  [17,23) N >> 3  [24,29) M >> 4
