@@ -24,8 +24,10 @@
 // Softmax runs without max subtraction: logits are bounded by clip + |E| (FusedPrep::bound).
 //
 // There is no CTA-wide barrier in the main loop: compute threads arrive on an mbarrier when their part of a
-// step (4 keys) is done, the issuer waits for it, and every tensor-core / TMA operation is issued two steps
-// ahead of its consumer and observed through an mbarrier, so warps drift apart and fill each other's stalls.
+// step (4 keys) is done and the issuer waits for it.  The handshake compute -> issuer -> tensor core -> compute
+// costs ~1700 cycles (measured), as much as a step's arithmetic, so every dependency spans TWO steps: the
+// S/EG products of step it+2 are issued when step it is done, and the e' update of step it (which needs the
+// H_hat W_r product issued when step it is done) runs during step it+2.
 #include "common.cuh"
 #include "fused.h"
 #include "umma.cuh"
@@ -47,15 +49,16 @@ constexpr uint32_t SM_MASK = SM_BAR + 256;                       // key-valid by
 constexpr uint32_t SM_TOTAL = SM_MASK + 4096 + 16;
 
 constexpr uint32_t TM_O = 0;
-constexpr uint32_t TM_IN = 64, TM_IN_COLS = 96, TM_PAIR = 48;  // 3 buffers x 2 pairs: S 16 | EG 32
+constexpr uint32_t TM_IN = 64, TM_IN_COLS = 96, TM_PAIR = 48;  // 2 buffers x 2 pairs: S 16 | EG 32   (step parity)
 constexpr uint32_t IN_S = 0, IN_EG = 16;
-constexpr uint32_t TM_OUT = 352, TM_OUT_COLS = 32, TM_OPAIR = 16;   // 2 buffers x 2 pairs: A~ 8 | H_hat 8 (bf16 A operands)
+constexpr uint32_t TM_DE = 256, TM_DE_COLS = 32;               // 2 buffers x 2 pairs: De 16             (step parity)
+constexpr uint32_t TM_OUT = 320, TM_OUT_COLS = 32, TM_OPAIR = 16;   // 2 buffers x 2 pairs: A~ 8 | H_hat 8 (bf16 A operands)
 
 constexpr uint32_t ID_N16 = idesc_bf16(128, 16, 0, 0);
 constexpr uint32_t ID_N32 = idesc_bf16(128, 32, 0, 0);
 constexpr uint32_t ID_PV = idesc_bf16(128, 64, 0, 1);
 
-struct Bars { uint64_t q_full, e_full[NS], mma1[3], mma2[3], step; uint32_t tmem_base; };
+struct Bars { uint64_t q_full, e_full[NS], mma1[2], mma2[2], step; uint32_t tmem_base; };
 
 }  // namespace
 
@@ -77,7 +80,7 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     if (lane == 0) {
       mbar_init(smem_u32(&bars->q_full), 1);
       for (int i = 0; i < NS; ++i) mbar_init(smem_u32(&bars->e_full[i]), 1);
-      for (int i = 0; i < 3; ++i) { mbar_init(smem_u32(&bars->mma1[i]), 1); mbar_init(smem_u32(&bars->mma2[i]), 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->mma1[i]), 1); mbar_init(smem_u32(&bars->mma2[i]), 1); }
       mbar_init(smem_u32(&bars->step), 512);          // every compute thread arrives once per step
       mbar_fence_init();
       tma_prefetch_desc(&tm_e); tma_prefetch_desc(&tm_eo); tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_kv);
@@ -125,63 +128,66 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
       mma_ss(d + IN_EG, mkdesc(loE + st * (STAGE_BYTES / 16) + 2 * j, HI_SW), mkdesc(loWeg, HI_NONE), ID_N32, 0);
     };
     const uint32_t bar_e0 = smem_u32(&bars->e_full[0]), bar_m1 = smem_u32(&bars->mma1[0]), bar_m2 = smem_u32(&bars->mma2[0]);
-    auto issue_mma1 = [&](int q, int buf) {            // both pairs of step q
-      const int T = q >> 1, st = T % NS;
+    auto issue_mma1 = [&](int q) {                     // both pairs of step q -> input buffer q & 1
+      const int T = q >> 1, st = T % NS, buf = q & 1;
       mbar_wait(bar_e0 + 8 * st, (T / NS) & 1);
       tc_fence_after();
       issue_mma1_pair(2 * q, st, buf);
       issue_mma1_pair(2 * q + 1, st, buf);
-      mma_commit(bar_m1 + 8 * buf);
     };
-    auto issue_mma2 = [&](int q, int buf) {
+    auto issue_mma2 = [&](int q) {                     // O += A~ Vexp ; De = H_hat Wr  (operands / result: parity q & 1)
       const int ob = q & 1;
 #pragma unroll
       for (int kq = 0; kq < 2; ++kq) {
         const int p = 2 * q + kq;
         const uint32_t ao = tmem + TM_OUT + ob * TM_OUT_COLS + kq * TM_OPAIR;
         mma_ts(tmem + TM_O, ao, mkdesc(loV + (p & 7) * 256, HI_SW), ID_PV, p > 0);
-        mma_ts(tmem + TM_IN + buf * TM_IN_COLS + kq * TM_PAIR + IN_EG, ao + 8, mkdesc(loWr, HI_NONE), ID_N16, 0);
+        mma_ts(tmem + TM_DE + ob * TM_DE_COLS + kq * 16, ao + 8, mkdesc(loWr, HI_NONE), ID_N16, 0);
       }
-      mma_commit(bar_m2 + 8 * buf);
     };
     if (leader) {
       mbar_expect_tx(smem_u32(&bars->q_full), 16384);
       tma_load_3d(sbase + SM_Q, &tm_q, smem_u32(&bars->q_full), 0, l0, b);
       for (int T = 0; T < NT && T < NS; ++T) load_tile(T);
     }
-    __syncthreads();                                   // sync #0: Kexp/Vexp of steps 0,1 are built
+    __syncthreads();                                   // sync #0: Kexp/Vexp of steps 0, 1 are built
     if (leader) {
       tc_fence_after();
       mbar_wait(smem_u32(&bars->q_full), 0);
-      issue_mma1(0, 0);
-      if (NQ > 1) issue_mma1(1, 1);
+      issue_mma1(0);
+      mma_commit(bar_m1);                              // S / EG of step 0
+      if (NQ > 1) { issue_mma1(1); mma_commit(bar_m1 + 8); }
     }
     const uint32_t bar_step = smem_u32(&bars->step);
-    int ibuf = 0;                                      // it % 3
+    int next_store = 0;                                // tiles [0, next_store) have been handed to the TMA store
     for (int it = 0; it < NQ && warp == 16; ++it) {    // warps 17-19 go straight to the tail barrier
       if (leader) {
-        mbar_wait(bar_step, it & 1);                   // all compute threads finished step it (no CTA-wide barrier:
-        tc_fence_after();                              //  fast warps run ahead into step it+1 meanwhile)
-        issue_mma2(it, ibuf);
-        if (it + 2 < NQ) issue_mma1(it + 2, ibuf == 0 ? 2 : ibuf - 1);
-        if (it >= 3 && (it & 1) == 1) {                // tile stored at the previous sync: recycle its stage
-          const int T = (it - 3) >> 1;
+        mbar_wait(bar_step, it & 1);                   // all compute threads finished step it
+        tc_fence_after();
+        fence_proxy_async_smem();                      // the compute threads' shared-memory writes of step it
+        issue_mma2(it);                                //  (ordered before this point by the mbarrier) -> async proxy
+        if (it + 2 < NQ) issue_mma1(it + 2);
+        mma_commit(bar_m2 + 8 * (it & 1));             // ONE completion per handshake: products of step it and
+                                                       // S / EG of step it+2, both consumed during step it+2
+        // step it contained the e' update of step it-2; tile T (steps 2T, 2T+1) is complete when it == 2T+3
+        if (it >= 4 && (it & 1) == 0) {                // tile stored at the previous handshake: recycle its stage
+          const int T = (it - 4) >> 1;
           tma_store_wait_read<0>();
           if (T + NS < NT) load_tile(T + NS);
         }
-        if (it >= 2 && (it & 1) == 0) {                // phase B of tile T's second step ran: e' is complete in place
-          const int T = (it - 2) >> 1;
+        if (it >= 3 && (it & 1) == 1) {
+          const int T = (it - 3) >> 1;
           tma_store_3d(&tm_eo, sbase + SM_STAGE + (T % NS) * STAGE_BYTES + ST_E, T * 64, l0, b);
           tma_store_commit();
+          next_store = T + 1;
         }
       }
-      if (++ibuf == 3) ibuf = 0;
       __syncwarp();
     }
-    __syncthreads();                                   // sync #(NQ+1): phase B of the last step is done
+    __syncthreads();                                   // sync #(NQ+1): every e' update is done
     if (leader) {
-      const int T = NT - 1;
-      tma_store_3d(&tm_eo, sbase + SM_STAGE + (T % NS) * STAGE_BYTES + ST_E, T * 64, l0, b);
+      for (int T = next_store; T < NT; ++T)
+        tma_store_3d(&tm_eo, sbase + SM_STAGE + (T % NS) * STAGE_BYTES + ST_E, T * 64, l0, b);
       tma_store_commit();
       tma_store_wait_all<0>();
     }
@@ -223,10 +229,10 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
   };
 
   // ---- phase A: pair p, this thread's 4 heads of both keys ------------------------------------------
-  auto phase_a = [&](int p, int st, int buf) {
+  auto phase_a = [&](int p, int st) {
     const int j = p & 3, ob = (p >> 1) & 1;
     const uint8_t *es = smem + SM_STAGE + st * STAGE_BYTES;
-    const uint32_t tin = tlane + TM_IN + buf * TM_IN_COLS + kq * TM_PAIR;
+    const uint32_t tin = tlane + TM_IN + ob * TM_IN_COLS + kq * TM_PAIR;
     const uint32_t tout = tlane + TM_OUT + ob * TM_OUT_COLS + kq * TM_OPAIR;
     uint32_t sreg[8], egreg[16];
     tmem_ld8(tin + IN_S + g * 8, sreg);
@@ -292,12 +298,12 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
   };
 
   // ---- phase B: e' = e + H_hat W_r + b_r for key g of pair p, in place over the e stage ---------------
-  auto phase_b = [&](int p, int st, int buf) {
-    const int j = p & 3;
+  auto phase_b = [&](int p, int st) {
+    const int j = p & 3, ob = (p >> 1) & 1;
     uint8_t *es = smem + SM_STAGE + st * STAGE_BYTES;
     const int ks = 2 * j + g;
     uint32_t dr[8];
-    tmem_ld8(tlane + TM_IN + buf * TM_IN_COLS + kq * TM_PAIR + IN_EG + g * 8, dr);
+    tmem_ld8(tlane + TM_DE + ob * TM_DE_COLS + kq * 16 + g * 8, dr);
     uint4 *pe = (uint4 *)(es + ST_E + trow + (((uint32_t)ks ^ tx7) << 4));
     const uint4 ev = *pe;
     const float x[8] = {bf16_lo(ev.x), bf16_hi(ev.x), bf16_lo(ev.y), bf16_hi(ev.y),
@@ -320,18 +326,16 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
   if (NQ > 1) build(2 + kq, 0);
   fence_proxy_async_smem();
   __syncthreads();                                     // sync #0
-  int st_a = 0, buf_a = 0, par_a = 0;                  // step it
-  int st_p = 0, buf_p = 0, par_p = 0;                  // step it - 1
-  int st_n = 1 % NS, par_n = 0;                        // step it + 2 (its tile's stage / load parity)
+  int st_a = 0;                                        // stage of step it
+  int st_b = 0;                                        // stage of step it - 2
+  int st_n = 1 % NS, par_n = 0;                        // stage / load parity of step it + 2
   for (int it = 0; it < NQ; ++it) {
-    mbar_wait(bar_mma1 + 8 * buf_a, par_a);
+    const uint32_t ob8 = 8u * (uint32_t)(it & 1);
+    if (it >= 2) mbar_wait(bar_mma2 + ob8, ((it - 2) >> 1) & 1);   // handshake it-2: S / EG of this step, products of step it-2
+    else mbar_wait(bar_mma1 + ob8, 0);                 // steps 0, 1: issued before the loop
     tc_fence_after();
-    phase_a(2 * it + kq, st_a, buf_a);
-    if (it >= 1) {
-      mbar_wait(bar_mma2 + 8 * buf_p, par_p);
-      tc_fence_after();
-      phase_b(2 * (it - 1) + kq, st_p, buf_p);
-    }
+    phase_a(2 * it + kq, st_a);
+    if (it >= 2) phase_b(2 * (it - 2) + kq, st_b);
     if (it + 2 < NQ) {
       if ((it & 1) == 0) mbar_wait(bar_e + 8 * st_n, par_n);        // first step of tile (it+2)>>1
       build(2 * (it + 2) + kq, st_n);
@@ -340,16 +344,17 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     fence_proxy_async_smem();
     tc_fence_before();
     mbar_arrive(bar_step);                             // step it done by this thread
-    st_p = st_a; buf_p = buf_a; par_p = par_a;
-    if (++buf_a == 3) { buf_a = 0; par_a ^= 1; }
     if (it & 1) {                                      // steps it+1 and it+3 open new tiles
       if (++st_a == NS) st_a = 0;
       if (++st_n == NS) { st_n = 0; par_n ^= 1; }
+      if (it >= 3) { if (++st_b == NS) st_b = 0; }     // step it-1 opens a new tile
     }
   }
-  mbar_wait(bar_mma2 + 8 * buf_p, par_p);
-  tc_fence_after();
-  phase_b(2 * (NQ - 1) + kq, st_p, buf_p);
+  for (int q = (NQ >= 2 ? NQ - 2 : 0); q < NQ; ++q) {  // e' updates of the last two steps
+    mbar_wait(bar_mma2 + 8 * (q & 1), (q >> 1) & 1);
+    tc_fence_after();
+    phase_b(2 * q + kq, (q >> 1) % NS);
+  }
   fence_proxy_async_smem();
   __syncthreads();                                     // sync #(NQ+1)
 
