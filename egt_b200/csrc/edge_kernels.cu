@@ -74,43 +74,66 @@ __global__ void __launch_bounds__(EPB) edge_out_fwd_kernel(EdgeParams p) {
   }
 }
 
+// Both backward kernels are persistent: a CTA walks pair-chunks of EPB pairs with a grid stride, keeps its
+// share of the weight-gradient sums in registers across chunks and issues its atomics ONCE at the end
+// (one atomic per output per CTA instead of one per output per 128 pairs).
+constexpr int MAXO_R = 8;     // h * d_e   <= 16 * 64 outputs / EPB threads
+constexpr int MAXO_P = 16;    // d_e * J   <= 64 * 32 outputs / EPB threads
+
 // dynamic smem: xs[EPB][h] (H_hat), ys[EPB][d_e] (de')
 template <typename T>
 __global__ void __launch_bounds__(EPB) edge_out_bwd_kernel(EdgeParams p) {
   extern __shared__ float sm[];
   float *xs = sm;
   float *ys = sm + EPB * p.h;
-  size_t pair = (size_t)blockIdx.x * EPB + threadIdx.x;
-  bool live = pair < p.pairs;
-  float dh[HMAX];
+  float accw[MAXO_R], accb = 0.f;
 #pragma unroll
-  for (int hh = 0; hh < HMAX; ++hh) dh[hh] = 0.f;
-  for (int c = 0; c < p.d_e; ++c) {
-    float g = live ? ldf((const T *)p.de_out + pair * p.d_e + c) : 0.f;
-    ys[threadIdx.x * p.d_e + c] = g;
+  for (int k = 0; k < MAXO_R; ++k) accw[k] = 0.f;
+  for (size_t chunk = blockIdx.x; chunk * EPB < p.pairs; chunk += gridDim.x) {
+    size_t pair = chunk * EPB + threadIdx.x;
+    bool live = pair < p.pairs;
+    float dh[HMAX];
+#pragma unroll
+    for (int hh = 0; hh < HMAX; ++hh) dh[hh] = 0.f;
+    for (int c = 0; c < p.d_e; ++c) {
+      float g = live ? ldf((const T *)p.de_out + pair * p.d_e + c) : 0.f;
+      ys[threadIdx.x * p.d_e + c] = g;
+#pragma unroll
+      for (int hh = 0; hh < HMAX; ++hh)
+        if (hh < p.h) dh[hh] += g * __ldg(p.w_r + hh * p.d_e + c);
+    }
 #pragma unroll
     for (int hh = 0; hh < HMAX; ++hh)
-      if (hh < p.h) dh[hh] += g * __ldg(p.w_r + hh * p.d_e + c);
-  }
+      if (hh < p.h) {
+        xs[threadIdx.x * p.h + hh] = (live && p.h_hat) ? ldf((const T *)p.h_hat + pair * p.h + hh) : 0.f;
+        if (live && p.d_h_ext) stf((T *)p.d_h_ext + pair * p.h + hh, dh[hh]);
+      }
+    if (!p.g_w_r) continue;                 // uniform over the grid: no barrier is skipped by a subset of threads
+    __syncthreads();
 #pragma unroll
-  for (int hh = 0; hh < HMAX; ++hh)
-    if (hh < p.h) {
-      xs[threadIdx.x * p.h + hh] = (live && p.h_hat) ? ldf((const T *)p.h_hat + pair * p.h + hh) : 0.f;
-      if (live && p.d_h_ext) stf((T *)p.d_h_ext + pair * p.h + hh, dh[hh]);
+    for (int k = 0; k < MAXO_R; ++k) {
+      int o = threadIdx.x + k * EPB;
+      if (o < p.h * p.d_e) {
+        int hh = o / p.d_e, c = o % p.d_e;
+        float acc = 0.f;
+        for (int q = 0; q < EPB; ++q) acc += xs[q * p.h + hh] * ys[q * p.d_e + c];
+        accw[k] += acc;
+      }
     }
+    if (threadIdx.x < p.d_e) {
+      float acc = 0.f;
+      for (int q = 0; q < EPB; ++q) acc += ys[q * p.d_e + threadIdx.x];
+      accb += acc;
+    }
+    __syncthreads();
+  }
   if (!p.g_w_r) return;
-  __syncthreads();
-  for (int o = threadIdx.x; o < p.h * p.d_e; o += EPB) {
-    int hh = o / p.d_e, c = o % p.d_e;
-    float acc = 0.f;
-    for (int q = 0; q < EPB; ++q) acc += xs[q * p.h + hh] * ys[q * p.d_e + c];
-    atomicAdd(p.g_w_r + o, acc);
+#pragma unroll
+  for (int k = 0; k < MAXO_R; ++k) {
+    int o = threadIdx.x + k * EPB;
+    if (o < p.h * p.d_e) atomicAdd(p.g_w_r + o, accw[k]);
   }
-  for (int c = threadIdx.x; c < p.d_e; c += EPB) {
-    float acc = 0.f;
-    for (int q = 0; q < EPB; ++q) acc += ys[q * p.d_e + c];
-    atomicAdd(p.g_b_r + c, acc);
-  }
+  if (threadIdx.x < p.d_e) atomicAdd(p.g_b_r + threadIdx.x, accb);
 }
 
 // dynamic smem: xs[EPB][d_e] (normalised input without affine, or raw e), ds[EPB][J], dbs[J]
@@ -120,10 +143,15 @@ __global__ void __launch_bounds__(EPB) edge_proj_bwd_kernel(EdgeParams p) {
   const int J = p.gated ? 2 * p.h : p.h;
   float *xs = sm;
   float *ds = sm + EPB * p.d_e;
-  float *dbs = ds + EPB * J;
-  size_t pair = (size_t)blockIdx.x * EPB + threadIdx.x;
-  bool live = pair < p.pairs;
+  float *dbs = ds + EPB * J;                 // column sums of ds over ALL chunks of this CTA
   const int tid = threadIdx.x;
+  float accw[MAXO_P];
+#pragma unroll
+  for (int k = 0; k < MAXO_P; ++k) accw[k] = 0.f;
+  if (tid < J) dbs[tid] = 0.f;
+  for (size_t chunk = blockIdx.x; chunk * EPB < p.pairs; chunk += gridDim.x) {
+  size_t pair = chunk * EPB + threadIdx.x;
+  bool live = pair < p.pairs;
   float dEp[HMAX], dGv[HMAX];
 #pragma unroll
   for (int hh = 0; hh < HMAX; ++hh) { dEp[hh] = 0.f; dGv[hh] = 0.f; }
@@ -205,25 +233,41 @@ __global__ void __launch_bounds__(EPB) edge_proj_bwd_kernel(EdgeParams p) {
   for (int j = tid; j < J; j += EPB) {
     float acc = 0.f;
     for (int q = 0; q < EPB; ++q) acc += ds[q * J + j];
-    dbs[j] = acc;
-    atomicAdd(j < p.h ? p.g_b_e + j : p.g_b_g + (j - p.h), acc);
+    dbs[j] += acc;
+  }
+  // dWn[c,j] += sum_p xn[p,c]*ds[p,j]
+#pragma unroll
+  for (int k = 0; k < MAXO_P; ++k) {
+    int o = tid + k * EPB;
+    if (o < p.d_e * J) {
+      int c = o / J, j = o % J;
+      float acc = 0.f;
+      for (int q = 0; q < EPB; ++q) acc += xs[q * p.d_e + c] * ds[q * J + j];
+      accw[k] += acc;
+    }
   }
   __syncthreads();
-  // dWn[c,j] = sum_p xn[p,c]*ds[p,j];  dW = gamma*dWn + beta*db ; dgamma[c] += sum_j W[c,j] dWn[c,j]
-  for (int o = tid; o < p.d_e * J; o += EPB) {
-    int c = o / J, j = o % J;
-    float acc = 0.f;
-    for (int q = 0; q < EPB; ++q) acc += xs[q * p.d_e + c] * ds[q * J + j];
-    const float *W = j < p.h ? p.w_e : p.w_g;
-    float *gW = j < p.h ? p.g_w_e : p.g_w_g;
-    int jj = j < p.h ? j : j - p.h;
-    if (p.has_ln) {
-      float w = __ldg(W + c * p.h + jj);
-      atomicAdd(gW + c * p.h + jj, __ldg(p.ln_g + c) * acc + __ldg(p.ln_b + c) * dbs[j]);
-      atomicAdd(p.g_ln_g + c, w * acc);
-      atomicAdd(p.g_ln_b + c, w * dbs[j]);
-    } else {
-      atomicAdd(gW + c * p.h + jj, acc);
+  }   // chunk loop
+  __syncthreads();
+  for (int j = tid; j < J; j += EPB) atomicAdd(j < p.h ? p.g_b_e + j : p.g_b_g + (j - p.h), dbs[j]);
+  // dW = gamma*dWn + beta*db ; dgamma[c] += sum_j W[c,j] dWn[c,j] ; dbeta[c] += sum_j W[c,j] db[j]
+#pragma unroll
+  for (int k = 0; k < MAXO_P; ++k) {
+    int o = tid + k * EPB;
+    if (o < p.d_e * J) {
+      int c = o / J, j = o % J;
+      const float acc = accw[k];
+      const float *W = j < p.h ? p.w_e : p.w_g;
+      float *gW = j < p.h ? p.g_w_e : p.g_w_g;
+      int jj = j < p.h ? j : j - p.h;
+      if (p.has_ln) {
+        float w = __ldg(W + c * p.h + jj);
+        atomicAdd(gW + c * p.h + jj, __ldg(p.ln_g + c) * acc + __ldg(p.ln_b + c) * dbs[j]);
+        atomicAdd(p.g_ln_g + c, w * acc);
+        atomicAdd(p.g_ln_b + c, w * dbs[j]);
+      } else {
+        atomicAdd(gW + c * p.h + jj, acc);
+      }
     }
   }
 }
@@ -237,6 +281,10 @@ __global__ void __launch_bounds__(EPB) edge_proj_bwd_kernel(EdgeParams p) {
   } while (0)
 
 static unsigned pair_grid(const EdgeParams &p) { return (unsigned)((p.pairs + EPB - 1) / EPB); }
+static unsigned persistent_grid(const EdgeParams &p) {
+  unsigned g = pair_grid(p);
+  return g < 148u * 8u ? g : 148u * 8u;
+}
 
 int edge_proj_fwd_launch(const EdgeParams &p, int dtype, cudaStream_t st) {
   DISPATCH_T(dtype, edge_proj_fwd_kernel, pair_grid(p), EPB, 0, st, p);
@@ -252,7 +300,7 @@ int edge_out_bwd_launch(const EdgeParams &p, int dtype, cudaStream_t st) {
     EGT_CHECK_CUDA(cudaFuncSetAttribute(edge_out_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     EGT_CHECK_CUDA(cudaFuncSetAttribute(edge_out_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  DISPATCH_T(dtype, edge_out_bwd_kernel, pair_grid(p), EPB, smem, st, p);
+  DISPATCH_T(dtype, edge_out_bwd_kernel, persistent_grid(p), EPB, smem, st, p);
   return EGT_OK;
 }
 int edge_proj_bwd_launch(const EdgeParams &p, int dtype, cudaStream_t st) {
@@ -262,7 +310,7 @@ int edge_proj_bwd_launch(const EdgeParams &p, int dtype, cudaStream_t st) {
     EGT_CHECK_CUDA(cudaFuncSetAttribute(edge_proj_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     EGT_CHECK_CUDA(cudaFuncSetAttribute(edge_proj_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  DISPATCH_T(dtype, edge_proj_bwd_kernel, pair_grid(p), EPB, smem, st, p);
+  DISPATCH_T(dtype, edge_proj_bwd_kernel, persistent_grid(p), EPB, smem, st, p);
   return EGT_OK;
 }
 
