@@ -323,9 +323,19 @@ def run_ours(args, w):
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
-    if rank != 0:
+    def finish():
+        """Leave without tearing the process group down: destroying it while captured CUDA graphs still hold
+        NCCL work has been seen to hang; every rank has already passed the final barrier."""
+        sys.stdout.flush()
+        sys.stderr.flush()
         if world > 1:
-            dist.destroy_process_group()
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
     peaks = measured_peaks()
     graphs = B * world * args.steps
@@ -369,8 +379,7 @@ def run_ours(args, w):
         line['cpu_baseline'] = dict(value=cpu['value'], unit='graphs/s', cores=cpu['cores'], kind=cpu['kind'],
                                     sample=cpu['sample'])
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 def main():
