@@ -1,0 +1,91 @@
+// peer_allreduce.cu -- one-shot all-reduce (sum) of the flat weight-gradient buffer over NVLink peer memory.
+//
+//   reference: the gradient all-reduce tf.distribute.MirroredStrategy performs once per step
+//   (lib/training/training_base.py:230-238).  The payload is tiny (17 K floats per block at the headline
+//   widths), so the collective is pure latency; a ring / tree through NCCL costs tens of microseconds at
+//   8 ranks.  Here every rank publishes its gradient in a symmetric (peer-mapped) buffer, signals each peer
+//   with one flag per CTA, and then sums all peers' buffers directly over NVLink / NVSwitch loads.
+//
+// One launch per step, capturable in a CUDA graph: everything that changes from call to call (the epoch
+// and the half of the double buffer in use) lives in device memory, not in kernel arguments.
+//   buffers   [world] device pointers to each rank's symmetric buffer of 2 * n floats (double buffered: a
+//             rank overwrites half k%2 only after it has passed the flag exchange of call k+1, which every
+//             peer enters after finishing its reads of call k)
+//   pads      [world] device pointers to each rank's signal pad (uint32): slot [cta][peer] flags, then
+//             [PAR_EPOCH + cta] this CTA's call counter.  Pads start zeroed.
+#include "common.cuh"
+
+namespace egt {
+
+constexpr int PAR_MAXW = 8, PAR_MAXCTA = 32, PAR_EPOCH = PAR_MAXCTA * PAR_MAXW;
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_volatile_f4(const float4 *p) {   // peer data: never from a stale L1 line
+  float4 v;
+  asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(256) peer_allreduce_kernel(const uint64_t *buffers, const uint64_t *pads, float *grad,
+                                                             int n4, int rank, int world) {
+  __shared__ uint32_t s_epoch;
+  const int tid = threadIdx.x, cta = blockIdx.x;
+  uint32_t *my_pad = (uint32_t *)pads[rank];
+  if (tid == 0) s_epoch = my_pad[PAR_EPOCH + cta];
+  __syncthreads();
+  const uint32_t epoch = s_epoch;
+  const size_t half = (size_t)(epoch & 1u) * (size_t)n4;            // in float4 units
+  const int per = (n4 + gridDim.x - 1) / gridDim.x;
+  const int i0 = cta * per, i1 = min(n4, i0 + per);
+  // 1. publish this rank's slice
+  float4 *mine = (float4 *)buffers[rank] + half;
+  const float4 *g4 = (const float4 *)grad;
+  for (int i = i0 + tid; i < i1; i += blockDim.x) mine[i] = g4[i];
+  __threadfence_system();
+  __syncthreads();
+  // 2. flag every peer, wait for every peer's flag (monotonic epochs: >= tolerates a peer that is already a call ahead)
+  if (tid < world) {
+    st_release_sys((uint32_t *)pads[tid] + cta * PAR_MAXW + rank, epoch + 1u);
+    const uint32_t *slot = my_pad + cta * PAR_MAXW + tid;
+    long long t0 = clock64();
+    while (ld_acquire_sys(slot) < epoch + 1u) {
+      if (clock64() - t0 > 20000000000ll) __trap();                // a missing peer must not hang the box
+    }
+  }
+  __syncthreads();
+  // 3. sum the peers' slices in rank order (bitwise identical result on every rank)
+  for (int i = i0 + tid; i < i1; i += blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < world; ++r) {
+      const float4 v = ld_volatile_f4((const float4 *)buffers[r] + half + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    ((float4 *)grad)[i] = acc;
+  }
+  if (tid == 0) my_pad[PAR_EPOCH + cta] = epoch + 1u;
+}
+
+}  // namespace egt
+
+extern "C" int egt_peer_allreduce(const uint64_t *buffer_ptrs_dev, const uint64_t *signal_pad_ptrs_dev, float *grad,
+                                  int64_t n, int rank, int world, void *stream) {
+  using namespace egt;
+  EGT_REQUIRE(buffer_ptrs_dev && signal_pad_ptrs_dev && grad, EGT_E_ARG, "peer_allreduce: NULL pointer");
+  EGT_REQUIRE(world >= 1 && world <= PAR_MAXW && rank >= 0 && rank < world, EGT_E_ARG, "peer_allreduce: world/rank out of range");
+  EGT_REQUIRE(n > 0 && n % 4 == 0 && ((uintptr_t)grad & 15) == 0, EGT_E_ALIGN, "peer_allreduce: n must be a multiple of 4 and grad 16-byte aligned");
+  const int n4 = (int)(n / 4);
+  int ctas = (n4 + 511) / 512;
+  if (ctas > PAR_MAXCTA) ctas = PAR_MAXCTA;
+  if (ctas < 1) ctas = 1;
+  LaunchScope _ls("peer_allreduce_kernel", (cudaStream_t)stream);
+  peer_allreduce_kernel<<<ctas, 256, 0, (cudaStream_t)stream>>>(buffer_ptrs_dev, signal_pad_ptrs_dev, grad, n4, rank, world);
+  EGT_CHECK_CUDA(cudaGetLastError());
+  return EGT_OK;
+}

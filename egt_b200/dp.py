@@ -20,6 +20,54 @@ def shard_batch(t: torch.Tensor, rank: int, world: int) -> torch.Tensor:
     return t[rank * per:(rank + 1) * per]
 
 
+class _PeerAllReduce:
+    """One-shot all-reduce over NVLink peer memory (csrc/peer_allreduce.cu): every rank publishes its
+    gradient in a symmetric buffer and sums all peers' buffers with direct loads.  The payload is a few
+    tens of KB, so this is a latency play: one small kernel instead of a ring / tree through NCCL."""
+
+    def __init__(self, numel: int, device: torch.device):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib as L
+        self._C, self._L = C, L
+        self.numel = numel
+        self.buf = symm.empty(2 * numel, dtype=torch.float32, device=device)
+        self.hdl = symm.rendezvous(self.buf, dist.group.WORLD)
+        assert self.hdl.signal_pad_size >= 4 * (32 * 8 + 32), 'signal pad too small'
+        self.buf.zero_()
+        torch.cuda.synchronize(device)
+        dist.barrier()
+
+    def __call__(self, grad: torch.Tensor):
+        C, L = self._C, self._L
+        lib = L.load()
+        L.check(lib.egt_peer_allreduce(C.c_void_p(self.hdl.buffer_ptrs_dev), C.c_void_p(self.hdl.signal_pad_ptrs_dev),
+                                       C.c_void_p(grad.data_ptr()), self.numel, self.hdl.rank, self.hdl.world_size,
+                                       C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+
+_peer_cache = {}
+
+
+def _peer_allreduce_for(grad: torch.Tensor):
+    """The peer-memory all-reduce for this gradient buffer, or None when it cannot be used (CPU / gloo,
+    more than 8 ranks, unaligned size, symmetric memory unavailable, or EGT_PEER_ALLREDUCE=0)."""
+    import os
+    if os.environ.get('EGT_PEER_ALLREDUCE', '1') == '0' or not grad.is_cuda or not grad.is_contiguous():
+        return None
+    if grad.dtype != torch.float32 or grad.numel() % 4 or grad.data_ptr() % 16 or dist.get_world_size() > 8:
+        return None
+    key = (grad.numel(), grad.device.index)
+    if key not in _peer_cache:
+        try:
+            _peer_cache[key] = _PeerAllReduce(grad.numel(), grad.device)
+        except Exception as ex:   # no symmetric memory on this system: the NCCL collective is always available
+            import warnings
+            warnings.warn(f'egt_b200: peer-memory all-reduce unavailable ({type(ex).__name__}: {ex}); using NCCL')
+            _peer_cache[key] = None
+    return _peer_cache[key]
+
+
 def allreduce_flat_grads(blocks: Iterable, async_op: bool = False):
     """Sum ``block.flat.grad`` over ranks.  With one block this is literally one collective on one
     buffer; several blocks are coalesced into one flat tensor first so it stays one collective."""
@@ -29,6 +77,10 @@ def allreduce_flat_grads(blocks: Iterable, async_op: bool = False):
     if not grads:
         return None
     if len(grads) == 1:
+        peer = None if async_op else _peer_allreduce_for(grads[0])
+        if peer is not None:
+            peer(grads[0])
+            return None
         return dist.all_reduce(grads[0], op=dist.ReduceOp.SUM, async_op=async_op)
     flat = torch.cat([g.reshape(-1) for g in grads])
     work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=False)

@@ -187,6 +187,14 @@ long egt_launch_count(void);
 int egt_profile_enable(int on);
 int egt_profile_read(char *names_host, double *ms_host, long *counts_host, int max_entries);
 
+/* ---- data parallelism: the single gradient all-reduce of MirroredStrategy (training_base.py:230-238) --- */
+/* One-shot SUM all-reduce of `grad` (n float32, n % 4 == 0) over peer-mapped memory (NVLink / NVSwitch).
+ * buffer_ptrs_dev / signal_pad_ptrs_dev: device arrays of `world` pointers to every rank's symmetric buffer
+ * (>= 2*n floats) and zero-initialised signal pad (>= 1.1 KB), as torch symmetric memory hands out.
+ * Stream-ordered, no host synchronisation, CUDA-graph capturable; all ranks must call it equally often. */
+int egt_peer_allreduce(const uint64_t *buffer_ptrs_dev, const uint64_t *signal_pad_ptrs_dev, float *grad,
+                       int64_t n, int rank, int world, void *stream);
+
 /* Counter-based uniform in [0,1) used for the random key mask / dropout (testing hook; host code).
  * stream_id 0 = random mask, 1 = attention dropout.  idx = ((b*N + l)*N + m)*h + hh. */
 float egt_rng_uniform_host(uint64_t seed, uint64_t offset, uint32_t stream_id, uint64_t idx);
