@@ -12,22 +12,30 @@ namespace egt {
 __device__ __forceinline__ void fused_prep_body(const egt_block_weights_t &w, float clip_lo, float clip_hi,
                                                 FusedPrep *out, const int tid) {
   __shared__ float wp[2][FDE][FH];   // W' rounded to bf16
+  __shared__ float sW[2][FDE][FH], sWr[FH][FDE], sgam[FDE], sbet[FDE], sbias[2][FH];
+  {   // every global load of the prep is issued here, at once
+    int eg = tid / 64, c = (tid / 8) % 8, hh = tid % 8;
+    sW[eg][c][hh] = (eg ? w.attention_gates_kernel : w.dense_edge_b_kernel)[c * FH + hh];
+    if (tid < 64) sWr[tid / FDE][tid % FDE] = w.dense_edge_r_kernel[tid];
+    else if (tid < 72) sgam[tid - 64] = w.norm_edge_gamma[tid - 64];
+    else if (tid < 80) sbet[tid - 72] = w.norm_edge_beta[tid - 72];
+    else if (tid < 96) sbias[(tid - 80) / FH][(tid - 80) % FH] = ((tid - 80) / FH ? w.attention_gates_bias : w.dense_edge_b_bias)[(tid - 80) % FH];
+    else if (tid < 104) out->br[tid - 96] = w.dense_edge_r_bias[tid - 96];
+  }
+  __syncthreads();
   {
     int eg = tid / 64, c = (tid / 8) % 8, hh = tid % 8;
-    const float *W = eg ? w.attention_gates_kernel : w.dense_edge_b_kernel;
-    float v = __bfloat162float(__float2bfloat16_rn(w.norm_edge_gamma[c] * W[c * FH + hh]));
+    float v = __bfloat162float(__float2bfloat16_rn(sgam[c] * sW[eg][c][hh]));
     wp[eg][c][hh] = v;
     out->wp[eg][c][hh] = v;
   }
   __syncthreads();
   if (tid < 16) {
     int eg = tid / 8, hh = tid % 8;
-    const float *W = eg ? w.attention_gates_kernel : w.dense_edge_b_kernel;
-    const float *bias = eg ? w.attention_gates_bias : w.dense_edge_b_bias;
-    float u = 0.f, v = bias[hh], n2 = 0.f;
+    float u = 0.f, v = sbias[eg][hh], n2 = 0.f;
     for (int c = 0; c < FDE; ++c) {
       u += wp[eg][c][hh];
-      v += w.norm_edge_beta[c] * W[c * FH + hh];
+      v += sbet[c] * sW[eg][c][hh];
       n2 += wp[eg][c][hh] * wp[eg][c][hh];
     }
     (eg ? out->uG : out->uE)[hh] = u;
@@ -39,7 +47,6 @@ __device__ __forceinline__ void fused_prep_body(const egt_block_weights_t &w, fl
       if (hh == 0) out->bound = bnd;
     }
   }
-  if (tid < FDE) out->br[tid] = w.dense_edge_r_bias[tid];
   // wblk: n = key*16 + eg*8 + hh ; k = key'*8 + c            (N = 32, K = 16)
   for (int i = tid; i < 32 * 16; i += 128) {
     int n = i / 16, k = i % 16;
@@ -53,9 +60,9 @@ __device__ __forceinline__ void fused_prep_body(const egt_block_weights_t &w, fl
     int n = i / 16, k = i % 16;
     int key = n / 8, a = n % 8, key2 = k / 8, b = k % 8;
     out->wrblk[(k / 8) * (16 * 8) + n * 8 + (k % 8)] =
-        __float2bfloat16_rn(key == key2 ? w.dense_edge_r_kernel[b * FDE + a] : 0.f);
+        __float2bfloat16_rn(key == key2 ? sWr[b][a] : 0.f);
     out->wrtblk[(k / 8) * (16 * 8) + n * 8 + (k % 8)] =
-        __float2bfloat16_rn(key == key2 ? w.dense_edge_r_kernel[a * FDE + b] : 0.f);
+        __float2bfloat16_rn(key == key2 ? sWr[a][b] : 0.f);
   }
   // backward images (head-group ordered, fused.h)
   for (int i = tid; i < 32 * 16; i += 128) {      // b_eg
@@ -68,12 +75,12 @@ __device__ __forceinline__ void fused_prep_body(const egt_block_weights_t &w, fl
     {
       int g = n / 8, key = (n / 4) % 2, hh = 4 * g + n % 4, key2 = k / 8, c = k % 8;
       out->b_hx[(k / 8) * (16 * 8) + n * 8 + (k % 8)] =
-          __float2bfloat16_rn(key == key2 ? w.dense_edge_r_kernel[hh * FDE + c] : 0.f);
+          __float2bfloat16_rn(key == key2 ? sWr[hh][c] : 0.f);
     }
     {
       int key2 = n / 8, c = n % 8, g = k / 8, key = (k / 4) % 2, hh = 4 * g + k % 4;
       out->b_wr[(k / 8) * (16 * 8) + n * 8 + (k % 8)] =
-          __float2bfloat16_rn(key == key2 ? w.dense_edge_r_kernel[hh * FDE + c] : 0.f);
+          __float2bfloat16_rn(key == key2 ? sWr[hh][c] : 0.f);
     }
     for (int g = 0; g < 2; ++g) {
       int key2 = n / 8, c = n % 8, key = k / 8, eg = (k / 4) % 2, hh = 4 * g + k % 4;

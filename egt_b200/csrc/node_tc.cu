@@ -12,6 +12,7 @@
 // weight gradients) use the tile itself as an MN-major A operand next to a tile of ones, so rows 0-63 of
 // the accumulator hold dW and row 64 holds the column sum (the bias gradient); they accumulate in TMEM
 // over the CTA's tiles and are flushed once with atomics.
+#include <stdlib.h>
 #include "common.cuh"
 #include "fused.h"
 #include "umma.cuh"
@@ -45,24 +46,54 @@ __device__ __forceinline__ uint4 pack8(const float *x) {
 // consecutive floats of a row of W into one 16-byte chunk of the image.
 //   MN-major (n contiguous), 128B swizzle, atoms of 64 n: used for x @ W       (contraction over W's rows)
 __device__ __forceinline__ void build_w_mn(uint8_t *img, const float *W, int kdim, int ndim, int tid, int nthr) {
-  const int nch = ndim >> 3;
-  for (int i = tid; i < kdim * nch; i += nthr) {
-    const int k = i / nch, n = (i % nch) << 3;
-    const float4 a = *(const float4 *)(W + (size_t)k * ndim + n), b = *(const float4 *)(W + (size_t)k * ndim + n + 4);
-    const float y[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    const uint32_t off = (uint32_t)(n >> 6) * (uint32_t)(kdim * 128) + (uint32_t)(k >> 3) * 1024u + (uint32_t)(k & 7) * 128u +
-                         ((uint32_t)((((n & 63) >> 3) ^ k) & 7) << 4);
-    *(uint4 *)(img + off) = pack8(y);
+  const int nch = ndim >> 3, total = kdim * nch;
+  for (int i0 = tid; i0 < total; i0 += 4 * nthr) {      // 4 chunks per pass: 8 independent 16-byte loads in flight
+    float4 a[4], b[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * nthr;
+      if (i < total) {
+        const int k = i / nch, n = (i % nch) << 3;
+        a[u] = *(const float4 *)(W + (size_t)k * ndim + n);
+        b[u] = *(const float4 *)(W + (size_t)k * ndim + n + 4);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * nthr;
+      if (i < total) {
+        const int k = i / nch, n = (i % nch) << 3;
+        const float y[8] = {a[u].x, a[u].y, a[u].z, a[u].w, b[u].x, b[u].y, b[u].z, b[u].w};
+        const uint32_t off = (uint32_t)(n >> 6) * (uint32_t)(kdim * 128) + (uint32_t)(k >> 3) * 1024u + (uint32_t)(k & 7) * 128u +
+                             ((uint32_t)((((n & 63) >> 3) ^ k) & 7) << 4);
+        *(uint4 *)(img + off) = pack8(y);
+      }
+    }
   }
 }
 //   K-major image of W^T, i.e. B[n = row of W][k = column of W]: used for x @ W^T (contraction over W's columns)
 __device__ __forceinline__ void build_wt_k(uint8_t *img, const float *W, int nrows, int kcols, int tid, int nthr) {
-  const int kch = kcols >> 3;
-  for (int i = tid; i < nrows * kch; i += nthr) {
-    const int n = i / kch, k = (i % kch) << 3;
-    const float4 a = *(const float4 *)(W + (size_t)n * kcols + k), b = *(const float4 *)(W + (size_t)n * kcols + k + 4);
-    const float y[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    *(uint4 *)(img + (uint32_t)(k >> 6) * (uint32_t)(nrows * 128) + sw128_off(n, k & 63)) = pack8(y);
+  const int kch = kcols >> 3, total = nrows * kch;
+  for (int i0 = tid; i0 < total; i0 += 4 * nthr) {
+    float4 a[4], b[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * nthr;
+      if (i < total) {
+        const int n = i / kch, k = (i % kch) << 3;
+        a[u] = *(const float4 *)(W + (size_t)n * kcols + k);
+        b[u] = *(const float4 *)(W + (size_t)n * kcols + k + 4);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * nthr;
+      if (i < total) {
+        const int n = i / kch, k = (i % kch) << 3;
+        const float y[8] = {a[u].x, a[u].y, a[u].z, a[u].w, b[u].x, b[u].y, b[u].z, b[u].w};
+        *(uint4 *)(img + (uint32_t)(k >> 6) * (uint32_t)(nrows * 128) + sw128_off(n, k & 63)) = pack8(y);
+      }
+    }
   }
 }
 // 16-byte vector reduction into global memory (sm_90+)
@@ -514,7 +545,8 @@ __global__ void __launch_bounds__(128) node_bwd2_kernel(const NodeBwd2Args a) {
 // ------------------------------------------------------------------------------------------------
 static int node_grid(int R) {
   int tiles = (R + 127) / 128;
-  return tiles < 148 ? tiles : 148;
+  static const int cap = getenv("EGT_NODE_GRID") ? atoi(getenv("EGT_NODE_GRID")) : 148;
+  return tiles < cap ? tiles : cap;
 }
 template <typename K>
 static int set_smem(K kernel, int bytes) {
