@@ -1,5 +1,6 @@
 // abi.cu -- extern "C" entry points of libegt_b200.so (see include/egt_b200.h).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <mutex>
 #include <vector>
@@ -44,6 +45,13 @@ LaunchScope::LaunchScope(const char *name, cudaStream_t stream) : slot(-1), st(s
 }
 LaunchScope::~LaunchScope() {
   if (e1) cudaEventRecord(e1, st);
+}
+
+bool pdl_enabled() {
+  // measured on B200 (C0): overlapping the successor's set-up with the predecessor's tail made the step 7 %
+  // SLOWER (0.246 vs 0.229 ms) -- the early CTAs compete for the SMs the tail still needs -- so it is opt-in
+  static const bool on = getenv("EGT_PDL") && atoi(getenv("EGT_PDL")) != 0;
+  return on;
 }
 
 static size_t esize(int dtype) { return dtype == EGT_F32 ? 4 : 2; }

@@ -43,6 +43,29 @@ struct LaunchScope {
     }                                           \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------
+// Kernels of one step run back to back on one stream.  Each kernel lets its successor start early
+// (pdl_trigger) and does its own set-up (shared-memory / TMEM / barrier initialisation, weight images)
+// before it waits for its predecessor's memory to be visible (pdl_wait).  Rule kept by every kernel of this
+// library: no global WRITE and no global read of anything but the block's parameters before pdl_wait().
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();   // EGT_PDL=1 turns the launch attribute on (abi.cu; off by default, it measured slower)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- element access templated on the activation dtype --------------------------------
 template <typename T> __device__ __forceinline__ float ldf(const T *p);
 template <> __device__ __forceinline__ float ldf<float>(const float *p) { return *p; }

@@ -87,6 +87,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
   const int N = a.N;
   const int NT = (N + 7) / 8, NP = (N + 1) / 2;       // 8-key tiles, key pairs
 
+  pdl_trigger();
   if (warp == 8) {
     if (lane == 0) {
       mbar_init(smem_u32(&bars->q_full), 1);
@@ -100,7 +101,9 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     }
     __syncwarp();
     tmem_alloc(smem_u32(&bars->tmem_base), 512);
+    pdl_wait();
   } else {
+    pdl_wait();                                        // prep / dV_att come from the preceding kernel
     if (tid < 160) ((uint4 *)(smem + SM_W))[tid] = ((const uint4 *)a.prep->b_eg)[tid];   // b_eg | b_hx | b_de
     if (tid < 32) ((float *)(smem + SM_CONST))[tid] = a.prep->uE[tid];                  // uE vE uG vG
     for (int i = tid; i < 2 * ((N + 1) / 2); i += 256)                                   // key-valid bytes
@@ -615,9 +618,8 @@ int fused_bwd_launch(const FusedBwdArgs &a, const void *e, const void *de_out, v
   }
   dim3 grid((a.N + 127) / 128, a.B);
   LaunchScope _ls("fused_bwd_kernel", st);
-  if (a.rand_mask) fused_bwd_kernel<true><<<grid, 384, smem, st>>>(tm_e, tm_dei, tm_de, tm_q, tm_kv, a);
-  else fused_bwd_kernel<false><<<grid, 384, smem, st>>>(tm_e, tm_dei, tm_de, tm_q, tm_kv, a);
-  EGT_CHECK_CUDA(cudaGetLastError());
+  if (a.rand_mask) EGT_CHECK_CUDA(launch_pdl(fused_bwd_kernel<true>, grid, dim3(384), smem, st, tm_e, tm_dei, tm_de, tm_q, tm_kv, a));
+  else EGT_CHECK_CUDA(launch_pdl(fused_bwd_kernel<false>, grid, dim3(384), smem, st, tm_e, tm_dei, tm_de, tm_q, tm_kv, a));
   return EGT_OK;
 }
 

@@ -76,6 +76,7 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
   const int N = a.N;
   const int NT = (N + 7) / 8, NQ = (N + 3) / 4;       // 8-key tiles, pipeline steps of 4 keys (two pairs)
 
+  pdl_trigger();
   if (warp == 16) {
     if (lane == 0) {
       mbar_init(smem_u32(&bars->q_full), 1);
@@ -87,7 +88,9 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     }
     __syncwarp();
     tmem_alloc(smem_u32(&bars->tmem_base), 512);
+    pdl_wait();
   } else if (warp < 16) {
+    pdl_wait();                                        // prep / qkv come from the preceding kernel
     if (tid < 64) ((uint4 *)(smem + SM_W))[tid] = ((const uint4 *)a.prep->b_eg)[tid];            // b_eg
     else if (tid < 96) ((uint4 *)(smem + SM_W + 1024))[tid - 64] = ((const uint4 *)a.prep->b_wr)[tid - 64];
     if (tid < 40) ((float *)(smem + SM_CONST))[tid] = a.prep->uE[tid];                            // uE vE uG vG br
@@ -427,9 +430,8 @@ int fused_fwd_launch(const FusedFwdArgs &a, const void *e, void *e_out, const vo
   }
   dim3 grid((a.N + 127) / 128, a.B);
   LaunchScope _ls("fused_fwd_kernel", st);
-  if (a.rand_mask) fused_fwd_kernel<true><<<grid, 640, smem, st>>>(tm_e, tm_eo, tm_q, tm_kv, a);
-  else fused_fwd_kernel<false><<<grid, 640, smem, st>>>(tm_e, tm_eo, tm_q, tm_kv, a);
-  EGT_CHECK_CUDA(cudaGetLastError());
+  if (a.rand_mask) EGT_CHECK_CUDA(launch_pdl(fused_fwd_kernel<true>, grid, dim3(640), smem, st, tm_e, tm_eo, tm_q, tm_kv, a));
+  else EGT_CHECK_CUDA(launch_pdl(fused_fwd_kernel<false>, grid, dim3(640), smem, st, tm_e, tm_eo, tm_q, tm_kv, a));
   return EGT_OK;
 }
 

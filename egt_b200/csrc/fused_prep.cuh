@@ -12,7 +12,7 @@ namespace egt {
 __device__ __forceinline__ void fused_prep_body(const egt_block_weights_t &w, float clip_lo, float clip_hi,
                                                 FusedPrep *out, const int tid) {
   __shared__ float wp[2][FDE][FH];   // W' rounded to bf16
-  __shared__ float sW[2][FDE][FH], sWr[FH][FDE], sgam[FDE], sbet[FDE], sbias[2][FH];
+  __shared__ float sW[2][FDE][FH], sWr[FH][FDE], sgam[FDE], sbet[FDE], sbias[2][FH], sbr[FDE];
   {   // every global load of the prep is issued here, at once
     int eg = tid / 64, c = (tid / 8) % 8, hh = tid % 8;
     sW[eg][c][hh] = (eg ? w.attention_gates_kernel : w.dense_edge_b_kernel)[c * FH + hh];
@@ -20,9 +20,11 @@ __device__ __forceinline__ void fused_prep_body(const egt_block_weights_t &w, fl
     else if (tid < 72) sgam[tid - 64] = w.norm_edge_gamma[tid - 64];
     else if (tid < 80) sbet[tid - 72] = w.norm_edge_beta[tid - 72];
     else if (tid < 96) sbias[(tid - 80) / FH][(tid - 80) % FH] = ((tid - 80) / FH ? w.attention_gates_bias : w.dense_edge_b_bias)[(tid - 80) % FH];
-    else if (tid < 104) out->br[tid - 96] = w.dense_edge_r_bias[tid - 96];
+    else if (tid < 104) sbr[tid - 96] = w.dense_edge_r_bias[tid - 96];
   }
+  pdl_wait();                        // parameters were read above; everything below writes global memory
   __syncthreads();
+  if (tid < FDE) out->br[tid] = sbr[tid];
   {
     int eg = tid / 64, c = (tid / 8) % 8, hh = tid % 8;
     float v = __bfloat162float(__float2bfloat16_rn(sgam[c] * sW[eg][c][hh]));

@@ -130,11 +130,13 @@ __global__ void __launch_bounds__(128) node_qkv_kernel(const NodeQkvArgs a) {
   NodeBars *bars = (NodeBars *)(smem + TILE + 24576 + 1536);
   const int t = threadIdx.x;
   const int nwork = a.prep_out ? gridDim.x - 1 : gridDim.x;
+  pdl_trigger();
   if ((int)blockIdx.x == nwork) { fused_prep_body(a.w, a.clip_lo, a.clip_hi, a.prep_out, t); return; }
   node_setup(bars, t, 256);
   build_w_mn(sW, a.W, ND, 3 * ND, t, 128);
   if (t < ND) { sgb[t] = a.gamma[t]; sgb[ND + t] = a.beta[t]; }
   for (int i = t; i < 3 * ND; i += 128) sgb[2 * ND + i] = a.bias[i];
+  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -216,9 +218,11 @@ __global__ void __launch_bounds__(128) node_out_kernel(const NodeOutArgs a) {
   float *sb = (float *)(smem + TILE + 8192);
   NodeBars *bars = (NodeBars *)(smem + TILE + 8192 + 256);
   const int t = threadIdx.x;
+  pdl_trigger();
   node_setup(bars, t, 64);
   build_w_mn(sW, a.W, ND, ND, t, 128);
   if (t < ND) sb[t] = a.bias[t];
+  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -287,10 +291,12 @@ __global__ void __launch_bounds__(128) node_bwd1_kernel(const NodeBwd1Args a) {
   NodeBars *bars = (NodeBars *)(smem + 3 * TILE + 8192);
   const int t = threadIdx.x;
   const int nwork = a.prep_out ? gridDim.x - 1 : gridDim.x;
+  pdl_trigger();
   if ((int)blockIdx.x == nwork) { fused_prep_body(a.w, a.clip_lo, a.clip_hi, a.prep_out, t); return; }
   node_setup(bars, t, 128);
   build_wt_k(sW, a.W, ND, ND, t, 128);
   fill_ones(sOnes, t, 128);
+  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -389,11 +395,13 @@ __global__ void __launch_bounds__(128) node_bwd2_kernel(const NodeBwd2Args a) {
   NodeBars *bars = (NodeBars *)(sgb + 2 * ND);
   const int t = threadIdx.x;
   const int nwork = a.partials ? gridDim.x - 1 : gridDim.x;
-  if ((int)blockIdx.x == nwork) { fused_bwd_finalize_body(a.partials, a.nparts, a.w, a.g, t, 128); return; }
+  pdl_trigger();
+  if ((int)blockIdx.x == nwork) { pdl_wait(); fused_bwd_finalize_body(a.partials, a.nparts, a.w, a.g, t, 128); return; }
   node_setup(bars, t, 256);
   build_wt_k(sW, a.W, ND, 3 * ND, t, 128);
   fill_ones(sOnes, t, 128);
   if (t < ND) { sgb[t] = a.gamma[t]; sgb[ND + t] = a.beta[t]; }
+  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -562,8 +570,7 @@ int node_qkv_launch(const void *h, const float *gamma, const float *beta, float 
   static bool once = false;
   if (!once) { int rc = set_smem(node_qkv_kernel, smem); if (rc) return rc; once = true; }
   LaunchScope _ls("node_qkv_kernel", st);
-  node_qkv_kernel<<<node_grid(R) + (prep_out ? 1 : 0), 128, smem, st>>>(a);
-  EGT_CHECK_CUDA(cudaGetLastError());
+  EGT_CHECK_CUDA(launch_pdl(node_qkv_kernel, dim3(node_grid(R) + (prep_out ? 1 : 0)), dim3(128), smem, st, a));
   return EGT_OK;
 }
 
@@ -572,8 +579,7 @@ int node_out_launch(const void *v_att, const void *h, const float *W, const floa
   NodeOutArgs a{(const __nv_bfloat16 *)v_att, (const __nv_bfloat16 *)h, W, bias, (__nv_bfloat16 *)h_out, R};
   const int smem = TILE + 8192 + 256 + 64 + 1024;
   LaunchScope _ls("node_out_kernel", st);
-  node_out_kernel<<<node_grid(R), 128, smem, st>>>(a);
-  EGT_CHECK_CUDA(cudaGetLastError());
+  EGT_CHECK_CUDA(launch_pdl(node_out_kernel, dim3(node_grid(R)), dim3(128), smem, st, a));
   return EGT_OK;
 }
 
@@ -584,8 +590,7 @@ int node_bwd1_launch(const void *dh_out, const void *v_att, const float *W, void
   static bool once = false;
   if (!once) { int rc = set_smem(node_bwd1_kernel, smem); if (rc) return rc; once = true; }
   LaunchScope _ls("node_bwd1_kernel", st);
-  node_bwd1_kernel<<<node_grid(R) + (prep_out ? 1 : 0), 128, smem, st>>>(a);
-  EGT_CHECK_CUDA(cudaGetLastError());
+  EGT_CHECK_CUDA(launch_pdl(node_bwd1_kernel, dim3(node_grid(R) + (prep_out ? 1 : 0)), dim3(128), smem, st, a));
   return EGT_OK;
 }
 
@@ -599,8 +604,7 @@ int node_bwd2_launch(const void *h, const void *dh_out, const float *dqkv, const
   static bool once = false;
   if (!once) { int rc = set_smem(node_bwd2_kernel, smem); if (rc) return rc; once = true; }
   LaunchScope _ls("node_bwd2_kernel", st);
-  node_bwd2_kernel<<<node_grid(R) + (partials ? 1 : 0), 128, smem, st>>>(a);
-  EGT_CHECK_CUDA(cudaGetLastError());
+  EGT_CHECK_CUDA(launch_pdl(node_bwd2_kernel, dim3(node_grid(R) + (partials ? 1 : 0)), dim3(128), smem, st, a));
   return EGT_OK;
 }
 

@@ -37,6 +37,8 @@ __global__ void __launch_bounds__(256) peer_allreduce_kernel(const uint64_t *buf
                                                              int n4, int rank, int world) {
   __shared__ uint32_t s_epoch;
   const int tid = threadIdx.x, cta = blockIdx.x;
+  pdl_trigger();
+  pdl_wait();
   uint32_t *my_pad = (uint32_t *)pads[rank];
   if (tid == 0) s_epoch = my_pad[PAR_EPOCH + cta];
   __syncthreads();
@@ -85,7 +87,6 @@ extern "C" int egt_peer_allreduce(const uint64_t *buffer_ptrs_dev, const uint64_
   if (ctas > PAR_MAXCTA) ctas = PAR_MAXCTA;
   if (ctas < 1) ctas = 1;
   LaunchScope _ls("peer_allreduce_kernel", (cudaStream_t)stream);
-  peer_allreduce_kernel<<<ctas, 256, 0, (cudaStream_t)stream>>>(buffer_ptrs_dev, signal_pad_ptrs_dev, grad, n4, rank, world);
-  EGT_CHECK_CUDA(cudaGetLastError());
+  EGT_CHECK_CUDA(launch_pdl(peer_allreduce_kernel, dim3(ctas), dim3(256), 0, (cudaStream_t)stream, buffer_ptrs_dev, signal_pad_ptrs_dev, grad, n4, rank, world));
   return EGT_OK;
 }
