@@ -404,3 +404,50 @@ def test_fused_path_matches_staged_and_oracle(N, B, training, rmp):
     # weight gradients of the two paths agree to bf16 accumulation noise
     wa, wb = outs[0][2][2], outs[1][2][2]
     assert float((wa - wb).abs().max()) <= 3e-2 * float(wb.abs().max())
+
+
+def test_block_step_replays_as_cuda_graph():
+    """bench.py replays the step as a CUDA graph: a captured forward+backward must give the same result as
+    the eager launches when new data is copied into the static input buffers."""
+    import egt_b200
+    torch.manual_seed(3)
+    B, N, d, de, nh = 6, 96, 64, 8, 8
+    blk = egt_b200.EGTBlock(model_width=d, edge_width=de, num_heads=nh, scale_degree=True).to(DEV)
+    with torch.no_grad():
+        blk.flat.add_(0.05 * torch.randn_like(blk.flat))
+    mask = (torch.arange(N)[None] < torch.tensor([96, 80, 64, 50, 96, 7])[:, None]).to(DEV)
+    hs = torch.zeros(B, N, d, device=DEV, dtype=torch.bfloat16)
+    es = torch.zeros(B, N, N, de, device=DEV, dtype=torch.bfloat16)
+    dh = torch.randn(B, N, d, device=DEV).bfloat16()
+    dE = torch.randn(B, N, N, de, device=DEV).bfloat16()
+
+    def step(h, e):
+        h = h.detach().requires_grad_(True)
+        e = e.detach().requires_grad_(True)
+        blk.flat.grad = None
+        h2, e2 = blk(h, e, mask)
+        torch.autograd.backward([h2, e2], [dh, dE])
+        return h2.detach(), e2.detach(), h.grad, e.grad, blk.flat.grad
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        step(hs, es)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        outs = step(hs, es)
+    for trial in range(2):
+        h = torch.randn(B, N, d, device=DEV).bfloat16()
+        e = torch.randn(B, N, N, de, device=DEV).bfloat16()
+        hs.copy_(h)
+        es.copy_(e)
+        g.replay()
+        torch.cuda.synchronize()
+        got = [o.clone() for o in outs]
+        ref = step(h, e)
+        for a, b, nm in zip(got[:4], ref[:4], ('h2', 'e2', 'dh', 'de')):
+            assert torch.equal(a, b), f'{nm} differs between graph replay and eager launches (trial {trial})'
+        # weight gradients are accumulated with atomics across CTAs: equal up to summation order
+        torch.testing.assert_close(got[4], ref[4], rtol=1e-3, atol=1e-3 * float(ref[4].abs().max()))
