@@ -350,8 +350,10 @@ int egt_block_fwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
     fa.rand_mask = a.training && a.random_mask_prob > 0.f;
     fa.rand_thr = (uint32_t)ceilf(a.random_mask_prob * 65536.0f - 0.5f);
     fa.seed = a.seed; fa.offset = a.offset;
-    if ((rc = fused_fwd_launch(fa, io->e, io->e_out, io->qkv, st))) return rc;
-    return node_out_launch(io->v_att, io->h, w->dense_mha_kernel, w->dense_mha_bias, io->h_out, R, st);
+    // the output projection + residual runs in the same kernel (V_att goes from registers to the tensor core)
+    fa.w_o = w->dense_mha_kernel; fa.b_o = w->dense_mha_bias;
+    fa.h = (const __nv_bfloat16 *)io->h; fa.h_out = (__nv_bfloat16 *)io->h_out;
+    return fused_fwd_launch(fa, io->e, io->e_out, io->qkv, st);
   }
 
   EdgeParams ep = make_edge_params(cfg, w);

@@ -46,6 +46,10 @@ struct FusedFwdArgs {
   int scale_degree, scaler_type, num_virtual_nodes;
   int rand_mask; uint32_t rand_thr;   // mask element when its 16 random bits < rand_thr
   uint64_t seed, offset;
+  // output projection fused behind the attention (graph_xformer_model_base.py:136-140); w_o == NULL = off
+  const float *w_o, *b_o;             // dense_mha kernel [64,64], bias [64]
+  const __nv_bfloat16 *h;             // [B,N,64] residual input
+  __nv_bfloat16 *h_out;               // [B,N,64]
 };
 
 // Partial weight-gradient sums one backward CTA writes (fused_bwd_finalize_kernel folds them):

@@ -46,7 +46,8 @@ constexpr uint32_t SM_W = SM_KVX + 8 * 4096;                   // b_eg 1024 | b_
 constexpr uint32_t SM_CONST = SM_W + 1536;                     // uE vE uG vG br (40 floats)
 constexpr uint32_t SM_BAR = SM_CONST + 256;
 constexpr uint32_t SM_MASK = SM_BAR + 256;                       // key-valid bytes, zero padded (N <= 4096)
-constexpr uint32_t SM_TOTAL = SM_MASK + 4096 + 16;
+constexpr uint32_t SM_WO = (SM_MASK + 4096 + 16 + 1023) & ~1023u;   // W_O operand image (MN-major, 8 KB) | b_O (64 floats)
+constexpr uint32_t SM_TOTAL = SM_WO + 8192 + 256;
 
 constexpr uint32_t TM_O = 0;
 constexpr uint32_t TM_IN = 64, TM_IN_COLS = 96, TM_PAIR = 48;  // 2 buffers x 2 pairs: S 16 | EG 32   (step parity)
@@ -58,7 +59,7 @@ constexpr uint32_t ID_N16 = idesc_bf16(128, 16, 0, 0);
 constexpr uint32_t ID_N32 = idesc_bf16(128, 32, 0, 0);
 constexpr uint32_t ID_PV = idesc_bf16(128, 64, 0, 1);
 
-struct Bars { uint64_t q_full, e_full[NS], mma1[2], mma2[2], step; uint32_t tmem_base; };
+struct Bars { uint64_t q_full, e_full[NS], mma1[2], mma2[2], step, oproj; uint32_t tmem_base; };
 
 }  // namespace
 
@@ -83,12 +84,26 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
       for (int i = 0; i < NS; ++i) mbar_init(smem_u32(&bars->e_full[i]), 1);
       for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->mma1[i]), 1); mbar_init(smem_u32(&bars->mma2[i]), 1); }
       mbar_init(smem_u32(&bars->step), 512);          // every compute thread arrives once per step
+      mbar_init(smem_u32(&bars->oproj), 1);
       mbar_fence_init();
       tma_prefetch_desc(&tm_e); tma_prefetch_desc(&tm_eo); tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_kv);
     }
     __syncwarp();
     tmem_alloc(smem_u32(&bars->tmem_base), 512);
     pdl_wait();
+  } else if (warp > 16) {
+    if (a.w_o) {   // W_O (float32 [64,64], "x @ W") -> MN-major 128B-swizzled bf16 operand image; b_O
+      const int u = tid - 17 * 32;                     // 0 .. 95
+      for (int i = u; i < 64 * 8; i += 96) {
+        const int k = i >> 3, n = (i & 7) << 3;
+        const float4 w0 = *(const float4 *)(a.w_o + k * 64 + n), w1 = *(const float4 *)(a.w_o + k * 64 + n + 4);
+        uint4 v;
+        v.x = pack_bf16(w0.x, w0.y); v.y = pack_bf16(w0.z, w0.w); v.z = pack_bf16(w1.x, w1.y); v.w = pack_bf16(w1.z, w1.w);
+        *(uint4 *)(smem + SM_WO + (uint32_t)(k >> 3) * 1024u + (uint32_t)(k & 7) * 128u + ((uint32_t)(((n >> 3) ^ k) & 7) << 4)) = v;
+      }
+      if (u < 64) ((float *)(smem + SM_WO + 8192))[u] = a.b_o[u];
+      fence_proxy_async_smem();
+    }
   } else if (warp < 16) {
     pdl_wait();                                        // prep / qkv come from the preceding kernel
     if (tid < 64) ((uint4 *)(smem + SM_W))[tid] = ((const uint4 *)a.prep->b_eg)[tid];            // b_eg
@@ -196,6 +211,19 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     }
     __syncwarp();
     __syncthreads();                                   // partial row sums exchanged
+    if (a.w_o) {
+      __syncthreads();                                 // V_att tile staged (over the Q tile)
+      if (leader) {
+        tc_fence_after();
+        constexpr uint32_t ID_OP = idesc_bf16(128, 64, 0, 1);
+        const uint32_t loA = desc_lo(sbase + SM_Q, 16), loB = desc_lo(sbase + SM_WO, 8192);
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+          mma_ss(tmem + TM_IN, mkdesc(loA + 2 * s, HI_SW), mkdesc(loB + 128 * s, HI_SW), ID_OP, s > 0);
+        mma_commit(smem_u32(&bars->oproj));
+      }
+      __syncwarp();
+    }
     __syncthreads();                                   // final
     if (warp == 16) tmem_dealloc(tmem, 512);
     return;
@@ -398,6 +426,19 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
         }
         dst[dd * 2] = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));   // channels dd*8 + 4g .. +3
       }
+      if (a.w_o) {   // same values into the A tile of the output projection (rows l >= N stay zero: TMA OOB fill of Q)
+#pragma unroll
+        for (int dd = 0; dd < 4; ++dd) {
+          float v[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float lo4 = __uint_as_float(o[dd * 8 + i]), hi4 = __uint_as_float(o[dd * 8 + 4 + i]);
+            v[i] = (g ? hi4 : lo4) * f[i];
+          }
+          *(uint2 *)(smem + SM_Q + trow + (((uint32_t)(4 * kq + dd) ^ tx7) << 4) + 8 * g) =
+              make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+        }
+      }
       if (kq == 0) {
         const size_t ps = ((size_t)b * N + l) * FH + 4 * g, rs = (size_t)a.B * N * FH;
 #pragma unroll
@@ -406,6 +447,34 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
           a.lse[rs + ps + i] = psum[i] > 0.f ? __logf(psum[i]) : 0.f;
           a.deg[ps + i] = gsum[i];
         }
+      }
+    }
+  }
+  if (a.w_o) {   // h' = h + V_att W_O + b_O  (graph_xformer_model_base.py:136-140)
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();                                   // V_att tile staged
+    mbar_wait(smem_u32(&bars->oproj), 0);
+    tc_fence_after();
+    uint32_t o[16];
+    const int c0 = 16 * (2 * kq + g);                  // this thread's 16 output channels of row l
+    tmem_ld16(tlane + TM_IN + c0, o);
+    tmem_ld_wait();
+    if (rowvalid) {
+      const float *bo = (const float *)(smem + SM_WO + 8192) + c0;
+      const uint4 *hp = (const uint4 *)(a.h + ((size_t)b * N + l) * FD + c0);
+      uint4 *op = (uint4 *)(a.h_out + ((size_t)b * N + l) * FD + c0);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const uint4 hv = hp[q];
+        const float hr[8] = {bf16_lo(hv.x), bf16_hi(hv.x), bf16_lo(hv.y), bf16_hi(hv.y),
+                             bf16_lo(hv.z), bf16_hi(hv.z), bf16_lo(hv.w), bf16_hi(hv.w)};
+        float y[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) y[c] = __uint_as_float(o[8 * q + c]) + bo[8 * q + c] + hr[c];
+        uint4 ov;
+        ov.x = pack_bf16(y[0], y[1]); ov.y = pack_bf16(y[2], y[3]); ov.z = pack_bf16(y[4], y[5]); ov.w = pack_bf16(y[6], y[7]);
+        op[q] = ov;
       }
     }
   }
