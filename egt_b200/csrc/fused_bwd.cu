@@ -53,16 +53,17 @@ constexpr uint32_t SM_TOTAL = SM_MASK + 4096 + 16;
 static_assert(SM_TOTAL + 1024 <= 232448, "shared memory budget");
 
 constexpr uint32_t TM_DQ = 0, TM_DK = 64, TM_DV = 128;
-constexpr uint32_t TM_IN = 192, TM_IN_COLS = 80;               // 3 buffers: S 16 | dA 16 | EG 32 | dHx 16
+constexpr uint32_t TM_IN = 192, TM_IN_COLS = 80;               // 2 buffers (pair parity): S 16 | dA 16 | EG 32 | dHx 16
 constexpr uint32_t IN_S = 0, IN_DA = 16, IN_EG = 32, IN_HX = 64;
-constexpr uint32_t TM_OUT = 432, TM_OUT_COLS = 32;             // 2 buffers: dS 8 | dZ 16 (bf16 A operands)
+constexpr uint32_t TM_DX = 352, TM_DX_COLS = 16;               // 2 buffers (pair parity): d x^ 16
+constexpr uint32_t TM_OUT = 384, TM_OUT_COLS = 32;             // 2 buffers (pair parity): dS 8 | dZ 16 (bf16 A operands)
 
 constexpr uint32_t ID_N16 = idesc_bf16(128, 16, 0, 0);
 constexpr uint32_t ID_N32 = idesc_bf16(128, 32, 0, 0);
 constexpr uint32_t ID_DQ = idesc_bf16(128, 64, 0, 1);
 constexpr uint32_t ID_T = idesc_bf16(128, 64, 1, 1);
 
-struct Bars { uint64_t q_full, e_full[NS], mma1[3], mma2[3], tbar, step; uint32_t tmem_base; };
+struct Bars { uint64_t q_full, e_full[NS], mma1[2], mma2[2], tbar, step; uint32_t tmem_base; };
 
 __device__ __forceinline__ float sel8(const uint32_t *o, int hh) {
   const uint32_t a0 = (hh & 1) ? o[1] : o[0], a1 = (hh & 1) ? o[3] : o[2];
@@ -92,7 +93,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     if (lane == 0) {
       mbar_init(smem_u32(&bars->q_full), 1);
       for (int i = 0; i < NS; ++i) mbar_init(smem_u32(&bars->e_full[i]), 1);
-      for (int i = 0; i < 3; ++i) { mbar_init(smem_u32(&bars->mma1[i]), 1); mbar_init(smem_u32(&bars->mma2[i]), 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->mma1[i]), 1); mbar_init(smem_u32(&bars->mma2[i]), 1); }
       mbar_init(smem_u32(&bars->tbar), 1);
       mbar_init(smem_u32(&bars->step), 256);          // every compute thread arrives once per key pair
       mbar_fence_init();
@@ -138,8 +139,8 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     const uint32_t loWeg = desc_lo(sbase + SM_W, 512), loWhx = desc_lo(sbase + SM_W + 1024, 256);
     const uint32_t loWde = desc_lo(sbase + SM_W + 1536, 256);
     const uint32_t bar_e0 = smem_u32(&bars->e_full[0]), bar_m1 = smem_u32(&bars->mma1[0]), bar_m2 = smem_u32(&bars->mma2[0]);
-    auto issue_mma1 = [&](int p, int buf) {
-      const int T = p >> 2, j = p & 3, st = T % NS, slot = p & 3;
+    auto issue_mma1 = [&](int p) {                     // -> input buffer p & 1 (no commit: see the handshake below)
+      const int T = p >> 2, j = p & 3, st = T % NS, slot = p & 3, buf = p & 1;
       mbar_wait(bar_e0 + 8 * st, (T / NS) & 1);
       tc_fence_after();
       const uint32_t d = tmem + TM_IN + buf * TM_IN_COLS;
@@ -152,16 +153,16 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
         mma_ss(d + IN_DA, mkdesc(loDO + 2 * s, HI_SW), mkdesc(v0 + 2 * s, HI_SW), ID_N16, s > 0);
       mma_ss(d + IN_EG, mkdesc(loE + e0, HI_SW), mkdesc(loWeg, HI_NONE), ID_N32, 0);
       mma_ss(d + IN_HX, mkdesc(loDE + e0, HI_SW), mkdesc(loWhx, HI_NONE), ID_N16, 0);
-      mma_commit(bar_m1 + 8 * buf);
     };
-    auto issue_mma2 = [&](int p, int buf) {
+    auto issue_mma2 = [&](int p) {                     // dQ += dS Kexp ; d x^ = [dE|dG] W'^T   (operands / result: parity p & 1)
       const int ob = p & 1, slot = p & 3;
       const uint32_t ao = tmem + TM_OUT + ob * TM_OUT_COLS;
       mma_ts(tmem + TM_DQ, ao, mkdesc(loKmn + slot * 256, HI_SW), ID_DQ, p > 0);
-      const uint32_t dd = tmem + TM_IN + buf * TM_IN_COLS + IN_EG;
+      const uint32_t dd = tmem + TM_DX + ob * TM_DX_COLS;
       mma_ts(dd, ao + 8, mkdesc(loWde, HI_NONE), ID_N16, 0);
       mma_ts(dd, ao + 16, mkdesc(loWde + 32, HI_NONE), ID_N16, 1);
-      mma_commit(bar_m2 + 8 * buf);
+    };
+    auto issue_t = [&](int p) {
       if ((p & 7) == 7 || p == NP - 1) {                // a 16-key block of dS^T / A~^T is complete
         const uint32_t loT = desc_lo(sbase + SM_TR, 16384), loQm = desc_lo(sbase + SM_Q, 16384);
         const uint32_t loDOm = desc_lo(sbase + SM_DO, 16384);
@@ -183,35 +184,41 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     if (leader) {
       tc_fence_after();
       mbar_wait(smem_u32(&bars->q_full), 0);
-      issue_mma1(0, 0);
-      if (NP > 1) issue_mma1(1, 1);
+      issue_mma1(0);
+      mma_commit(bar_m1);
+      if (NP > 1) { issue_mma1(1); mma_commit(bar_m1 + 8); }
     }
     const uint32_t bar_step = smem_u32(&bars->step);
-    int ibuf = 0;                                      // it % 3
+    int next_store = 0;                                // tiles [0, next_store) have been handed to the TMA store
     for (int it = 0; it < NP && warp == 8; ++it) {     // warps 9-11 go straight to the tail barrier
       if (leader) {
-        mbar_wait(bar_step, it & 1);                   // all compute threads finished pair it (no CTA-wide barrier:
-        tc_fence_after();                              //  fast warps run ahead into pair it+1 meanwhile)
-        issue_mma2(it, ibuf);
-        if (it + 2 < NP) issue_mma1(it + 2, ibuf == 0 ? 2 : ibuf - 1);
-        if (it >= 2 && ((it - 2) & 3) == 3) {          // tile stored at the previous sync: recycle its stage
-          const int T = (it - 2) >> 2;
+        mbar_wait(bar_step, it & 1);                   // all compute threads finished pair it (no CTA-wide barrier)
+        tc_fence_after();
+        fence_proxy_async_smem();
+        issue_mma2(it);
+        if (it + 2 < NP) issue_mma1(it + 2);
+        mma_commit(bar_m2 + 8 * (it & 1));             // ONE completion per handshake: products of pair it and the
+                                                       // inputs of pair it+2, both consumed during pair it+2
+        issue_t(it);                                   // (the 16-key transposed products have their own barrier)
+        // pair it contained the de update of pair it-2; tile T (pairs 4T .. 4T+3) is complete when it == 4T+5
+        if (it >= 6 && ((it - 6) & 3) == 0) {          // tile stored at the previous handshake: recycle its stage
+          const int T = (it - 6) >> 2;
           tma_store_wait_read<0>();
           if (T + NS < NT) load_tile(T + NS);
         }
-        if (it >= 1 && ((it - 1) & 3) == 3) {          // phase B of tile T's last pair ran: de is complete in place
-          const int T = (it - 1) >> 2;
+        if (it >= 5 && ((it - 5) & 3) == 0) {
+          const int T = (it - 5) >> 2;
           tma_store_3d(&tm_de, sbase + SM_STAGE + (T % NS) * STAGE_BYTES + ST_DE, T * 64, l0, b);
           tma_store_commit();
+          next_store = T + 1;
         }
       }
-      if (++ibuf == 3) ibuf = 0;
       __syncwarp();
     }
-    __syncthreads();                                   // sync #(NP+1): phase B of the last pair is done
+    __syncthreads();                                   // sync #(NP+1): every de update is done
     if (leader) {
-      const int T = NT - 1;
-      tma_store_3d(&tm_de, sbase + SM_STAGE + (T % NS) * STAGE_BYTES + ST_DE, T * 64, l0, b);
+      for (int T = next_store; T < NT; ++T)
+        tma_store_3d(&tm_de, sbase + SM_STAGE + (T % NS) * STAGE_BYTES + ST_DE, T * 64, l0, b);
       tma_store_commit();
       tma_store_wait_all<0>();
     }
@@ -334,8 +341,8 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
 
   // ---- phase A: pair p, this thread's 4 heads of both keys ------------------------------------------
   float cur_r = 0.f, cur_nrm = 0.f, prev_r = 0.f, prev_nrm = 0.f;   // LN statistics of key g of the current / previous pair
-  auto phase_a = [&](int p, int st, int buf) {
-    const int j = p & 3, ob = p & 1;
+  auto phase_a = [&](int p, int st) {
+    const int j = p & 3, ob = p & 1, buf = p & 1;
     const uint8_t *es = smem + SM_STAGE + st * STAGE_BYTES;
     const uint32_t tin = tlane + TM_IN + buf * TM_IN_COLS;
     const uint32_t tout = tlane + TM_OUT + ob * TM_OUT_COLS;
@@ -431,12 +438,12 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
   };
 
   // ---- phase B: LayerNorm backward + residual for key g of pair p -> de, in place over de' -----------
-  auto phase_b = [&](int p, int st, int buf, const float r, const float nrm) {
+  auto phase_b = [&](int p, int st, const float r, const float nrm) {
     const int j = p & 3;
     uint8_t *es = smem + SM_STAGE + st * STAGE_BYTES;
     const int ks = 2 * j + g;
     uint32_t dr[8];
-    tmem_ld8(tlane + TM_IN + buf * TM_IN_COLS + IN_EG + g * 8, dr);
+    tmem_ld8(tlane + TM_DX + (p & 1) * TM_DX_COLS + g * 8, dr);
     const uint32_t eoff = trow + (((uint32_t)ks ^ tx7) << 4);
     const uint4 ev = *(const uint4 *)(es + ST_E + eoff);
     const float x[8] = {bf16_lo(ev.x), bf16_hi(ev.x), bf16_lo(ev.y), bf16_hi(ev.y),
@@ -499,31 +506,30 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
   if (NP > 1) build(1, 0);
   fence_proxy_async_smem();
   __syncthreads();                                     // sync #0
-  int st_a = 0, buf_a = 0, par_a = 0;                  // pair it
-  int st_p = 0, buf_p = 0, par_p = 0;                  // pair it - 1
-  int st_n = 0, par_n = 0;                             // pair it + 2 (its tile's stage / load parity)
+  int st_a = 0;                                        // stage of pair it
+  int st_b = 0;                                        // stage of pair it - 2
+  int st_n = 0, par_n = 0;                             // stage / load parity of pair it + 2
+  float h1_r = 0.f, h1_nrm = 0.f, h2_r = 0.f, h2_nrm = 0.f;   // LN statistics (key g) of pairs it-1, it-2
   for (int it = 0; it < NP; ++it) {
     if (((it + 2) & 3) == 0 || it == 0) {              // pair it+2 sits in tile (it+2)>>2
       const int T2 = (it + 2) >> 2;
       st_n = T2 % NS; par_n = (T2 / NS) & 1;
     }
-    mbar_wait(bar_mma1 + 8 * buf_a, par_a);
+    const uint32_t ob8 = 8u * (uint32_t)(it & 1);
+    if (it >= 2) mbar_wait(bar_mma2 + ob8, ((it - 2) >> 1) & 1);   // handshake it-2: inputs of this pair, products of pair it-2
+    else mbar_wait(bar_mma1 + ob8, 0);                 // pairs 0, 1: issued before the loop
     tc_fence_after();
-    phase_a(it, st_a, buf_a);
-    if (it >= 1) {
-      mbar_wait(bar_mma2 + 8 * buf_p, par_p);
-      tc_fence_after();
-      phase_b(it - 1, st_p, buf_p, prev_r, prev_nrm);
-      if (((it - 1) & 7) == 7) {                       // dS^T / A~^T block (it-1)/8 went through the tensor core
-        const int kb = (it - 1) >> 3;
-        if ((kb & 1) == g) {
-          mbar_wait(bar_t, kb & 1);
-          tc_fence_after();
-          t_epilogue(kb);
-        }
+    phase_a(it, st_a);
+    if (it >= 2) phase_b(it - 2, st_b, h2_r, h2_nrm);
+    if (it >= 1 && ((it - 1) & 7) == 7) {              // dS^T / A~^T block (it-1)/8 went through the tensor core
+      const int kb = (it - 1) >> 3;
+      if ((kb & 1) == g) {
+        mbar_wait(bar_t, kb & 1);
+        tc_fence_after();
+        t_epilogue(kb);
       }
     }
-    prev_r = cur_r; prev_nrm = cur_nrm;
+    h2_r = h1_r; h2_nrm = h1_nrm; h1_r = cur_r; h1_nrm = cur_nrm;
     if (it + 2 < NP) {
       if (((it + 2) & 3) == 0) mbar_wait(bar_e + 8 * st_n, par_n);   // first pair of a tile
       build(it + 2, st_n);
@@ -532,13 +538,15 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     fence_proxy_async_smem();
     tc_fence_before();
     mbar_arrive(bar_step);                             // pair it done by this thread
-    st_p = st_a; buf_p = buf_a; par_p = par_a;
-    if (++buf_a == 3) { buf_a = 0; par_a ^= 1; }
     if (((it + 1) & 3) == 0) { if (++st_a == NS) st_a = 0; }
+    if (it >= 2 && ((it - 1) & 3) == 0) { if (++st_b == NS) st_b = 0; }   // pair it-1 opens a new tile
   }
-  mbar_wait(bar_mma2 + 8 * buf_p, par_p);
-  tc_fence_after();
-  phase_b(NP - 1, st_p, buf_p, prev_r, prev_nrm);
+  for (int q = (NP >= 2 ? NP - 2 : 0); q < NP; ++q) {  // de updates of the last two pairs
+    mbar_wait(bar_mma2 + 8 * (q & 1), (q >> 1) & 1);
+    tc_fence_after();
+    if (q == NP - 1) phase_b(q, (q >> 2) % NS, h1_r, h1_nrm);
+    else phase_b(q, (q >> 2) % NS, h2_r, h2_nrm);
+  }
   fence_proxy_async_smem();
   __syncthreads();                                     // sync #(NP+1)
   {
