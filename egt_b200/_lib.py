@@ -19,7 +19,25 @@ EGT_E_SHAPE, EGT_E_DTYPE, EGT_E_ALIGN, EGT_E_ARCH, EGT_E_CUDA, EGT_E_ARG = -1, -
 EXPORTS = ['egt_abi_version', 'egt_last_error', 'egt_last_path', 'egt_rng_uniform_host',
            'egt_block_param_layout', 'egt_attn_fwd', 'egt_attn_bwd', 'egt_block_workspace_bytes',
            'egt_block_fwd', 'egt_block_bwd', 'egt_launch_count', 'egt_profile_enable', 'egt_profile_read',
-           'egt_debug_umma_probe', 'egt_debug_force_staged', 'egt_peer_allreduce']
+           'egt_debug_umma_probe', 'egt_debug_force_staged', 'egt_peer_allreduce',
+           'egt_ffn_fwd', 'egt_ffn_bwd']
+
+FFN_FIELDS = ['norm_gamma', 'norm_beta', 'lr1_kernel', 'lr1_bias', 'lr2_kernel', 'lr2_bias']
+
+
+class FfnCfg(C.Structure):
+    """egt_ffn_cfg_t (include/egt_b200.h)."""
+    _fields_ = [('rows', C.c_int64), ('width', C.c_int32), ('hidden', C.c_int32), ('dtype', C.c_int32),
+                ('activation', C.c_int32), ('ln_eps', C.c_float)]
+
+
+class FfnWeights(C.Structure):
+    _fields_ = [(f, C.c_void_p) for f in FFN_FIELDS]
+
+
+class FfnGrads(C.Structure):
+    _fields_ = [(f, C.c_void_p) for f in FFN_FIELDS]
+
 
 WEIGHT_FIELDS = ['norm_mha_gamma', 'norm_mha_beta', 'dense_qkv_kernel', 'dense_qkv_bias',
                  'dense_mha_kernel', 'dense_mha_bias', 'norm_edge_gamma', 'norm_edge_beta',
@@ -97,6 +115,10 @@ def load():
     lib.egt_block_bwd.restype = C.c_int
     lib.egt_block_bwd.argtypes = [C.POINTER(BlockCfg), C.POINTER(BlockWeights), C.POINTER(BlockGrads),
                                   C.POINTER(BlockBwdIO), vp]
+    lib.egt_ffn_fwd.restype = C.c_int
+    lib.egt_ffn_fwd.argtypes = [C.POINTER(FfnCfg), C.POINTER(FfnWeights), vp, vp, vp]
+    lib.egt_ffn_bwd.restype = C.c_int
+    lib.egt_ffn_bwd.argtypes = [C.POINTER(FfnCfg), C.POINTER(FfnWeights), C.POINTER(FfnGrads), vp, vp, vp, vp]
     lib.egt_peer_allreduce.restype = C.c_int
     lib.egt_peer_allreduce.argtypes = [vp, vp, vp, C.c_int64, C.c_int, C.c_int, vp]
     lib.egt_launch_count.restype = C.c_long

@@ -145,3 +145,91 @@ class EGTBlock(nn.Module):
         seed, offset = self.rng.next() if training else (0, 0)
         return ops.egt_block(h, e, mask, self.flat, self.spec, self.layout, edge_mask=edge_mask,
                              training=training, seed=seed, offset=offset)
+
+
+class EGTFFN(nn.Module):
+    """Feed-forward half of a layer for ONE channel (node: ``width = model_width``; edge: ``width =
+    edge_width``): ``y = x + Dense_w(act(Dense_round(w*ffn_multiplier)(LayerNorm(x))))`` --
+    ``ffnlr1 / ffnact / ffnlr2`` of graph_xformer_model_base.py:229-258 as ``ffn_block`` (:309-324) chains
+    them.  Weights live in one flat float32 parameter; names follow the reference
+    (``norm_fnn_{channel}_{tag}``, ``fnn_lr1_{channel}_{tag}``, ``fnn_lr2_{channel}_{tag}``)."""
+
+    _NAMES = {'norm_gamma': ('norm_fnn', 'gamma'), 'norm_beta': ('norm_fnn', 'beta'),
+              'lr1_kernel': ('fnn_lr1', 'kernel'), 'lr1_bias': ('fnn_lr1', 'bias'),
+              'lr2_kernel': ('fnn_lr2', 'kernel'), 'lr2_bias': ('fnn_lr2', 'bias')}
+
+    def __init__(self, width, channel='node', tag='00', ffn_multiplier=2., activation='elu', ln_eps=1e-3):
+        super().__init__()
+        assert channel in ('node', 'edge')
+        self.width, self.hidden = int(width), int(round(width * ffn_multiplier))   # graph_xformer_model_base.py:236
+        self.channel, self.tag, self.activation, self.ln_eps = channel, tag, activation, ln_eps
+        total, self.layout = ops.ffn_layout(self.width, self.hidden)
+        self.flat = nn.Parameter(torch.zeros(total, dtype=torch.float32))
+        self.reset_parameters()
+
+    def view(self, field):
+        off, shape = self.layout[field]
+        return self.flat.data[off:off + math.prod(shape)].view(shape)
+
+    def grad_view(self, field):
+        if self.flat.grad is None:
+            return None
+        off, shape = self.layout[field]
+        return self.flat.grad[off:off + math.prod(shape)].view(shape)
+
+    def reset_parameters(self, seed=4321):
+        g = torch.Generator().manual_seed(seed)
+        for f in self.layout:
+            v = self.view(f)
+            if f.endswith('kernel'):
+                lim = math.sqrt(6.0 / (v.shape[0] + v.shape[1]))
+                v.copy_((torch.rand(v.shape, generator=g) * 2 - 1) * lim)
+            elif f.endswith('gamma'):
+                v.fill_(1.)
+            else:
+                v.zero_()
+
+    def load_keras_weights(self, weights: Dict[str, torch.Tensor], strict=True):
+        """Keys ``'{stem}_{channel}_{tag}/{weight}'`` as in the reference checkpoint, or the oracle's
+        ``'ffn_{channel}/{norm|lr1|lr2}/{weight}'``."""
+        short = {'norm_fnn': 'norm', 'fnn_lr1': 'lr1', 'fnn_lr2': 'lr2'}
+        for f in self.layout:
+            stem, wn = self._NAMES[f]
+            for key in (f'{stem}_{self.channel}_{self.tag}/{wn}', f'ffn_{self.channel}/{short[stem]}/{wn}'):
+                if key in weights:
+                    w = torch.as_tensor(weights[key], dtype=torch.float32)
+                    assert tuple(w.shape) == tuple(self.layout[f][1]), f'{key}: {tuple(w.shape)} != {self.layout[f][1]}'
+                    self.view(f).copy_(w)
+                    break
+            else:
+                if strict:
+                    raise KeyError(f'missing weight for {stem}_{self.channel}_{self.tag}/{wn}')
+
+    def forward(self, x):
+        return ops.egt_ffn(x, self.flat, self.width, self.hidden, self.layout, self.activation, self.ln_eps)
+
+
+class EGTLayer(nn.Module):
+    """One full EGT layer as the reference's loop body builds it (graph_xformer_model_base.py:335-341):
+    ``edge_update(tag, h, e)`` (the attention block) followed by ``ffn_block(tag, h, e)`` (node FFN, and the
+    edge FFN when the edge channel is residual / constrained)."""
+
+    def __init__(self, tag='00', ffn_multiplier=2., activation='elu', seed=0, **block_kwargs):
+        super().__init__()
+        self.block = EGTBlock(tag=tag, seed=seed, **block_kwargs)
+        sp = self.block.spec
+        self.ffn_node = EGTFFN(sp.model_width, 'node', tag, ffn_multiplier, activation, sp.ln_eps)
+        self.ffn_edge = EGTFFN(sp.edge_width, 'edge', tag, ffn_multiplier, activation, sp.ln_eps) if sp.is_residual else None
+
+    def load_keras_weights(self, weights, strict=True):
+        self.block.load_keras_weights({k: v for k, v in weights.items() if not k.startswith('ffn') and 'fnn' not in k}, strict)
+        self.ffn_node.load_keras_weights(weights, strict)
+        if self.ffn_edge is not None:
+            self.ffn_edge.load_keras_weights(weights, strict)
+
+    def forward(self, h, e, mask=None, edge_mask=None, training=None):
+        h, e = self.block(h, e, mask, edge_mask=edge_mask, training=training)
+        h = self.ffn_node(h)
+        if self.ffn_edge is not None:
+            e = self.ffn_edge(e)
+        return h, e

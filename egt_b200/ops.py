@@ -333,3 +333,62 @@ def egt_block(h, e, mask, flat, spec: BlockSpec, layout, edge_mask=None, trainin
     if spec.is_residual:
         return out
     return out, e
+
+
+# ------------------------------------------------------------------------------------------
+# feed-forward half of a layer ("next" row)
+# ------------------------------------------------------------------------------------------
+def ffn_layout(width: int, hidden: int):
+    """(total floats, {field: (offset, shape)}) of one channel's flat FFN parameter buffer."""
+    shapes = [(width,), (width,), (width, hidden), (hidden,), (hidden, width), (width,)]
+    out, off = {}, 0
+    for name, shp in zip(L.FFN_FIELDS, shapes):
+        n = 1
+        for v in shp:
+            n *= v
+        out[name] = (off, shp)
+        off += (n + 3) // 4 * 4                      # keep every tensor 16-byte aligned
+    return off, out
+
+
+class _EGTFfnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, flat, width, hidden, act_code, ln_eps, layout):
+        lib = L.load()
+        _need_cuda(x, flat)
+        assert x.shape[-1] == width, f'x has {x.shape[-1]} channels, width={width}'
+        x = x.contiguous()
+        cfg = L.FfnCfg()
+        cfg.rows, cfg.width, cfg.hidden = x.numel() // width, width, hidden
+        cfg.dtype, cfg.activation, cfg.ln_eps = _dtype_code(x), act_code, ln_eps
+        y = torch.empty_like(x)
+        w = L.FfnWeights()
+        for f in L.FFN_FIELDS:
+            setattr(w, f, flat.data_ptr() + 4 * layout[f][0])
+        L.check(lib.egt_ffn_fwd(C.byref(cfg), C.byref(w), _ptr(x), _ptr(y), _stream()))
+        ctx.save_for_backward(x, flat)
+        ctx.cfg, ctx.layout = cfg, layout
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = L.load()
+        x, flat = ctx.saved_tensors
+        cfg, layout = ctx.cfg, ctx.layout
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        dflat = torch.zeros_like(flat)
+        w, g = L.FfnWeights(), L.FfnGrads()
+        for f in L.FFN_FIELDS:
+            setattr(w, f, flat.data_ptr() + 4 * layout[f][0])
+            setattr(g, f, dflat.data_ptr() + 4 * layout[f][0])
+        L.check(lib.egt_ffn_bwd(C.byref(cfg), C.byref(w), C.byref(g), _ptr(x), _ptr(dy), _ptr(dx), _stream()))
+        return dx, dflat, None, None, None, None, None
+
+
+def egt_ffn(x, flat, width, hidden, layout, activation='elu', ln_eps=1e-3):
+    """``ffnlr1 -> ffnact -> ffnlr2`` for one channel (graph_xformer_model_base.py:229-258)."""
+    key = activation.lower() if isinstance(activation, str) else activation
+    if key not in _ACT:
+        raise ValueError(f'unsupported activation {activation!r}')
+    return _EGTFfnFn.apply(x, flat, width, hidden, _ACT[key], ln_eps, layout)

@@ -187,6 +187,30 @@ long egt_launch_count(void);
 int egt_profile_enable(int on);
 int egt_profile_read(char *names_host, double *ms_host, long *counts_host, int max_entries);
 
+/* ---- feed-forward half of a layer ("next" row) ---------------------------------------- */
+/* ffnlr1 / ffnact / ffnlr2 of graph_xformer_model_base.py:229-258 as ffn_block (:309-324) applies them to one
+ * channel:  y = x + Dense_w( act( Dense_hidden( LayerNorm(x) ) ) ),  hidden = round(w * ffn_multiplier).
+ * rows = B*N with w = model_width for the node channel, rows = B*N*N with w = edge_width for the edge channel.
+ * x, y, dy, dx: [rows, width] of the activation dtype; weights / gradients float32, Keras layouts. */
+typedef struct egt_ffn_cfg {
+  int64_t rows;
+  int32_t width, hidden;
+  int32_t dtype;            /* EGT_F32 | EGT_BF16 */
+  int32_t activation;       /* EGT_ACT_* (config.activation, default 'elu') */
+  float ln_eps;             /* keras LayerNormalization default 1e-3 */
+} egt_ffn_cfg_t;
+typedef struct egt_ffn_weights {
+  const float *norm_gamma, *norm_beta;     /* [w]          norm_fnn_{node|edge}_{tag} */
+  const float *lr1_kernel, *lr1_bias;      /* [w,hidden]   fnn_lr1_{node|edge}_{tag}  */
+  const float *lr2_kernel, *lr2_bias;      /* [hidden,w]   fnn_lr2_{node|edge}_{tag}  */
+} egt_ffn_weights_t;
+typedef struct egt_ffn_grads {             /* accumulators: the library ADDS into them */
+  float *norm_gamma, *norm_beta, *lr1_kernel, *lr1_bias, *lr2_kernel, *lr2_bias;
+} egt_ffn_grads_t;
+int egt_ffn_fwd(const egt_ffn_cfg_t *cfg, const egt_ffn_weights_t *w, const void *x, void *y, void *stream);
+int egt_ffn_bwd(const egt_ffn_cfg_t *cfg, const egt_ffn_weights_t *w, const egt_ffn_grads_t *g, const void *x,
+                const void *dy, void *dx, void *stream);
+
 /* ---- data parallelism: the single gradient all-reduce of MirroredStrategy (training_base.py:230-238) --- */
 /* One-shot SUM all-reduce of `grad` (n float32, n % 4 == 0) over peer-mapped memory (NVLink / NVSwitch).
  * buffer_ptrs_dev / signal_pad_ptrs_dev: device arrays of `world` pointers to every rank's symmetric buffer
