@@ -136,7 +136,9 @@ def run_reference(args, w):
                 steps=r['steps'], warmup=args.warmup, ms_per_step=r['ms_per_step'], higher_is_better=True,
                 scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
                 config=dict(workload=args.workload, **{k: w[k] for k in ('N', 'd', 'd_e', 'h')},
-                            graphs_per_step=None, note=w['note']),
+                            graphs_per_gpu=w['B'], global_batch=w['B'] * args.gpus, parallelism=f'dp{args.gpus}',
+                            note=w['note'], random_mask_prob=args.random_mask_prob, scale_degree=bool(args.scale_degree),
+                            path='cpu-oracle-port'),
                 cpu_baseline=dict(value=r['value'], unit='graphs/s', cores=r['cores'], kind=r['kind'],
                                   sample=r['sample']),
                 e2e=dict(value=r['value'], unit='graphs/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),

@@ -451,3 +451,25 @@ def test_block_step_replays_as_cuda_graph():
             assert torch.equal(a, b), f'{nm} differs between graph replay and eager launches (trial {trial})'
         # weight gradients are accumulated with atomics across CTAs: equal up to summation order
         torch.testing.assert_close(got[4], ref[4], rtol=1e-3, atol=1e-3 * float(ref[4].abs().max()))
+
+
+def test_fused_forward_then_backward_without_edge_gradient():
+    """When nothing downstream uses e', autograd hands the block no gradient for it: the backward then runs
+    the staged kernels on what the fused forward saved (pre-scaled Q, log row sums with a zero reference)."""
+    import egt_b200
+    from egt_b200 import _lib as L
+    lib = L.load()
+    B, N, d, de, nh = 3, 70, 64, 8, 8
+    cfg = O.BlockConfig(model_width=d, edge_width=de, num_heads=nh, scale_degree=True)
+    params = O.init_block_params(cfg, seed=9, dtype=torch.float64)
+    h, e, mask = O.synthetic_batch(B, N, d, de, seed=4, ragged=True, dtype=torch.float64)
+    blk, (hg, eg, h2, e2), (hr, er, pr, h2r, e2r) = _run_block(cfg, params, h, e, mask, None, False, torch.bfloat16,
+                                                               grads=True)
+    assert lib.egt_last_path() == 1
+    g = torch.Generator().manual_seed(3)
+    dh = torch.randn(h2.shape, generator=g).bfloat16()
+    gin = torch.autograd.grad([h2], [hg, eg], [dh.to(DEV)])
+    assert lib.egt_last_path() == 0
+    rin = torch.autograd.grad([h2r], [hr, er], [dh.double()])
+    _close(gin[0], rin[0], torch.bfloat16, 'dh')
+    _close(gin[1], rin[1], torch.bfloat16, 'de')
