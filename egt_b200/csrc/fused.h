@@ -20,12 +20,8 @@ constexpr int FH = 8, FDK = 8, FD = 64, FDE = 8;
 //   e^ W = r * (e W') - r*mu * u + v,   W' = gamma (.) W,  u = colsum(W'),  v = beta W + b
 // so that the tensor core multiplies the RAW edge tile and the per-pair (mu, r) are applied in registers.
 struct FusedPrep {
-  // tcgen05 B-operand images (bf16, un-swizzled K-major 8x16B core matrices), see fused_prep.cu
-  __nv_bfloat16 wblk[2 * 32 * 8];     // [E|G] projection of a key PAIR:   N = 32, K = 16
-  __nv_bfloat16 wrblk[2 * 16 * 8];    // edge write-back of a key pair:    N = 16, K = 16
-  __nv_bfloat16 wtblk[4 * 16 * 8];    // backward d e^ = dZ W'^T:          N = 16, K = 32
-  __nv_bfloat16 wrtblk[2 * 16 * 8];   // backward dH_ext = de' W_r^T:      N = 16, K = 16
-  // backward images; output columns are ordered by head GROUP g = hh / 4 (fused_bwd.cu: warps 0-3 own heads
+  // tcgen05 B-operand images (bf16, un-swizzled K-major 8x16B core matrices), see fused_prep.cuh.
+  // Output columns are ordered by head GROUP g = hh / 4 (fused_bwd.cu: warps 0-3 own heads
   // 0-3, warps 4-7 heads 4-7), hh4 = hh % 4, for a key pair (key, key' in {0,1}):
   __nv_bfloat16 b_eg[2 * 32 * 8];     // [E|G] projection: N = 32 (g,key,eg,hh4), K = 16 (key',c): W'_eg[c,hh]
   __nv_bfloat16 b_hx[2 * 16 * 8];     // dH_ext = de' W_r^T: N = 16 (g,key,hh4), K = 16 (key',c): W_r[hh,c]
@@ -70,10 +66,8 @@ struct FusedBwdArgs {
   uint64_t seed, offset;
 };
 
-struct FusedTensorMaps { CUtensorMap e, e_out, q, kv; };
-
 bool fused_supported(const egt_block_cfg_t *cfg, int dtype);
-int fused_prep_launch(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, FusedPrep *prep, cudaStream_t st);
+int fused_prep_launch(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, FusedPrep *prep, cudaStream_t st);   // stand-alone form (tests / tools)
 // qkv: [B,N,192] bf16 with the Q third pre-multiplied by dk^-0.5
 int fused_fwd_launch(const FusedFwdArgs &a, const void *e, void *e_out, const void *qkv, cudaStream_t st);
 

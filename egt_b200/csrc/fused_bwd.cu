@@ -26,8 +26,9 @@
 // (packed fp32x2 FMAs) and folded by fused_bwd_finalize_kernel.
 //
 // There is no CTA-wide barrier in the main loop: compute threads arrive on an mbarrier when their part of a
-// key pair is done, the issuer waits for it, and every tensor-core / TMA operation is issued two pairs ahead
-// of its consumer and observed through an mbarrier, so warps drift apart and fill each other's stalls.
+// key pair is done and the issuer waits for it.  Every dependency spans TWO pairs (same structure as
+// fused_fwd.cu): the S / dA / EG / dHx products of pair it+2 are issued when pair it is done, and the de
+// update of pair it (which needs the d x^ product issued when pair it is done) runs during pair it+2.
 #include "common.cuh"
 #include "fused.h"
 #include "umma.cuh"
@@ -340,7 +341,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
   };
 
   // ---- phase A: pair p, this thread's 4 heads of both keys ------------------------------------------
-  float cur_r = 0.f, cur_nrm = 0.f, prev_r = 0.f, prev_nrm = 0.f;   // LN statistics of key g of the current / previous pair
+  float cur_r = 0.f, cur_nrm = 0.f;   // LN statistics of key g of the pair phase A just processed
   auto phase_a = [&](int p, int st) {
     const int j = p & 3, ob = p & 1, buf = p & 1;
     const uint8_t *es = smem + SM_STAGE + st * STAGE_BYTES;
@@ -500,7 +501,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
   };
 
   // ---- pipeline ------------------------------------------------------------------------------------
-  // running indices instead of divisions: pair it -> (stage st_a, TMEM buffer buf_a, parity par_a)
+  // running indices instead of divisions
   mbar_wait(bar_e, 0);
   build(0, 0);
   if (NP > 1) build(1, 0);

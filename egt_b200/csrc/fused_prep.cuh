@@ -49,24 +49,7 @@ __device__ __forceinline__ void fused_prep_body(const egt_block_weights_t &w, fl
       if (hh == 0) out->bound = bnd;
     }
   }
-  // wblk: n = key*16 + eg*8 + hh ; k = key'*8 + c            (N = 32, K = 16)
-  for (int i = tid; i < 32 * 16; i += 128) {
-    int n = i / 16, k = i % 16;
-    int key = n / 16, eg = (n / 8) % 2, hh = n % 8, key2 = k / 8, c = k % 8;
-    float v = key == key2 ? wp[eg][c][hh] : 0.f;
-    out->wblk[(k / 8) * (32 * 8) + n * 8 + (k % 8)] = __float2bfloat16_rn(v);
-  }
-  // wrblk: n = key*8 + c ; k = key'*8 + hh                   (N = 16, K = 16)   value W_r[hh][c]
-  // wrtblk: n = key*8 + hh ; k = key'*8 + c                  (N = 16, K = 16)   value W_r[hh][c]
-  for (int i = tid; i < 16 * 16; i += 128) {
-    int n = i / 16, k = i % 16;
-    int key = n / 8, a = n % 8, key2 = k / 8, b = k % 8;
-    out->wrblk[(k / 8) * (16 * 8) + n * 8 + (k % 8)] =
-        __float2bfloat16_rn(key == key2 ? sWr[b][a] : 0.f);
-    out->wrtblk[(k / 8) * (16 * 8) + n * 8 + (k % 8)] =
-        __float2bfloat16_rn(key == key2 ? sWr[a][b] : 0.f);
-  }
-  // backward images (head-group ordered, fused.h)
+  // operand images (head-group ordered, fused.h)
   for (int i = tid; i < 32 * 16; i += 128) {      // b_eg
     int n = i / 16, k = i % 16;
     int g = n / 16, key = (n / 8) % 2, eg = (n / 4) % 2, hh = 4 * g + n % 4, key2 = k / 8, c = k % 8;
@@ -88,12 +71,6 @@ __device__ __forceinline__ void fused_prep_body(const egt_block_weights_t &w, fl
       int key2 = n / 8, c = n % 8, key = k / 8, eg = (k / 4) % 2, hh = 4 * g + k % 4;
       out->b_de[g][(k / 8) * (16 * 8) + n * 8 + (k % 8)] = __float2bfloat16_rn(key == key2 ? wp[eg][c][hh] : 0.f);
     }
-  }
-  // wtblk: n = key*8 + c ; k = key'*16 + eg*8 + hh           (N = 16, K = 32)   value W'_eg[c][hh]
-  for (int i = tid; i < 16 * 32; i += 128) {
-    int n = i / 32, k = i % 32;
-    int key = n / 8, c = n % 8, key2 = k / 16, eg = (k / 8) % 2, hh = k % 8;
-    out->wtblk[(k / 8) * (16 * 8) + n * 8 + (k % 8)] = __float2bfloat16_rn(key == key2 ? wp[eg][c][hh] : 0.f);
   }
 }
 

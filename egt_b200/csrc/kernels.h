@@ -91,8 +91,4 @@ int edge_out_fwd_launch(const EdgeParams &p, int dtype, cudaStream_t st);
 int edge_out_bwd_launch(const EdgeParams &p, int dtype, cudaStream_t st);
 int edge_proj_bwd_launch(const EdgeParams &p, int dtype, cudaStream_t st);
 
-// ---- fused tcgen05 forward (attn_fused_fwd.cu) -----------------------------------------
-struct FusedFwdParams;
-bool fused_fwd_supported(const egt_block_cfg_t *cfg);
-
 }  // namespace egt
