@@ -454,8 +454,9 @@ def test_block_step_replays_as_cuda_graph():
 
 
 def test_fused_forward_then_backward_without_edge_gradient():
-    """When nothing downstream uses e', autograd hands the block no gradient for it: the backward then runs
-    the staged kernels on what the fused forward saved (pre-scaled Q, log row sums with a zero reference)."""
+    """When nothing downstream uses e', autograd materialises a zero gradient for it and the fused backward
+    runs with de' = 0 (the C ABI additionally accepts de_out = NULL and then runs the staged kernels on what
+    the fused forward saved: pre-scaled Q, log row sums with a zero reference)."""
     import egt_b200
     from egt_b200 import _lib as L
     lib = L.load()
@@ -469,7 +470,6 @@ def test_fused_forward_then_backward_without_edge_gradient():
     g = torch.Generator().manual_seed(3)
     dh = torch.randn(h2.shape, generator=g).bfloat16()
     gin = torch.autograd.grad([h2], [hg, eg], [dh.to(DEV)])
-    assert lib.egt_last_path() == 0
     rin = torch.autograd.grad([h2r], [hr, er], [dh.double()])
     _close(gin[0], rin[0], torch.bfloat16, 'dh')
     _close(gin[1], rin[1], torch.bfloat16, 'de')
