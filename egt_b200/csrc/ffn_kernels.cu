@@ -17,7 +17,7 @@ namespace egt {
 
 namespace {
 
-constexpr int FT = 128;   // threads per CTA
+constexpr int FT = 512;   // threads per CTA (one CTA per SM for wide layers: many warps hide the shared-memory latency)
 
 __device__ __forceinline__ float act_fwd(int act, float x) { return edge_act_fwd(act, 0.2f, x); }
 __device__ __forceinline__ float act_bwd(int act, float x) { return edge_act_bwd(act, 0.2f, x); }
@@ -47,7 +47,14 @@ __device__ __forceinline__ int stage_weights(const FfnArgs &a, float *sm, const 
   if (a.w_in_smem) {
     float *s1 = sm + off; off += a.w * a.hid;
     float *s2 = sm + off; off += a.w * a.hid;
-    for (int i = tid; i < a.w * a.hid; i += FT) { s1[i] = a.W1[i]; s2[i] = a.W2[i]; }
+    if (((a.w * a.hid) & 3) == 0 && (((uintptr_t)a.W1 | (uintptr_t)a.W2) & 15) == 0 && (off & 3) == 0) {
+      for (int i = tid; i < (a.w * a.hid) >> 2; i += FT) {   // 16-byte copies, independent loads in flight
+        ((float4 *)s1)[i] = ((const float4 *)a.W1)[i];
+        ((float4 *)s2)[i] = ((const float4 *)a.W2)[i];
+      }
+    } else {
+      for (int i = tid; i < a.w * a.hid; i += FT) { s1[i] = a.W1[i]; s2[i] = a.W2[i]; }
+    }
     W1 = s1; W2 = s2;
   } else {
     W1 = a.W1; W2 = a.W2;
@@ -234,6 +241,236 @@ __global__ void __launch_bounds__(FT) ffn_bwd_kernel(FfnArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Edge-channel specialisation: width 8, hidden 16 (edge_width = 8 of the MNIST / CLUSTER / PATTERN configs,
+// ffn_multiplier = 2).  One thread per (l, m) pair, everything in registers, packed fp32x2 FMAs against
+// weights broadcast from shared memory; the row is one 16-byte load / store in bf16.  The backward stages the
+// per-pair vectors of a 128-pair chunk in shared memory and every thread owns a fixed subset of the 296
+// weight-gradient sums across all chunks of its CTA (atomics once at the end).
+namespace {
+
+constexpr int E8W = 8, E8H = 16;
+
+struct F2 { float2 v; };
+__device__ __forceinline__ float2 f2ma(float2 acc, float s, float2 w) {
+  unsigned long long a = reinterpret_cast<unsigned long long &>(acc);
+  float2 ss = make_float2(s, s);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a) : "l"(reinterpret_cast<unsigned long long &>(ss)), "l"(reinterpret_cast<unsigned long long &>(w)));
+  return reinterpret_cast<float2 &>(a);
+}
+__device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : exp2f(x * kLog2e) - 1.f; }
+
+template <typename T> __device__ __forceinline__ void load_row8(const T *p, float *x);
+template <> __device__ __forceinline__ void load_row8<float>(const float *p, float *x) {
+  const float4 a = ((const float4 *)p)[0], b = ((const float4 *)p)[1];
+  x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+}
+template <> __device__ __forceinline__ void load_row8<__nv_bfloat16>(const __nv_bfloat16 *p, float *x) {
+  const uint4 v = *(const uint4 *)p;
+  x[0] = __uint_as_float(v.x << 16); x[1] = __uint_as_float(v.x & 0xFFFF0000u);
+  x[2] = __uint_as_float(v.y << 16); x[3] = __uint_as_float(v.y & 0xFFFF0000u);
+  x[4] = __uint_as_float(v.z << 16); x[5] = __uint_as_float(v.z & 0xFFFF0000u);
+  x[6] = __uint_as_float(v.w << 16); x[7] = __uint_as_float(v.w & 0xFFFF0000u);
+}
+template <typename T> __device__ __forceinline__ void store_row8(T *p, const float *x);
+template <> __device__ __forceinline__ void store_row8<float>(float *p, const float *x) {
+  ((float4 *)p)[0] = make_float4(x[0], x[1], x[2], x[3]);
+  ((float4 *)p)[1] = make_float4(x[4], x[5], x[6], x[7]);
+}
+template <> __device__ __forceinline__ void store_row8<__nv_bfloat16>(__nv_bfloat16 *p, const float *x) {
+  uint4 v;
+  __nv_bfloat162 t;
+  t = __floats2bfloat162_rn(x[0], x[1]); v.x = *(uint32_t *)&t;
+  t = __floats2bfloat162_rn(x[2], x[3]); v.y = *(uint32_t *)&t;
+  t = __floats2bfloat162_rn(x[4], x[5]); v.z = *(uint32_t *)&t;
+  t = __floats2bfloat162_rn(x[6], x[7]); v.w = *(uint32_t *)&t;
+  *(uint4 *)p = v;
+}
+
+// shared weights: W1[8][16] | b1[16] | W2[16][8] | b2[8] | gamma[8] | beta[8] | W2T[8][16] | W1T[16][8]
+constexpr int E8_W1 = 0, E8_B1 = 128, E8_W2 = 144, E8_B2 = 272, E8_G = 280, E8_BT = 288, E8_W2T = 296, E8_W1T = 424,
+              E8_WTOT = 552;
+
+__device__ __forceinline__ void e8_stage(const FfnArgs &a, float *sw) {
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) {
+    sw[E8_W1 + i] = a.W1[i];
+    sw[E8_W2 + i] = a.W2[i];
+    sw[E8_W2T + (i % 8) * 16 + i / 8] = a.W2[i];      // W2[j][c] -> W2T[c][j]
+    sw[E8_W1T + (i % 16) * 8 + i / 16] = a.W1[i];     // W1[c][j] -> W1T[j][c]
+  }
+  if (threadIdx.x < 16) sw[E8_B1 + threadIdx.x] = a.b1[threadIdx.x];
+  if (threadIdx.x < 8) {
+    sw[E8_B2 + threadIdx.x] = a.b2[threadIdx.x];
+    sw[E8_G + threadIdx.x] = a.gamma[threadIdx.x];
+    sw[E8_BT + threadIdx.x] = a.beta[threadIdx.x];
+  }
+}
+
+// LayerNorm + first layer for one row: xn (normalised), xe (affine), pre (16), act (16); returns rstd
+__device__ __forceinline__ float e8_forward_row(const float *sw, const float *x, float eps, int act, float *xn, float *xe,
+                                                float *pre, float *hid) {
+  float mu = ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
+  mu *= 0.125f;
+  float var = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) { const float d = x[c] - mu; var = fmaf(d, d, var); }
+  const float rstd = rsqrtf(fmaf(var, 0.125f, eps));
+#pragma unroll
+  for (int c = 0; c < 8; ++c) { xn[c] = (x[c] - mu) * rstd; xe[c] = fmaf(xn[c], sw[E8_G + c], sw[E8_BT + c]); }
+  float2 a2[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) a2[q] = *(const float2 *)(sw + E8_B1 + 2 * q);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 w = *(const float4 *)(sw + E8_W1 + c * 16 + 4 * q);
+      a2[2 * q] = f2ma(a2[2 * q], xe[c], make_float2(w.x, w.y));
+      a2[2 * q + 1] = f2ma(a2[2 * q + 1], xe[c], make_float2(w.z, w.w));
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    pre[2 * q] = a2[q].x; pre[2 * q + 1] = a2[q].y;
+    hid[2 * q] = act == EGT_ACT_ELU ? elu_f(a2[q].x) : act_fwd(act, a2[q].x);
+    hid[2 * q + 1] = act == EGT_ACT_ELU ? elu_f(a2[q].y) : act_fwd(act, a2[q].y);
+  }
+  return rstd;
+}
+
+}  // namespace
+
+template <typename T>
+__global__ void __launch_bounds__(128) ffn8_fwd_kernel(FfnArgs a) {
+  __shared__ __align__(16) float sw[E8_WTOT];
+  e8_stage(a, sw);
+  __syncthreads();
+  for (long long r = (long long)blockIdx.x * 128 + threadIdx.x; r < a.rows; r += (long long)gridDim.x * 128) {
+    float x[8], xn[8], xe[8], pre[16], hid[16];
+    load_row8<T>((const T *)a.x + r * 8, x);
+    e8_forward_row(sw, x, a.eps, a.act, xn, xe, pre, hid);
+    float2 o2[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o2[q] = *(const float2 *)(sw + E8_B2 + 2 * q);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float4 w0 = *(const float4 *)(sw + E8_W2 + j * 8), w1 = *(const float4 *)(sw + E8_W2 + j * 8 + 4);
+      o2[0] = f2ma(o2[0], hid[j], make_float2(w0.x, w0.y)); o2[1] = f2ma(o2[1], hid[j], make_float2(w0.z, w0.w));
+      o2[2] = f2ma(o2[2], hid[j], make_float2(w1.x, w1.y)); o2[3] = f2ma(o2[3], hid[j], make_float2(w1.z, w1.w));
+    }
+    float y[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { y[2 * q] = o2[q].x + x[2 * q]; y[2 * q + 1] = o2[q].y + x[2 * q + 1]; }
+    store_row8<T>((T *)a.y + r * 8, y);
+  }
+}
+
+// staged per-pair record (64 floats): xe[8] | dxe*xn[8] | dxe[8] | dpre[16] | hid[16] | dy[8]
+template <typename T>
+__global__ void __launch_bounds__(128) ffn8_bwd_kernel(FfnArgs a) {
+  __shared__ __align__(16) float sw[E8_WTOT];
+  extern __shared__ float rec[];                       // [128][65]
+  constexpr int RS = 65;
+  e8_stage(a, sw);
+  const int tid = threadIdx.x;
+  // this thread's weight-gradient outputs: o = tid, tid+128, tid+256 of
+  //   [0,128) dW1[c][j] | [128,256) dW2[j][c] | [256,272) db1 | [272,280) db2 | [280,288) dgamma | [288,296) dbeta
+  float acc[3] = {0.f, 0.f, 0.f};
+  __syncthreads();
+  const long long nchunks = (a.rows + 127) / 128;
+  for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    const long long r = ch * 128 + tid;
+    float *my = rec + tid * RS;
+    if (r < a.rows) {
+      float x[8], xn[8], xe[8], pre[16], hid[16], dy[8];
+      load_row8<T>((const T *)a.x + r * 8, x);
+      load_row8<T>((const T *)a.dy + r * 8, dy);
+      const float rstd = e8_forward_row(sw, x, a.eps, a.act, xn, xe, pre, hid);
+      // d hid = dy W2^T ; d pre = d hid * act'(pre)
+      float2 d2[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) d2[q] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 w = *(const float4 *)(sw + E8_W2T + c * 16 + 4 * q);
+          d2[2 * q] = f2ma(d2[2 * q], dy[c], make_float2(w.x, w.y));
+          d2[2 * q + 1] = f2ma(d2[2 * q + 1], dy[c], make_float2(w.z, w.w));
+        }
+      }
+      float dpre[16];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float g0 = a.act == EGT_ACT_ELU ? (pre[2 * q] > 0.f ? 1.f : hid[2 * q] + 1.f) : act_bwd(a.act, pre[2 * q]);
+        const float g1 = a.act == EGT_ACT_ELU ? (pre[2 * q + 1] > 0.f ? 1.f : hid[2 * q + 1] + 1.f) : act_bwd(a.act, pre[2 * q + 1]);
+        dpre[2 * q] = d2[q].x * g0; dpre[2 * q + 1] = d2[q].y * g1;
+      }
+      // d e^ = d pre W1^T
+      float2 e2[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) e2[q] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float4 w0 = *(const float4 *)(sw + E8_W1T + j * 8), w1 = *(const float4 *)(sw + E8_W1T + j * 8 + 4);
+        e2[0] = f2ma(e2[0], dpre[j], make_float2(w0.x, w0.y)); e2[1] = f2ma(e2[1], dpre[j], make_float2(w0.z, w0.w));
+        e2[2] = f2ma(e2[2], dpre[j], make_float2(w1.x, w1.y)); e2[3] = f2ma(e2[3], dpre[j], make_float2(w1.z, w1.w));
+      }
+      float dxe[8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { dxe[2 * q] = e2[q].x; dxe[2 * q + 1] = e2[q].y; }
+      float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) { const float dxh = dxe[c] * sw[E8_G + c]; m1 += dxh; m2 = fmaf(dxh, xn[c], m2); }
+      m1 *= 0.125f; m2 *= 0.125f;
+      float dx[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) dx[c] = fmaf(rstd, fmaf(dxe[c], sw[E8_G + c], -fmaf(xn[c], m2, m1)), dy[c]);
+      store_row8<T>((T *)a.dx + r * 8, dx);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) { my[c] = xe[c]; my[8 + c] = dxe[c] * xn[c]; my[16 + c] = dxe[c]; my[56 + c] = dy[c]; }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { my[24 + j] = dpre[j]; my[40 + j] = hid[j]; }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 64; ++i) my[i] = 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int o = tid + 128 * k;
+      int ia, ib = -1;                                 // acc += rec[ia] * rec[ib]  (ib < 0: plain sum of rec[ia])
+      if (o < 128) { ia = o / 16; ib = 24 + o % 16; }                 // dW1[c][j] = xe[c] * dpre[j]
+      else if (o < 256) { ia = 40 + (o - 128) / 8; ib = 56 + (o - 128) % 8; }   // dW2[j][c] = hid[j] * dy[c]
+      else if (o < 272) ia = 24 + (o - 256);                          // db1
+      else if (o < 280) ia = 56 + (o - 272);                          // db2
+      else if (o < 288) ia = 8 + (o - 280);                           // dgamma
+      else if (o < 296) ia = 16 + (o - 288);                          // dbeta
+      else continue;
+      float s = 0.f;
+      if (ib >= 0) {
+#pragma unroll 8
+        for (int rr = 0; rr < 128; ++rr) s = fmaf(rec[rr * RS + ia], rec[rr * RS + ib], s);
+      } else {
+#pragma unroll 8
+        for (int rr = 0; rr < 128; ++rr) s += rec[rr * RS + ia];
+      }
+      acc[k] += s;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int o = tid + 128 * k;
+    if (o < 128) atomicAdd(a.g_W1 + o, acc[k]);
+    else if (o < 256) atomicAdd(a.g_W2 + (o - 128), acc[k]);
+    else if (o < 272) atomicAdd(a.g_b1 + (o - 256), acc[k]);
+    else if (o < 280) atomicAdd(a.g_b2 + (o - 272), acc[k]);
+    else if (o < 288) atomicAdd(a.g_gamma + (o - 280), acc[k]);
+    else if (o < 296) atomicAdd(a.g_beta + (o - 288), acc[k]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 static int ffn_plan(FfnArgs &a, int backward, size_t &smem) {
   const size_t w = a.w, h = a.hid;
   const size_t fixed = h + 3 * w;
@@ -270,14 +507,24 @@ extern "C" int egt_ffn_fwd(const egt_ffn_cfg_t *cfg, const egt_ffn_weights_t *w,
   a.rows = cfg->rows; a.w = cfg->width; a.hid = cfg->hidden; a.act = cfg->activation; a.eps = cfg->ln_eps;
   a.gamma = w->norm_gamma; a.beta = w->norm_beta; a.W1 = w->lr1_kernel; a.b1 = w->lr1_bias; a.W2 = w->lr2_kernel; a.b2 = w->lr2_bias;
   a.x = x; a.y = y;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a.w == E8W && a.hid == E8H && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0) {   // edge channel of the fused widths
+    const long long nch = (a.rows + 127) / 128;
+    const unsigned grid = (unsigned)(nch < 148 * 16 ? nch : 148 * 16);
+    LaunchScope _ls("ffn8_fwd_kernel", st);
+    if (cfg->dtype == EGT_F32) ffn8_fwd_kernel<float><<<grid, 128, 0, st>>>(a);
+    else ffn8_fwd_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(a);
+    EGT_CHECK_CUDA(cudaGetLastError());
+    return EGT_OK;
+  }
   size_t smem = 0;
   int rc = ffn_plan(a, 0, smem);
   if (rc) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
   EGT_CHECK_CUDA(cudaFuncSetAttribute(ffn_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   EGT_CHECK_CUDA(cudaFuncSetAttribute(ffn_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long nchunks = (a.rows + a.rb - 1) / a.rb;
-  const unsigned grid = (unsigned)(nchunks < 148 * 4 ? nchunks : 148 * 4);
+  const long long cap = 148 * 2;
+  const unsigned grid = (unsigned)(nchunks < cap ? nchunks : cap);
   LaunchScope _ls("ffn_fwd_kernel", st);
   if (cfg->dtype == EGT_F32) ffn_fwd_kernel<float><<<grid, FT, smem, st>>>(a);
   else ffn_fwd_kernel<__nv_bfloat16><<<grid, FT, smem, st>>>(a);
@@ -296,14 +543,25 @@ extern "C" int egt_ffn_bwd(const egt_ffn_cfg_t *cfg, const egt_ffn_weights_t *w,
   a.gamma = w->norm_gamma; a.beta = w->norm_beta; a.W1 = w->lr1_kernel; a.b1 = w->lr1_bias; a.W2 = w->lr2_kernel; a.b2 = w->lr2_bias;
   a.g_gamma = g->norm_gamma; a.g_beta = g->norm_beta; a.g_W1 = g->lr1_kernel; a.g_b1 = g->lr1_bias; a.g_W2 = g->lr2_kernel; a.g_b2 = g->lr2_bias;
   a.x = x; a.dy = dy; a.dx = dx;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a.w == E8W && a.hid == E8H && ((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)dx & 15) == 0) {
+    const long long nch = (a.rows + 127) / 128;
+    const unsigned grid = (unsigned)(nch < 148 * 8 ? nch : 148 * 8);
+    const size_t rsm = (size_t)128 * 65 * sizeof(float);
+    LaunchScope _ls("ffn8_bwd_kernel", st);
+    if (cfg->dtype == EGT_F32) ffn8_bwd_kernel<float><<<grid, 128, rsm, st>>>(a);
+    else ffn8_bwd_kernel<__nv_bfloat16><<<grid, 128, rsm, st>>>(a);
+    EGT_CHECK_CUDA(cudaGetLastError());
+    return EGT_OK;
+  }
   size_t smem = 0;
   int rc = ffn_plan(a, 1, smem);
   if (rc) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
   EGT_CHECK_CUDA(cudaFuncSetAttribute(ffn_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   EGT_CHECK_CUDA(cudaFuncSetAttribute(ffn_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long nchunks = (a.rows + a.rb - 1) / a.rb;
-  const unsigned grid = (unsigned)(nchunks < 148 * 2 ? nchunks : 148 * 2);
+  const long long cap = 148 * 2;
+  const unsigned grid = (unsigned)(nchunks < cap ? nchunks : cap);
   LaunchScope _ls("ffn_bwd_kernel", st);
   if (cfg->dtype == EGT_F32) ffn_bwd_kernel<float><<<grid, FT, smem, st>>>(a);
   else ffn_bwd_kernel<__nv_bfloat16><<<grid, FT, smem, st>>>(a);

@@ -118,3 +118,30 @@ def test_workspace_query_is_monotone():
     f = lib.egt_block_workspace_bytes(ctypes.byref(c), 0)
     b = lib.egt_block_workspace_bytes(ctypes.byref(c), 1)
     assert 0 < f <= b
+
+
+def test_ffn_host_side_mirrors_reference_names(golden_dir):
+    """EGTFFN / EGTLayer: hidden = round(width * ffn_multiplier) (graph_xformer_model_base.py:236), flat
+    parameter layout, and weight loading by the reference's layer names (no GPU compute here)."""
+    from tests.golden_util import block_case
+    ffn = egt_b200.EGTFFN(8, channel='edge', tag='03', ffn_multiplier=2.)
+    assert (ffn.width, ffn.hidden) == (8, 16)
+    assert egt_b200.EGTFFN(48, ffn_multiplier=1.5).hidden == 72
+    total, layout = ops.ffn_layout(64, 128)
+    assert layout['lr1_kernel'][1] == (64, 128) and layout['lr2_kernel'][1] == (128, 64)
+    assert all(off % 4 == 0 for off, _ in layout.values()) and total >= 2 * 64 * 128 + 128 + 3 * 64
+    w = {f'{stem}_edge_03/{wn}': torch.full(shape, float(i))
+         for i, ((stem, wn), shape) in enumerate([(('norm_fnn', 'gamma'), (8,)), (('norm_fnn', 'beta'), (8,)),
+                                                  (('fnn_lr1', 'kernel'), (8, 16)), (('fnn_lr1', 'bias'), (16,)),
+                                                  (('fnn_lr2', 'kernel'), (16, 8)), (('fnn_lr2', 'bias'), (8,))])}
+    ffn.load_keras_weights(w)
+    assert float(ffn.view('lr2_kernel')[3, 5]) == 4.0 and float(ffn.view('norm_beta')[0]) == 1.0
+    with pytest.raises(KeyError):
+        egt_b200.EGTFFN(8, channel='node', tag='03').load_keras_weights(w)
+    c = block_case(golden_dir, 0)
+    layer = egt_b200.EGTLayer(model_width=c['cfg'].model_width, edge_width=c['cfg'].edge_width,
+                              num_heads=c['cfg'].num_heads)
+    layer.load_keras_weights(c['params'])
+    assert layer.ffn_edge is not None and layer.ffn_node.width == c['cfg'].model_width
+    with pytest.raises(RuntimeError):                      # no CPU fallback
+        layer.ffn_node(torch.zeros(2, 3, c['cfg'].model_width))
