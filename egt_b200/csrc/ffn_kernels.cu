@@ -183,7 +183,11 @@ __global__ void __launch_bounds__(FT) ffn_bwd_kernel(FfnArgs a) {
     for (int o = tid; o < a.rb * a.hid; o += FT) {           // d pre = (dy W2^T) act'(pre)
       const int rr = o / a.hid, j = o % a.hid;
       float acc = 0.f;
-      for (int c = 0; c < a.w; ++c) acc = fmaf(xs[rr * a.w + c], W2[j * a.w + c], acc);
+      int c = lane % a.w;                                      // rotated start: W2 rows are a.w floats apart, so
+      for (int k = 0; k < a.w; ++k) {                          // lanes with consecutive j would hit one bank
+        acc = fmaf(xs[rr * a.w + c], W2[j * a.w + c], acc);
+        if (++c == a.w) c = 0;
+      }
       ds[o] = rr < nr ? acc * act_bwd(a.act, ds[o]) : 0.f;
     }
     __syncthreads();
@@ -203,7 +207,11 @@ __global__ void __launch_bounds__(FT) ffn_bwd_kernel(FfnArgs a) {
     for (int o = tid; o < a.rb * a.w; o += FT) {             // xe <- d e^ = dpre W1^T
       const int rr = o / a.w, c = o % a.w;
       float acc = 0.f;
-      for (int j = 0; j < a.hid; ++j) acc = fmaf(ds[rr * a.hid + j], W1[c * a.hid + j], acc);
+      int j = lane % a.hid;                                    // rotated start (W1 rows are a.hid floats apart)
+      for (int k = 0; k < a.hid; ++k) {
+        acc = fmaf(ds[rr * a.hid + j], W1[c * a.hid + j], acc);
+        if (++j == a.hid) j = 0;
+      }
       xe[o] = acc;
     }
     __syncthreads();
@@ -230,8 +238,18 @@ __global__ void __launch_bounds__(FT) ffn_bwd_kernel(FfnArgs a) {
     }
     __syncthreads();
   }
-  if (a.acc_in_smem)
-    for (int i = tid; i < a.w * a.hid; i += FT) { atomicAdd(a.g_W1 + i, aW1[i]); atomicAdd(a.g_W2 + i, aW2[i]); }
+  if (a.acc_in_smem) {
+    const int n = a.w * a.hid;
+    if ((n & 3) == 0 && (((uintptr_t)a.g_W1 | (uintptr_t)a.g_W2) & 15) == 0 && ((aW1 - sm) & 3) == 0) {
+      for (int i = tid; i < n >> 2; i += FT) {         // 16-byte vector reductions (sm_90+)
+        const float4 u = ((const float4 *)aW1)[i], v = ((const float4 *)aW2)[i];
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.g_W1 + 4 * i), "f"(u.x), "f"(u.y), "f"(u.z), "f"(u.w) : "memory");
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.g_W2 + 4 * i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+      }
+    } else {
+      for (int i = tid; i < n; i += FT) { atomicAdd(a.g_W1 + i, aW1[i]); atomicAdd(a.g_W2 + i, aW2[i]); }
+    }
+  }
   for (int i = tid; i < a.hid; i += FT) atomicAdd(a.g_b1 + i, ab1[i]);
   for (int i = tid; i < a.w; i += FT) {
     atomicAdd(a.g_b2 + i, ab2[i]);
