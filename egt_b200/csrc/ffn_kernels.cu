@@ -386,13 +386,19 @@ __global__ void __launch_bounds__(128) ffn8_fwd_kernel(FfnArgs a) {
 template <typename T>
 __global__ void __launch_bounds__(128) ffn8_bwd_kernel(FfnArgs a) {
   __shared__ __align__(16) float sw[E8_WTOT];
-  extern __shared__ float rec[];                       // [128][65]
-  constexpr int RS = 65;
+  extern __shared__ __align__(8) float rec[];          // [128][RS]
+  constexpr int RS = 66;                              // even: the paired column sums use 8-byte loads
   e8_stage(a, sw);
   const int tid = threadIdx.x;
-  // this thread's weight-gradient outputs: o = tid, tid+128, tid+256 of
-  //   [0,128) dW1[c][j] | [128,256) dW2[j][c] | [256,272) db1 | [272,280) db2 | [280,288) dgamma | [288,296) dbeta
-  float acc[3] = {0.f, 0.f, 0.f};
+  // this thread's weight-gradient outputs: TWO adjacent products sharing their first factor
+  //   tid <  64: dW1[c][j], dW1[c][j+1]   (c = tid / 8,  j = 2 * (tid % 8))    = sum xe[c] * dpre[j..j+1]
+  //   tid >= 64: dW2[j][c], dW2[j][c+1]   (j = (tid-64) / 4, c = 2 * ((tid-64) % 4)) = sum hid[j] * dy[c..c+1]
+  // and, for tid < 40, one plain column sum: db1[16] | db2[8] | dgamma[8] | dbeta[8]
+  const int pa = tid < 64 ? tid / 8 : 40 + (tid - 64) / 4;
+  const int pb = tid < 64 ? 24 + 2 * (tid % 8) : 56 + 2 * ((tid - 64) % 4);
+  const int ps = tid < 16 ? 24 + tid : tid < 24 ? 56 + (tid - 16) : tid < 32 ? 8 + (tid - 24) : 16 + (tid - 32);
+  float2 acc2 = make_float2(0.f, 0.f);
+  float accs = 0.f;
   __syncthreads();
   const long long nchunks = (a.rows + 127) / 128;
   for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
@@ -453,40 +459,31 @@ __global__ void __launch_bounds__(128) ffn8_bwd_kernel(FfnArgs a) {
       for (int i = 0; i < 64; ++i) my[i] = 0.f;
     }
     __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const int o = tid + 128 * k;
-      int ia, ib = -1;                                 // acc += rec[ia] * rec[ib]  (ib < 0: plain sum of rec[ia])
-      if (o < 128) { ia = o / 16; ib = 24 + o % 16; }                 // dW1[c][j] = xe[c] * dpre[j]
-      else if (o < 256) { ia = 40 + (o - 128) / 8; ib = 56 + (o - 128) % 8; }   // dW2[j][c] = hid[j] * dy[c]
-      else if (o < 272) ia = 24 + (o - 256);                          // db1
-      else if (o < 280) ia = 56 + (o - 272);                          // db2
-      else if (o < 288) ia = 8 + (o - 280);                           // dgamma
-      else if (o < 296) ia = 16 + (o - 288);                          // dbeta
-      else continue;
-      float s = 0.f;
-      if (ib >= 0) {
 #pragma unroll 8
-        for (int rr = 0; rr < 128; ++rr) s = fmaf(rec[rr * RS + ia], rec[rr * RS + ib], s);
-      } else {
+    for (int rr = 0; rr < 128; ++rr) {
+      const float fa = rec[rr * RS + pa];
+      const float2 fb = *(const float2 *)(rec + rr * RS + pb);
+      acc2 = f2ma(acc2, fa, fb);
+    }
+    if (tid < 40) {
 #pragma unroll 8
-        for (int rr = 0; rr < 128; ++rr) s += rec[rr * RS + ia];
-      }
-      acc[k] += s;
+      for (int rr = 0; rr < 128; ++rr) accs += rec[rr * RS + ps];
     }
     __syncthreads();
   }
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const int o = tid + 128 * k;
-    if (o < 128) atomicAdd(a.g_W1 + o, acc[k]);
-    else if (o < 256) atomicAdd(a.g_W2 + (o - 128), acc[k]);
-    else if (o < 272) atomicAdd(a.g_b1 + (o - 256), acc[k]);
-    else if (o < 280) atomicAdd(a.g_b2 + (o - 272), acc[k]);
-    else if (o < 288) atomicAdd(a.g_gamma + (o - 280), acc[k]);
-    else if (o < 296) atomicAdd(a.g_beta + (o - 288), acc[k]);
+  if (tid < 64) {
+    atomicAdd(a.g_W1 + (tid / 8) * 16 + 2 * (tid % 8), acc2.x);
+    atomicAdd(a.g_W1 + (tid / 8) * 16 + 2 * (tid % 8) + 1, acc2.y);
+  } else {
+    atomicAdd(a.g_W2 + ((tid - 64) / 4) * 8 + 2 * ((tid - 64) % 4), acc2.x);
+    atomicAdd(a.g_W2 + ((tid - 64) / 4) * 8 + 2 * ((tid - 64) % 4) + 1, acc2.y);
   }
+  if (tid < 16) atomicAdd(a.g_b1 + tid, accs);
+  else if (tid < 24) atomicAdd(a.g_b2 + (tid - 16), accs);
+  else if (tid < 32) atomicAdd(a.g_gamma + (tid - 24), accs);
+  else if (tid < 40) atomicAdd(a.g_beta + (tid - 32), accs);
 }
+
 
 // ------------------------------------------------------------------------------------------------
 static int ffn_plan(FfnArgs &a, int backward, size_t &smem) {
@@ -565,7 +562,7 @@ extern "C" int egt_ffn_bwd(const egt_ffn_cfg_t *cfg, const egt_ffn_weights_t *w,
   if (a.w == E8W && a.hid == E8H && ((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)dx & 15) == 0) {
     const long long nch = (a.rows + 127) / 128;
     const unsigned grid = (unsigned)(nch < 148 * 8 ? nch : 148 * 8);
-    const size_t rsm = (size_t)128 * 65 * sizeof(float);
+    const size_t rsm = (size_t)128 * 66 * sizeof(float);
     LaunchScope _ls("ffn8_bwd_kernel", st);
     if (cfg->dtype == EGT_F32) ffn8_bwd_kernel<float><<<grid, 128, rsm, st>>>(a);
     else ffn8_bwd_kernel<__nv_bfloat16><<<grid, 128, rsm, st>>>(a);
