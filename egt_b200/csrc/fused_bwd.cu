@@ -6,9 +6,12 @@
 //   [B,N,N,h] touches HBM: e and de' stream in once by TMA, de streams out once by TMA, everything
 //   else (E, G, H_hat, P, g, dE, dG, dS) is recomputed / consumed on chip.
 //
-// One CTA = one graph b and 128 query rows.  Thread t of warps 0-3 and of warps 4-7 both own query row
-// l0+t == TMEM lane t; warps 0-3 ("group 0") handle heads 0-3, warps 4-7 heads 4-7, so every SM
-// sub-partition has two resident compute warps.  Warp 8 issues TMA and tcgen05.mma.
+// One CTA = one graph b and 128 query rows, four warpgroups (setmaxnreg 192 / 192 / 64 / 64):
+//   warps 0-3, 4-7   "main": thread t of both groups owns query row l0+t == TMEM lane t; group 0 handles
+//                    heads 0-3, group 1 heads 4-7 (phase A below, all the per-(l,m,h) arithmetic)
+//   warp 8           issuer of TMA and tcgen05.mma (warps 9-11 only complete its warpgroup)
+//   warps 12-15      "helper": per-(l,m) work that needs no head split -- LayerNorm backward + residual (de),
+//                    the expanded K / V operands of the coming pairs, and the dK / dV read-out
 //
 // Keys are processed in PAIRS.  For pair p the tensor core produces, in TMEM (columns ordered (g,key,hh4)):
 //     S   [128x16] = Qs   [128x64] * Kexp^T       Kexp[(g,key,hh4), c] = K[key,c] * [c % 8 == hh]
@@ -64,7 +67,7 @@ constexpr uint32_t ID_N32 = idesc_bf16(128, 32, 0, 0);
 constexpr uint32_t ID_DQ = idesc_bf16(128, 64, 0, 1);
 constexpr uint32_t ID_T = idesc_bf16(128, 64, 1, 1);
 
-struct Bars { uint64_t q_full, e_full[NS], mma1[2], mma2[2], tbar, step; uint32_t tmem_base; };
+struct Bars { uint64_t q_full, e_full[NS], mma1[2], mma2[2], tbar, step[2]; uint32_t tmem_base; };
 
 __device__ __forceinline__ float sel8(const uint32_t *o, int hh) {
   const uint32_t a0 = (hh & 1) ? o[1] : o[0], a1 = (hh & 1) ? o[3] : o[2];
@@ -76,7 +79,7 @@ __device__ __forceinline__ float sel8(const uint32_t *o, int hh) {
 }  // namespace
 
 template <bool RAND>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(512, 1)
 fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant__ CUtensorMap tm_dei,
                  const __grid_constant__ CUtensorMap tm_de, const __grid_constant__ CUtensorMap tm_q,
                  const __grid_constant__ CUtensorMap tm_kv, const FusedBwdArgs a) {
@@ -96,7 +99,9 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
       for (int i = 0; i < NS; ++i) mbar_init(smem_u32(&bars->e_full[i]), 1);
       for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->mma1[i]), 1); mbar_init(smem_u32(&bars->mma2[i]), 1); }
       mbar_init(smem_u32(&bars->tbar), 1);
-      mbar_init(smem_u32(&bars->step), 256);          // every compute thread arrives once per key pair
+      // every main and helper thread arrives once per key pair; pairs alternate between two barriers because a
+      // thread may finish pair it+1 before a slower one finishes pair it (dependencies span two pairs)
+      mbar_init(smem_u32(&bars->step[0]), 384); mbar_init(smem_u32(&bars->step[1]), 384);
       mbar_fence_init();
       tma_prefetch_desc(&tm_e); tma_prefetch_desc(&tm_dei); tma_prefetch_desc(&tm_de);
       tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_kv);
@@ -104,22 +109,24 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     __syncwarp();
     tmem_alloc(smem_u32(&bars->tmem_base), 512);
     pdl_wait();
-  } else {
+  } else if (warp < 8) {
     pdl_wait();                                        // prep / dV_att come from the preceding kernel
     if (tid < 160) ((uint4 *)(smem + SM_W))[tid] = ((const uint4 *)a.prep->b_eg)[tid];   // b_eg | b_hx | b_de
     if (tid < 32) ((float *)(smem + SM_CONST))[tid] = a.prep->uE[tid];                  // uE vE uG vG
     for (int i = tid; i < 2 * ((N + 1) / 2); i += 256)                                   // key-valid bytes
       smem[SM_MASK + i] = i < N ? (a.mask ? (uint8_t)(a.mask[(size_t)blockIdx.y * N + i] != 0) : (uint8_t)1) : (uint8_t)0;
     fence_proxy_async_smem();
+  } else if (warp >= 12) {
+    pdl_wait();                                        // the helper adds into d_qkv, zeroed earlier on the stream
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
-  if (warp >= 8) {
+  if (warp >= 8 && warp < 12) {
     // ====================== issuer warpgroup (warp 8 issues; warps 9-11 only keep the barriers) ======
-    reg_dealloc<40>();
+    reg_dealloc<64>();   // 256 x 192 + 128 x 64 + 128 x 64 == 512 x 128: setmaxnreg only moves registers inside the CTA's launch allocation
     const bool leader = warp == 8 && lane == 0;
     auto load_tile = [&](int T) {
       const int st = T % NS;
@@ -189,11 +196,11 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
       mma_commit(bar_m1);
       if (NP > 1) { issue_mma1(1); mma_commit(bar_m1 + 8); }
     }
-    const uint32_t bar_step = smem_u32(&bars->step);
+    const uint32_t bar_step = smem_u32(&bars->step[0]);
     int next_store = 0;                                // tiles [0, next_store) have been handed to the TMA store
     for (int it = 0; it < NP && warp == 8; ++it) {     // warps 9-11 go straight to the tail barrier
       if (leader) {
-        mbar_wait(bar_step, it & 1);                   // all compute threads finished pair it (no CTA-wide barrier)
+        mbar_wait(bar_step + 8 * (it & 1), (it >> 1) & 1);   // main and helper threads finished pair it (no CTA-wide barrier)
         tc_fence_after();
         fence_proxy_async_smem();
         issue_mma2(it);
@@ -231,8 +238,168 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     return;
   }
 
-  // ================================= compute threads (warps 0-7) =================================
-  reg_alloc<232>();
+  const uint32_t bar_mma2 = smem_u32(&bars->mma2[0]);
+  const uint32_t bar_e = smem_u32(&bars->e_full[0]), bar_t = smem_u32(&bars->tbar), bar_step = smem_u32(&bars->step[0]);
+
+  if (warp >= 12) {
+    // ================================= helper warpgroup (warps 12-15) ================================
+    // Per-(query row, key) work that does not split by head: thread t owns query row l0+t for BOTH keys of a pair.
+    reg_dealloc<64>();
+    const int t = tid & 127;
+    const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t trow = (uint32_t)t * 128u, tx7 = (uint32_t)(t & 7);
+    float dbr[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) dbr[c] = 0.f;
+
+    // expanded K / V operands of pair p2 (stage st2) into slot p2 & 3: one 16-byte chunk of each per thread
+    const int b_n = t >> 3, b_dd = t & 7, b_hh = 4 * (b_n >> 3) + (b_n & 3);
+    const uint32_t b_src = (uint32_t)ST_K + (uint32_t)((b_n >> 2) & 1) * 128u + (uint32_t)(b_dd * 8 + b_hh) * 2u;
+    const uint32_t b_dst = SM_KVX + (uint32_t)b_n * 128u + ((uint32_t)((b_dd ^ b_n) & 7) << 4);
+    auto build = [&](int p2, int st2) {
+      const uint8_t *src = smem + SM_STAGE + st2 * STAGE_BYTES + b_src + (p2 & 3) * 256;
+#pragma unroll
+      for (int kv = 0; kv < 2; ++kv) {
+        const uint32_t val = *(const uint16_t *)(src + kv * (ST_V - ST_K));
+        const uint32_t wv = val << ((b_hh & 1) * 16);
+        uint4 ch;
+        ch.x = (b_hh >> 1) == 0 ? wv : 0u; ch.y = (b_hh >> 1) == 1 ? wv : 0u;
+        ch.z = (b_hh >> 1) == 2 ? wv : 0u; ch.w = (b_hh >> 1) == 3 ? wv : 0u;
+        *(uint4 *)(smem + b_dst + kv * 2048 + (p2 & 3) * 4096) = ch;
+      }
+    };
+
+    // LayerNorm backward + residual for both keys of pair p -> de, in place over de'
+    auto phase_b = [&](int p, int st) {
+      uint8_t *es = smem + SM_STAGE + st * STAGE_BYTES;
+      uint32_t dr[16];
+      tmem_ld16(tlane + TM_DX + (p & 1) * TM_DX_COLS, dr);
+      tmem_ld_wait();
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        const uint32_t eoff = trow + (((uint32_t)(2 * (p & 3) + kk) ^ tx7) << 4);
+        const uint4 ev = *(const uint4 *)(es + ST_E + eoff);
+        float x[8] = {bf16_lo(ev.x), bf16_hi(ev.x), bf16_lo(ev.y), bf16_hi(ev.y),
+                      bf16_lo(ev.z), bf16_hi(ev.z), bf16_lo(ev.w), bf16_hi(ev.w)};
+        float mu = ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
+        mu *= 0.125f;
+        float var = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { x[c] -= mu; var = fmaf(x[c], x[c], var); }
+        const float r = rsqrtf(fmaf(var, 0.125f, 1e-3f));
+        float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          x[c] *= r;                                   // x^
+          const float dxh = __uint_as_float(dr[8 * kk + c]);
+          m1 += dxh;
+          m2 = fmaf(dxh, x[c], m2);
+        }
+        m1 *= 0.125f; m2 *= 0.125f;
+        const uint4 dev = *(const uint4 *)(es + ST_DE + eoff);
+        const float dp[8] = {bf16_lo(dev.x), bf16_hi(dev.x), bf16_lo(dev.y), bf16_hi(dev.y),
+                             bf16_lo(dev.z), bf16_hi(dev.z), bf16_lo(dev.w), bf16_hi(dev.w)};
+        float o[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          o[c] = fmaf(r, __uint_as_float(dr[8 * kk + c]) - fmaf(x[c], m2, m1), dp[c]);
+          dbr[c] += dp[c];
+        }
+        uint4 ov;
+        ov.x = pack_bf16(o[0], o[1]); ov.y = pack_bf16(o[2], o[3]);
+        ov.z = pack_bf16(o[4], o[5]); ov.w = pack_bf16(o[6], o[7]);
+        *(uint4 *)(es + ST_DE + eoff) = ov;
+      }
+    };
+
+    // dK / dV of the 16-key block kb: lane t = (key, hh) picks the block diagonal
+    const bool single_tile = gridDim.x == 1;
+    auto t_epilogue = [&](int kb) {
+      const int m = 16 * kb + (t >> 3), hh = t & 7;
+      float *dst = a.d_qkv + ((size_t)b * N + (m < N ? m : 0)) * (3 * FD) + FD + hh;
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t o[32];
+          tmem_ld32(tlane + (which ? TM_DV : TM_DK) + 32 * half, o);   // warp-collective: never inside a divergent branch
+          tmem_ld_wait();
+          if (m < N) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float v = sel8(o + 8 * q, hh);
+              float *pd = dst + which * FD + (half * 4 + q) * 8;
+              if (single_tile) *pd = v;
+              else atomicAdd(pd, v);
+            }
+          }
+        }
+      }
+    };
+
+    mbar_wait(bar_e, 0);
+    build(0, 0);
+    if (NP > 1) build(1, 0);
+    fence_proxy_async_smem();
+    __syncthreads();                                   // sync #0
+    int st_b = 0;                                      // stage of pair it - 2
+    int st_n = 0, par_n = 0;                           // stage / load parity of pair it + 2
+    for (int it = 0; it < NP; ++it) {
+      if (((it + 2) & 3) == 0 || it == 0) {            // pair it+2 sits in tile (it+2)>>2
+        const int T2 = (it + 2) >> 2;
+        st_n = T2 % NS; par_n = (T2 / NS) & 1;
+      }
+      if (it >= 2) {
+        // handshake it-2: d x^ of pair it-2 is in tensor memory, and Kexp / Vexp slot (it+2) & 3 has been read
+        mbar_wait(bar_mma2 + 8u * (uint32_t)(it & 1), ((it - 2) >> 1) & 1);
+        tc_fence_after();
+        phase_b(it - 2, st_b);
+      }
+      if (it >= 1 && ((it - 1) & 7) == 7) {            // dS^T / A~^T block (it-1)/8 went through the tensor core
+        const int kb = (it - 1) >> 3;
+        mbar_wait(bar_t, kb & 1);
+        tc_fence_after();
+        t_epilogue(kb);
+      }
+      if (it + 2 < NP) {
+        if (((it + 2) & 3) == 0) mbar_wait(bar_e + 8 * st_n, par_n);   // first pair of a tile
+        build(it + 2, st_n);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_step + 8u * (uint32_t)(it & 1));  // this thread's share of pair it is done
+      if (it >= 2 && ((it - 1) & 3) == 0) { if (++st_b == NS) st_b = 0; }   // pair it-1 opens a new tile
+    }
+    for (int q = (NP >= 2 ? NP - 2 : 0); q < NP; ++q) { // de updates of the last two pairs
+      mbar_wait(bar_mma2 + 8 * (q & 1), (q >> 1) & 1);
+      tc_fence_after();
+      phase_b(q, (q >> 2) % NS);
+    }
+    fence_proxy_async_smem();
+    __syncthreads();                                   // sync #(NP+1)
+    {
+      const int kb = (NP - 1) >> 3;                    // last (possibly partial) 16-key block
+      mbar_wait(bar_t, kb & 1);
+      tc_fence_after();
+      t_epilogue(kb);
+    }
+    __syncthreads();                                   // reduction scratch zeroed
+    {
+      float *red = (float *)(smem + SM_TR);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float v = warp_sum(dbr[c]);
+        if (lane == 0) atomicAdd(red + 208 + c, v);
+      }
+    }
+    __syncthreads();                                   // partial sums complete
+    tc_fence_before();
+    __syncthreads();                                   // final
+    return;
+  }
+
+  // ================================= main compute threads (warps 0-7) ==============================
+  reg_alloc<192>();
   const int g = tid >> 7, t = tid & 127;
   const int l = l0 + t;
   const bool rowvalid = l < N;
@@ -242,8 +409,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
   const float lo = a.clip_lo, hi = a.clip_hi;
   const uint32_t trow = (uint32_t)t * 128u, tx7 = (uint32_t)(t & 7);
   const uint32_t trbase = (uint32_t)(t >> 3) * 1024u + tx7 * 128u + (uint32_t)g * 8u;
-  const uint32_t bar_mma1 = smem_u32(&bars->mma1[0]), bar_mma2 = smem_u32(&bars->mma2[0]);
-  const uint32_t bar_e = smem_u32(&bars->e_full[0]), bar_t = smem_u32(&bars->tbar), bar_step = smem_u32(&bars->step);
+  const uint32_t bar_mma1 = smem_u32(&bars->mma1[0]);
 
   // ---- per-row quantities: D = sum_dd dV_att * V_att, scaler s, ddeg, log2 row sum; dO tile ---------
   float Dr[4], ddeg[4], l2[4];
@@ -303,30 +469,15 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
 
   // ---- weight-gradient partial sums (registers) ---------------------------------------------------
   float2 ME[8][2], MG[8][2], WR[4][4], sE[2], sG[2];
-  float dbr[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     ME[c][0] = ME[c][1] = MG[c][0] = MG[c][1] = make_float2(0.f, 0.f);
-    dbr[c] = 0.f;
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int q = 0; q < 4; ++q) WR[i][q] = make_float2(0.f, 0.f);
   sE[0] = sE[1] = sG[0] = sG[1] = make_float2(0.f, 0.f);
-
-  // expanded K / V operands of pair p2 (stage st2) into slot p2 & 3: one 16-byte chunk per thread
-  const int b_n = (tid & 127) >> 3, b_dd = tid & 7, b_hh = 4 * (b_n >> 3) + (b_n & 3);
-  const uint32_t b_src = (uint32_t)(g ? ST_V : ST_K) + (uint32_t)((b_n >> 2) & 1) * 128u + (uint32_t)(b_dd * 8 + b_hh) * 2u;
-  const uint32_t b_dst = SM_KVX + (uint32_t)g * 2048u + (uint32_t)b_n * 128u + ((uint32_t)((b_dd ^ b_n) & 7) << 4);
-  auto build = [&](int p2, int st2) {
-    const uint32_t val = *(const uint16_t *)(smem + SM_STAGE + st2 * STAGE_BYTES + b_src + (p2 & 3) * 256);
-    const uint32_t wv = val << ((b_hh & 1) * 16);
-    uint4 ch;
-    ch.x = (b_hh >> 1) == 0 ? wv : 0u; ch.y = (b_hh >> 1) == 1 ? wv : 0u;
-    ch.z = (b_hh >> 1) == 2 ? wv : 0u; ch.w = (b_hh >> 1) == 3 ? wv : 0u;
-    *(uint4 *)(smem + b_dst + (p2 & 3) * 4096) = ch;
-  };
 
   auto ln_stats = [&](const uint4 ev, float *x, float &r, float &nrm) {
     x[0] = bf16_lo(ev.x); x[1] = bf16_hi(ev.x); x[2] = bf16_lo(ev.y); x[3] = bf16_hi(ev.y);
@@ -341,7 +492,6 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
   };
 
   // ---- phase A: pair p, this thread's 4 heads of both keys ------------------------------------------
-  float cur_r = 0.f, cur_nrm = 0.f;   // LN statistics of key g of the pair phase A just processed
   auto phase_a = [&](int p, int st) {
     const int j = p & 3, ob = p & 1, buf = p & 1;
     const uint8_t *es = smem + SM_STAGE + st * STAGE_BYTES;
@@ -363,7 +513,6 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
       const uint32_t eoff = trow + (((uint32_t)ks ^ tx7) << 4);
       float x[8], r, nrm;
       ln_stats(*(const uint4 *)(es + ST_E + eoff), x, r, nrm);
-      if (kk == g) { cur_r = r; cur_nrm = nrm; }
       const uint4 dev = *(const uint4 *)(es + ST_DE + eoff);
       const bool kvalid = rowvalid && smask[m] != 0;
       uint32_t rb0 = 0u, rb1 = 0u;
@@ -438,124 +587,27 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     }
   };
 
-  // ---- phase B: LayerNorm backward + residual for key g of pair p -> de, in place over de' -----------
-  auto phase_b = [&](int p, int st, const float r, const float nrm) {
-    const int j = p & 3;
-    uint8_t *es = smem + SM_STAGE + st * STAGE_BYTES;
-    const int ks = 2 * j + g;
-    uint32_t dr[8];
-    tmem_ld8(tlane + TM_DX + (p & 1) * TM_DX_COLS + g * 8, dr);
-    const uint32_t eoff = trow + (((uint32_t)ks ^ tx7) << 4);
-    const uint4 ev = *(const uint4 *)(es + ST_E + eoff);
-    const float x[8] = {bf16_lo(ev.x), bf16_hi(ev.x), bf16_lo(ev.y), bf16_hi(ev.y),
-                        bf16_lo(ev.z), bf16_hi(ev.z), bf16_lo(ev.w), bf16_hi(ev.w)};
-    const uint4 dev = *(const uint4 *)(es + ST_DE + eoff);
-    const float dp[8] = {bf16_lo(dev.x), bf16_hi(dev.x), bf16_lo(dev.y), bf16_hi(dev.y),
-                         bf16_lo(dev.z), bf16_hi(dev.z), bf16_lo(dev.w), bf16_hi(dev.w)};
-    tmem_ld_wait();
-    float xh[8], m1 = 0.f, m2 = 0.f;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      xh[c] = fmaf(r, x[c], nrm);
-      const float dxh = __uint_as_float(dr[c]);
-      m1 += dxh;
-      m2 = fmaf(dxh, xh[c], m2);
-    }
-    m1 *= 0.125f; m2 *= 0.125f;
-    float o[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const float dxh = __uint_as_float(dr[c]);
-      o[c] = fmaf(r, dxh - fmaf(xh[c], m2, m1), dp[c]);
-      dbr[c] += dp[c];
-    }
-    uint4 ov;
-    ov.x = pack_bf16(o[0], o[1]); ov.y = pack_bf16(o[2], o[3]);
-    ov.z = pack_bf16(o[4], o[5]); ov.w = pack_bf16(o[6], o[7]);
-    *(uint4 *)(es + ST_DE + eoff) = ov;
-  };
-
-  // ---- dK / dV of the 16-key block kb: lane t = (key, hh) picks the block diagonal --------------------
-  const bool single_tile = gridDim.x == 1;
-  auto t_epilogue = [&](int kb) {
-    const int m = 16 * kb + (t >> 3), hh = t & 7;
-    float *dst = a.d_qkv + ((size_t)b * N + (m < N ? m : 0)) * (3 * FD) + FD + hh;
-#pragma unroll
-    for (int which = 0; which < 2; ++which) {
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t o[32];
-        tmem_ld32(tlane + (which ? TM_DV : TM_DK) + 32 * half, o);
-        tmem_ld_wait();
-        if (m < N) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float v = sel8(o + 8 * q, hh);
-            float *pd = dst + which * FD + (half * 4 + q) * 8;
-            if (single_tile) *pd = v;
-            else atomicAdd(pd, v);
-          }
-        }
-      }
-    }
-  };
-
   // ---- pipeline ------------------------------------------------------------------------------------
-  // running indices instead of divisions
-  mbar_wait(bar_e, 0);
-  build(0, 0);
-  if (NP > 1) build(1, 0);
-  fence_proxy_async_smem();
+  mbar_wait(bar_e, 0);                                 // tile 0 (e, de') has landed
+  fence_proxy_async_smem();                            // the dO tile written above is a tensor-core operand
   __syncthreads();                                     // sync #0
-  int st_a = 0;                                        // stage of pair it
-  int st_b = 0;                                        // stage of pair it - 2
-  int st_n = 0, par_n = 0;                             // stage / load parity of pair it + 2
-  float h1_r = 0.f, h1_nrm = 0.f, h2_r = 0.f, h2_nrm = 0.f;   // LN statistics (key g) of pairs it-1, it-2
+  int st_a = 0, par_a = 0;                             // stage / load parity of pair it
   for (int it = 0; it < NP; ++it) {
-    if (((it + 2) & 3) == 0 || it == 0) {              // pair it+2 sits in tile (it+2)>>2
-      const int T2 = (it + 2) >> 2;
-      st_n = T2 % NS; par_n = (T2 / NS) & 1;
-    }
     const uint32_t ob8 = 8u * (uint32_t)(it & 1);
-    if (it >= 2) mbar_wait(bar_mma2 + ob8, ((it - 2) >> 1) & 1);   // handshake it-2: inputs of this pair, products of pair it-2
+    if (it >= 2) mbar_wait(bar_mma2 + ob8, ((it - 2) >> 1) & 1);   // handshake it-2: inputs of this pair; products of pair it-2 consumed
     else mbar_wait(bar_mma1 + ob8, 0);                 // pairs 0, 1: issued before the loop
+    if ((it & 3) == 0) mbar_wait(bar_e + 8 * st_a, par_a);          // first pair of a tile: e / de' are read from shared memory too
     tc_fence_after();
     phase_a(it, st_a);
-    if (it >= 2) phase_b(it - 2, st_b, h2_r, h2_nrm);
-    if (it >= 1 && ((it - 1) & 7) == 7) {              // dS^T / A~^T block (it-1)/8 went through the tensor core
-      const int kb = (it - 1) >> 3;
-      if ((kb & 1) == g) {
-        mbar_wait(bar_t, kb & 1);
-        tc_fence_after();
-        t_epilogue(kb);
-      }
-    }
-    h2_r = h1_r; h2_nrm = h1_nrm; h1_r = cur_r; h1_nrm = cur_nrm;
-    if (it + 2 < NP) {
-      if (((it + 2) & 3) == 0) mbar_wait(bar_e + 8 * st_n, par_n);   // first pair of a tile
-      build(it + 2, st_n);
-    }
     tmem_st_wait();
     fence_proxy_async_smem();
     tc_fence_before();
-    mbar_arrive(bar_step);                             // pair it done by this thread
-    if (((it + 1) & 3) == 0) { if (++st_a == NS) st_a = 0; }
-    if (it >= 2 && ((it - 1) & 3) == 0) { if (++st_b == NS) st_b = 0; }   // pair it-1 opens a new tile
+    mbar_arrive(bar_step + ob8);                       // pair it done by this thread
+    if (((it + 1) & 3) == 0) { if (++st_a == NS) { st_a = 0; par_a ^= 1; } }
   }
-  for (int q = (NP >= 2 ? NP - 2 : 0); q < NP; ++q) {  // de updates of the last two pairs
-    mbar_wait(bar_mma2 + 8 * (q & 1), (q >> 1) & 1);
-    tc_fence_after();
-    if (q == NP - 1) phase_b(q, (q >> 2) % NS, h1_r, h1_nrm);
-    else phase_b(q, (q >> 2) % NS, h2_r, h2_nrm);
-  }
-  fence_proxy_async_smem();
   __syncthreads();                                     // sync #(NP+1)
-  {
-    const int kb = (NP - 1) >> 3;                      // last (possibly partial) 16-key block
-    mbar_wait(bar_t, kb & 1);
-    tc_fence_after();
-    if ((kb & 1) == g) t_epilogue(kb);
-  }
+  mbar_wait(bar_t, ((NP - 1) >> 3) & 1);               // the last transposed products
+  tc_fence_after();
   // dQ: all tcgen05.mma of this CTA have completed (tbar was committed last)
   {
     uint32_t o[32];
@@ -585,7 +637,6 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
       put(c * 16 + 4 * g + 2, ME[c][1].x); put(c * 16 + 4 * g + 3, ME[c][1].y);
       put(c * 16 + 8 + 4 * g + 0, MG[c][0].x); put(c * 16 + 8 + 4 * g + 1, MG[c][0].y);
       put(c * 16 + 8 + 4 * g + 2, MG[c][1].x); put(c * 16 + 8 + 4 * g + 3, MG[c][1].y);
-      put(208 + c, dbr[c]);
     }
     put(128 + 4 * g + 0, sE[0].x); put(128 + 4 * g + 1, sE[0].y); put(128 + 4 * g + 2, sE[1].x); put(128 + 4 * g + 3, sE[1].y);
     put(136 + 4 * g + 0, sG[0].x); put(136 + 4 * g + 1, sG[0].y); put(136 + 4 * g + 2, sG[1].x); put(136 + 4 * g + 3, sG[1].y);
@@ -627,8 +678,8 @@ int fused_bwd_launch(const FusedBwdArgs &a, const void *e, const void *de_out, v
   }
   dim3 grid((a.N + 127) / 128, a.B);
   LaunchScope _ls("fused_bwd_kernel", st);
-  if (a.rand_mask) EGT_CHECK_CUDA(launch_pdl(fused_bwd_kernel<true>, grid, dim3(384), smem, st, tm_e, tm_dei, tm_de, tm_q, tm_kv, a));
-  else EGT_CHECK_CUDA(launch_pdl(fused_bwd_kernel<false>, grid, dim3(384), smem, st, tm_e, tm_dei, tm_de, tm_q, tm_kv, a));
+  if (a.rand_mask) EGT_CHECK_CUDA(launch_pdl(fused_bwd_kernel<true>, grid, dim3(512), smem, st, tm_e, tm_dei, tm_de, tm_q, tm_kv, a));
+  else EGT_CHECK_CUDA(launch_pdl(fused_bwd_kernel<false>, grid, dim3(512), smem, st, tm_e, tm_dei, tm_de, tm_q, tm_kv, a));
   return EGT_OK;
 }
 
