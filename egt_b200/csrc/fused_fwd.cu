@@ -59,7 +59,7 @@ constexpr uint32_t ID_N16 = idesc_bf16(128, 16, 0, 0);
 constexpr uint32_t ID_N32 = idesc_bf16(128, 32, 0, 0);
 constexpr uint32_t ID_PV = idesc_bf16(128, 64, 0, 1);
 
-struct Bars { uint64_t q_full, e_full[NS], mma1[2], mma2[2], step, oproj; uint32_t tmem_base; };
+struct Bars { uint64_t q_full, e_full[NS], mma1[2], mma2[2], step[2], oproj; uint32_t tmem_base; };
 
 }  // namespace
 
@@ -83,7 +83,9 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
       mbar_init(smem_u32(&bars->q_full), 1);
       for (int i = 0; i < NS; ++i) mbar_init(smem_u32(&bars->e_full[i]), 1);
       for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->mma1[i]), 1); mbar_init(smem_u32(&bars->mma2[i]), 1); }
-      mbar_init(smem_u32(&bars->step), 512);          // every compute thread arrives once per step
+      // every compute thread arrives once per step; steps alternate between two barriers because a warp may
+      // finish step it+1 before a slower one finishes step it (dependencies span two steps)
+      mbar_init(smem_u32(&bars->step[0]), 512); mbar_init(smem_u32(&bars->step[1]), 512);
       mbar_init(smem_u32(&bars->oproj), 1);
       mbar_fence_init();
       tma_prefetch_desc(&tm_e); tma_prefetch_desc(&tm_eo); tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_kv);
@@ -176,11 +178,11 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
       mma_commit(bar_m1);                              // S / EG of step 0
       if (NQ > 1) { issue_mma1(1); mma_commit(bar_m1 + 8); }
     }
-    const uint32_t bar_step = smem_u32(&bars->step);
+    const uint32_t bar_step = smem_u32(&bars->step[0]);
     int next_store = 0;                                // tiles [0, next_store) have been handed to the TMA store
     for (int it = 0; it < NQ && warp == 16; ++it) {    // warps 17-19 go straight to the tail barrier
       if (leader) {
-        mbar_wait(bar_step, it & 1);                   // all compute threads finished step it
+        mbar_wait(bar_step + 8 * (it & 1), (it >> 1) & 1);   // all compute threads finished step it
         tc_fence_after();
         fence_proxy_async_smem();                      // the compute threads' shared-memory writes of step it
         issue_mma2(it);                                //  (ordered before this point by the mbarrier) -> async proxy
@@ -238,7 +240,7 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
   const float *cst = (const float *)(smem + SM_CONST);
   const uint8_t *smask = smem + SM_MASK;
   const uint32_t bar_mma1 = smem_u32(&bars->mma1[0]), bar_mma2 = smem_u32(&bars->mma2[0]);
-  const uint32_t bar_e = smem_u32(&bars->e_full[0]), bar_step = smem_u32(&bars->step);
+  const uint32_t bar_e = smem_u32(&bars->e_full[0]), bar_step = smem_u32(&bars->step[0]);
   const float lo = a.clip_lo, hi = a.clip_hi;
   float psum[4], gsum[4];
 #pragma unroll
@@ -374,7 +376,7 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     tmem_st_wait();
     fence_proxy_async_smem();
     tc_fence_before();
-    mbar_arrive(bar_step);                             // step it done by this thread
+    mbar_arrive(bar_step + ob8);                       // step it done by this thread
     if (it & 1) {                                      // steps it+1 and it+3 open new tiles
       if (++st_a == NS) st_a = 0;
       if (++st_n == NS) { st_n = 0; par_n ^= 1; }

@@ -90,5 +90,7 @@ int edge_proj_fwd_launch(const EdgeParams &p, int dtype, cudaStream_t st);
 int edge_out_fwd_launch(const EdgeParams &p, int dtype, cudaStream_t st);
 int edge_out_bwd_launch(const EdgeParams &p, int dtype, cudaStream_t st);
 int edge_proj_bwd_launch(const EdgeParams &p, int dtype, cudaStream_t st);
+// shape-specialised versions (edge_fast.cu); kind 0..3 in the order above; returns 1 when the shape is not covered
+int edge_fast_launch(int kind, const EdgeParams &p, int dtype, cudaStream_t st);
 
 }  // namespace egt
