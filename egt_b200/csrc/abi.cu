@@ -454,6 +454,7 @@ int egt_block_bwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
   P.d_v_att = ws.d_v_att; P.d_h_hat = have_de_out ? ws.dHext : nullptr; P.d_qkv = ws.d_qkv;
   P.dE = ws.dE; P.dG = a.gate_input ? ws.dG : nullptr; P.row_ws = ws.row_ws;
   P.h_hat = have_de_out ? ws.Hhat : nullptr;     // row pass re-materialises H_hat for dW_r
+  P.v_att = const_cast<void *>(io->v_att);       // saved forward output: D = sum_dd dV_att * V_att (attn_fast.cu)
   if (fused) { P.dq_scale = P.scale; P.scale = 1.0f; }   // the fused forward saved a pre-scaled Q
   if ((rc = attn_staged_bwd(P, a.dtype, st))) return rc;
   if (have_de_out) {   // dW_r += H_hat^T de' ; db_r += colsum(de')

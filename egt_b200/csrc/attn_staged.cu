@@ -319,9 +319,11 @@ static int launch_bwd(const AttnParams &P, cudaStream_t st) {
 }
 
 int attn_staged_fwd(const AttnParams &P, int dtype, cudaStream_t st) {
+  if (!staged_force_generic()) { const int rc = attn_fast_launch(0, P, dtype, st); if (rc <= 0) return rc; }
   return dtype == EGT_F32 ? launch_fwd<float>(P, st) : launch_fwd<__nv_bfloat16>(P, st);
 }
 int attn_staged_bwd(const AttnParams &P, int dtype, cudaStream_t st) {
+  if (!staged_force_generic()) { const int rc = attn_fast_launch(1, P, dtype, st); if (rc <= 0) return rc; }
   return dtype == EGT_F32 ? launch_bwd<float>(P, st) : launch_bwd<__nv_bfloat16>(P, st);
 }
 

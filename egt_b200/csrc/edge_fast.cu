@@ -378,9 +378,17 @@ __global__ void __launch_bounds__(FPB) edge_proj_bwd_fast(EdgeParams p) {
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-unsigned fast_grid(const EdgeParams &p, int ctas_per_sm) {
+// persistent grid: as many CTAs as are resident at once (occupancy x SM count), never more than there are chunks
+template <typename K>
+unsigned resident_ctas(K kernel, size_t smem) {
+  int per_sm = 1, sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, FPB, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  return (unsigned)(sms * per_sm);
+}
+inline unsigned fast_grid(const EdgeParams &p, unsigned cap) {
   const size_t chunks = (p.pairs + FPB - 1) / FPB;
-  const size_t cap = (size_t)148 * ctas_per_sm;
   return (unsigned)(chunks < cap ? chunks : cap);
 }
 
@@ -389,12 +397,14 @@ int launch_kind(int kind, const EdgeParams &p, cudaStream_t st) {
   switch (kind) {
     case 0: {
       LaunchScope _ls("edge_proj_fwd_kernel", st);
-      edge_proj_fwd_fast<T, DE, H><<<fast_grid(p, 8), FPB, 0, st>>>(p);
+      static const unsigned cap = resident_ctas(edge_proj_fwd_fast<T, DE, H>, 0);
+      edge_proj_fwd_fast<T, DE, H><<<fast_grid(p, cap), FPB, 0, st>>>(p);
       break;
     }
     case 1: {
       LaunchScope _ls("edge_out_fwd_kernel", st);
-      edge_out_fwd_fast<T, DE, H><<<fast_grid(p, 8), FPB, 0, st>>>(p);
+      static const unsigned cap = resident_ctas(edge_out_fwd_fast<T, DE, H>, 0);
+      edge_out_fwd_fast<T, DE, H><<<fast_grid(p, cap), FPB, 0, st>>>(p);
       break;
     }
     case 2: {
@@ -405,7 +415,8 @@ int launch_kind(int kind, const EdgeParams &p, cudaStream_t st) {
         attr = true;
       }
       LaunchScope _ls("edge_out_bwd_kernel", st);
-      edge_out_bwd_fast<T, DE, H><<<fast_grid(p, 3), FPB, smem, st>>>(p);
+      static const unsigned cap = resident_ctas(edge_out_bwd_fast<T, DE, H>, smem);
+      edge_out_bwd_fast<T, DE, H><<<fast_grid(p, cap), FPB, smem, st>>>(p);
       break;
     }
     default: {
@@ -417,7 +428,8 @@ int launch_kind(int kind, const EdgeParams &p, cudaStream_t st) {
         attr = true;
       }
       LaunchScope _ls("edge_proj_bwd_kernel", st);
-      edge_proj_bwd_fast<T, DE, H><<<fast_grid(p, 2), FPB, smem, st>>>(p);
+      static const unsigned cap = resident_ctas(edge_proj_bwd_fast<T, DE, H>, smem);
+      edge_proj_bwd_fast<T, DE, H><<<fast_grid(p, cap), FPB, smem, st>>>(p);
       break;
     }
   }

@@ -281,9 +281,10 @@ __global__ void __launch_bounds__(EPB) edge_proj_bwd_kernel(EdgeParams p) {
     EGT_CHECK_CUDA(cudaGetLastError());                                             \
   } while (0)
 
-// EGT_EDGE_GENERIC=1 keeps every call on the any-shape kernels of this file (tests compare both sets)
-static bool force_generic() {
-  const char *e = getenv("EGT_EDGE_GENERIC");
+// EGT_STAGED_GENERIC=1 keeps every staged call on the any-shape kernels (edge_kernels.cu, attn_staged.cu);
+// read per call so a test can compare both sets in one process
+bool staged_force_generic() {
+  const char *e = getenv("EGT_STAGED_GENERIC");
   return e && e[0] == '1';
 }
 
@@ -294,17 +295,17 @@ static unsigned persistent_grid(const EdgeParams &p) {
 }
 
 int edge_proj_fwd_launch(const EdgeParams &p, int dtype, cudaStream_t st) {
-  if (!force_generic()) { const int rc = edge_fast_launch(0, p, dtype, st); if (rc <= 0) return rc; }
+  if (!staged_force_generic()) { const int rc = edge_fast_launch(0, p, dtype, st); if (rc <= 0) return rc; }
   DISPATCH_T(dtype, edge_proj_fwd_kernel, pair_grid(p), EPB, 0, st, p);
   return EGT_OK;
 }
 int edge_out_fwd_launch(const EdgeParams &p, int dtype, cudaStream_t st) {
-  if (!force_generic()) { const int rc = edge_fast_launch(1, p, dtype, st); if (rc <= 0) return rc; }
+  if (!staged_force_generic()) { const int rc = edge_fast_launch(1, p, dtype, st); if (rc <= 0) return rc; }
   DISPATCH_T(dtype, edge_out_fwd_kernel, pair_grid(p), EPB, 0, st, p);
   return EGT_OK;
 }
 int edge_out_bwd_launch(const EdgeParams &p, int dtype, cudaStream_t st) {
-  if (!force_generic()) { const int rc = edge_fast_launch(2, p, dtype, st); if (rc <= 0) return rc; }
+  if (!staged_force_generic()) { const int rc = edge_fast_launch(2, p, dtype, st); if (rc <= 0) return rc; }
   size_t smem = (size_t)EPB * (p.h + p.d_e) * sizeof(float);
   if (smem > 48 * 1024) {
     EGT_CHECK_CUDA(cudaFuncSetAttribute(edge_out_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -314,7 +315,7 @@ int edge_out_bwd_launch(const EdgeParams &p, int dtype, cudaStream_t st) {
   return EGT_OK;
 }
 int edge_proj_bwd_launch(const EdgeParams &p, int dtype, cudaStream_t st) {
-  if (!force_generic()) { const int rc = edge_fast_launch(3, p, dtype, st); if (rc <= 0) return rc; }
+  if (!staged_force_generic()) { const int rc = edge_fast_launch(3, p, dtype, st); if (rc <= 0) return rc; }
   int J = p.gated ? 2 * p.h : p.h;
   size_t smem = ((size_t)EPB * (p.d_e + J) + J) * sizeof(float);
   if (smem > 48 * 1024) {

@@ -28,6 +28,9 @@ struct AttnParams {
 
 int attn_staged_fwd(const AttnParams &P, int dtype, cudaStream_t st);
 int attn_staged_bwd(const AttnParams &P, int dtype, cudaStream_t st);
+// shape-specialised versions (attn_fast.cu); kind 0 forward, 1 backward; returns 1 when the shape is not covered
+int attn_fast_launch(int kind, const AttnParams &P, int dtype, cudaStream_t st);
+bool staged_force_generic();   // EGT_STAGED_GENERIC=1
 
 // ---- node side (node_kernels.cu) -------------------------------------------------------
 // out[r,:] = (LN? LN(x[r,:]) : x[r,:]) @ W (+bias) (+res[r,:]);  W is [din,dout] (trans=0) or

@@ -263,6 +263,15 @@ def test_block_forward_backward_vs_oracle(case, dtype):
         assert err < tol, f'grad {name}: rel-to-max err {err:.3e}'
 
 
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('case', [0, 3, 9, 10, 11, 12])
+def test_any_shape_staged_kernels_vs_oracle(case, dtype, monkeypatch):
+    """The shape-specialised staged kernels (edge_fast.cu, attn_fast.cu) take the common (d_e, h, dk); the
+    any-shape kernels behind them (edge_kernels.cu, attn_staged.cu) must stay correct on those shapes too."""
+    monkeypatch.setenv('EGT_STAGED_GENERIC', '1')
+    test_block_forward_backward_vs_oracle(case, dtype)
+
+
 def test_block_mask_is_bit_exact_and_padding_is_inert():
     """Padded KEYS never influence valid rows: perturbing padded nodes / padded edge columns leaves
     h' and e' at valid positions bit-identical (egt_layers.py:91-94)."""
