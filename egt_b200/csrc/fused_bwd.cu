@@ -502,14 +502,19 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     const float4 uG4 = *(const float4 *)(cst + 16 + 4 * g), vG4 = *(const float4 *)(cst + 24 + 4 * g);
     const float uE[4] = {uE4.x, uE4.y, uE4.z, uE4.w}, vE[4] = {vE4.x, vE4.y, vE4.z, vE4.w};
     const float uG[4] = {uG4.x, uG4.y, uG4.z, uG4.w}, vG[4] = {vG4.x, vG4.y, vG4.z, vG4.w};
+    // the tensor-core products of both keys are requested at once: one tcgen05.wait::ld per pair
+    uint32_t sreg2[2][4], dareg2[2][4], egreg2[2][8], hxreg2[2][4];
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      tmem_ld4(tin + IN_S + g * 8 + kk * 4, sreg2[kk]);
+      tmem_ld4(tin + IN_DA + g * 8 + kk * 4, dareg2[kk]);
+      tmem_ld8(tin + IN_EG + g * 16 + kk * 8, egreg2[kk]);
+      tmem_ld4(tin + IN_HX + g * 8 + kk * 4, hxreg2[kk]);
+    }
 #pragma unroll
     for (int kk = 0; kk < 2; ++kk) {
       const int ks = 2 * j + kk, m = 2 * p + kk;
-      uint32_t sreg[4], dareg[4], egreg[8], hxreg[4];
-      tmem_ld4(tin + IN_S + g * 8 + kk * 4, sreg);
-      tmem_ld4(tin + IN_DA + g * 8 + kk * 4, dareg);
-      tmem_ld8(tin + IN_EG + g * 16 + kk * 8, egreg);
-      tmem_ld4(tin + IN_HX + g * 8 + kk * 4, hxreg);
+      const uint32_t *sreg = sreg2[kk], *dareg = dareg2[kk], *egreg = egreg2[kk], *hxreg = hxreg2[kk];
       const uint32_t eoff = trow + (((uint32_t)ks ^ tx7) << 4);
       float x[8], r, nrm;
       ln_stats(*(const uint4 *)(es + ST_E + eoff), x, r, nrm);
@@ -522,7 +527,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
                                    (uint32_t)(a.offset >> 32), (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
         rb0 = g ? ph.z : ph.x; rb1 = g ? ph.w : ph.y;      // heads 4g..4g+3 use words 2g, 2g+1
       }
-      tmem_ld_wait();
+      if (kk == 0) tmem_ld_wait();
       float dS[4], At[4], dH[4], dGv[4], Hh[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
