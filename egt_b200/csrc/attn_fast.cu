@@ -3,7 +3,7 @@
 // Same three passes and the same arithmetic per (l, m, head) as attn_staged.cu (which stays as the any-shape
 // fallback), restructured for the memory system:
 //   * a CTA owns a block of rows (queries in the forward / row pass, keys in the column pass) of one graph; a
-//     thread owns one row and HPT (4 or 2) consecutive heads, so E / G / M / H_hat / dE / dG move as one vector
+//     thread owns one row and HPT (4, 2 or 1) consecutive heads, so E / G / M / H_hat / dE / dG move as one vector
 //     access per pair and a warp touches one contiguous span;
 //   * the other side's vectors (K,V or Q,dV_att) are staged 32 rows at a time in shared memory as fp32
 //     [row][head group][head][dk] (+4 floats per group, which spreads the groups over the banks) and read back
@@ -28,22 +28,25 @@ template <typename T, int V> __device__ __forceinline__ void loadv(const T *p, f
   if constexpr (sizeof(T) == 4 && V == 4) {
     const float4 v = __ldg((const float4 *)p);
     x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
-  } else if constexpr (sizeof(T) == 4) {
+  } else if constexpr (sizeof(T) == 4 && V == 2) {
     const float2 v = __ldg((const float2 *)p);
     x[0] = v.x; x[1] = v.y;
   } else if constexpr (V == 4) {
     const uint2 v = __ldg((const uint2 *)p);
     x[0] = bf16_lo(v.x); x[1] = bf16_hi(v.x); x[2] = bf16_lo(v.y); x[3] = bf16_hi(v.y);
-  } else {
+  } else if constexpr (V == 2) {
     const uint32_t v = __ldg((const uint32_t *)p);
     x[0] = bf16_lo(v); x[1] = bf16_hi(v);
+  } else {
+    x[0] = ldf(p);
   }
 }
 template <typename T, int V> __device__ __forceinline__ void storev(T *p, const float *x) {
   if constexpr (sizeof(T) == 4 && V == 4) *(float4 *)p = make_float4(x[0], x[1], x[2], x[3]);
-  else if constexpr (sizeof(T) == 4) *(float2 *)p = make_float2(x[0], x[1]);
+  else if constexpr (sizeof(T) == 4 && V == 2) *(float2 *)p = make_float2(x[0], x[1]);
   else if constexpr (V == 4) *(uint2 *)p = make_uint2(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]));
-  else *(uint32_t *)p = pack_bf16(x[0], x[1]);
+  else if constexpr (V == 2) *(uint32_t *)p = pack_bf16(x[0], x[1]);
+  else stf(p, x[0]);
 }
 
 // 1/(1+exp(-x)) with the hardware reciprocal; x = -1e9 gives exp -> +inf -> exactly 0 (the masked-gate contract)
@@ -113,9 +116,10 @@ template <int H_, int DKP_, int HPT_>
 struct Geo {
   static constexpr int H = H_, DKP = DKP_, HPT = HPT_;
   static constexpr int HG = H / HPT;                      // head groups == threads per row
-  static constexpr int ROWS = (HG >= 8) ? 32 : 64;        // rows per CTA
+  static constexpr int ROWS = (HG >= 16) ? 16 : (HG >= 8) ? 32 : 64;   // rows per CTA
   static constexpr int NT = ROWS * HG;                    // threads per CTA
-  static constexpr int GS = HPT * DKP + 4;                // floats per staged head group (GS/4 is odd: no bank conflicts)
+  // floats per staged head group; GS/4 odd, so the groups a warp reads start in different banks
+  static constexpr int GS = HPT * DKP + (((HPT * DKP / 4) & 1) ? 8 : 4);
   static constexpr int RS = HG * GS;                      // floats per staged row
 };
 
@@ -427,14 +431,17 @@ int launch3(int kind, const AttnParams &P, cudaStream_t st) {
   return EGT_OK;
 }
 
-// Heads per thread, measured on B200 (C5 / C3 / C1 widths): two in the forward (more warps in flight beat wider
-// accesses); in the backward two while the four dk-vectors per head fit 128 registers (dk <= 8), else four.
-// EGT_ATTN_HPT=<f><b> (e.g. 42) overrides for experiments.
+// Heads per thread, measured on B200 (C5 / C3 / C1 widths): as few as the shared-memory budget allows -- more
+// warps in flight beat wider accesses for this latency-bound arithmetic: one with 8 heads, two with 16.
+// EGT_ATTN_HPT=<f><b> (e.g. 42: four in the forward, two in the backward) overrides for experiments.
 template <typename T, int H, int DKP, bool PLAIN>
 int launch_hpt(int kind, const AttnParams &P, cudaStream_t st) {
-  int hf = 2, hb = DKP > 8 ? 4 : 2;
+  int hf = H <= 8 ? 1 : 2, hb = H <= 8 ? 1 : 2;
   if (const char *e = getenv("EGT_ATTN_HPT")) { hf = e[0] - '0'; hb = e[1] - '0'; }
   const int hpt = kind == 0 ? hf : hb;
+  if constexpr (H <= 8) {                              // (16 heads x 1 would exceed the static shared-memory limit)
+    if (hpt == 1) return launch3<T, Geo<H, DKP, 1>, Geo<H, DKP, 1>, PLAIN>(kind, P, st);
+  }
   if (hpt == 2) return launch3<T, Geo<H, DKP, 2>, Geo<H, DKP, 2>, PLAIN>(kind, P, st);
   return launch3<T, Geo<H, DKP, 4>, Geo<H, DKP, 4>, PLAIN>(kind, P, st);
 }
