@@ -7,8 +7,11 @@
 
 namespace egt {
 
-// One CTA of 128 threads.  B-operand images are K-major without swizzle: element (n, k) of an [N x K]
+// Threads 0..127 of one CTA.  B-operand images are K-major without swizzle: element (n, k) of an [N x K]
 // matrix lives at  (k/8) * (N*16) + n*16 + (k%8)*2  bytes (8x16-byte core matrices, LBO = N*16, SBO = 128).
+// barrier among the 128 threads (warps 0-3) that run fused_prep_body; the hosting CTA may be larger
+__device__ __forceinline__ void prep_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
 __device__ __forceinline__ void fused_prep_body(const egt_block_weights_t &w, float clip_lo, float clip_hi,
                                                 FusedPrep *out, const int tid) {
   __shared__ float wp[2][FDE][FH];   // W' rounded to bf16
@@ -23,7 +26,7 @@ __device__ __forceinline__ void fused_prep_body(const egt_block_weights_t &w, fl
     else if (tid < 104) sbr[tid - 96] = w.dense_edge_r_bias[tid - 96];
   }
   pdl_wait();                        // parameters were read above; everything below writes global memory
-  __syncthreads();
+  prep_sync();
   if (tid < FDE) out->br[tid] = sbr[tid];
   {
     int eg = tid / 64, c = (tid / 8) % 8, hh = tid % 8;
@@ -31,7 +34,7 @@ __device__ __forceinline__ void fused_prep_body(const egt_block_weights_t &w, fl
     wp[eg][c][hh] = v;
     out->wp[eg][c][hh] = v;
   }
-  __syncthreads();
+  prep_sync();
   if (tid < 16) {
     int eg = tid / 8, hh = tid % 8;
     float u = 0.f, v = sbias[eg][hh], n2 = 0.f;

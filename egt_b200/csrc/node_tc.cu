@@ -122,56 +122,65 @@ struct NodeQkvArgs {
   egt_block_weights_t w; float clip_lo, clip_hi; FusedPrep *prep_out;   // extra CTA: fused_prep_body (NULL = off)
 };
 
-__global__ void __launch_bounds__(128) node_qkv_kernel(const NodeQkvArgs a) {
+// 256 threads: two threads per row.  LayerNorm prologue: threads 2r, 2r+1 share row r (32 channels each, partial
+// sums exchanged by shuffle); epilogue: thread (lane t, half) reads TMEM lane t and converts output columns
+// 96*half .. 96*half+95.
+__global__ void __launch_bounds__(256) node_qkv_kernel(const NodeQkvArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t *sA = smem, *sW = smem + TILE;                     // A 16 KB | W image 3 x 8 KB
   float *sgb = (float *)(smem + TILE + 24576);               // gamma, beta, bias(192)
   NodeBars *bars = (NodeBars *)(smem + TILE + 24576 + 1536);
-  const int t = threadIdx.x;
+  const int tid = threadIdx.x, t = tid & 127, half = tid >> 7;
   const int nwork = a.prep_out ? gridDim.x - 1 : gridDim.x;
   pdl_trigger();
-  if ((int)blockIdx.x == nwork) { fused_prep_body(a.w, a.clip_lo, a.clip_hi, a.prep_out, t); return; }
-  node_setup(bars, t, 256);
-  build_w_mn(sW, a.W, ND, 3 * ND, t, 128);
-  if (t < ND) { sgb[t] = a.gamma[t]; sgb[ND + t] = a.beta[t]; }
-  for (int i = t; i < 3 * ND; i += 128) sgb[2 * ND + i] = a.bias[i];
+  if ((int)blockIdx.x == nwork) {
+    if (tid < 128) fused_prep_body(a.w, a.clip_lo, a.clip_hi, a.prep_out, tid);
+    return;
+  }
+  node_setup(bars, tid, 256);
+  build_w_mn(sW, a.W, ND, 3 * ND, tid, 256);
+  if (tid < ND) { sgb[tid] = a.gamma[tid]; sgb[ND + tid] = a.beta[tid]; }
+  if (tid < 3 * ND) sgb[2 * ND + tid] = a.bias[tid];
   pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
-  const uint32_t tlane = tmem + ((uint32_t)((t >> 5) * 32) << 16);
+  const uint32_t tlane = tmem + ((uint32_t)(((tid >> 5) & 3) * 32) << 16);
   constexpr uint32_t IDESC = idesc_bf16(128, 192, 0, 1);
   uint32_t phase = 0;
+  const int pr = tid >> 1, ph = tid & 1;                     // prologue: row within the tile, channel half
   for (int tile = blockIdx.x; tile * 128 < a.R; tile += nwork) {
-    const int r = tile * 128 + t;
-    {   // LayerNorm of this thread's row -> bf16 A tile
-      uint4 v[8];
-      float x[64];
-      const uint4 *src = (const uint4 *)(a.h + (size_t)(r < a.R ? r : 0) * ND);
+    {   // LayerNorm of row pr, channels 32 ph .. 32 ph + 31 -> bf16 A tile
+      const int r = tile * 128 + pr;
+      float x[32];
+      const uint4 *src = (const uint4 *)(a.h + (size_t)(r < a.R ? r : 0) * ND + 32 * ph);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { v[j] = r < a.R ? src[j] : make_uint4(0, 0, 0, 0); unpack8(v[j], x + 8 * j); }
+      for (int j = 0; j < 4; ++j) unpack8(r < a.R ? src[j] : make_uint4(0, 0, 0, 0), x + 8 * j);
       float mu = 0.f;
 #pragma unroll
-      for (int c = 0; c < 64; ++c) mu += x[c];
+      for (int c = 0; c < 32; ++c) mu += x[c];
+      mu += __shfl_xor_sync(0xffffffffu, mu, 1);
       mu *= (1.f / 64.f);
       float var = 0.f;
 #pragma unroll
-      for (int c = 0; c < 64; ++c) { const float dlt = x[c] - mu; var = fmaf(dlt, dlt, var); }
+      for (int c = 0; c < 32; ++c) { const float dlt = x[c] - mu; var = fmaf(dlt, dlt, var); }
+      var += __shfl_xor_sync(0xffffffffu, var, 1);
       const float rs = rsqrtf(var * (1.f / 64.f) + a.eps);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < 4; ++j) {
         float y[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) y[c] = fmaf((x[8 * j + c] - mu) * rs, sgb[8 * j + c], sgb[ND + 8 * j + c]);
-        *(uint4 *)(sA + sw128_off(t, 8 * j)) = pack8(y);
+        for (int c = 0; c < 8; ++c)
+          y[c] = fmaf((x[8 * j + c] - mu) * rs, sgb[32 * ph + 8 * j + c], sgb[ND + 32 * ph + 8 * j + c]);
+        *(uint4 *)(sA + sw128_off(pr, 32 * ph + 8 * j)) = pack8(y);
       }
     }
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
-    if (t == 0) {
+    if (tid == 0) {
       tc_fence_after();
 #pragma unroll
       for (int s = 0; s < 4; ++s)
@@ -182,8 +191,9 @@ __global__ void __launch_bounds__(128) node_qkv_kernel(const NodeQkvArgs a) {
     mbar_wait(smem_u32(&bars->bar), phase);
     phase ^= 1;
     tc_fence_after();
+    const int r = tile * 128 + t;
 #pragma unroll 1
-    for (int ch = 0; ch < 6; ++ch) {
+    for (int ch = 3 * half; ch < 3 * half + 3; ++ch) {
       uint32_t o[32];
       tmem_ld32(tlane + 32 * ch, o);
       tmem_ld_wait();
@@ -202,7 +212,7 @@ __global__ void __launch_bounds__(128) node_qkv_kernel(const NodeQkvArgs a) {
     tc_fence_before();
     __syncthreads();
   }
-  if (t < 32) tmem_dealloc(tmem, 256);
+  if (tid < 32) tmem_dealloc(tmem, 256);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -570,7 +580,7 @@ int node_qkv_launch(const void *h, const float *gamma, const float *beta, float 
   static bool once = false;
   if (!once) { int rc = set_smem(node_qkv_kernel, smem); if (rc) return rc; once = true; }
   LaunchScope _ls("node_qkv_kernel", st);
-  EGT_CHECK_CUDA(launch_pdl(node_qkv_kernel, dim3(node_grid(R) + (prep_out ? 1 : 0)), dim3(128), smem, st, a));
+  EGT_CHECK_CUDA(launch_pdl(node_qkv_kernel, dim3(node_grid(R) + (prep_out ? 1 : 0)), dim3(256), smem, st, a));
   return EGT_OK;
 }
 
