@@ -78,7 +78,7 @@ __device__ __forceinline__ void axpy_s(float a, const float *smem_x, float *y) {
 struct Elem { float S_raw, Hh, x, gin, keep; };
 template <bool PLAIN>
 __device__ __forceinline__ Elem eval_elem(const AttnParams &P, float dot, float Ev, float Gv, float negkey, float Mv,
-                                          size_t pe) {
+                                          int b, int l, int m, int hh) {
   Elem e;
   float s = dot * P.scale;                                        // :79
   e.S_raw = s;
@@ -94,12 +94,12 @@ __device__ __forceinline__ Elem eval_elem(const AttnParams &P, float dot, float 
       e.x += neg; e.gin += neg;
     }
     if (P.rand_mask) {                                            // :103-108
-      const float u = rng_uniform(P.seed, P.offset, 0u, pe);
+      const float u = rng_uniform(P.seed, P.offset, 0u, rng_elem_index(b, l, m, hh, P.N, P.h));
       const float neg = u < P.random_mask_prob ? -kNegMask : 0.f;
       e.x += neg; e.gin += neg;
     }
     if (P.dropout) {
-      const float u = rng_uniform(P.seed, P.offset, 1u, pe);
+      const float u = rng_uniform(P.seed, P.offset, 1u, rng_elem_index(b, l, m, hh, P.N, P.h));
       e.keep = u >= P.attn_dropout ? 1.f / (1.f - P.attn_dropout) : 0.f;
     }
   }
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(G::NT) attn_fwd_fast(AttnParams P) {
       const float *kg = Ks + mk * G::RS + hg * G::GS, *vg = Vs + mk * G::RS + hg * G::GS;
 #pragma unroll
       for (int i = 0; i < HPT; ++i) {
-        const Elem e = eval_elem<PLAIN>(P, dot_s<DKP>(q[i], kg + i * DKP), Ev[i], Gv[i], nk, Mv[i], pe + i);
+        const Elem e = eval_elem<PLAIN>(P, dot_s<DKP>(q[i], kg + i * DKP), Ev[i], Gv[i], nk, Mv[i], b, lc, m0 + mk, HPT * hg + i);
         Hh[i] = e.Hh;
         if (e.x > mrun[i]) {                                     // online softmax, as attn_staged.cu
           const float corr = __expf(mrun[i] - e.x);
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(G::NT) attn_bwd_row_fast(AttnParams P) {
         const float *kg = Ks + mk * G::RS + hg * G::GS, *vg = Vs + mk * G::RS + hg * G::GS;
 #pragma unroll
         for (int i = 0; i < HPT; ++i) {
-          const Elem e = eval_elem<PLAIN>(P, dot_s<DKP>(q[i], kg + i * DKP), Ev[i], Gv[i], nk, Mv[i], pe + i);
+          const Elem e = eval_elem<PLAIN>(P, dot_s<DKP>(q[i], kg + i * DKP), Ev[i], Gv[i], nk, Mv[i], b, lc, m0 + mk, HPT * hg + i);
           const float p = __expf((e.x - lse[i]) - lsum[i]);
           const float g = P.G ? sigmoid_rcp(e.gin) : 1.f;
           const float dAp = dot_s<DKP>(dva[i], vg + i * DKP);
@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(G::NT) attn_bwd_col_fast(AttnParams P) {
         const float *qp = qg + i * DKP, *dp = dg + i * DKP;
         const float4 st = *(const float4 *)&rst[lk][HPT * hg + i][0];
         // q . k accumulates in the same order as in the row pass, so both passes see the same S_raw
-        const Elem e = eval_elem<PLAIN>(P, dot_s<DKP>(k[i], qp), Ev[i], Gv[i], nk, Mv[i], pe + i);
+        const Elem e = eval_elem<PLAIN>(P, dot_s<DKP>(k[i], qp), Ev[i], Gv[i], nk, Mv[i], b, l0 + lk, mc, HPT * hg + i);
         const float p = __expf((e.x - st.x) - st.y);
         const float g = P.G ? sigmoid_rcp(e.gin) : 1.f;
         const float dAp = dot_s<DKP>(v[i], dp);

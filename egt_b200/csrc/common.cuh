@@ -126,6 +126,16 @@ __host__ __device__ __forceinline__ float rng_uniform(uint64_t seed, uint64_t of
   return ((float)bits + 0.5f) * (1.0f / 65536.0f);
 }
 
+// Element (b, l, m, hh) of a [B,N,N,h] tensor -> RNG element index.  The eight uniforms of one Philox call cover
+// two consecutive keys x four consecutive heads, so a thread that owns (row, key pair, head quad) -- the work
+// split of the fused kernels -- draws all of its bits with a single call.
+__host__ __device__ __forceinline__ uint64_t rng_elem_index(uint64_t b, uint64_t l, uint64_t m, uint32_t hh, uint64_t N,
+                                                            uint32_t h) {
+  const uint64_t np = (N + 1) >> 1, nq = (h + 3u) >> 2;
+  const uint64_t call = ((b * N + l) * np + (m >> 1)) * nq + (uint64_t)(hh >> 2);
+  return (call << 3) | ((m & 1) << 2) | (uint64_t)(hh & 3u);
+}
+
 // activation of edge_channel_contrib (graph_xformer_model_base.py:149-162)
 __device__ __forceinline__ float edge_act_fwd(int act, float alpha, float x) {
   switch (act) {

@@ -504,6 +504,13 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     const float uG[4] = {uG4.x, uG4.y, uG4.z, uG4.w}, vG[4] = {vG4.x, vG4.y, vG4.z, vG4.w};
     // the tensor-core products of both keys are requested at once: one tcgen05.wait::ld per pair
     uint32_t sreg2[2][4], dareg2[2][4], egreg2[2][8], hxreg2[2][4];
+    uint32_t rbw[4] = {0u, 0u, 0u, 0u};
+    if (RAND) {   // one Philox call = this thread's 2 keys x 4 heads (rng_elem_index, common.cuh)
+      const uint64_t qd = rng_elem_index((uint64_t)b, (uint64_t)l, (uint64_t)(2 * p), 4u * (uint32_t)g, (uint64_t)N, FH) >> 3;
+      const Philox4 ph = philox4x32_10((uint32_t)qd, (uint32_t)(qd >> 32), (uint32_t)a.offset,
+                                       (uint32_t)(a.offset >> 32), (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+      rbw[0] = ph.x; rbw[1] = ph.y; rbw[2] = ph.z; rbw[3] = ph.w;          // key kk, head 4g+i: 16-bit lane 4kk+i
+    }
 #pragma unroll
     for (int kk = 0; kk < 2; ++kk) {
       tmem_ld4(tin + IN_S + g * 8 + kk * 4, sreg2[kk]);
@@ -520,13 +527,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
       ln_stats(*(const uint4 *)(es + ST_E + eoff), x, r, nrm);
       const uint4 dev = *(const uint4 *)(es + ST_DE + eoff);
       const bool kvalid = rowvalid && smask[m] != 0;
-      uint32_t rb0 = 0u, rb1 = 0u;
-      if (RAND) {
-        const uint64_t qd = ((uint64_t)b * N + (uint64_t)l) * N + (uint64_t)m;
-        Philox4 ph = philox4x32_10((uint32_t)qd, (uint32_t)(qd >> 32), (uint32_t)a.offset,
-                                   (uint32_t)(a.offset >> 32), (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
-        rb0 = g ? ph.z : ph.x; rb1 = g ? ph.w : ph.y;      // heads 4g..4g+3 use words 2g, 2g+1
-      }
+      const uint32_t rb0 = rbw[2 * kk], rb1 = rbw[2 * kk + 1];
       if (kk == 0) tmem_ld_wait();
       float dS[4], At[4], dH[4], dGv[4], Hh[4];
 #pragma unroll

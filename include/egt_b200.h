@@ -219,8 +219,11 @@ int egt_ffn_bwd(const egt_ffn_cfg_t *cfg, const egt_ffn_weights_t *w, const egt_
 int egt_peer_allreduce(const uint64_t *buffer_ptrs_dev, const uint64_t *signal_pad_ptrs_dev, float *grad,
                        int64_t n, int rank, int world, void *stream);
 
-/* Counter-based uniform in [0,1) used for the random key mask / dropout (testing hook; host code).
- * stream_id 0 = random mask, 1 = attention dropout.  idx = ((b*N + l)*N + m)*h + hh. */
+/* Counter-based uniform in (0,1) used for the random key mask / dropout (testing hook; host code).
+ * stream_id 0 = random mask, 1 = attention dropout.  idx is the RNG element index: Philox call idx >> 3, 16-bit
+ * lane idx & 7.  Element (b,l,m,hh) of a [B,N,N,h] tensor uses
+ *   idx = ((((b*N + l)*ceil(N/2) + m/2)*ceil(h/4) + hh/4) << 3) | (m & 1) << 2 | (hh & 3)
+ * (one call = two consecutive keys x four consecutive heads; csrc/common.cuh rng_elem_index, tests/philox.py). */
 float egt_rng_uniform_host(uint64_t seed, uint64_t offset, uint32_t stream_id, uint64_t idx);
 
 /* Testing hook: nonzero routes every shape through the staged kernels (process-wide). */

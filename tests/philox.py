@@ -41,6 +41,15 @@ def uniform(seed, offset, stream_id, idx):
     return ((bits.astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 65536.0)).astype(np.float32)
 
 
+def elem_index(B, N, h):
+    """RNG element index of every (b, l, m, hh) (common.cuh: rng_elem_index): one Philox call = 2 consecutive
+    keys x 4 consecutive heads."""
+    b, l, m, hh = np.meshgrid(np.arange(B, dtype=np.uint64), np.arange(N, dtype=np.uint64), np.arange(N, dtype=np.uint64),
+                              np.arange(h, dtype=np.uint64), indexing='ij')
+    npair, nq = np.uint64((N + 1) // 2), np.uint64((h + 3) // 4)
+    u = np.uint64
+    return ((((b * u(N) + l) * npair + (m >> u(1))) * nq + (hh >> u(2))) << u(3)) | ((m & u(1)) << u(2)) | (hh & u(3))
+
+
 def noise_tensor(seed, offset, stream_id, B, N, h):
-    idx = np.arange(B * N * N * h, dtype=np.uint64).reshape(B, N, N, h)
-    return uniform(seed, offset, stream_id, idx)
+    return uniform(seed, offset, stream_id, elem_index(B, N, h))
