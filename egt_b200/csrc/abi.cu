@@ -103,6 +103,7 @@ static int check_device() {
 // workspace carving -------------------------------------------------------------------------
 struct BlockWs {
   char *E, *G, *Hhat, *dHext, *dE, *dG;      // [pairs,h] dtype
+  char *dS, *As;                              // [pairs,h] dtype (staged backward: row pass -> column pass)
   float *row_ws;                              // [2,B,N,h]
   char *d_v_att, *d_qkv;                      // [R,d], [R,3d] dtype
   float *hn, *dhn;                            // [R,d] f32
@@ -145,6 +146,8 @@ static BlockWs carve(const egt_block_cfg_t *c, int backward, void *base, bool ha
       if (c->gate_attention) w.dG = take(pairs * a.h * es);
     }
     w.row_ws = (float *)take(2 * R * a.h * sizeof(float));
+    w.dS = take(pairs * a.h * es);
+    w.As = take(pairs * a.h * es);
     w.d_v_att = take(R * d * es);
     w.d_qkv = take(R * 3 * d * es);
     w.hn = (float *)take(R * d * sizeof(float));
@@ -455,6 +458,7 @@ int egt_block_bwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
   P.dE = ws.dE; P.dG = a.gate_input ? ws.dG : nullptr; P.row_ws = ws.row_ws;
   P.h_hat = have_de_out ? ws.Hhat : nullptr;     // row pass re-materialises H_hat for dW_r
   P.v_att = const_cast<void *>(io->v_att);       // saved forward output: D = sum_dd dV_att * V_att (attn_fast.cu)
+  P.dS_ws = ws.dS; P.As_ws = ws.As;
   if (fused) { P.dq_scale = P.scale; P.scale = 1.0f; }   // the fused forward saved a pre-scaled Q
   if ((rc = attn_staged_bwd(P, a.dtype, st))) return rc;
   if (have_de_out) {   // dW_r += H_hat^T de' ; db_r += colsum(de')

@@ -10,7 +10,8 @@
 //     as broadcast float4, instead of 2*dk scalar global loads per element;
 //   * sizes (h, padded dk) and the rarely used features (attention mask, random mask, dropout) are compile-time,
 //     so every per-head vector lives in registers and the common case carries no dead branches.
-// With a saved V_att the row pass takes  D = sum_dd dV_att * V_att  (= s * sum_m A~ dA) and skips its first sweep.
+// With a saved V_att the row pass takes  D = sum_dd dV_att * V_att  (= s * sum_m A~ dA) and skips its first sweep;
+// with workspace for dS and s*A~ (block-level backward) the column pass is two plain accumulations.
 #include "common.cuh"
 #include "kernels.h"
 #include "umma.cuh"
@@ -288,7 +289,7 @@ __global__ void __launch_bounds__(G::NT) attn_bwd_row_fast(AttnParams P) {
       const int kend = N - m0 < AKB ? N - m0 : AKB;
       for (int mk = 0; mk < kend; ++mk) {
         const size_t pair = rowbase + m0 + mk, pe = pair * H + HPT * hg;
-        float Ev[HPT], Gv[HPT], Mv[HPT], dhh[HPT], Hh[HPT], dEo[HPT], dGo[HPT];
+        float Ev[HPT], Gv[HPT], Mv[HPT], dhh[HPT], Hh[HPT], dEo[HPT], dGo[HPT], dSo[HPT], Aso[HPT];
 #pragma unroll
         for (int i = 0; i < HPT; ++i) { Ev[i] = 0.f; Gv[i] = 0.f; Mv[i] = 1.f; dhh[i] = 0.f; }
         if (P.E) loadv<T, HPT>((const T *)P.E + pe, Ev);
@@ -312,13 +313,16 @@ __global__ void __launch_bounds__(G::NT) attn_bwd_row_fast(AttnParams P) {
             dEo[i] = dH;
             dGo[i] = (dA * p + ddeg[i]) * g * (1.f - g);
             const bool inside = !P.has_clip || (e.S_raw >= P.clip_lo && e.S_raw <= P.clip_hi);
-            axpy_s<DKP>(inside ? dH * P.scale : 0.f, kg + i * DKP, dq[i]);
+            dSo[i] = inside ? dH * P.scale : 0.f;
+            Aso[i] = p * g * e.keep * sc[i];
+            axpy_s<DKP>(dSo[i], kg + i * DKP, dq[i]);
           }
         }
         if (pass == 1 && rowvalid) {
           if (P.h_hat) storev<T, HPT>((T *)P.h_hat + pe, Hh);
           if (P.dG) storev<T, HPT>((T *)P.dG + pe, dGo);
           if (P.dE) storev<T, HPT>((T *)P.dE + pe, dEo);
+          if (P.dS_ws) { storev<T, HPT>((T *)P.dS_ws + pe, dSo); storev<T, HPT>((T *)P.As_ws + pe, Aso); }
         }
       }
     }
@@ -412,6 +416,55 @@ __global__ void __launch_bounds__(G::NT) attn_bwd_col_fast(AttnParams P) {
       }
 }
 
+// column pass when the row pass left dS and s*A~ in the workspace: dK[m] = sum_l dS[l,m] Q[l], dV[m] = sum_l sA~[l,m] dV_att[l]
+template <typename T, typename G>
+__global__ void __launch_bounds__(G::NT) attn_bwd_col_pre(AttnParams P) {
+  constexpr int H = G::H, DKP = G::DKP, HPT = G::HPT, HG = G::HG;
+  __shared__ __align__(16) float Qs[AKB * G::RS];
+  __shared__ __align__(16) float Ds[AKB * G::RS];                // dV_att rows
+  const int tid = threadIdx.x, hg = tid % HG, r = tid / HG;
+  const int b = blockIdx.y, N = P.N, dk = P.dk, d = H * dk;
+  const int m = blockIdx.x * G::ROWS + r;
+  const bool colvalid = m < N;
+  const int mc = colvalid ? m : N - 1;
+  const T *qkv = (const T *)P.qkv + (size_t)b * N * 3 * d;
+  const T *dvatt = (const T *)P.d_v_att + (size_t)b * N * d;
+  float dka[HPT][DKP], dva_[HPT][DKP];
+#pragma unroll
+  for (int i = 0; i < HPT; ++i)
+#pragma unroll
+    for (int dd = 0; dd < DKP; ++dd) { dka[i][dd] = 0.f; dva_[i][dd] = 0.f; }
+  for (int l0 = 0; l0 < N; l0 += AKB) {
+    __syncthreads();
+    stage_pair<T, G>(Qs, Ds, qkv, (size_t)3 * d, dvatt, (size_t)d, l0, N, dk, tid);
+    __syncthreads();
+    const int lend = N - l0 < AKB ? N - l0 : AKB;
+#pragma unroll 2
+    for (int lk = 0; lk < lend; ++lk) {
+      const size_t pe = (((size_t)b * N + l0 + lk) * N + mc) * H + HPT * hg;
+      float dSv[HPT], Asv[HPT];
+      loadv<T, HPT>((const T *)P.dS_ws + pe, dSv);
+      loadv<T, HPT>((const T *)P.As_ws + pe, Asv);
+      const float *qg = Qs + lk * G::RS + hg * G::GS, *dg = Ds + lk * G::RS + hg * G::GS;
+#pragma unroll
+      for (int i = 0; i < HPT; ++i) {
+        axpy_s<DKP>(dSv[i], qg + i * DKP, dka[i]);
+        axpy_s<DKP>(Asv[i], dg + i * DKP, dva_[i]);
+      }
+    }
+  }
+  if (!colvalid) return;
+  T *o = (T *)P.d_qkv + ((size_t)b * N + m) * 3 * d + d;
+#pragma unroll
+  for (int i = 0; i < HPT; ++i)
+#pragma unroll
+    for (int dd = 0; dd < DKP; ++dd)
+      if (dd < dk) {
+        stf(o + dd * H + HPT * hg + i, dka[i][dd]);
+        stf(o + d + dd * H + HPT * hg + i, dva_[i][dd]);
+      }
+}
+
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 template <typename T, typename GF, typename GB, bool PLAIN>
@@ -425,7 +478,11 @@ int launch3(int kind, const AttnParams &P, cudaStream_t st) {
     const dim3 grid((unsigned)((P.N + GB::ROWS - 1) / GB::ROWS), (unsigned)P.B);
     { LaunchScope _ls("attn_staged_bwd_row", st); attn_bwd_row_fast<T, GB, PLAIN><<<grid, GB::NT, 0, st>>>(P); }
     EGT_CHECK_CUDA(cudaGetLastError());
-    { LaunchScope _ls("attn_staged_bwd_col", st); attn_bwd_col_fast<T, GB, PLAIN><<<grid, GB::NT, 0, st>>>(P); }
+    {
+      LaunchScope _ls("attn_staged_bwd_col", st);
+      if (P.dS_ws && P.As_ws) attn_bwd_col_pre<T, GB><<<grid, GB::NT, 0, st>>>(P);
+      else attn_bwd_col_fast<T, GB, PLAIN><<<grid, GB::NT, 0, st>>>(P);
+    }
     EGT_CHECK_CUDA(cudaGetLastError());
   }
   return EGT_OK;
@@ -460,7 +517,7 @@ int launch_shape(int kind, const AttnParams &P, cudaStream_t st) {
 // have no specialised kernel (the caller then runs attn_staged.cu), EGT_OK or a negative status otherwise.
 int attn_fast_launch(int kind, const AttnParams &P, int dtype, cudaStream_t st) {
   if (P.a_tild || P.N < 1 || P.B > 65535) return 1;
-  const void *ptrs[] = {P.E, P.G, P.attn_mask == EGT_MASK_DENSE ? P.M : nullptr, P.h_hat, P.d_h_hat, P.dE, P.dG};
+  const void *ptrs[] = {P.E, P.G, P.attn_mask == EGT_MASK_DENSE ? P.M : nullptr, P.h_hat, P.d_h_hat, P.dE, P.dG, P.dS_ws, P.As_ws};
   for (const void *q : ptrs)
     if (!aligned16(q)) return 1;
   const bool plain = P.attn_mask == EGT_MASK_NONE && !P.rand_mask && !P.dropout;

@@ -23,6 +23,8 @@ struct AttnParams {
   const void *d_v_att, *d_h_hat;
   void *d_qkv, *dE, *dG;
   float *row_ws;                     // [2,B,N,h]: D, s
+  void *dS_ws, *As_ws;               // optional [B,N,N,h] dtype: dS and s*A~ from the row pass, so that the column pass
+                                     // is two plain accumulations (attn_fast.cu); NULL = the column pass recomputes
   float dq_scale;                    // dQ is multiplied by this on store (1, or dk^-0.5 when qkv holds a pre-scaled Q)
 };
 
