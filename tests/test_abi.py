@@ -111,6 +111,24 @@ def test_rng_host_hook_matches_numpy_replica():
     assert 0.09 < (big < 0.1).mean() < 0.11 and big.min() > 0 and big.max() < 1
 
 
+def test_rng_element_index_is_a_bijection_with_the_documented_layout():
+    """include/egt_b200.h / csrc/common.cuh rng_elem_index: distinct elements draw distinct uniforms, and one
+    Philox call (index >> 3) covers two consecutive keys x four consecutive heads of one query row."""
+    for B, N, h in [(2, 5, 8), (1, 4, 4), (2, 7, 16), (1, 1, 8), (1, 6, 6)]:
+        idx = philox.elem_index(B, N, h)
+        assert idx.shape == (B, N, N, h)
+        assert np.unique(idx).size == idx.size
+        call, lane = idx >> np.uint64(3), idx & np.uint64(7)
+        for b in range(B):
+            for l in range(N):
+                for m in range(N):
+                    for hh in range(h):
+                        same = call[b, l] == call[b, l, m, hh]
+                        mm, hq = np.nonzero(same)
+                        assert set(mm) <= {m - (m & 1), m - (m & 1) + 1} and set(hq // 4) == {hh // 4}
+                        assert lane[b, l, m, hh] == (m & 1) * 4 + (hh & 3)
+
+
 def test_workspace_query_is_monotone():
     lib = L.load()
     spec = ops.BlockSpec(model_width=64, edge_width=8, num_heads=8)
