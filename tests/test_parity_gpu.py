@@ -298,9 +298,11 @@ def test_block_mask_is_bit_exact_and_padding_is_inert():
 
 
 @pytest.mark.parametrize('N,d,de,nh,B', [(128, 64, 8, 8, 16), (190, 96, 8, 8, 4), (188, 64, 8, 8, 4),
-                                         (75, 64, 8, 8, 16), (37, 64, 64, 8, 16), (512, 128, 32, 16, 2)])
+                                         (75, 64, 8, 8, 16), (37, 64, 64, 8, 16), (512, 128, 32, 16, 2),
+                                         (512, 64, 8, 8, 3), (64, 64, 8, 8, 16), (256, 64, 8, 8, 3)])
 def test_block_full_size_vs_oracle_sample(N, d, de, nh, B):
-    """BASELINE.json shapes at full N: oracle on two graphs of the batch + permutation equivariance."""
+    """BASELINE.json shapes at full N and the N = 64 / 256 / 512 points of the sweep on the fused path: oracle on two
+    graphs of the batch + permutation equivariance."""
     import egt_b200
     cfg = O.BlockConfig(model_width=d, edge_width=de, num_heads=nh, scale_degree=True)
     params = O.init_block_params(cfg, dtype=torch.float64)
