@@ -1,7 +1,15 @@
 """Hot spots of an ncu source-page CSV (SASS view): instruction mix by opcode weighted by executed count,
 and the top stall-sample instructions."""
-import csv, sys, collections
-rows = list(csv.reader(open(sys.argv[1])))
+import csv, io, subprocess, sys, collections
+
+# usage: ncu_hot.py <source-page.csv | report.ncu-rep> [top N] [kernel-name regex, .ncu-rep only]
+if sys.argv[1].endswith('.ncu-rep'):
+    cmd = ['ncu', '-i', sys.argv[1], '--page', 'source', '--csv']
+    if len(sys.argv) > 3:
+        cmd += ['--kernel-name', 'regex:' + sys.argv[3]]
+    rows = list(csv.reader(io.StringIO(subprocess.run(cmd, capture_output=True, text=True).stdout)))
+else:
+    rows = list(csv.reader(open(sys.argv[1])))
 hdr = rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
 ops = collections.Counter(); samples = collections.Counter(); total = 0
