@@ -348,7 +348,7 @@ int egt_block_fwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
     memset(&fa, 0, sizeof(fa));
     fa.B = a.B; fa.N = a.N; fa.mask = io->mask; fa.prep = (const FusedPrep *)ws.prep;
     fa.v_att = (__nv_bfloat16 *)io->v_att; fa.lse = io->lse; fa.deg = io->deg;
-    fa.clip_lo = a.clip_lo; fa.clip_hi = a.clip_hi;
+    fa.clip_lo = a.clip_lo; fa.clip_hi = a.clip_hi; fa.ln_eps = cfg->ln_eps;
     fa.scale_degree = a.scale_degree; fa.scaler_type = a.scaler_type; fa.num_virtual_nodes = a.num_virtual_nodes;
     fa.rand_mask = a.training && a.random_mask_prob > 0.f;
     fa.rand_thr = (uint32_t)ceilf(a.random_mask_prob * 65536.0f - 0.5f);
@@ -415,7 +415,7 @@ int egt_block_bwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
     fb.B = a.B; fb.N = a.N; fb.mask = io->mask; fb.prep = (const FusedPrep *)ws.prep;
     fb.v_att = (const __nv_bfloat16 *)io->v_att; fb.d_v_att = (const __nv_bfloat16 *)ws.d_v_att;
     fb.lse = io->lse; fb.deg = io->deg; fb.d_qkv = ws.d_qkv_f32; fb.partials = ws.partials;
-    fb.clip_lo = a.clip_lo; fb.clip_hi = a.clip_hi; fb.dq_scale = 1.0f / sqrtf((float)a.dk);
+    fb.clip_lo = a.clip_lo; fb.clip_hi = a.clip_hi; fb.dq_scale = 1.0f / sqrtf((float)a.dk); fb.ln_eps = cfg->ln_eps;
     fb.scale_degree = a.scale_degree; fb.scaler_type = a.scaler_type; fb.num_virtual_nodes = a.num_virtual_nodes;
     fb.rand_mask = a.training && a.random_mask_prob > 0.f;
     fb.rand_thr = (uint32_t)ceilf(a.random_mask_prob * 65536.0f - 0.5f);

@@ -306,6 +306,10 @@ int edge_out_fwd_launch(const EdgeParams &p, int dtype, cudaStream_t st) {
 }
 int edge_out_bwd_launch(const EdgeParams &p, int dtype, cudaStream_t st) {
   if (!staged_force_generic()) { const int rc = edge_fast_launch(2, p, dtype, st); if (rc <= 0) return rc; }
+  // each thread of the generic kernel owns at most MAXO_R of the h * d_e outputs of dW_r
+  EGT_REQUIRE(p.h * p.d_e <= MAXO_R * EPB && p.d_e <= EPB, EGT_E_SHAPE,
+              "edge write-back backward: h * d_e = %d exceeds the %d outputs the generic kernel accumulates", p.h * p.d_e,
+              MAXO_R * EPB);
   size_t smem = (size_t)EPB * (p.h + p.d_e) * sizeof(float);
   if (smem > 48 * 1024) {
     EGT_CHECK_CUDA(cudaFuncSetAttribute(edge_out_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -317,6 +321,10 @@ int edge_out_bwd_launch(const EdgeParams &p, int dtype, cudaStream_t st) {
 int edge_proj_bwd_launch(const EdgeParams &p, int dtype, cudaStream_t st) {
   if (!staged_force_generic()) { const int rc = edge_fast_launch(3, p, dtype, st); if (rc <= 0) return rc; }
   int J = p.gated ? 2 * p.h : p.h;
+  // each thread of the generic kernel owns at most MAXO_P of the d_e * J outputs of dW_E | dW_G
+  EGT_REQUIRE(p.d_e * J <= MAXO_P * EPB, EGT_E_SHAPE,
+              "edge projection backward: d_e * %d = %d exceeds the %d outputs the generic kernel accumulates", J, p.d_e * J,
+              MAXO_P * EPB);
   size_t smem = ((size_t)EPB * (p.d_e + J) + J) * sizeof(float);
   if (smem > 48 * 1024) {
     EGT_CHECK_CUDA(cudaFuncSetAttribute(edge_proj_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -14,6 +14,9 @@
 namespace egt {
 
 constexpr int FH = 8, FDK = 8, FD = 64, FDE = 8;
+// exponent budget of the un-normalised softmax: exp(H_hat - max(bound - budget, 0)) <= e^75, and 4096 of them
+// still sum below FLT_MAX
+constexpr float kSoftmaxBudget = 75.f;
 
 // Derived weights, rebuilt on the device at the start of every forward / backward call (the weights
 // change every optimiser step).  LayerNorm_e is folded into the projections:
@@ -38,7 +41,7 @@ struct FusedFwdArgs {
   const FusedPrep *prep;
   __nv_bfloat16 *v_att;               // [B,N,64]
   float *lse, *deg;                   // [2,B,N,8], [B,N,8]
-  float clip_lo, clip_hi;
+  float clip_lo, clip_hi, ln_eps;
   int scale_degree, scaler_type, num_virtual_nodes;
   int rand_mask; uint32_t rand_thr;   // mask element when its 16 random bits < rand_thr
   uint64_t seed, offset;
@@ -57,10 +60,10 @@ struct FusedBwdArgs {
   const uint8_t *mask;                // [B,N] or NULL
   const FusedPrep *prep;
   const __nv_bfloat16 *v_att, *d_v_att;   // [B,N,64] saved forward output / its upstream gradient
-  const float *lse, *deg;             // [2,B,N,8] (only the log row-sum half is read), [B,N,8]
+  const float *lse, *deg;             // [2,B,N,8] (reference point | log row sum), [B,N,8]
   float *d_qkv;                       // [B,N,192] float32: dQ | dK | dV
   float *partials;                    // [gridDim.x * gridDim.y][FPART]
-  float clip_lo, clip_hi, dq_scale;
+  float clip_lo, clip_hi, dq_scale, ln_eps;
   int scale_degree, scaler_type, num_virtual_nodes;
   int rand_mask; uint32_t rand_thr;
   uint64_t seed, offset;

@@ -286,7 +286,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
         float var = 0.f;
 #pragma unroll
         for (int c = 0; c < 8; ++c) { x[c] -= mu; var = fmaf(x[c], x[c], var); }
-        const float r = rsqrtf(fmaf(var, 0.125f, 1e-3f));
+        const float r = rsqrtf(fmaf(var, 0.125f, a.ln_eps));
         float m1 = 0.f, m2 = 0.f;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -460,7 +460,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
         const float ds = s != 0.f ? D / s : 0.f;
         dg = a.scaler_type == EGT_SCALER_LOG ? ds / (1.f + dgv) : ds;
       }
-      if (rowvalid) lsum = a.lse[rs + ps + hh];
+      if (rowvalid) lsum = a.lse[ps + hh] + a.lse[rs + ps + hh];   // reference point + log row sum
       Dr[i] = rowvalid ? D : 0.f;
       ddeg[i] = rowvalid ? dg : 0.f;
       l2[i] = lsum * kLog2e;
@@ -487,7 +487,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     float var = 0.f;
 #pragma unroll
     for (int c = 0; c < 8; ++c) { const float dlt = x[c] - mu; var = fmaf(dlt, dlt, var); }
-    r = rsqrtf(fmaf(var, 0.125f, 1e-3f));
+    r = rsqrtf(fmaf(var, 0.125f, a.ln_eps));
     nrm = -r * mu;
   };
 

@@ -13,6 +13,7 @@
 //             peer enters after finishing its reads of call k)
 //   pads      [world] device pointers to each rank's signal pad (uint32): slot [cta][peer] flags, then
 //             [PAR_EPOCH + cta] this CTA's call counter.  Pads start zeroed.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace egt {
@@ -34,7 +35,7 @@ __device__ __forceinline__ float4 ld_volatile_f4(const float4 *p) {   // peer da
 }
 
 __global__ void __launch_bounds__(256) peer_allreduce_kernel(const uint64_t *buffers, const uint64_t *pads, float *grad,
-                                                             int n4, int rank, int world) {
+                                                             int n4, int rank, int world, long long timeout_cycles) {
   __shared__ uint32_t s_epoch;
   const int tid = threadIdx.x, cta = blockIdx.x;
   pdl_trigger();
@@ -56,9 +57,13 @@ __global__ void __launch_bounds__(256) peer_allreduce_kernel(const uint64_t *buf
   if (tid < world) {
     st_release_sys((uint32_t *)pads[tid] + cta * PAR_MAXW + rank, epoch + 1u);
     const uint32_t *slot = my_pad + cta * PAR_MAXW + tid;
+    // A peer that is merely late (evaluation or a checkpoint on one rank, a data-loader stall) must be waited
+    // for; only a peer that never shows up may end the launch.  timeout_cycles <= 0 waits for ever
+    // (EGT_PEER_TIMEOUT_S, default 600 s -- far beyond any step, short of a box-level hang).
     long long t0 = clock64();
     while (ld_acquire_sys(slot) < epoch + 1u) {
-      if (clock64() - t0 > 20000000000ll) __trap();                // a missing peer must not hang the box
+      __nanosleep(64);
+      if (timeout_cycles > 0 && clock64() - t0 > timeout_cycles) __trap();
     }
   }
   __syncthreads();
@@ -86,7 +91,13 @@ extern "C" int egt_peer_allreduce(const uint64_t *buffer_ptrs_dev, const uint64_
   int ctas = (n4 + 511) / 512;
   if (ctas > PAR_MAXCTA) ctas = PAR_MAXCTA;
   if (ctas < 1) ctas = 1;
+  // seconds -> SM clock cycles at the nominal 2 GHz (an upper bound of the real clock: the wait is at least this long)
+  static const long long timeout_cycles = [] {
+    const char *e = getenv("EGT_PEER_TIMEOUT_S");
+    const double s = e ? atof(e) : 600.0;
+    return s > 0 ? (long long)(s * 2.0e9) : 0ll;
+  }();
   LaunchScope _ls("peer_allreduce_kernel", (cudaStream_t)stream);
-  EGT_CHECK_CUDA(launch_pdl(peer_allreduce_kernel, dim3(ctas), dim3(256), 0, (cudaStream_t)stream, buffer_ptrs_dev, signal_pad_ptrs_dev, grad, n4, rank, world));
+  EGT_CHECK_CUDA(launch_pdl(peer_allreduce_kernel, dim3(ctas), dim3(256), 0, (cudaStream_t)stream, buffer_ptrs_dev, signal_pad_ptrs_dev, grad, n4, rank, world, timeout_cycles));
   return EGT_OK;
 }

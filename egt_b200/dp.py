@@ -73,9 +73,15 @@ def allreduce_flat_grads(blocks: Iterable, async_op: bool = False):
     buffer; several blocks are coalesced into one flat tensor first so it stays one collective."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return None
-    grads = [b.flat.grad for b in blocks if b.flat.grad is not None]
-    if not grads:
+    blocks = list(blocks)
+    if not blocks:
         return None
+    # every rank must take part with the SAME buffers (the peer kernel counts its calls per buffer): a block
+    # that got no gradient on this rank contributes zeros instead of silently dropping out of the collective
+    for b in blocks:
+        if b.flat.grad is None:
+            b.flat.grad = torch.zeros_like(b.flat)
+    grads = [b.flat.grad for b in blocks]
     if len(grads) == 1:
         peer = None if async_op else _peer_allreduce_for(grads[0])
         if peer is not None:
