@@ -7,12 +7,15 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "fused.h"
+#include "wide.h"
 
 namespace egt {
 
 static thread_local char g_err[512] = "";
 static thread_local int g_last_path = 0;
-static int g_force_staged = 0;    // egt_debug_force_staged(): route every shape through the staged kernels
+static int g_force_staged = 0;
+bool wide_bwd_enabled() { return false; }   // until wide_bwd.cu lands the wide forward pairs with the staged backward
+    // egt_debug_force_staged(): route every shape through the staged kernels
 
 void set_error(int code, const char *fmt, ...) {
   va_list ap;
@@ -122,13 +125,15 @@ static BlockWs carve(const egt_block_cfg_t *c, int backward, void *base, bool ha
   auto take = [&](size_t bytes) { char *p = b ? b + off : nullptr; off += align_up(bytes); return p; };
   bool edge = c->edge_channel_type != EGT_EDGE_NONE;
   bool residual = c->edge_channel_type >= EGT_EDGE_RESIDUAL;
-  const bool fused = fused_supported(c, a.dtype) && !g_force_staged;
-  if (fused) w.prep = take(sizeof(FusedPrep));
+  const bool wide = wide_supported(c, a.dtype) && !g_force_staged;
+  const bool fused = (fused_supported(c, a.dtype) && !g_force_staged) || wide;
+  if (fused) w.prep = take(wide ? sizeof(WidePrep) : sizeof(FusedPrep));
   if (fused && !backward) { w.total = off; return w; }
-  if (fused && backward && has_de_out) {      // fused backward: nothing of shape [pairs,h] is materialised
+  if (fused && backward && has_de_out && (!wide || wide_bwd_enabled())) {      // fused backward: nothing of shape [pairs,h] is materialised
     w.d_v_att = take(R * d * es);
     w.d_qkv_f32 = (float *)take(R * 3 * d * sizeof(float));
-    w.partials = (float *)take((size_t)a.B * ((a.N + 127) / 128) * FPART * sizeof(float));
+    w.partials = (float *)take(wide ? wide_bwd_partials_floats(c) * sizeof(float)
+                                    : (size_t)a.B * ((a.N + 127) / 128) * FPART * sizeof(float));
     w.hn = (float *)take(R * d * sizeof(float));
     w.dhn = (float *)take(R * d * sizeof(float));
     w.total = off;
@@ -328,6 +333,33 @@ int egt_block_fwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
   EGT_REQUIRE(io->workspace_bytes >= need && (io->workspace || need <= 256), EGT_E_ARG,
               "workspace too small: %zu < %zu", io->workspace_bytes, need);
   BlockWs ws = carve(cfg, 0, io->workspace);
+  const bool wide = !fused && wide_supported(cfg, a.dtype) && !g_force_staged;
+  if (wide) {    // width-generic fused path (wide_fwd.cu); Q is stored pre-scaled by dk^-0.5
+    LinearArgs lq;
+    memset(&lq, 0, sizeof(lq));
+    lq.x = io->h; lq.W = w->dense_qkv_kernel; lq.bias = w->dense_qkv_bias; lq.out = io->qkv;
+    lq.ln_gamma = w->norm_mha_gamma; lq.ln_beta = w->norm_mha_beta; lq.ln_eps = cfg->ln_eps;
+    lq.scale = 1.0f / sqrtf((float)a.dk); lq.scale_cols = d;
+    lq.R = R; lq.din = d; lq.dout = 3 * d;
+    if ((rc = linear_launch(lq, a.dtype, st))) return rc;
+    if ((rc = wide_prep_launch(cfg, w, (WidePrep *)ws.prep, st))) return rc;
+    g_last_path = 1;
+    WideFwdArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.B = a.B; fa.N = a.N; fa.mask = io->mask; fa.prep = (const WidePrep *)ws.prep;
+    fa.v_att = (__nv_bfloat16 *)io->v_att; fa.lse = io->lse; fa.deg = io->deg;
+    fa.clip_lo = a.clip_lo; fa.clip_hi = a.clip_hi; fa.ln_eps = cfg->ln_eps;
+    fa.scale_degree = a.scale_degree; fa.scaler_type = a.scaler_type; fa.num_virtual_nodes = a.num_virtual_nodes;
+    fa.rand_mask = a.training && a.random_mask_prob > 0.f;
+    fa.rand_thr = (uint32_t)ceilf(a.random_mask_prob * 65536.0f - 0.5f);
+    fa.seed = a.seed; fa.offset = a.offset;
+    if ((rc = wide_fwd_launch(cfg, fa, io->e, io->e_out, io->qkv, st))) return rc;
+    LinearArgs lo;   // h' = V_att W_O + b_O + h  (graph_xformer_model_base.py:136-140)
+    memset(&lo, 0, sizeof(lo));
+    lo.x = io->v_att; lo.W = w->dense_mha_kernel; lo.bias = w->dense_mha_bias; lo.res = io->h; lo.out = io->h_out;
+    lo.R = R; lo.din = d; lo.dout = d;
+    return linear_launch(lo, a.dtype, st);
+  }
   if (fused) {   // Q is stored pre-scaled by dk^-0.5; the kernel's extra CTA writes the derived weights
     if ((rc = node_qkv_launch(io->h, w->norm_mha_gamma, w->norm_mha_beta, cfg->ln_eps, w->dense_qkv_kernel,
                               w->dense_qkv_bias, 1.0f / sqrtf((float)a.dk), io->qkv, R, w, a.clip_lo, a.clip_hi,
@@ -400,8 +432,9 @@ int egt_block_bwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
               io->workspace_bytes, need);
   const bool have_de = io->de_out != nullptr;
   BlockWs ws = carve(cfg, 1, io->workspace, have_de);
-  const bool fused = fused_supported(cfg, a.dtype) && !g_force_staged;
-  const bool fused_bwd = fused && have_de;
+  const bool wide = wide_supported(cfg, a.dtype) && !g_force_staged;
+  const bool fused = (fused_supported(cfg, a.dtype) && !g_force_staged) || wide;   // the forward saved a pre-scaled Q
+  const bool fused_bwd = fused && !wide && have_de;
   g_last_path = fused_bwd ? 1 : 0;
 
   if (fused_bwd) {

@@ -12,7 +12,7 @@ namespace egt {
 using namespace umma;
 
 struct ProbeParams {
-  int a_mode, b_mode;        // 0 K-major SW128, 1 TMEM (A only), 2 MN-major SW128, 3 K-major none, 4 MN-major none
+  int a_mode, b_mode;        // 0 K-major SW128, 1 TMEM (A only), 2 MN-major SW128, 3 K-major none, 4 MN-major none, 5 K-major SW128 with 16-row atoms (B only)
   int N, ksteps;
   uint32_t a_lbo, a_sbo, b_lbo, b_sbo;
   uint32_t a_off[8], b_off[8];   // start-address byte offset (smem) or column offset (TMEM) of k-step s
@@ -23,13 +23,14 @@ struct ProbeParams {
 __device__ __forceinline__ uint32_t image_off(int mode, uint32_t mn, uint32_t k, uint32_t lbo, uint32_t sbo) {
   switch (mode) {
     case 0: return (k >> 6) * 16384u + sw128_off(mn, k & 63u);
+    case 5: return (k >> 6) * 2048u + sw128_off(mn, k & 63u);          // 16-row atoms (expanded K / V operands)
     case 2: return (mn >> 6) * lbo + (k >> 3) * sbo + (k & 7u) * 128u + (((((mn & 63u) >> 3) ^ k) & 7u) << 4) + ((mn & 7u) << 1);
     case 3: return (k >> 3) * lbo + (mn >> 3) * sbo + (mn & 7u) * 16u + ((k & 7u) << 1);
     case 4: return (mn >> 3) * sbo + (k >> 3) * lbo + (k & 7u) * 16u + ((mn & 7u) << 1);
   }
   return 0;
 }
-__device__ __forceinline__ uint32_t layout_of(int mode) { return (mode == 0 || mode == 2) ? LAYOUT_SW128 : LAYOUT_NONE; }
+__device__ __forceinline__ uint32_t layout_of(int mode) { return (mode == 0 || mode == 2 || mode == 5) ? LAYOUT_SW128 : LAYOUT_NONE; }
 
 __global__ void __launch_bounds__(128) umma_probe_kernel(ProbeParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];

@@ -1,0 +1,112 @@
+// wide_prep.cu -- per-call derived weights of the width-generic fused path (wide.h) and its shape gate.
+//
+//   reference: the parameters are those of norm_edge / attention_gates / dense_edge_b / dense_edge_r
+//   (lib/models/graph_xformer_model_base.py:153-161,195,201-218); the folding of LayerNorm into the projections is
+//   the one of fused_prep.cuh.
+#include <math.h>
+#include "common.cuh"
+#include "wide.h"
+
+namespace egt {
+
+bool wide_supported(const egt_block_cfg_t *c, int dtype) {
+  const egt_attn_cfg_t &a = c->attn;
+  const bool shape = (a.h == 16 && a.dk == 8 && c->d_e == 32) || (a.h == 8 && a.dk == 8 && c->d_e == 64) ||
+                     (a.h == 8 && a.dk == 12 && c->d_e == 8);
+  return dtype == EGT_BF16 && shape && c->edge_channel_type == EGT_EDGE_RESIDUAL && c->gate_attention && a.has_clip &&
+         a.clip_lo <= a.clip_hi && c->edge_act == EGT_ACT_NONE && !(a.training && a.attn_dropout > 0.f) && a.N >= 1 &&
+         a.N <= 4096;
+}
+
+namespace {
+
+// element offset of (n, k) in an un-swizzled K-major [N x K] operand image (8x16-byte core matrices)
+__device__ __forceinline__ int img(int n, int k, int N) { return (k >> 3) * (N * 8) + n * 8 + (k & 7); }
+
+__global__ void __launch_bounds__(256) wide_prep_kernel(egt_block_weights_t w, int H, int DE, float clip_lo, float clip_hi,
+                                                        WidePrep *out) {
+  __shared__ float wp[2][WMAXDE][WMAXH];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 2 * DE * H; i += 256) {
+    const int eg = i / (DE * H), c = (i / H) % DE, hh = i % H;
+    const float wv = (eg ? w.attention_gates_kernel : w.dense_edge_b_kernel)[c * H + hh];
+    const float v = __bfloat162float(__float2bfloat16_rn(w.norm_edge_gamma[c] * wv));
+    wp[eg][c][hh] = v;
+    out->wp[eg][c][hh] = v;
+  }
+  for (int c = tid; c < DE; c += 256) out->br[c] = w.dense_edge_r_bias[c];
+  __syncthreads();
+  if (tid < 32) {
+    const int eg = tid / 16, hh = tid % 16;
+    float bnd = 0.f;
+    if (hh < H) {
+      const float *W = eg ? w.attention_gates_kernel : w.dense_edge_b_kernel;
+      float u = 0.f, v = (eg ? w.attention_gates_bias : w.dense_edge_b_bias)[hh], n2 = 0.f;
+      for (int c = 0; c < DE; ++c) {
+        u += wp[eg][c][hh];
+        v += w.norm_edge_beta[c] * W[c * H + hh];
+        n2 += wp[eg][c][hh] * wp[eg][c][hh];
+      }
+      (eg ? out->uG : out->uE)[hh] = u;
+      (eg ? out->vG : out->vE)[hh] = v;
+      // |LN(e)| has l2 norm <= sqrt(d_e)  =>  |E| <= sqrt(d_e) ||W'[:,hh]|| + |v|
+      if (eg == 0) bnd = fmaxf(fabsf(clip_lo), fabsf(clip_hi)) + sqrtf((float)DE * n2) + fabsf(v);
+    }
+    for (int o = 16; o > 0; o >>= 1) bnd = fmaxf(bnd, __shfl_xor_sync(0xffffffffu, bnd, o));
+    if (tid == 0) out->bound = bnd;
+  }
+  const int EGN = 2 * H, DEP = DE < 16 ? 16 : DE, DEW = DEP;
+  const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
+  // column n of the [E|G] product <-> (eg, hh):  n = (hh/8)*16 + eg*8 + hh%8
+  for (int i = tid; i < 2 * EGN * DEW; i += 256) {         // w_eg[v]
+    const int v = i / (EGN * DEW), n = (i / DEW) % EGN, k = i % DEW;
+    const int eg = (n >> 3) & 1, hh = 8 * (n >> 4) + (n & 7);
+    float x;
+    if (DE >= 16) x = wp[eg][k][hh];
+    else x = (k >> 3) == v ? wp[eg][k & 7][hh] : 0.f;
+    out->w_eg[v][img(n, k, EGN)] = __float2bfloat16_rn(x);
+  }
+  for (int i = tid; i < DEP * 16; i += 256) {              // w_r, b_r
+    const int n = i / 16, k = i % 16;
+    out->w_r[img(n, k, DEP)] = (k < H && n < DE) ? __float2bfloat16_rn(w.dense_edge_r_kernel[k * DE + n]) : zero;
+    float b = 0.f;
+    if (n < DE) {
+      const float full = w.dense_edge_r_bias[n];
+      const float hi = __bfloat162float(__float2bfloat16_rn(full));
+      b = k == 0 ? hi : k == 1 ? full - hi : 0.f;
+    }
+    out->b_r[img(n, k, DEP)] = __float2bfloat16_rn(b);
+  }
+  for (int i = tid; i < 2 * 16 * 16; i += 256) {           // i16[v]
+    const int v = i / 256, n = (i / 16) % 16, k = i % 16;
+    const bool one = DE >= 16 ? n == k : (n < 8 && k == n + 8 * v);
+    out->i16[v][img(n, k, 16)] = __float2bfloat16_rn(one ? 1.f : 0.f);
+  }
+  for (int i = tid; i < 2 * 16 * DEW; i += 256) {          // w_hx[v]: n = head, k = edge channel
+    const int v = i / (16 * DEW), n = (i / DEW) % 16, k = i % DEW;
+    float x = 0.f;
+    if (n < H) {
+      if (DE >= 16) x = w.dense_edge_r_kernel[n * DE + k];
+      else x = (k >> 3) == v ? w.dense_edge_r_kernel[n * DE + (k & 7)] : 0.f;
+    }
+    out->w_hx[v][img(n, k, 16)] = __float2bfloat16_rn(x);
+  }
+  for (int i = tid; i < DEP * EGN; i += 256) {             // w_dx: n = edge channel, k = column of [E|G]
+    const int n = i / EGN, k = i % EGN;
+    const int eg = (k >> 3) & 1, hh = 8 * (k >> 4) + (k & 7);
+    out->w_dx[img(n, k, DEP)] = __float2bfloat16_rn(n < DE ? wp[eg][n][hh] : 0.f);
+  }
+}
+
+}  // namespace
+
+int wide_prep_launch(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, WidePrep *prep, cudaStream_t st) {
+  LaunchScope _ls("wide_prep_kernel", st);
+  wide_prep_kernel<<<1, 256, 0, st>>>(*w, cfg->attn.h, cfg->d_e, cfg->attn.clip_lo, cfg->attn.clip_hi, prep);
+  EGT_CHECK_CUDA(cudaGetLastError());
+  return EGT_OK;
+}
+
+size_t wide_bwd_partials_floats(const egt_block_cfg_t *) { return 0; }
+
+}  // namespace egt
