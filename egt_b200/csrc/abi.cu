@@ -14,7 +14,6 @@ namespace egt {
 static thread_local char g_err[512] = "";
 static thread_local int g_last_path = 0;
 static int g_force_staged = 0;
-bool wide_bwd_enabled() { return false; }   // until wide_bwd.cu lands the wide forward pairs with the staged backward
     // egt_debug_force_staged(): route every shape through the staged kernels
 
 void set_error(int code, const char *fmt, ...) {
@@ -129,7 +128,7 @@ static BlockWs carve(const egt_block_cfg_t *c, int backward, void *base, bool ha
   const bool fused = (fused_supported(c, a.dtype) && !g_force_staged) || wide;
   if (fused) w.prep = take(wide ? sizeof(WidePrep) : sizeof(FusedPrep));
   if (fused && !backward) { w.total = off; return w; }
-  if (fused && backward && has_de_out && (!wide || wide_bwd_enabled())) {      // fused backward: nothing of shape [pairs,h] is materialised
+  if (fused && backward && has_de_out && (!wide || wide_bwd_supported(c))) {      // fused backward: nothing of shape [pairs,h] is materialised
     w.d_v_att = take(R * d * es);
     w.d_qkv_f32 = (float *)take(R * 3 * d * sizeof(float));
     w.partials = (float *)take(wide ? wide_bwd_partials_floats(c) * sizeof(float)
@@ -435,7 +434,55 @@ int egt_block_bwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
   const bool wide = wide_supported(cfg, a.dtype) && !g_force_staged;
   const bool fused = (fused_supported(cfg, a.dtype) && !g_force_staged) || wide;   // the forward saved a pre-scaled Q
   const bool fused_bwd = fused && !wide && have_de;
-  g_last_path = fused_bwd ? 1 : 0;
+  const bool wide_bwd = wide && have_de && wide_bwd_supported(cfg);
+  g_last_path = (fused_bwd || wide_bwd) ? 1 : 0;
+
+  if (wide_bwd) {   // width-generic fused backward (wide_bwd.cu); node side on the staged kernels
+    LinearArgs l1;  // dV_att = dh' W_O^T ; dW_O += V_att^T dh' ; db_O += colsum(dh')
+    memset(&l1, 0, sizeof(l1));
+    l1.x = io->dh_out; l1.W = w->dense_mha_kernel; l1.trans = 1; l1.out = ws.d_v_att; l1.R = R; l1.din = d; l1.dout = d;
+    if ((rc = linear_launch(l1, a.dtype, st))) return rc;
+    XtyArgs x1;
+    memset(&x1, 0, sizeof(x1));
+    x1.X = io->v_att; x1.Y = io->dh_out; x1.dW = g->dense_mha_kernel; x1.db = g->dense_mha_bias; x1.R = R; x1.dx = d; x1.dy = d;
+    if ((rc = xty_launch(x1, a.dtype, st))) return rc;
+    if ((rc = wide_prep_launch(cfg, w, (WidePrep *)ws.prep, st))) return rc;
+    const int tiles = (a.N + 127) / 128;
+    if (tiles > 1) EGT_CHECK_CUDA(cudaMemsetAsync(ws.d_qkv_f32, 0, (size_t)R * 3 * d * sizeof(float), st));
+    WideBwdArgs fb;
+    memset(&fb, 0, sizeof(fb));
+    fb.B = a.B; fb.N = a.N; fb.mask = io->mask; fb.prep = (const WidePrep *)ws.prep;
+    fb.v_att = (const __nv_bfloat16 *)io->v_att; fb.d_v_att = (const __nv_bfloat16 *)ws.d_v_att;
+    fb.lse = io->lse; fb.deg = io->deg; fb.d_qkv = ws.d_qkv_f32; fb.partials = ws.partials;
+    fb.clip_lo = a.clip_lo; fb.clip_hi = a.clip_hi; fb.dq_scale = 1.0f / sqrtf((float)a.dk); fb.ln_eps = cfg->ln_eps;
+    fb.scale_degree = a.scale_degree; fb.scaler_type = a.scaler_type; fb.num_virtual_nodes = a.num_virtual_nodes;
+    fb.rand_mask = a.training && a.random_mask_prob > 0.f;
+    fb.rand_thr = (uint32_t)ceilf(a.random_mask_prob * 65536.0f - 0.5f);
+    fb.seed = a.seed; fb.offset = a.offset;
+    if ((rc = wide_bwd_launch(cfg, fb, io->e, io->de_out, io->de, io->qkv, st))) return rc;
+    if ((rc = wide_bwd_finalize_launch(cfg, ws.partials, w, g, (const WidePrep *)ws.prep, st))) return rc;
+    // node side: hn = LN(h); dW_qkv += hn^T dqkv; dhn = dqkv W_qkv^T; dh = LN_bwd(dhn) + dh'
+    LinearArgs l2;
+    memset(&l2, 0, sizeof(l2));
+    l2.x = io->h; l2.ln_gamma = w->norm_mha_gamma; l2.ln_beta = w->norm_mha_beta; l2.ln_eps = cfg->ln_eps;
+    l2.xn_out = ws.hn; l2.R = R; l2.din = d; l2.dout = 0;
+    if ((rc = linear_launch(l2, a.dtype, st))) return rc;
+    XtyArgs x2;
+    memset(&x2, 0, sizeof(x2));
+    x2.X = ws.hn; x2.x_f32 = 1; x2.Y = ws.d_qkv_f32; x2.y_f32 = 1; x2.dW = g->dense_qkv_kernel; x2.db = g->dense_qkv_bias;
+    x2.R = R; x2.dx = d; x2.dy = 3 * d;
+    if ((rc = xty_launch(x2, a.dtype, st))) return rc;
+    LinearArgs l3;
+    memset(&l3, 0, sizeof(l3));
+    l3.x = ws.d_qkv_f32; l3.x_f32 = 1; l3.W = w->dense_qkv_kernel; l3.trans = 1; l3.out = ws.dhn; l3.out_f32 = 1;
+    l3.R = R; l3.din = 3 * d; l3.dout = d;
+    if ((rc = linear_launch(l3, a.dtype, st))) return rc;
+    LnBwdArgs lb;
+    memset(&lb, 0, sizeof(lb));
+    lb.x = io->h; lb.dy = ws.dhn; lb.dres = io->dh_out; lb.gamma = w->norm_mha_gamma; lb.eps = cfg->ln_eps;
+    lb.dx = io->dh; lb.dgamma = g->norm_mha_gamma; lb.dbeta = g->norm_mha_beta; lb.R = R; lb.D = d;
+    return ln_bwd_launch(lb, a.dtype, st);
+  }
 
   if (fused_bwd) {
     if ((rc = node_bwd1_launch(io->dh_out, io->v_att, w->dense_mha_kernel, ws.d_v_att, g->dense_mha_kernel,

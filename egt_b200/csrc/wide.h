@@ -26,7 +26,10 @@ constexpr int WMAXH = 16, WMAXDE = 64;
 struct WidePrep {
   // [E|G] projection of ONE key: N = 2h columns ordered (hh/8, eg, hh%8), K = max(d_e,16) raw edge channels.
   // d_e = 8: the K window covers the key pair (key & ~1, key | 1); image v = key & 1 holds W' in rows 8v..8v+7.
-  __nv_bfloat16 w_eg[2][(WMAXDE / 8) * 2 * WMAXH * 8];
+  // W' is kept as bf16 hi + bf16 lo (K doubled: rows K.. hold the part of W' the first rounding lost), so the
+  // projections of the bf16 edge channels are exact to ~2^-17 -- large trained weights move logits by hundreds
+  // of bf16 ulps otherwise.
+  __nv_bfloat16 w_eg[2][2 * (WMAXDE / 8) * 2 * WMAXH * 8];
   __nv_bfloat16 w_r[2 * WMAXDE * 8];        // edge write-back H^ W_r: N = max(d_e,16), K = 16 heads (zero padded)
   __nv_bfloat16 b_r[2 * WMAXDE * 8];        // bias of the write-back as a K = 16 operand: k = 0 bf16(b_r), k = 1 the rest
   __nv_bfloat16 i16[2][2 * 16 * 8];         // 16 x 16 identity (d_e = 8: the two halves of the key-pair window)
@@ -35,7 +38,7 @@ struct WidePrep {
   __nv_bfloat16 w_dx[(2 * WMAXH / 8) * WMAXDE * 8];   // d x^ = [dE|dG] W'^T: N = max(d_e,16), K = 2h (same order as w_eg's N)
   float uE[WMAXH], vE[WMAXH], uG[WMAXH], vG[WMAXH];
   float br[WMAXDE];
-  float wp[2][WMAXDE][WMAXH];               // W'_E, W'_G as rounded to bf16
+  float wp[2][WMAXDE][WMAXH];               // W'_E, W'_G (float32; hi + lo is what the forward multiplies by)
   float bound;                              // sup |masked logit| given these weights (fused.h)
 };
 
@@ -73,6 +76,7 @@ int wide_fwd_launch(const egt_block_cfg_t *cfg, const WideFwdArgs &a, const void
                     cudaStream_t st);
 int wide_bwd_launch(const egt_block_cfg_t *cfg, const WideBwdArgs &a, const void *e, const void *de_out, void *de,
                     const void *qkv, cudaStream_t st);
+bool wide_bwd_supported(const egt_block_cfg_t *cfg);   // shapes wide_bwd.cu instantiates (others pair with the staged backward)
 size_t wide_bwd_partials_floats(const egt_block_cfg_t *cfg);
 int wide_bwd_finalize_launch(const egt_block_cfg_t *cfg, const float *partials, const egt_block_weights_t *w,
                              const egt_block_grads_t *g, const WidePrep *prep, cudaStream_t st);

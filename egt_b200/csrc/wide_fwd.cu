@@ -47,7 +47,7 @@ wide_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
   constexpr uint32_t STAGE_BYTES = (ST_V + C::KV_ROWS + 1023) & ~1023u;
   constexpr uint32_t TX_BYTES = C::NBOX * 16384 + 2 * TK * D * 2;
   constexpr uint32_t SM_W = SM_STAGE + NS * STAGE_BYTES;               // w_eg[2] | w_r | b_r | i16[2]
-  constexpr uint32_t W_EG = 0, W_EG_SZ = C::DEW * C::EGN * 2, W_R = 2 * W_EG_SZ, W_R_SZ = C::DEP * 32;
+  constexpr uint32_t W_EG = 0, W_EG_SZ = 2 * C::DEW * C::EGN * 2, W_R = 2 * W_EG_SZ, W_R_SZ = C::DEP * 32;
   constexpr uint32_t W_B = W_R + W_R_SZ, W_I = W_B + W_R_SZ, W_TOTAL = W_I + 1024;
   constexpr uint32_t SM_ONES = SM_W + W_TOTAL;                         // 4 KB of bf16 1.0 (A operand of the bias product)
   constexpr uint32_t SM_CONST = SM_ONES + 4096;                        // uE vE uG vG (4 x 16 floats)
@@ -153,8 +153,8 @@ wide_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
         const uint32_t le = lo_e(st, kt);
         const uint32_t lw = loWeg + (DE >= 16 ? 0u : (uint32_t)(kt & 1) * (W_EG_SZ / 16));
 #pragma unroll
-        for (int s = 0; s < C::DEW / 16; ++s)
-          mma_ss(tg + G_EG, mkdesc(le + 2 * s, HI_SW), mkdesc(lw + 2 * s * C::EGN, HI_NONE), ID_EG, s > 0);
+        for (int s = 0; s < 2 * (C::DEW / 16); ++s)        // W' = hi + lo (wide.h): the e window is multiplied by both
+          mma_ss(tg + G_EG, mkdesc(le + 2 * (s % (C::DEW / 16)), HI_SW), mkdesc(lw + 2 * s * C::EGN, HI_NONE), ID_EG, s > 0);
       };
       auto issue_mma2 = [&](int q, int st, int kt, int vslot, bool first) {   // O += A~ Vexp ; e' = e I + H_hat W_r + b_r
         const uint32_t tg = tmem + TM_G + q * GC;

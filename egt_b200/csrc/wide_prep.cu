@@ -30,7 +30,9 @@ __global__ void __launch_bounds__(256) wide_prep_kernel(egt_block_weights_t w, i
   for (int i = tid; i < 2 * DE * H; i += 256) {
     const int eg = i / (DE * H), c = (i / H) % DE, hh = i % H;
     const float wv = (eg ? w.attention_gates_kernel : w.dense_edge_b_kernel)[c * H + hh];
-    const float v = __bfloat162float(__float2bfloat16_rn(w.norm_edge_gamma[c] * wv));
+    const float full = w.norm_edge_gamma[c] * wv;
+    const float hi = __bfloat162float(__float2bfloat16_rn(full));
+    const float v = hi + __bfloat162float(__float2bfloat16_rn(full - hi));   // what hi + lo represents
     wp[eg][c][hh] = v;
     out->wp[eg][c][hh] = v;
   }
@@ -58,13 +60,15 @@ __global__ void __launch_bounds__(256) wide_prep_kernel(egt_block_weights_t w, i
   const int EGN = 2 * H, DEP = DE < 16 ? 16 : DE, DEW = DEP;
   const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
   // column n of the [E|G] product <-> (eg, hh):  n = (hh/8)*16 + eg*8 + hh%8
-  for (int i = tid; i < 2 * EGN * DEW; i += 256) {         // w_eg[v]
+  for (int i = tid; i < 2 * EGN * DEW; i += 256) {         // w_eg[v]: hi part in k < DEW, lo part in DEW <= k < 2 DEW
     const int v = i / (EGN * DEW), n = (i / DEW) % EGN, k = i % DEW;
     const int eg = (n >> 3) & 1, hh = 8 * (n >> 4) + (n & 7);
     float x;
     if (DE >= 16) x = wp[eg][k][hh];
     else x = (k >> 3) == v ? wp[eg][k & 7][hh] : 0.f;
-    out->w_eg[v][img(n, k, EGN)] = __float2bfloat16_rn(x);
+    const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+    out->w_eg[v][img(n, k, EGN)] = hi;
+    out->w_eg[v][img(n, DEW + k, EGN)] = __float2bfloat16_rn(x - __bfloat162float(hi));
   }
   for (int i = tid; i < DEP * 16; i += 256) {              // w_r, b_r
     const int n = i / 16, k = i % 16;
@@ -106,7 +110,5 @@ int wide_prep_launch(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, W
   EGT_CHECK_CUDA(cudaGetLastError());
   return EGT_OK;
 }
-
-size_t wide_bwd_partials_floats(const egt_block_cfg_t *) { return 0; }
 
 }  // namespace egt

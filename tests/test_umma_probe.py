@@ -128,3 +128,11 @@ def _probe_b16(a_off, b_off):
                                      C.c_void_p(torch.cuda.current_stream().cuda_stream)))
     torch.cuda.synchronize()
     torch.testing.assert_close(D, A.float() @ B.float().t(), rtol=1e-4, atol=1e-3)
+
+
+def test_w6_ss_a_mnmajor_none_b_mnmajor_sw128():
+    """weight-gradient products at h = 8: A is an un-swizzled MN-major image written row by row (k = query row),
+    B the raw edge tile as it lies in the TMA stage (MN-major, 128B swizzle), K = 128."""
+    ksteps, K = 8, 128
+    _probe(MNNONE, MNSW, 32, ksteps, 128, (K // 8) * 128, K * 128, 1024, [2 * s * 128 for s in range(ksteps)],
+           [2 * s * 1024 for s in range(ksteps)])
