@@ -161,8 +161,8 @@ wide_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
       for (int T = 0; T < NT && T < NS; ++T) load_tile(T);
     }
     __syncthreads();                                     // sync B: dO tile, first expanded operands
-    if (warp == 4 * NG && lane == 0) {
-      // =============================== tcgen05.mma issuer ===============================
+    if (warp == 4 * NG) {
+      // ====== tcgen05.mma issuer: the whole (converged) warp runs the loop, one elected lane issues (umma.cuh) ======
       constexpr uint32_t HI_SW = desc_hi(1024, LAYOUT_SW128), HI_NONE = desc_hi(128, LAYOUT_NONE), HI_TIMG = desc_hi(2048, LAYOUT_NONE);
       constexpr uint32_t ID_N16 = idesc_bf16(128, 16, 0, 0), ID_EG = idesc_bf16(128, EGN, 0, 0), ID_DX = idesc_bf16(128, DEP, 0, 0);
       constexpr uint32_t ID_DQ = idesc_bf16(128, D, 0, 1), ID_T = idesc_bf16(128, 16, 1, 1), ID_W = idesc_bf16(128, DEP, 1, 1);
@@ -181,54 +181,54 @@ wide_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
         const uint32_t loV = desc_lo(sbase + SM_KVX + (q * 3 + 2) * KV_MAT, 16);
 #pragma unroll
         for (int s = 0; s < C::DKS; ++s)
-          mma_ss(tg + G_S, mkdesc(loQ + (s >> 2) * 1024 + (s & 3) * 2, HI_SW), mkdesc(loK + (s >> 2) * 128 + (s & 3) * 2, HI_SW), ID_N16, s > 0);
+          mma_ss_w(tg + G_S, mkdesc(loQ + (s >> 2) * 1024 + (s & 3) * 2, HI_SW), mkdesc(loK + (s >> 2) * 128 + (s & 3) * 2, HI_SW), ID_N16, s > 0);
 #pragma unroll
         for (int s = 0; s < C::DKS; ++s)
-          mma_ss(tg + G_DA, mkdesc(loDO + (s >> 2) * 1024 + (s & 3) * 2, HI_SW), mkdesc(loV + (s >> 2) * 128 + (s & 3) * 2, HI_SW), ID_N16, s > 0);
+          mma_ss_w(tg + G_DA, mkdesc(loDO + (s >> 2) * 1024 + (s & 3) * 2, HI_SW), mkdesc(loV + (s >> 2) * 128 + (s & 3) * 2, HI_SW), ID_N16, s > 0);
         const uint32_t le = desc_lo(win(st, kt, ST_E), 16), ld = desc_lo(win(st, kt, ST_DE), 16);
         const uint32_t var = DE >= 16 ? 0u : (uint32_t)(kt & 1);
 #pragma unroll
         for (int s = 0; s < 2 * (C::DEW / 16); ++s)
-          mma_ss(tg + G_EG, mkdesc(le + 2 * (s % (C::DEW / 16)), HI_SW), mkdesc(loWeg + var * (W_EG_SZ / 16) + 2 * s * EGN, HI_NONE), ID_EG, s > 0);
+          mma_ss_w(tg + G_EG, mkdesc(le + 2 * (s % (C::DEW / 16)), HI_SW), mkdesc(loWeg + var * (W_EG_SZ / 16) + 2 * s * EGN, HI_NONE), ID_EG, s > 0);
 #pragma unroll
         for (int s = 0; s < C::DEW / 16; ++s)
-          mma_ss(tg + G_HX, mkdesc(ld + 2 * s, HI_SW), mkdesc(loWhx + var * (W_HX_SZ / 16) + 2 * s * 16, HI_NONE), ID_N16, s > 0);
+          mma_ss_w(tg + G_HX, mkdesc(ld + 2 * s, HI_SW), mkdesc(loWhx + var * (W_HX_SZ / 16) + 2 * s * 16, HI_NONE), ID_N16, s > 0);
       };
       auto issue_mma2 = [&](int q, int st, int kt, int kslot, bool first, bool first_w) {
         const uint32_t tg = tmem + TM_G + q * GC;
         // dQ += dS Kexp
-        mma_ts(tmem + TM_DQ, tg + G_DA, mkdesc(desc_lo(sbase + SM_KVX + (q * 3 + kslot) * KV_MAT, 2048), HI_SW), ID_DQ, first ? 0u : 1u);
+        mma_ts_w(tmem + TM_DQ, tg + G_DA, mkdesc(desc_lo(sbase + SM_KVX + (q * 3 + kslot) * KV_MAT, 2048), HI_SW), ID_DQ, first ? 0u : 1u);
         // T = de' I + (r dZ) W'^T
         const uint32_t ld = desc_lo(win(st, kt, ST_DE), 16);
         const uint32_t var = DE >= 16 ? 0u : (uint32_t)(kt & 1);
 #pragma unroll
         for (int s = 0; s < DEP / 16; ++s)
-          mma_ss(tg + G_DX + 16 * s, mkdesc(ld + (DE >= 16 ? 2 * s : 0), HI_SW), mkdesc(loI + var * 32, HI_NONE), ID_N16, 0);
+          mma_ss_w(tg + G_DX + 16 * s, mkdesc(ld + (DE >= 16 ? 2 * s : 0), HI_SW), mkdesc(loI + var * 32, HI_NONE), ID_N16, 0);
 #pragma unroll
         for (int s = 0; s < EGN / 16; ++s)
-          mma_ts(tg + G_DX, tg + G_S + 8 * s, mkdesc(loWdx + 2 * s * DEP, HI_NONE), ID_DX, 1);
+          mma_ts_w(tg + G_DX, tg + G_S + 8 * s, mkdesc(loWdx + 2 * s * DEP, HI_NONE), ID_DX, 1);
         // dK^T, dV^T of this key: contraction over the 128 query rows
         const uint32_t img = sbase + SM_IMG + q * IMG_G;
         const uint32_t loS = desc_lo(img + C::ZBYTES, 128), loA = desc_lo(img + C::ZBYTES + 4096, 128);
 #pragma unroll
-        for (int s = 0; s < 8; ++s) mma_ss(tg + G_T, mkdesc(loQm + 128 * s, HI_SW), mkdesc(loS + 16 * s, HI_TIMG), ID_T, s > 0);
+        for (int s = 0; s < 8; ++s) mma_ss_w(tg + G_T, mkdesc(loQm + 128 * s, HI_SW), mkdesc(loS + 16 * s, HI_TIMG), ID_T, s > 0);
 #pragma unroll
-        for (int s = 0; s < 8; ++s) mma_ss(tg + G_T + 16, mkdesc(loDOm + 128 * s, HI_SW), mkdesc(loA + 16 * s, HI_TIMG), ID_T, s > 0);
+        for (int s = 0; s < 8; ++s) mma_ss_w(tg + G_T + 16, mkdesc(loDOm + 128 * s, HI_SW), mkdesc(loA + 16 * s, HI_TIMG), ID_T, s > 0);
         // weight-gradient accumulators (all keys, both groups)
         const uint32_t loZ = desc_lo(img, C::ZNONE ? 128u : IMG_G);          // rows beyond the image's: whatever follows it (finite)
         constexpr uint32_t HI_Z = C::ZNONE ? HI_TIMG : HI_SW, ZSTEP = C::ZNONE ? 16u : 128u;
         const uint32_t we = desc_lo(win(st, kt, ST_E), 16384), wd = desc_lo(win(st, kt, ST_DE), 16384);
         const uint32_t wcol = DE >= 16 ? 0u : (uint32_t)(kt & 1) * DEP;       // d_e = 8: even / odd keys accumulate apart
 #pragma unroll
-        for (int s = 0; s < 8; ++s) mma_ss(tmem + TM_W1 + wcol, mkdesc(loZ + ZSTEP * s, HI_Z), mkdesc(we + 128 * s, HI_SW), ID_W, (first_w && s == 0) ? 0u : 1u);
+        for (int s = 0; s < 8; ++s) mma_ss_w(tmem + TM_W1 + wcol, mkdesc(loZ + ZSTEP * s, HI_Z), mkdesc(we + 128 * s, HI_SW), ID_W, (first_w && s == 0) ? 0u : 1u);
 #pragma unroll
-        for (int s = 0; s < 8; ++s) mma_ss(tmem + TM_W2 + wcol, mkdesc(loZ + ZSTEP * s, HI_Z), mkdesc(wd + 128 * s, HI_SW), ID_W, (first_w && s == 0) ? 0u : 1u);
+        for (int s = 0; s < 8; ++s) mma_ss_w(tmem + TM_W2 + wcol, mkdesc(loZ + ZSTEP * s, HI_Z), mkdesc(wd + 128 * s, HI_SW), ID_W, (first_w && s == 0) ? 0u : 1u);
       };
       tc_fence_after();
       mbar_wait(smem_u32(&bars->q_full), 0);
       mbar_wait(bar_e0, 0);
       tc_fence_after();
-      for (int q = 0; q < NG; ++q) { issue_mma1(q, 0, q, 0); mma_commit(bar_ready0 + 8 * q); }
+      for (int q = 0; q < NG; ++q) { issue_mma1(q, 0, q, 0); mma_commit_w(bar_ready0 + 8 * q); }
       int T = 0, i = 0, st = 0;
       for (int j = 0; j < J; ++j) {
         int T2 = T, i2 = i + 1, st2 = st;
@@ -244,7 +244,7 @@ wide_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
             if (i2 == 0 && q == 0) { mbar_wait(bar_e0 + 8 * st2, (T2 / NS) & 1); tc_fence_after(); }
             issue_mma1(q, st2, i2 * NG + q, (j + 1) & 1);
           }
-          mma_commit(bar_ready0 + 8 * q);
+          mma_commit_w(bar_ready0 + 8 * q);
         }
         T = T2; i = i2; st = st2;
       }

@@ -130,8 +130,8 @@ wide_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
       for (int T = 0; T < NT && T < NS; ++T) load_tile(T);
     }
     __syncthreads();                                     // sync B: first expanded operands are built
-    if (warp == 4 * NG && lane == 0) {
-      // =============================== tcgen05.mma issuer ===============================
+    if (warp == 4 * NG) {
+      // ====== tcgen05.mma issuer: the whole (converged) warp runs the loop, one elected lane issues (umma.cuh) ======
       constexpr uint32_t HI_SW = desc_hi(1024, LAYOUT_SW128), HI_NONE = desc_hi(128, LAYOUT_NONE);
       constexpr uint32_t ID_S = idesc_bf16(128, 16, 0, 0), ID_EG = idesc_bf16(128, C::EGN, 0, 0);
       constexpr uint32_t ID_PV = idesc_bf16(128, D, 0, 1), ID_EO = idesc_bf16(128, C::DEP, 0, 0);
@@ -149,30 +149,30 @@ wide_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
         const uint32_t loK = desc_lo(sbase + SM_KVX + q * 3 * KV_MAT, 16);
 #pragma unroll
         for (int s = 0; s < C::DKS; ++s)
-          mma_ss(tg + G_S, mkdesc(loQ + (s >> 2) * 1024 + (s & 3) * 2, HI_SW), mkdesc(loK + (s >> 2) * 128 + (s & 3) * 2, HI_SW), ID_S, s > 0);
+          mma_ss_w(tg + G_S, mkdesc(loQ + (s >> 2) * 1024 + (s & 3) * 2, HI_SW), mkdesc(loK + (s >> 2) * 128 + (s & 3) * 2, HI_SW), ID_S, s > 0);
         const uint32_t le = lo_e(st, kt);
         const uint32_t lw = loWeg + (DE >= 16 ? 0u : (uint32_t)(kt & 1) * (W_EG_SZ / 16));
 #pragma unroll
         for (int s = 0; s < 2 * (C::DEW / 16); ++s)        // W' = hi + lo (wide.h): the e window is multiplied by both
-          mma_ss(tg + G_EG, mkdesc(le + 2 * (s % (C::DEW / 16)), HI_SW), mkdesc(lw + 2 * s * C::EGN, HI_NONE), ID_EG, s > 0);
+          mma_ss_w(tg + G_EG, mkdesc(le + 2 * (s % (C::DEW / 16)), HI_SW), mkdesc(lw + 2 * s * C::EGN, HI_NONE), ID_EG, s > 0);
       };
       auto issue_mma2 = [&](int q, int st, int kt, int vslot, bool first) {   // O += A~ Vexp ; e' = e I + H_hat W_r + b_r
         const uint32_t tg = tmem + TM_G + q * GC;
         const uint32_t loV = desc_lo(sbase + SM_KVX + (q * 3 + 1 + vslot) * KV_MAT, 2048);
-        mma_ts(tmem + TM_O, tg + G_AOP, mkdesc(loV, HI_SW), ID_PV, first ? 0u : 1u);
+        mma_ts_w(tmem + TM_O, tg + G_AOP, mkdesc(loV, HI_SW), ID_PV, first ? 0u : 1u);
         const uint32_t le = lo_e(st, kt);
         const uint32_t li = loI + (DE >= 16 ? 0u : (uint32_t)(kt & 1) * 32u);
 #pragma unroll
         for (int s = 0; s < C::DEP / 16; ++s)
-          mma_ss(tg + G_EO + 16 * s, mkdesc(le + (DE >= 16 ? 2 * s : 0), HI_SW), mkdesc(li, HI_NONE), ID_S, 0);
-        mma_ts(tg + G_EO, tg + G_AOP + 8, mkdesc(loWr, HI_NONE), ID_EO, 1);
-        mma_ss(tg + G_EO, mkdesc(loOnes, HI_NONE), mkdesc(loWb, HI_NONE), ID_EO, 1);
+          mma_ss_w(tg + G_EO + 16 * s, mkdesc(le + (DE >= 16 ? 2 * s : 0), HI_SW), mkdesc(li, HI_NONE), ID_S, 0);
+        mma_ts_w(tg + G_EO, tg + G_AOP + 8, mkdesc(loWr, HI_NONE), ID_EO, 1);
+        mma_ss_w(tg + G_EO, mkdesc(loOnes, HI_NONE), mkdesc(loWb, HI_NONE), ID_EO, 1);
       };
       tc_fence_after();
       mbar_wait(smem_u32(&bars->q_full), 0);
       mbar_wait(bar_e0, 0);
       tc_fence_after();
-      for (int q = 0; q < NG; ++q) { issue_mma1(q, 0, q); mma_commit(bar_ready0 + 8 * q); }
+      for (int q = 0; q < NG; ++q) { issue_mma1(q, 0, q); mma_commit_w(bar_ready0 + 8 * q); }
       int T = 0, i = 0, st = 0;                          // tile / index inside the tile / stage of key j
       for (int j = 0; j < J; ++j) {
         int T2 = T, i2 = i + 1, st2 = st;                // the same for key j + 1
@@ -186,7 +186,7 @@ wide_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
             if (i2 == 0 && q == 0) { mbar_wait(bar_e0 + 8 * st2, (T2 / NS) & 1); tc_fence_after(); }
             issue_mma1(q, st2, i2 * NG + q);
           }
-          mma_commit(bar_ready0 + 8 * q);
+          mma_commit_w(bar_ready0 + 8 * q);
         }
         T = T2; i = i2; st = st2;
       }
