@@ -24,14 +24,18 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes (or the hint
+// expires) instead of returning after a few dozen cycles.  Without the hint a waiting warp re-polls ~70 times per
+// handshake (ncu: 42 % of all issued instructions of the wide kernels were this loop) and, being always eligible,
+// takes issue slots from the warps of the same SM sub-partition that do the arithmetic.
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.b32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(20000u)
       : "memory");
   return ok;
 }
@@ -40,8 +44,10 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
+  int polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) __trap();
+    __nanosleep(32);
+    if ((++polls & 63) == 0 && clock64() - t0 > 4000000000ll) __trap();
   }
 }
 
@@ -158,6 +164,267 @@ __device__ __forceinline__ void mma_commit_w(uint32_t bar) {
       "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
       "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
 }
+
+// ---- chains of tcgen05.mma over consecutive k-steps, ONE inline-asm statement each ----------------------------------
+// Every lane of a converged warp calls them (warp-uniform operands); one elected lane issues KS instructions whose
+// descriptor low words advance by (a_step, b_step) per k-step (16-byte units; TMEM columns for A in tensor memory).
+// One election and no C++-level register shuffling between the instructions: the issue cost per tcgen05.mma drops
+// from ~18 SASS instructions (one statement per instruction) to the two adds and the uniform-register moves.
+template <int KS> struct MmaChain;
+
+template <> struct MmaChain<1> {
+  static __device__ __forceinline__ void ss(uint32_t d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc,
+                                             uint32_t acc, uint32_t astep, uint32_t bstep) {
+    asm volatile(
+      "{\n\t.reg .pred pe, pa, pt;\n\t.reg .b32 al, bl;\n\t.reg .b64 da, db;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %6, 0;\n\tsetp.eq.b32 pt, %6, %6;\n\t"
+      "mov.b32 al, %1;\n\tmov.b32 bl, %3;\n\t"
+      "mov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pa;\n\t"
+      "}"
+      ::"r"(d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(acc), "r"(astep), "r"(bstep) : "memory");
+  }
+  static __device__ __forceinline__ void ts(uint32_t d, uint32_t a_tmem, uint32_t blo, uint32_t bhi, uint32_t idesc, uint32_t acc,
+                                             uint32_t astep, uint32_t bstep) {
+    asm volatile(
+      "{\n\t.reg .pred pe, pa, pt;\n\t.reg .b32 al, bl;\n\t.reg .b64 db;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %5, 0;\n\tsetp.eq.b32 pt, %5, %5;\n\t"
+      "mov.b32 al, %1;\n\tmov.b32 bl, %2;\n\t"
+      "mov.b64 db, {bl, %3};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [al], db, %4, pa;\n\t"
+      "}"
+      ::"r"(d), "r"(a_tmem), "r"(blo), "r"(bhi), "r"(idesc), "r"(acc), "r"(astep), "r"(bstep) : "memory");
+  }
+};
+template <> struct MmaChain<2> {
+  static __device__ __forceinline__ void ss(uint32_t d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc,
+                                             uint32_t acc, uint32_t astep, uint32_t bstep) {
+    asm volatile(
+      "{\n\t.reg .pred pe, pa, pt;\n\t.reg .b32 al, bl;\n\t.reg .b64 da, db;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %6, 0;\n\tsetp.eq.b32 pt, %6, %6;\n\t"
+      "mov.b32 al, %1;\n\tmov.b32 bl, %3;\n\t"
+      "mov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pa;\n\t"
+      "add.u32 al, al, %7;\n\tadd.u32 bl, bl, %8;\n\t"
+      "mov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n\t"
+      "}"
+      ::"r"(d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(acc), "r"(astep), "r"(bstep) : "memory");
+  }
+  static __device__ __forceinline__ void ts(uint32_t d, uint32_t a_tmem, uint32_t blo, uint32_t bhi, uint32_t idesc, uint32_t acc,
+                                             uint32_t astep, uint32_t bstep) {
+    asm volatile(
+      "{\n\t.reg .pred pe, pa, pt;\n\t.reg .b32 al, bl;\n\t.reg .b64 db;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %5, 0;\n\tsetp.eq.b32 pt, %5, %5;\n\t"
+      "mov.b32 al, %1;\n\tmov.b32 bl, %2;\n\t"
+      "mov.b64 db, {bl, %3};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [al], db, %4, pa;\n\t"
+      "add.u32 al, al, %6;\n\tadd.u32 bl, bl, %7;\n\t"
+      "mov.b64 db, {bl, %3};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [al], db, %4, pt;\n\t"
+      "}"
+      ::"r"(d), "r"(a_tmem), "r"(blo), "r"(bhi), "r"(idesc), "r"(acc), "r"(astep), "r"(bstep) : "memory");
+  }
+};
+template <> struct MmaChain<3> {
+  static __device__ __forceinline__ void ss(uint32_t d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc,
+                                             uint32_t acc, uint32_t astep, uint32_t bstep) {
+    asm volatile(
+      "{\n\t.reg .pred pe, pa, pt;\n\t.reg .b32 al, bl;\n\t.reg .b64 da, db;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %6, 0;\n\tsetp.eq.b32 pt, %6, %6;\n\t"
+      "mov.b32 al, %1;\n\tmov.b32 bl, %3;\n\t"
+      "mov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pa;\n\t"
+      "add.u32 al, al, %7;\n\tadd.u32 bl, bl, %8;\n\t"
+      "mov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n\t"
+      "add.u32 al, al, %7;\n\tadd.u32 bl, bl, %8;\n\t"
+      "mov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n\t"
+      "}"
+      ::"r"(d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(acc), "r"(astep), "r"(bstep) : "memory");
+  }
+  static __device__ __forceinline__ void ts(uint32_t d, uint32_t a_tmem, uint32_t blo, uint32_t bhi, uint32_t idesc, uint32_t acc,
+                                             uint32_t astep, uint32_t bstep) {
+    asm volatile(
+      "{\n\t.reg .pred pe, pa, pt;\n\t.reg .b32 al, bl;\n\t.reg .b64 db;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %5, 0;\n\tsetp.eq.b32 pt, %5, %5;\n\t"
+      "mov.b32 al, %1;\n\tmov.b32 bl, %2;\n\t"
+      "mov.b64 db, {bl, %3};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [al], db, %4, pa;\n\t"
+      "add.u32 al, al, %6;\n\tadd.u32 bl, bl, %7;\n\t"
+      "mov.b64 db, {bl, %3};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [al], db, %4, pt;\n\t"
+      "add.u32 al, al, %6;\n\tadd.u32 bl, bl, %7;\n\t"
+      "mov.b64 db, {bl, %3};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [al], db, %4, pt;\n\t"
+      "}"
+      ::"r"(d), "r"(a_tmem), "r"(blo), "r"(bhi), "r"(idesc), "r"(acc), "r"(astep), "r"(bstep) : "memory");
+  }
+};
+template <> struct MmaChain<4> {
+  static __device__ __forceinline__ void ss(uint32_t d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc,
+                                             uint32_t acc, uint32_t astep, uint32_t bstep) {
+    asm volatile(
+      "{\n\t.reg .pred pe, pa, pt;\n\t.reg .b32 al, bl;\n\t.reg .b64 da, db;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %6, 0;\n\tsetp.eq.b32 pt, %6, %6;\n\t"
+      "mov.b32 al, %1;\n\tmov.b32 bl, %3;\n\t"
+      "mov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pa;\n\t"
+      "add.u32 al, al, %7;\n\tadd.u32 bl, bl, %8;\n\t"
+      "mov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n\t"
+      "add.u32 al, al, %7;\n\tadd.u32 bl, bl, %8;\n\t"
+      "mov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n\t"
+      "add.u32 al, al, %7;\n\tadd.u32 bl, bl, %8;\n\t"
+      "mov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n\t"
+      "}"
+      ::"r"(d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(acc), "r"(astep), "r"(bstep) : "memory");
+  }
+  static __device__ __forceinline__ void ts(uint32_t d, uint32_t a_tmem, uint32_t blo, uint32_t bhi, uint32_t idesc, uint32_t acc,
+                                             uint32_t astep, uint32_t bstep) {
+    asm volatile(
+      "{\n\t.reg .pred pe, pa, pt;\n\t.reg .b32 al, bl;\n\t.reg .b64 db;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %5, 0;\n\tsetp.eq.b32 pt, %5, %5;\n\t"
+      "mov.b32 al, %1;\n\tmov.b32 bl, %2;\n\t"
+      "mov.b64 db, {bl, %3};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [al], db, %4, pa;\n\t"
+      "add.u32 al, al, %6;\n\tadd.u32 bl, bl, %7;\n\t"
+      "mov.b64 db, {bl, %3};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [al], db, %4, pt;\n\t"
+      "add.u32 al, al, %6;\n\tadd.u32 bl, bl, %7;\n\t"
+      "mov.b64 db, {bl, %3};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [al], db, %4, pt;\n\t"
+      "add.u32 al, al, %6;\n\tadd.u32 bl, bl, %7;\n\t"
+      "mov.b64 db, {bl, %3};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [al], db, %4, pt;\n\t"
+      "}"
+      ::"r"(d), "r"(a_tmem), "r"(blo), "r"(bhi), "r"(idesc), "r"(acc), "r"(astep), "r"(bstep) : "memory");
+  }
+};
+template <> struct MmaChain<6> {
+  static __device__ __forceinline__ void ss(uint32_t d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc,
+                                             uint32_t acc, uint32_t astep, uint32_t bstep) {
+    asm volatile(
+      "{\n\t.reg .pred pe, pa, pt;\n\t.reg .b32 al, bl;\n\t.reg .b64 da, db;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %6, 0;\n\tsetp.eq.b32 pt, %6, %6;\n\t"
+      "mov.b32 al, %1;\n\tmov.b32 bl, %3;\n\t"
+      "mov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pa;\n\t"
+      "add.u32 al, al, %7;\n\tadd.u32 bl, bl, %8;\n\t"
+      "mov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n\t"
+      "add.u32 al, al, %7;\n\tadd.u32 bl, bl, %8;\n\t"
+      "mov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n\t"
+      "add.u32 al, al, %7;\n\tadd.u32 bl, bl, %8;\n\t"
+      "mov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n\t"
+      "add.u32 al, al, %7;\n\tadd.u32 bl, bl, %8;\n\t"
+      "mov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n\t"
+      "add.u32 al, al, %7;\n\tadd.u32 bl, bl, %8;\n\t"
+      "mov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n\t"
+      "}"
+      ::"r"(d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(acc), "r"(astep), "r"(bstep) : "memory");
+  }
+  static __device__ __forceinline__ void ts(uint32_t d, uint32_t a_tmem, uint32_t blo, uint32_t bhi, uint32_t idesc, uint32_t acc,
+                                             uint32_t astep, uint32_t bstep) {
+    asm volatile(
+      "{\n\t.reg .pred pe, pa, pt;\n\t.reg .b32 al, bl;\n\t.reg .b64 db;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %5, 0;\n\tsetp.eq.b32 pt, %5, %5;\n\t"
+      "mov.b32 al, %1;\n\tmov.b32 bl, %2;\n\t"
+      "mov.b64 db, {bl, %3};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [al], db, %4, pa;\n\t"
+      "add.u32 al, al, %6;\n\tadd.u32 bl, bl, %7;\n\t"
+      "mov.b64 db, {bl, %3};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [al], db, %4, pt;\n\t"
+      "add.u32 al, al, %6;\n\tadd.u32 bl, bl, %7;\n\t"
+      "mov.b64 db, {bl, %3};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [al], db, %4, pt;\n\t"
+      "add.u32 al, al, %6;\n\tadd.u32 bl, bl, %7;\n\t"
+      "mov.b64 db, {bl, %3};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [al], db, %4, pt;\n\t"
+      "add.u32 al, al, %6;\n\tadd.u32 bl, bl, %7;\n\t"
+      "mov.b64 db, {bl, %3};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [al], db, %4, pt;\n\t"
+      "add.u32 al, al, %6;\n\tadd.u32 bl, bl, %7;\n\t"
+      "mov.b64 db, {bl, %3};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [al], db, %4, pt;\n\t"
+      "}"
+      ::"r"(d), "r"(a_tmem), "r"(blo), "r"(bhi), "r"(idesc), "r"(acc), "r"(astep), "r"(bstep) : "memory");
+  }
+};
+template <> struct MmaChain<8> {
+  static __device__ __forceinline__ void ss(uint32_t d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc,
+                                             uint32_t acc, uint32_t astep, uint32_t bstep) {
+    asm volatile(
+      "{\n\t.reg .pred pe, pa, pt;\n\t.reg .b32 al, bl;\n\t.reg .b64 da, db;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %6, 0;\n\tsetp.eq.b32 pt, %6, %6;\n\t"
+      "mov.b32 al, %1;\n\tmov.b32 bl, %3;\n\t"
+      "mov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pa;\n\t"
+      "add.u32 al, al, %7;\n\tadd.u32 bl, bl, %8;\n\t"
+      "mov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n\t"
+      "add.u32 al, al, %7;\n\tadd.u32 bl, bl, %8;\n\t"
+      "mov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n\t"
+      "add.u32 al, al, %7;\n\tadd.u32 bl, bl, %8;\n\t"
+      "mov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n\t"
+      "add.u32 al, al, %7;\n\tadd.u32 bl, bl, %8;\n\t"
+      "mov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n\t"
+      "add.u32 al, al, %7;\n\tadd.u32 bl, bl, %8;\n\t"
+      "mov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n\t"
+      "add.u32 al, al, %7;\n\tadd.u32 bl, bl, %8;\n\t"
+      "mov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n\t"
+      "add.u32 al, al, %7;\n\tadd.u32 bl, bl, %8;\n\t"
+      "mov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n\t"
+      "}"
+      ::"r"(d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(acc), "r"(astep), "r"(bstep) : "memory");
+  }
+  static __device__ __forceinline__ void ts(uint32_t d, uint32_t a_tmem, uint32_t blo, uint32_t bhi, uint32_t idesc, uint32_t acc,
+                                             uint32_t astep, uint32_t bstep) {
+    asm volatile(
+      "{\n\t.reg .pred pe, pa, pt;\n\t.reg .b32 al, bl;\n\t.reg .b64 db;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %5, 0;\n\tsetp.eq.b32 pt, %5, %5;\n\t"
+      "mov.b32 al, %1;\n\tmov.b32 bl, %2;\n\t"
+      "mov.b64 db, {bl, %3};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [al], db, %4, pa;\n\t"
+      "add.u32 al, al, %6;\n\tadd.u32 bl, bl, %7;\n\t"
+      "mov.b64 db, {bl, %3};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [al], db, %4, pt;\n\t"
+      "add.u32 al, al, %6;\n\tadd.u32 bl, bl, %7;\n\t"
+      "mov.b64 db, {bl, %3};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [al], db, %4, pt;\n\t"
+      "add.u32 al, al, %6;\n\tadd.u32 bl, bl, %7;\n\t"
+      "mov.b64 db, {bl, %3};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [al], db, %4, pt;\n\t"
+      "add.u32 al, al, %6;\n\tadd.u32 bl, bl, %7;\n\t"
+      "mov.b64 db, {bl, %3};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [al], db, %4, pt;\n\t"
+      "add.u32 al, al, %6;\n\tadd.u32 bl, bl, %7;\n\t"
+      "mov.b64 db, {bl, %3};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [al], db, %4, pt;\n\t"
+      "add.u32 al, al, %6;\n\tadd.u32 bl, bl, %7;\n\t"
+      "mov.b64 db, {bl, %3};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [al], db, %4, pt;\n\t"
+      "add.u32 al, al, %6;\n\tadd.u32 bl, bl, %7;\n\t"
+      "mov.b64 db, {bl, %3};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [al], db, %4, pt;\n\t"
+      "}"
+      ::"r"(d), "r"(a_tmem), "r"(blo), "r"(bhi), "r"(idesc), "r"(acc), "r"(astep), "r"(bstep) : "memory");
+  }
+};
+
 // All tcgen05.mma issued so far by this thread arrive (once) on `bar` when they complete.
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");

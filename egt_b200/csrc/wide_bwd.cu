@@ -136,7 +136,11 @@ wide_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
   tc_fence_before();
   __syncthreads();                                       // sync A
   tc_fence_after();
-  const uint32_t tmem = bars->tmem_base;
+  // A 512-column allocation is the whole tensor memory of the SM: its base is column 0, lane 0.  The issuer uses
+  // the literal so that every tcgen05.mma operand is a warp-uniform value for ptxas (a value loaded from shared
+  // memory is not, and costs vector -> uniform register moves per instruction).
+  if (bars->tmem_base != 0u) __trap();
+  constexpr uint32_t tmem = 0u;
   const uint32_t bar_e0 = smem_u32(&bars->e_full[0]), bar_td0 = smem_u32(&bars->tile_done[0]);
   const uint32_t bar_ready0 = smem_u32(&bars->ready[0]), bar_done0 = smem_u32(&bars->done[0]);
 
@@ -175,54 +179,50 @@ wide_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
         const int ch = DE >= 16 ? kt * DE : (kt & ~1) * DE;
         return sbase + SM_STAGE + st * STAGE_BYTES + which + (uint32_t)(ch >> 6) * 16384u + (uint32_t)(ch & 63) * 2u;
       };
+      // k-steps of a contraction over the channels of a [128 x d] tile: runs of <= 4 steps per 64-channel atom
+      auto chain_d = [&](uint32_t dcol, uint32_t loA, uint32_t loB) {
+#pragma unroll
+        for (int at = 0; at < C::NQA; ++at) {
+          constexpr int FULL = 4;
+          const int ks = C::DKS - 4 * at < FULL ? C::DKS - 4 * at : FULL;
+          if (ks == 4) MmaChain<4>::ss(dcol, loA + at * 1024, HI_SW, loB + at * 128, HI_SW, ID_N16, at > 0, 2, 2);
+          else if (ks == 3) MmaChain<3>::ss(dcol, loA + at * 1024, HI_SW, loB + at * 128, HI_SW, ID_N16, at > 0, 2, 2);
+          else if (ks == 2) MmaChain<2>::ss(dcol, loA + at * 1024, HI_SW, loB + at * 128, HI_SW, ID_N16, at > 0, 2, 2);
+          else if (ks == 1) MmaChain<1>::ss(dcol, loA + at * 1024, HI_SW, loB + at * 128, HI_SW, ID_N16, at > 0, 2, 2);
+        }
+      };
       auto issue_mma1 = [&](int q, int st, int kt, int kslot) {   // inputs of the group's next key
         const uint32_t tg = tmem + TM_G + q * GC;
-        const uint32_t loK = desc_lo(sbase + SM_KVX + (q * 3 + kslot) * KV_MAT, 16);
-        const uint32_t loV = desc_lo(sbase + SM_KVX + (q * 3 + 2) * KV_MAT, 16);
-#pragma unroll
-        for (int s = 0; s < C::DKS; ++s)
-          mma_ss_w(tg + G_S, mkdesc(loQ + (s >> 2) * 1024 + (s & 3) * 2, HI_SW), mkdesc(loK + (s >> 2) * 128 + (s & 3) * 2, HI_SW), ID_N16, s > 0);
-#pragma unroll
-        for (int s = 0; s < C::DKS; ++s)
-          mma_ss_w(tg + G_DA, mkdesc(loDO + (s >> 2) * 1024 + (s & 3) * 2, HI_SW), mkdesc(loV + (s >> 2) * 128 + (s & 3) * 2, HI_SW), ID_N16, s > 0);
+        chain_d(tg + G_S, loQ, desc_lo(sbase + SM_KVX + (q * 3 + kslot) * KV_MAT, 16));
+        chain_d(tg + G_DA, loDO, desc_lo(sbase + SM_KVX + (q * 3 + 2) * KV_MAT, 16));
         const uint32_t le = desc_lo(win(st, kt, ST_E), 16), ld = desc_lo(win(st, kt, ST_DE), 16);
         const uint32_t var = DE >= 16 ? 0u : (uint32_t)(kt & 1);
-#pragma unroll
-        for (int s = 0; s < 2 * (C::DEW / 16); ++s)
-          mma_ss_w(tg + G_EG, mkdesc(le + 2 * (s % (C::DEW / 16)), HI_SW), mkdesc(loWeg + var * (W_EG_SZ / 16) + 2 * s * EGN, HI_NONE), ID_EG, s > 0);
-#pragma unroll
-        for (int s = 0; s < C::DEW / 16; ++s)
-          mma_ss_w(tg + G_HX, mkdesc(ld + 2 * s, HI_SW), mkdesc(loWhx + var * (W_HX_SZ / 16) + 2 * s * 16, HI_NONE), ID_N16, s > 0);
+        constexpr int EK = C::DEW / 16;                    // W' = hi + lo (wide.h): the e window is multiplied by both
+        MmaChain<EK>::ss(tg + G_EG, le, HI_SW, loWeg + var * (W_EG_SZ / 16), HI_NONE, ID_EG, 0, 2, 2 * EGN);
+        MmaChain<EK>::ss(tg + G_EG, le, HI_SW, loWeg + var * (W_EG_SZ / 16) + 2 * EK * EGN, HI_NONE, ID_EG, 1, 2, 2 * EGN);
+        MmaChain<EK>::ss(tg + G_HX, ld, HI_SW, loWhx + var * (W_HX_SZ / 16), HI_NONE, ID_N16, 0, 2, 32);
       };
       auto issue_mma2 = [&](int q, int st, int kt, int kslot, bool first, bool first_w) {
         const uint32_t tg = tmem + TM_G + q * GC;
         // dQ += dS Kexp
-        mma_ts_w(tmem + TM_DQ, tg + G_DA, mkdesc(desc_lo(sbase + SM_KVX + (q * 3 + kslot) * KV_MAT, 2048), HI_SW), ID_DQ, first ? 0u : 1u);
+        MmaChain<1>::ts(tmem + TM_DQ, tg + G_DA, desc_lo(sbase + SM_KVX + (q * 3 + kslot) * KV_MAT, 2048), HI_SW, ID_DQ, first ? 0u : 1u, 0, 0);
         // T = de' I + (r dZ) W'^T
         const uint32_t ld = desc_lo(win(st, kt, ST_DE), 16);
         const uint32_t var = DE >= 16 ? 0u : (uint32_t)(kt & 1);
 #pragma unroll
         for (int s = 0; s < DEP / 16; ++s)
-          mma_ss_w(tg + G_DX + 16 * s, mkdesc(ld + (DE >= 16 ? 2 * s : 0), HI_SW), mkdesc(loI + var * 32, HI_NONE), ID_N16, 0);
-#pragma unroll
-        for (int s = 0; s < EGN / 16; ++s)
-          mma_ts_w(tg + G_DX, tg + G_S + 8 * s, mkdesc(loWdx + 2 * s * DEP, HI_NONE), ID_DX, 1);
+          MmaChain<1>::ss(tg + G_DX + 16 * s, ld + (DE >= 16 ? 2 * s : 0), HI_SW, loI + var * 32, HI_NONE, ID_N16, 0, 0, 0);
+        MmaChain<EGN / 16>::ts(tg + G_DX, tg + G_S, loWdx, HI_NONE, ID_DX, 1, 8, 2 * DEP);
         // dK^T, dV^T of this key: contraction over the 128 query rows
         const uint32_t img = sbase + SM_IMG + q * IMG_G;
-        const uint32_t loS = desc_lo(img + C::ZBYTES, 128), loA = desc_lo(img + C::ZBYTES + 4096, 128);
-#pragma unroll
-        for (int s = 0; s < 8; ++s) mma_ss_w(tg + G_T, mkdesc(loQm + 128 * s, HI_SW), mkdesc(loS + 16 * s, HI_TIMG), ID_T, s > 0);
-#pragma unroll
-        for (int s = 0; s < 8; ++s) mma_ss_w(tg + G_T + 16, mkdesc(loDOm + 128 * s, HI_SW), mkdesc(loA + 16 * s, HI_TIMG), ID_T, s > 0);
+        MmaChain<8>::ss(tg + G_T, loQm, HI_SW, desc_lo(img + C::ZBYTES, 128), HI_TIMG, ID_T, 0, 128, 16);
+        MmaChain<8>::ss(tg + G_T + 16, loDOm, HI_SW, desc_lo(img + C::ZBYTES + 4096, 128), HI_TIMG, ID_T, 0, 128, 16);
         // weight-gradient accumulators (all keys, both groups)
         const uint32_t loZ = desc_lo(img, C::ZNONE ? 128u : IMG_G);          // rows beyond the image's: whatever follows it (finite)
         constexpr uint32_t HI_Z = C::ZNONE ? HI_TIMG : HI_SW, ZSTEP = C::ZNONE ? 16u : 128u;
-        const uint32_t we = desc_lo(win(st, kt, ST_E), 16384), wd = desc_lo(win(st, kt, ST_DE), 16384);
         const uint32_t wcol = DE >= 16 ? 0u : (uint32_t)(kt & 1) * DEP;       // d_e = 8: even / odd keys accumulate apart
-#pragma unroll
-        for (int s = 0; s < 8; ++s) mma_ss_w(tmem + TM_W1 + wcol, mkdesc(loZ + ZSTEP * s, HI_Z), mkdesc(we + 128 * s, HI_SW), ID_W, (first_w && s == 0) ? 0u : 1u);
-#pragma unroll
-        for (int s = 0; s < 8; ++s) mma_ss_w(tmem + TM_W2 + wcol, mkdesc(loZ + ZSTEP * s, HI_Z), mkdesc(wd + 128 * s, HI_SW), ID_W, (first_w && s == 0) ? 0u : 1u);
+        MmaChain<8>::ss(tmem + TM_W1 + wcol, loZ, HI_Z, desc_lo(win(st, kt, ST_E), 16384), HI_SW, ID_W, first_w ? 0u : 1u, ZSTEP, 128);
+        MmaChain<8>::ss(tmem + TM_W2 + wcol, loZ, HI_Z, desc_lo(win(st, kt, ST_DE), 16384), HI_SW, ID_W, first_w ? 0u : 1u, ZSTEP, 128);
       };
       tc_fence_after();
       mbar_wait(smem_u32(&bars->q_full), 0);

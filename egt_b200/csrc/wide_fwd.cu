@@ -108,7 +108,11 @@ wide_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
   tc_fence_before();
   __syncthreads();                                       // sync A
   tc_fence_after();
-  const uint32_t tmem = bars->tmem_base;
+  // A 512-column allocation is the whole tensor memory of the SM: its base is column 0, lane 0.  The issuer uses
+  // the literal so that every tcgen05.mma operand is a warp-uniform value for ptxas (a value loaded from shared
+  // memory is not, and costs vector -> uniform register moves per instruction).
+  if (bars->tmem_base != 0u) __trap();
+  constexpr uint32_t tmem = 0u;
   const uint32_t bar_e0 = smem_u32(&bars->e_full[0]), bar_td0 = smem_u32(&bars->tile_done[0]);
   const uint32_t bar_ready0 = smem_u32(&bars->ready[0]), bar_done0 = smem_u32(&bars->done[0]);
 
@@ -148,25 +152,30 @@ wide_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
         const uint32_t tg = tmem + TM_G + q * GC;
         const uint32_t loK = desc_lo(sbase + SM_KVX + q * 3 * KV_MAT, 16);
 #pragma unroll
-        for (int s = 0; s < C::DKS; ++s)
-          mma_ss_w(tg + G_S, mkdesc(loQ + (s >> 2) * 1024 + (s & 3) * 2, HI_SW), mkdesc(loK + (s >> 2) * 128 + (s & 3) * 2, HI_SW), ID_S, s > 0);
+        for (int at = 0; at < C::NQA; ++at) {              // k-steps over the channels: runs of <= 4 per 64-channel atom
+          const int ks = C::DKS - 4 * at < 4 ? C::DKS - 4 * at : 4;
+          if (ks == 4) MmaChain<4>::ss(tg + G_S, loQ + at * 1024, HI_SW, loK + at * 128, HI_SW, ID_S, at > 0, 2, 2);
+          else if (ks == 3) MmaChain<3>::ss(tg + G_S, loQ + at * 1024, HI_SW, loK + at * 128, HI_SW, ID_S, at > 0, 2, 2);
+          else if (ks == 2) MmaChain<2>::ss(tg + G_S, loQ + at * 1024, HI_SW, loK + at * 128, HI_SW, ID_S, at > 0, 2, 2);
+          else if (ks == 1) MmaChain<1>::ss(tg + G_S, loQ + at * 1024, HI_SW, loK + at * 128, HI_SW, ID_S, at > 0, 2, 2);
+        }
         const uint32_t le = lo_e(st, kt);
         const uint32_t lw = loWeg + (DE >= 16 ? 0u : (uint32_t)(kt & 1) * (W_EG_SZ / 16));
-#pragma unroll
-        for (int s = 0; s < 2 * (C::DEW / 16); ++s)        // W' = hi + lo (wide.h): the e window is multiplied by both
-          mma_ss_w(tg + G_EG, mkdesc(le + 2 * (s % (C::DEW / 16)), HI_SW), mkdesc(lw + 2 * s * C::EGN, HI_NONE), ID_EG, s > 0);
+        constexpr int EK = C::DEW / 16;                    // W' = hi + lo (wide.h): the e window is multiplied by both
+        MmaChain<EK>::ss(tg + G_EG, le, HI_SW, lw, HI_NONE, ID_EG, 0, 2, 2 * C::EGN);
+        MmaChain<EK>::ss(tg + G_EG, le, HI_SW, lw + 2 * EK * C::EGN, HI_NONE, ID_EG, 1, 2, 2 * C::EGN);
       };
       auto issue_mma2 = [&](int q, int st, int kt, int vslot, bool first) {   // O += A~ Vexp ; e' = e I + H_hat W_r + b_r
         const uint32_t tg = tmem + TM_G + q * GC;
         const uint32_t loV = desc_lo(sbase + SM_KVX + (q * 3 + 1 + vslot) * KV_MAT, 2048);
-        mma_ts_w(tmem + TM_O, tg + G_AOP, mkdesc(loV, HI_SW), ID_PV, first ? 0u : 1u);
+        MmaChain<1>::ts(tmem + TM_O, tg + G_AOP, loV, HI_SW, ID_PV, first ? 0u : 1u, 0, 0);
         const uint32_t le = lo_e(st, kt);
         const uint32_t li = loI + (DE >= 16 ? 0u : (uint32_t)(kt & 1) * 32u);
 #pragma unroll
         for (int s = 0; s < C::DEP / 16; ++s)
-          mma_ss_w(tg + G_EO + 16 * s, mkdesc(le + (DE >= 16 ? 2 * s : 0), HI_SW), mkdesc(li, HI_NONE), ID_S, 0);
-        mma_ts_w(tg + G_EO, tg + G_AOP + 8, mkdesc(loWr, HI_NONE), ID_EO, 1);
-        mma_ss_w(tg + G_EO, mkdesc(loOnes, HI_NONE), mkdesc(loWb, HI_NONE), ID_EO, 1);
+          MmaChain<1>::ss(tg + G_EO + 16 * s, le + (DE >= 16 ? 2 * s : 0), HI_SW, li, HI_NONE, ID_S, 0, 0, 0);
+        MmaChain<1>::ts(tg + G_EO, tg + G_AOP + 8, loWr, HI_NONE, ID_EO, 1, 0, 0);
+        MmaChain<1>::ss(tg + G_EO, loOnes, HI_NONE, loWb, HI_NONE, ID_EO, 1, 0, 0);
       };
       tc_fence_after();
       mbar_wait(smem_u32(&bars->q_full), 0);
