@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, 'lib')
 LIB = os.path.join(LIBDIR, 'libegt_b200.so')
 SOURCES = ['abi.cu', 'attn_staged.cu', 'attn_fast.cu', 'edge_kernels.cu', 'edge_fast.cu', 'node_kernels.cu', 'umma_probe.cu', 'fused_prep.cu', 'fused_fwd.cu',
-           'fused_bwd.cu', 'wide_prep.cu', 'wide_fwd.cu', 'wide_bwd.cu', 'node_tc.cu', 'peer_allreduce.cu', 'ffn_kernels.cu']
+           'fused_bwd.cu', 'wide_prep.cu', 'wide_fwd.cu', 'wide_bwd.cu', 'node_blas.cu', 'node_tc.cu', 'peer_allreduce.cu', 'ffn_kernels.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xptxas', '-v']
 
@@ -63,7 +63,8 @@ def build_library(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=len(srcs)) as ex:
         objs = list(ex.map(compile_one, srcs))
-    cmd = [nvcc, '-shared', '-o', LIB] + objs      # static cudart; libcuda is resolved lazily at run time
+    cmd = [nvcc, '-shared', '-o', LIB] + objs + ['-lcublas']   # static cudart; libcuda is resolved lazily at run time;
+    # cuBLAS (node_blas.cu: plain node-channel GEMMs) resolves to the copy already loaded by the process, if any
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError('link failed:\n' + r.stdout + r.stderr)

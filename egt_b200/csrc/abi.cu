@@ -8,6 +8,7 @@
 #include "kernels.h"
 #include "fused.h"
 #include "wide.h"
+#include "node_blas.h"
 
 namespace egt {
 
@@ -110,6 +111,7 @@ struct BlockWs {
   char *d_v_att, *d_qkv;                      // [R,d], [R,3d] dtype
   float *hn, *dhn;                            // [R,d] f32
   char *prep;                                 // FusedPrep (fused path only)
+  char *nblas;                                // node_blas.cu scratch (wide path, d != 64)
   float *d_qkv_f32, *partials;                // fused backward: [R,3d] f32, [ctas,FPART] f32
   size_t total;
 };
@@ -127,6 +129,7 @@ static BlockWs carve(const egt_block_cfg_t *c, int backward, void *base, bool ha
   const bool wide = wide_supported(c, a.dtype) && !g_force_staged;
   const bool fused = (fused_supported(c, a.dtype) && !g_force_staged) || wide;
   if (fused) w.prep = take(wide ? sizeof(WidePrep) : sizeof(FusedPrep));
+  if (wide && !(d == 64 && a.h == 8) && node_blas_supported((int)d)) w.nblas = take(node_blas_workspace_bytes((int)R, (int)d));
   if (fused && !backward) { w.total = off; return w; }
   if (fused && backward && has_de_out && (!wide || wide_bwd_supported(c))) {      // fused backward: nothing of shape [pairs,h] is materialised
     w.d_v_att = take(R * d * es);
@@ -334,13 +337,21 @@ int egt_block_fwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
   BlockWs ws = carve(cfg, 0, io->workspace);
   const bool wide = !fused && wide_supported(cfg, a.dtype) && !g_force_staged;
   if (wide) {    // width-generic fused path (wide_fwd.cu); Q is stored pre-scaled by dk^-0.5
-    LinearArgs lq;
-    memset(&lq, 0, sizeof(lq));
-    lq.x = io->h; lq.W = w->dense_qkv_kernel; lq.bias = w->dense_qkv_bias; lq.out = io->qkv;
-    lq.ln_gamma = w->norm_mha_gamma; lq.ln_beta = w->norm_mha_beta; lq.ln_eps = cfg->ln_eps;
-    lq.scale = 1.0f / sqrtf((float)a.dk); lq.scale_cols = d;
-    lq.R = R; lq.din = d; lq.dout = 3 * d;
-    if ((rc = linear_launch(lq, a.dtype, st))) return rc;
+    const bool node_tc = d == 64 && a.h == 8;          // the tcgen05 node kernels (node_tc.cu) serve model width 64
+    if (node_tc) {
+      if ((rc = node_qkv_launch(io->h, w->norm_mha_gamma, w->norm_mha_beta, cfg->ln_eps, w->dense_qkv_kernel,
+                                w->dense_qkv_bias, 1.0f / sqrtf((float)a.dk), io->qkv, R, w, a.clip_lo, a.clip_hi, nullptr, st))) return rc;
+    } else if (ws.nblas) {
+      if ((rc = node_blas_qkv(io->h, w, cfg->ln_eps, 1.0f / sqrtf((float)a.dk), io->qkv, R, d, ws.nblas, st))) return rc;
+    } else {
+      LinearArgs lq;
+      memset(&lq, 0, sizeof(lq));
+      lq.x = io->h; lq.W = w->dense_qkv_kernel; lq.bias = w->dense_qkv_bias; lq.out = io->qkv;
+      lq.ln_gamma = w->norm_mha_gamma; lq.ln_beta = w->norm_mha_beta; lq.ln_eps = cfg->ln_eps;
+      lq.scale = 1.0f / sqrtf((float)a.dk); lq.scale_cols = d;
+      lq.R = R; lq.din = d; lq.dout = 3 * d;
+      if ((rc = linear_launch(lq, a.dtype, st))) return rc;
+    }
     if ((rc = wide_prep_launch(cfg, w, (WidePrep *)ws.prep, st))) return rc;
     g_last_path = 1;
     WideFwdArgs fa;
@@ -353,6 +364,8 @@ int egt_block_fwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
     fa.rand_thr = (uint32_t)ceilf(a.random_mask_prob * 65536.0f - 0.5f);
     fa.seed = a.seed; fa.offset = a.offset;
     if ((rc = wide_fwd_launch(cfg, fa, io->e, io->e_out, io->qkv, st))) return rc;
+    if (node_tc) return node_out_launch(io->v_att, io->h, w->dense_mha_kernel, w->dense_mha_bias, io->h_out, R, st);
+    if (ws.nblas) return node_blas_out(io->v_att, io->h, w, io->h_out, R, d, ws.nblas, st);
     LinearArgs lo;   // h' = V_att W_O + b_O + h  (graph_xformer_model_base.py:136-140)
     memset(&lo, 0, sizeof(lo));
     lo.x = io->v_att; lo.W = w->dense_mha_kernel; lo.bias = w->dense_mha_bias; lo.res = io->h; lo.out = io->h_out;
@@ -437,15 +450,23 @@ int egt_block_bwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
   const bool wide_bwd = wide && have_de && wide_bwd_supported(cfg);
   g_last_path = (fused_bwd || wide_bwd) ? 1 : 0;
 
-  if (wide_bwd) {   // width-generic fused backward (wide_bwd.cu); node side on the staged kernels
-    LinearArgs l1;  // dV_att = dh' W_O^T ; dW_O += V_att^T dh' ; db_O += colsum(dh')
-    memset(&l1, 0, sizeof(l1));
-    l1.x = io->dh_out; l1.W = w->dense_mha_kernel; l1.trans = 1; l1.out = ws.d_v_att; l1.R = R; l1.din = d; l1.dout = d;
-    if ((rc = linear_launch(l1, a.dtype, st))) return rc;
-    XtyArgs x1;
-    memset(&x1, 0, sizeof(x1));
-    x1.X = io->v_att; x1.Y = io->dh_out; x1.dW = g->dense_mha_kernel; x1.db = g->dense_mha_bias; x1.R = R; x1.dx = d; x1.dy = d;
-    if ((rc = xty_launch(x1, a.dtype, st))) return rc;
+  if (wide_bwd) {   // width-generic fused backward (wide_bwd.cu); node side on node_tc.cu (d = 64) or the staged kernels
+    const bool node_tc = d == 64 && a.h == 8;
+    if (node_tc) {
+      if ((rc = node_bwd1_launch(io->dh_out, io->v_att, w->dense_mha_kernel, ws.d_v_att, g->dense_mha_kernel,
+                                 g->dense_mha_bias, R, w, a.clip_lo, a.clip_hi, nullptr, st))) return rc;
+    } else if (ws.nblas) {
+      if ((rc = node_blas_bwd1(io->dh_out, io->v_att, w, g, ws.d_v_att, R, d, ws.nblas, st))) return rc;
+    } else {
+      LinearArgs l1;  // dV_att = dh' W_O^T ; dW_O += V_att^T dh' ; db_O += colsum(dh')
+      memset(&l1, 0, sizeof(l1));
+      l1.x = io->dh_out; l1.W = w->dense_mha_kernel; l1.trans = 1; l1.out = ws.d_v_att; l1.R = R; l1.din = d; l1.dout = d;
+      if ((rc = linear_launch(l1, a.dtype, st))) return rc;
+      XtyArgs x1;
+      memset(&x1, 0, sizeof(x1));
+      x1.X = io->v_att; x1.Y = io->dh_out; x1.dW = g->dense_mha_kernel; x1.db = g->dense_mha_bias; x1.R = R; x1.dx = d; x1.dy = d;
+      if ((rc = xty_launch(x1, a.dtype, st))) return rc;
+    }
     if ((rc = wide_prep_launch(cfg, w, (WidePrep *)ws.prep, st))) return rc;
     const int tiles = (a.N + 127) / 128;
     if (tiles > 1) EGT_CHECK_CUDA(cudaMemsetAsync(ws.d_qkv_f32, 0, (size_t)R * 3 * d * sizeof(float), st));
@@ -461,7 +482,19 @@ int egt_block_bwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
     fb.seed = a.seed; fb.offset = a.offset;
     if ((rc = wide_bwd_launch(cfg, fb, io->e, io->de_out, io->de, io->qkv, st))) return rc;
     if ((rc = wide_bwd_finalize_launch(cfg, ws.partials, w, g, (const WidePrep *)ws.prep, st))) return rc;
+    if (node_tc)
+      return node_bwd2_launch(io->h, io->dh_out, ws.d_qkv_f32, w->norm_mha_gamma, w->norm_mha_beta, cfg->ln_eps,
+                              w->dense_qkv_kernel, io->dh, g->dense_qkv_kernel, g->dense_qkv_bias, g->norm_mha_gamma,
+                              g->norm_mha_beta, R, nullptr, 0, w, g, st);
     // node side: hn = LN(h); dW_qkv += hn^T dqkv; dhn = dqkv W_qkv^T; dh = LN_bwd(dhn) + dh'
+    if (ws.nblas) {
+      if ((rc = node_blas_bwd2(io->h, ws.d_qkv_f32, w, g, cfg->ln_eps, ws.dhn, R, d, ws.nblas, st))) return rc;
+      LnBwdArgs lb;
+      memset(&lb, 0, sizeof(lb));
+      lb.x = io->h; lb.dy = ws.dhn; lb.dres = io->dh_out; lb.gamma = w->norm_mha_gamma; lb.eps = cfg->ln_eps;
+      lb.dx = io->dh; lb.dgamma = g->norm_mha_gamma; lb.dbeta = g->norm_mha_beta; lb.R = R; lb.D = d;
+      return ln_bwd_launch(lb, a.dtype, st);
+    }
     LinearArgs l2;
     memset(&l2, 0, sizeof(l2));
     l2.x = io->h; l2.ln_gamma = w->norm_mha_gamma; l2.ln_beta = w->norm_mha_beta; l2.ln_eps = cfg->ln_eps;

@@ -147,40 +147,32 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     const uint32_t loWeg = desc_lo(sbase + SM_W, 512), loWhx = desc_lo(sbase + SM_W + 1024, 256);
     const uint32_t loWde = desc_lo(sbase + SM_W + 1536, 256);
     const uint32_t bar_e0 = smem_u32(&bars->e_full[0]), bar_m1 = smem_u32(&bars->mma1[0]), bar_m2 = smem_u32(&bars->mma2[0]);
+    // tcgen05.mma is issued warp-collectively by warp 8 (umma.cuh): converged warp, one elected lane, k-chains in one
+    // asm statement.  TMA stays with lane 0.
     auto issue_mma1 = [&](int p) {                     // -> input buffer p & 1 (no commit: see the handshake below)
       const int T = p >> 2, j = p & 3, st = T % NS, slot = p & 3, buf = p & 1;
       mbar_wait(bar_e0 + 8 * st, (T / NS) & 1);
       tc_fence_after();
       const uint32_t d = tmem + TM_IN + buf * TM_IN_COLS;
       const uint32_t k0 = loK + slot * 256, v0 = loV + slot * 256, e0 = st * (STAGE_BYTES / 16) + 2 * j;
-#pragma unroll
-      for (int s = 0; s < 4; ++s)
-        mma_ss(d + IN_S, mkdesc(loQ + 2 * s, HI_SW), mkdesc(k0 + 2 * s, HI_SW), ID_N16, s > 0);
-#pragma unroll
-      for (int s = 0; s < 4; ++s)
-        mma_ss(d + IN_DA, mkdesc(loDO + 2 * s, HI_SW), mkdesc(v0 + 2 * s, HI_SW), ID_N16, s > 0);
-      mma_ss(d + IN_EG, mkdesc(loE + e0, HI_SW), mkdesc(loWeg, HI_NONE), ID_N32, 0);
-      mma_ss(d + IN_HX, mkdesc(loDE + e0, HI_SW), mkdesc(loWhx, HI_NONE), ID_N16, 0);
+      MmaChain<4>::ss(d + IN_S, loQ, HI_SW, k0, HI_SW, ID_N16, 0, 2, 2);
+      MmaChain<4>::ss(d + IN_DA, loDO, HI_SW, v0, HI_SW, ID_N16, 0, 2, 2);
+      MmaChain<1>::ss(d + IN_EG, loE + e0, HI_SW, loWeg, HI_NONE, ID_N32, 0, 0, 0);
+      MmaChain<1>::ss(d + IN_HX, loDE + e0, HI_SW, loWhx, HI_NONE, ID_N16, 0, 0, 0);
     };
     auto issue_mma2 = [&](int p) {                     // dQ += dS Kexp ; d x^ = [dE|dG] W'^T   (operands / result: parity p & 1)
       const int ob = p & 1, slot = p & 3;
       const uint32_t ao = tmem + TM_OUT + ob * TM_OUT_COLS;
-      mma_ts(tmem + TM_DQ, ao, mkdesc(loKmn + slot * 256, HI_SW), ID_DQ, p > 0);
-      const uint32_t dd = tmem + TM_DX + ob * TM_DX_COLS;
-      mma_ts(dd, ao + 8, mkdesc(loWde, HI_NONE), ID_N16, 0);
-      mma_ts(dd, ao + 16, mkdesc(loWde + 32, HI_NONE), ID_N16, 1);
+      MmaChain<1>::ts(tmem + TM_DQ, ao, loKmn + slot * 256, HI_SW, ID_DQ, p > 0, 0, 0);
+      MmaChain<2>::ts(tmem + TM_DX + ob * TM_DX_COLS, ao + 8, loWde, HI_NONE, ID_N16, 0, 8, 32);
     };
     auto issue_t = [&](int p) {
       if ((p & 7) == 7 || p == NP - 1) {                // a 16-key block of dS^T / A~^T is complete
         const uint32_t loT = desc_lo(sbase + SM_TR, 16384), loQm = desc_lo(sbase + SM_Q, 16384);
         const uint32_t loDOm = desc_lo(sbase + SM_DO, 16384);
-#pragma unroll
-        for (int s = 0; s < 8; ++s)
-          mma_ss(tmem + TM_DK, mkdesc(loT + 128 * s, HI_SW), mkdesc(loQm + 128 * s, HI_SW), ID_T, s > 0);
-#pragma unroll
-        for (int s = 0; s < 8; ++s)
-          mma_ss(tmem + TM_DV, mkdesc(loT + 2048 + 128 * s, HI_SW), mkdesc(loDOm + 128 * s, HI_SW), ID_T, s > 0);
-        mma_commit(smem_u32(&bars->tbar));
+        MmaChain<8>::ss(tmem + TM_DK, loT, HI_SW, loQm, HI_SW, ID_T, 0, 128, 128);
+        MmaChain<8>::ss(tmem + TM_DV, loT + 2048, HI_SW, loDOm, HI_SW, ID_T, 0, 128, 128);
+        mma_commit_w(smem_u32(&bars->tbar));
       }
     };
     if (leader) {
@@ -189,25 +181,25 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
       for (int T = 0; T < NT && T < NS; ++T) load_tile(T);
     }
     __syncthreads();                                   // sync #0: dO tile, Kexp/Vexp of pairs 0,1 are built
-    if (leader) {
+    if (warp == 8) {
       tc_fence_after();
       mbar_wait(smem_u32(&bars->q_full), 0);
       issue_mma1(0);
-      mma_commit(bar_m1);
-      if (NP > 1) { issue_mma1(1); mma_commit(bar_m1 + 8); }
+      mma_commit_w(bar_m1);
+      if (NP > 1) { issue_mma1(1); mma_commit_w(bar_m1 + 8); }
     }
     const uint32_t bar_step = smem_u32(&bars->step[0]);
     int next_store = 0;                                // tiles [0, next_store) have been handed to the TMA store
     for (int it = 0; it < NP && warp == 8; ++it) {     // warps 9-11 go straight to the tail barrier
-      if (leader) {
-        mbar_wait(bar_step + 8 * (it & 1), (it >> 1) & 1);   // main and helper threads finished pair it (no CTA-wide barrier)
-        tc_fence_after();
-        fence_proxy_async_smem();
-        issue_mma2(it);
-        if (it + 2 < NP) issue_mma1(it + 2);
-        mma_commit(bar_m2 + 8 * (it & 1));             // ONE completion per handshake: products of pair it and the
+      mbar_wait(bar_step + 8 * (it & 1), (it >> 1) & 1);   // main and helper threads finished pair it (no CTA-wide barrier)
+      tc_fence_after();
+      fence_proxy_async_smem();
+      issue_mma2(it);
+      if (it + 2 < NP) issue_mma1(it + 2);
+      mma_commit_w(bar_m2 + 8 * (it & 1));             // ONE completion per handshake: products of pair it and the
                                                        // inputs of pair it+2, both consumed during pair it+2
-        issue_t(it);                                   // (the 16-key transposed products have their own barrier)
+      issue_t(it);                                     // (the 16-key transposed products have their own barrier)
+      if (lane == 0) {
         // pair it contained the de update of pair it-2; tile T (pairs 4T .. 4T+3) is complete when it == 4T+5
         if (it >= 6 && ((it - 6) & 3) == 0) {          // tile stored at the previous handshake: recycle its stage
           const int T = (it - 6) >> 2;

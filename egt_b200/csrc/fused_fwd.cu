@@ -142,14 +142,14 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     const uint32_t loQ = desc_lo(sbase + SM_Q, 16), loK = desc_lo(sbase + SM_KVX, 16);
     const uint32_t loV = desc_lo(sbase + SM_KVX + 2048, 2048), loE = desc_lo(sbase + SM_STAGE + ST_E, 16);
     const uint32_t loWeg = desc_lo(sbase + SM_W, 512), loWr = desc_lo(sbase + SM_W + 1024, 256);
+    // tcgen05.mma is issued warp-collectively by warp 16 (umma.cuh: converged warp, one elected lane, k-chains in one
+    // asm statement): issuing from inside `if (lane == 0)` costs > 100 cycles per instruction and was most of the
+    // ~1700-cycle handshake measured in round 1.  TMA stays with lane 0.
     auto issue_mma1_pair = [&](int p, int st, int buf) {
       const int j = p & 3, slot = p & 7;
       const uint32_t d = tmem + TM_IN + buf * TM_IN_COLS + (p & 1) * TM_PAIR;
-      const uint32_t k0 = loK + slot * 256;            // 4096 B per slot
-#pragma unroll
-      for (int s = 0; s < 4; ++s)
-        mma_ss(d + IN_S, mkdesc(loQ + 2 * s, HI_SW), mkdesc(k0 + 2 * s, HI_SW), ID_N16, s > 0);
-      mma_ss(d + IN_EG, mkdesc(loE + st * (STAGE_BYTES / 16) + 2 * j, HI_SW), mkdesc(loWeg, HI_NONE), ID_N32, 0);
+      MmaChain<4>::ss(d + IN_S, loQ, HI_SW, loK + slot * 256, HI_SW, ID_N16, 0, 2, 2);   // 4096 B per slot
+      MmaChain<1>::ss(d + IN_EG, loE + st * (STAGE_BYTES / 16) + 2 * j, HI_SW, loWeg, HI_NONE, ID_N32, 0, 0, 0);
     };
     const uint32_t bar_e0 = smem_u32(&bars->e_full[0]), bar_m1 = smem_u32(&bars->mma1[0]), bar_m2 = smem_u32(&bars->mma2[0]);
     auto issue_mma1 = [&](int q) {                     // both pairs of step q -> input buffer q & 1
@@ -165,8 +165,8 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
       for (int kq = 0; kq < 2; ++kq) {
         const int p = 2 * q + kq;
         const uint32_t ao = tmem + TM_OUT + ob * TM_OUT_COLS + kq * TM_OPAIR;
-        mma_ts(tmem + TM_O, ao, mkdesc(loV + (p & 7) * 256, HI_SW), ID_PV, p > 0);
-        mma_ts(tmem + TM_DE + ob * TM_DE_COLS + kq * 16, ao + 8, mkdesc(loWr, HI_NONE), ID_N16, 0);
+        MmaChain<1>::ts(tmem + TM_O, ao, loV + (p & 7) * 256, HI_SW, ID_PV, p > 0, 0, 0);
+        MmaChain<1>::ts(tmem + TM_DE + ob * TM_DE_COLS + kq * 16, ao + 8, loWr, HI_NONE, ID_N16, 0, 0, 0);
       }
     };
     if (leader) {
@@ -175,24 +175,24 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
       for (int T = 0; T < NT && T < NS; ++T) load_tile(T);
     }
     __syncthreads();                                   // sync #0: Kexp/Vexp of steps 0, 1 are built
-    if (leader) {
+    if (warp == 16) {
       tc_fence_after();
       mbar_wait(smem_u32(&bars->q_full), 0);
       issue_mma1(0);
-      mma_commit(bar_m1);                              // S / EG of step 0
-      if (NQ > 1) { issue_mma1(1); mma_commit(bar_m1 + 8); }
+      mma_commit_w(bar_m1);                            // S / EG of step 0
+      if (NQ > 1) { issue_mma1(1); mma_commit_w(bar_m1 + 8); }
     }
     const uint32_t bar_step = smem_u32(&bars->step[0]);
     int next_store = 0;                                // tiles [0, next_store) have been handed to the TMA store
     for (int it = 0; it < NQ && warp == 16; ++it) {    // warps 17-19 go straight to the tail barrier
-      if (leader) {
-        mbar_wait(bar_step + 8 * (it & 1), (it >> 1) & 1);   // all compute threads finished step it
-        tc_fence_after();
-        fence_proxy_async_smem();                      // the compute threads' shared-memory writes of step it
-        issue_mma2(it);                                //  (ordered before this point by the mbarrier) -> async proxy
-        if (it + 2 < NQ) issue_mma1(it + 2);
-        mma_commit(bar_m2 + 8 * (it & 1));             // ONE completion per handshake: products of step it and
+      mbar_wait(bar_step + 8 * (it & 1), (it >> 1) & 1);   // all compute threads finished step it
+      tc_fence_after();
+      fence_proxy_async_smem();                        // the compute threads' shared-memory writes of step it
+      issue_mma2(it);                                  //  (ordered before this point by the mbarrier) -> async proxy
+      if (it + 2 < NQ) issue_mma1(it + 2);
+      mma_commit_w(bar_m2 + 8 * (it & 1));             // ONE completion per handshake: products of step it and
                                                        // S / EG of step it+2, both consumed during step it+2
+      if (lane == 0) {
         // step it contained the e' update of step it-2; tile T (steps 2T, 2T+1) is complete when it == 2T+3
         if (it >= 4 && (it & 1) == 0) {                // tile stored at the previous handshake: recycle its stage
           const int T = (it - 4) >> 1;
@@ -219,14 +219,11 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     __syncthreads();                                   // partial row sums exchanged
     if (a.w_o) {
       __syncthreads();                                 // V_att tile staged (over the Q tile)
-      if (leader) {
+      if (warp == 16) {
         tc_fence_after();
         constexpr uint32_t ID_OP = idesc_bf16(128, 64, 0, 1);
-        const uint32_t loA = desc_lo(sbase + SM_Q, 16), loB = desc_lo(sbase + SM_WO, 8192);
-#pragma unroll
-        for (int s = 0; s < 4; ++s)
-          mma_ss(tmem + TM_IN, mkdesc(loA + 2 * s, HI_SW), mkdesc(loB + 128 * s, HI_SW), ID_OP, s > 0);
-        mma_commit(smem_u32(&bars->oproj));
+        MmaChain<4>::ss(tmem + TM_IN, desc_lo(sbase + SM_Q, 16), HI_SW, desc_lo(sbase + SM_WO, 8192), HI_SW, ID_OP, 0, 2, 128);
+        mma_commit_w(smem_u32(&bars->oproj));
       }
       __syncwarp();
     }

@@ -425,6 +425,41 @@ template <> struct MmaChain<8> {
   }
 };
 
+
+// 8-step chain whose k-steps >= nsteps are predicated off (contraction over the query rows of a partly filled tile)
+__device__ __forceinline__ void mma_chain8_n(uint32_t d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc,
+                                             uint32_t acc, uint32_t astep, uint32_t bstep, uint32_t nsteps) {
+  asm volatile(
+      "{\n\t.reg .pred pe, pa, pt, pk;\n\t.reg .b32 al, bl;\n\t.reg .b64 da, db;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %6, 0;\n\tsetp.eq.b32 pt, %6, %6;\n\t"
+      "mov.b32 al, %1;\n\tmov.b32 bl, %3;\n\t"
+      "mov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pa;\n\t"
+      "add.u32 al, al, %7;\n\tadd.u32 bl, bl, %8;\n\tmov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "setp.gt.u32 pk, %9, 1;\n\tand.pred pk, pk, pe;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n\t"
+      "add.u32 al, al, %7;\n\tadd.u32 bl, bl, %8;\n\tmov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "setp.gt.u32 pk, %9, 2;\n\tand.pred pk, pk, pe;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n\t"
+      "add.u32 al, al, %7;\n\tadd.u32 bl, bl, %8;\n\tmov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "setp.gt.u32 pk, %9, 3;\n\tand.pred pk, pk, pe;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n\t"
+      "add.u32 al, al, %7;\n\tadd.u32 bl, bl, %8;\n\tmov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "setp.gt.u32 pk, %9, 4;\n\tand.pred pk, pk, pe;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n\t"
+      "add.u32 al, al, %7;\n\tadd.u32 bl, bl, %8;\n\tmov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "setp.gt.u32 pk, %9, 5;\n\tand.pred pk, pk, pe;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n\t"
+      "add.u32 al, al, %7;\n\tadd.u32 bl, bl, %8;\n\tmov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "setp.gt.u32 pk, %9, 6;\n\tand.pred pk, pk, pe;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n\t"
+      "add.u32 al, al, %7;\n\tadd.u32 bl, bl, %8;\n\tmov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "setp.gt.u32 pk, %9, 7;\n\tand.pred pk, pk, pe;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n\t"
+      "}"
+      ::"r"(d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(acc), "r"(astep), "r"(bstep), "r"(nsteps) : "memory");
+}
+
 // All tcgen05.mma issued so far by this thread arrive (once) on `bar` when they complete.
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");

@@ -191,6 +191,12 @@ wide_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
           else if (ks == 1) MmaChain<1>::ss(dcol, loA + at * 1024, HI_SW, loB + at * 128, HI_SW, ID_N16, at > 0, 2, 2);
         }
       };
+      // contraction over the query rows of the tile: rows >= N are zero in every operand, so ceil(rows / 16) k-steps do
+      const int rows_here = N - l0 < 128 ? N - l0 : 128, KR = (rows_here + 15) >> 4;
+      auto chain_rows = [&](uint32_t dcol, uint32_t loA, uint32_t hiA, uint32_t loB, uint32_t hiB, uint32_t idesc, uint32_t acc,
+                            uint32_t astep, uint32_t bstep) {
+        mma_chain8_n(dcol, loA, hiA, loB, hiB, idesc, acc, astep, bstep, (uint32_t)KR);
+      };
       auto issue_mma1 = [&](int q, int st, int kt, int kslot) {   // inputs of the group's next key
         const uint32_t tg = tmem + TM_G + q * GC;
         chain_d(tg + G_S, loQ, desc_lo(sbase + SM_KVX + (q * 3 + kslot) * KV_MAT, 16));
@@ -215,14 +221,14 @@ wide_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
         MmaChain<EGN / 16>::ts(tg + G_DX, tg + G_S, loWdx, HI_NONE, ID_DX, 1, 8, 2 * DEP);
         // dK^T, dV^T of this key: contraction over the 128 query rows
         const uint32_t img = sbase + SM_IMG + q * IMG_G;
-        MmaChain<8>::ss(tg + G_T, loQm, HI_SW, desc_lo(img + C::ZBYTES, 128), HI_TIMG, ID_T, 0, 128, 16);
-        MmaChain<8>::ss(tg + G_T + 16, loDOm, HI_SW, desc_lo(img + C::ZBYTES + 4096, 128), HI_TIMG, ID_T, 0, 128, 16);
+        chain_rows(tg + G_T, loQm, HI_SW, desc_lo(img + C::ZBYTES, 128), HI_TIMG, ID_T, 0, 128, 16);
+        chain_rows(tg + G_T + 16, loDOm, HI_SW, desc_lo(img + C::ZBYTES + 4096, 128), HI_TIMG, ID_T, 0, 128, 16);
         // weight-gradient accumulators (all keys, both groups)
         const uint32_t loZ = desc_lo(img, C::ZNONE ? 128u : IMG_G);          // rows beyond the image's: whatever follows it (finite)
         constexpr uint32_t HI_Z = C::ZNONE ? HI_TIMG : HI_SW, ZSTEP = C::ZNONE ? 16u : 128u;
         const uint32_t wcol = DE >= 16 ? 0u : (uint32_t)(kt & 1) * DEP;       // d_e = 8: even / odd keys accumulate apart
-        MmaChain<8>::ss(tmem + TM_W1 + wcol, loZ, HI_Z, desc_lo(win(st, kt, ST_E), 16384), HI_SW, ID_W, first_w ? 0u : 1u, ZSTEP, 128);
-        MmaChain<8>::ss(tmem + TM_W2 + wcol, loZ, HI_Z, desc_lo(win(st, kt, ST_DE), 16384), HI_SW, ID_W, first_w ? 0u : 1u, ZSTEP, 128);
+        chain_rows(tmem + TM_W1 + wcol, loZ, HI_Z, desc_lo(win(st, kt, ST_E), 16384), HI_SW, ID_W, first_w ? 0u : 1u, ZSTEP, 128);
+        chain_rows(tmem + TM_W2 + wcol, loZ, HI_Z, desc_lo(win(st, kt, ST_DE), 16384), HI_SW, ID_W, first_w ? 0u : 1u, ZSTEP, 128);
       };
       tc_fence_after();
       mbar_wait(smem_u32(&bars->q_full), 0);
@@ -603,6 +609,22 @@ wide_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
   __syncthreads();                                       // sync C
 }
 
+// Column sums of the per-CTA partial rows: one thread per column, every CTA of the grid a slice of the columns.
+__global__ void __launch_bounds__(128) wide_bwd_colsum_kernel(const float *partials, int nparts, int PART, float *sums) {
+  const int col = blockIdx.x * 128 + threadIdx.x;
+  if (col >= PART) return;
+  const int per = (nparts + gridDim.y - 1) / gridDim.y, i0 = blockIdx.y * per, i1 = min(nparts, i0 + per);
+  float acc[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) acc[u] = 0.f;
+  int i = i0;
+  for (; i + 8 <= i1; i += 8)
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc[u] += partials[(size_t)(i + u) * PART + col];
+  for (; i < i1; ++i) acc[0] += partials[(size_t)i * PART + col];
+  atomicAdd(sums + col, ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7])));
+}
+
 // Folds the per-CTA partial sums into the weight gradients (the library ADDS into them), see fused_prep.cuh.
 //   partial row layout: Mraw[j][c] (j = column of [E|G] in the order (hh/8, eg, hh%8)) | Wr[hh][c] | dbr[c] | sZ[(eg, hh)]
 //   sum x^_c dZ_j = Mraw[j][c] - mean_c' Mraw[j][c']        (x^ = r e - r mu, and sum_c' e_c' / d_e = mu)
@@ -688,7 +710,7 @@ bool wide_bwd_supported(const egt_block_cfg_t *cfg) {
 
 size_t wide_bwd_partials_floats(const egt_block_cfg_t *cfg) {
   const size_t H = cfg->attn.h, DE = cfg->d_e, EGN = 2 * H;
-  return (size_t)cfg->attn.B * ((cfg->attn.N + 127) / 128) * (EGN * DE + H * DE + DE + EGN);
+  return ((size_t)cfg->attn.B * ((cfg->attn.N + 127) / 128) + 1) * (EGN * DE + H * DE + DE + EGN);   // + the row of column sums
 }
 
 int wide_bwd_launch(const egt_block_cfg_t *cfg, const WideBwdArgs &a, const void *e, const void *de_out, void *de,
@@ -704,9 +726,14 @@ int wide_bwd_finalize_launch(const egt_block_cfg_t *cfg, const float *partials, 
                              const egt_block_grads_t *g, const WidePrep *, cudaStream_t st) {
   const int H = cfg->attn.h, DE = cfg->d_e, EGN = 2 * H;
   const int nparts = cfg->attn.B * ((cfg->attn.N + 127) / 128);
-  const size_t smem = (size_t)(EGN * DE + H * DE + DE + EGN + EGN) * sizeof(float);
+  const int PART = EGN * DE + H * DE + DE + EGN;
+  const size_t smem = (size_t)(PART + EGN) * sizeof(float);
+  float *sums = const_cast<float *>(partials) + (size_t)nparts * PART;
   LaunchScope _ls("wide_bwd_finalize_kernel", st);
-  wide_bwd_finalize_kernel<<<1, 256, smem, st>>>(partials, nparts, H, DE, *w, *g);
+  EGT_CHECK_CUDA(cudaMemsetAsync(sums, 0, (size_t)PART * sizeof(float), st));
+  const int ysplit = nparts >= 64 ? 16 : nparts >= 8 ? 4 : 1;
+  wide_bwd_colsum_kernel<<<dim3((PART + 127) / 128, ysplit), 128, 0, st>>>(partials, nparts, PART, sums);
+  wide_bwd_finalize_kernel<<<1, 256, smem, st>>>(sums, 1, H, DE, *w, *g);
   EGT_CHECK_CUDA(cudaGetLastError());
   return EGT_OK;
 }
