@@ -32,6 +32,11 @@ WORKLOADS = {
     'S64':   dict(N=64, d=64, d_e=8, h=8, B=128, note='sweep N=64'),
     'S256':  dict(N=256, d=64, d_e=8, h=8, B=128, note='sweep N=256'),
     'S512':  dict(N=512, d=64, d_e=8, h=8, B=64, note='sweep N=512'),
+    # the N sweep at the widths of BASELINE config 5 (d=128, d_e=32, h=16), B/GPU = 64
+    'W64':   dict(N=64, d=128, d_e=32, h=16, B=64, note='sweep N=64 at C5 widths'),
+    'W128':  dict(N=128, d=128, d_e=32, h=16, B=64, note='sweep N=128 at C5 widths'),
+    'W256':  dict(N=256, d=128, d_e=32, h=16, B=64, note='sweep N=256 at C5 widths'),
+    'C1s':   dict(N=37, d=48, d_e=48, h=8, B=128, note='ZINC 100K widths (dk=6): staged kernels'),
 }
 METRIC = 'EGT-layer fwd+bwd graphs/sec'
 
@@ -174,19 +179,45 @@ def run_ours(args, w):
         mm = torch.ones(B, N, dtype=torch.bool).pin_memory()
         host.append((hh, ee, mm))
     devs = [tuple(t.to(dev) for t in s) for s in host]
-    dh = torch.randn(B, N, d, generator=g).bfloat16().to(dev)
-    de = torch.randn(B, N, N, d_e, generator=g).bfloat16().to(dev)
+    # upstream gradients rotate with the input sets (a single buffer would stay warm in the 126 MB L2)
+    ups = [(torch.randn(B, N, d, generator=g).bfloat16().to(dev), torch.randn(B, N, N, d_e, generator=g).bfloat16().to(dev))
+           for _ in range(nsets)]
     grad_host = torch.empty(blk.flat.numel(), dtype=torch.float32).pin_memory()
 
-    def step(i, inputs=None):
+    def step(i, inputs=None, block=None):
+        block = block or blk
         hh, ee, mm = inputs if inputs is not None else devs[i % nsets]
+        dh, de = ups[i % nsets]
         hh = hh.detach().requires_grad_(True)
         ee = ee.detach().requires_grad_(True)
-        blk.flat.grad = None
-        h2, e2 = blk(hh, ee, mm)
+        block.flat.grad = None
+        h2, e2 = block(hh, ee, mm)
         torch.autograd.backward([h2, e2], [dh, de])
-        egt_b200.allreduce_flat_grads([blk])
+        egt_b200.allreduce_flat_grads([block])
         return hh.grad, ee.grad
+
+    # ---- self-check of the gradient all-reduce (N > 1): the peer-memory kernel against NCCL on the same buffer ----
+    allreduce_check = None
+    if world > 1:
+        step(0)
+        mine = blk.flat.grad.clone()                   # already summed over ranks by the step
+        blk.flat.grad = None
+        hh, ee, mm = devs[0]
+        hh = hh.detach().requires_grad_(True); ee = ee.detach().requires_grad_(True)
+        h2, e2 = blk(hh, ee, mm)
+        torch.autograd.backward([h2, e2], list(ups[0]))
+        ref = blk.flat.grad.clone()                    # this rank's gradient, not reduced
+        dist.all_reduce(ref, op=dist.ReduceOp.SUM)
+        err = float((mine - ref).abs().max())
+        scale = float(ref.abs().max())
+        ok = err <= 1e-3 * max(scale, 1e-6)            # weight gradients accumulate with atomics: summation order differs
+        flag = torch.tensor([0 if ok else 1], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        allreduce_check = dict(max_abs_err=err, max_abs_ref=scale, ok=bool(flag.item() == 0), ranks=world)
+        if not allreduce_check['ok']:
+            if rank == 0:
+                print(json.dumps(dict(error='gradient all-reduce mismatch', allreduce_check=allreduce_check)), flush=True)
+            os._exit(3)
 
     def timed(fn, steps):
         if world > 1:
@@ -322,6 +353,22 @@ def run_ours(args, w):
         return float(t.item())
 
     ms_e2e = timed_e2e(args.steps)
+
+    # ---- the shipped training setting (every reference config: random_mask_prob = 0.1, training = True) ----
+    # timed with eager launches: the key mask's Philox offset is a launch argument, so a replayed CUDA graph would
+    # draw the same mask every step (egt_b200.ops refuses that capture)
+    train_line = None
+    if args.random_mask_prob == 0 and not args.no_train_line:
+        blk_t = egt_b200.EGTBlock(model_width=d, edge_width=d_e, num_heads=h, scale_degree=bool(args.scale_degree),
+                                  random_mask_prob=0.1, seed=2000 + rank).to(dev)
+        blk_t.train(True)
+        for i in range(3):
+            step(i, block=blk_t)
+        ms_eager = timed(lambda i: step(i), args.steps)
+        ms_train = timed(lambda i: step(i, block=blk_t), args.steps)
+        train_line = dict(random_mask_prob=0.1, training=True, cuda_graphs=False, ms_per_step=ms_train / args.steps,
+                          value=B * world * args.steps / (ms_train / 1e3), unit='graphs/s',
+                          eager_ms_per_step_without_mask=ms_eager / args.steps)
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -351,11 +398,12 @@ def run_ours(args, w):
     dom_avg_ms = dom[1][0] / max(1, dom[1][1])
     achieved = per_launch_bytes / (dom_avg_ms * 1e-3) / 1e9 if dom_avg_ms > 0 else 0.0
     step_bytes = B * alg_bytes_per_graph(N, d, d_e, h)
-    step_gbs = step_bytes * args.steps / (ms * 1e-3) / 1e9 / 1.0
+    step_gbs = step_bytes * args.steps / (ms * 1e-3) / 1e9          # per GPU: step_bytes are one rank's bytes
     traffic = None
     tp = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(dom_name)
+        tj = json.load(open(tp))
+        traffic = tj.get(f'{args.workload}:{dom_name}', tj.get(dom_name) if args.workload == 'C0' else None)
     cpu = cpu_reference_run(w, steps=1000, warmup=1, budget_s=args.cpu_budget) if world == 1 and not args.no_cpu else None
     line = dict(
         metric=METRIC, value=value, unit='graphs/s', n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
@@ -366,17 +414,21 @@ def run_ours(args, w):
                     scale_degree=bool(args.scale_degree),
                     l2=f'rotating {nsets} input sets per rank (working set > 126 MB L2)',
                     path='fused-tcgen05' if path == 1 else 'staged', cuda_graphs=bool(use_graphs),
-                    e2e='H2D of h,e,mask on a copy stream one step ahead (2 device buffer sets); D2H of the flat weight gradient + host sync every step'),
+                    e2e='one TRAINING step per iteration: H2D of h,e,mask on a copy stream one step ahead (2 device buffer sets); the result read back is the flat weight gradient (what an optimiser step consumes) + host sync every step'),
         roofline=dict(bound='hbm', kernel=dom_name, achieved=achieved, peak=peaks['hbm_gbs'], unit='GB/s',
                       frac=achieved / peaks['hbm_gbs'], traffic=traffic, peak_source=peaks['source'],
                       kernel_share_of_step=dom[1][0] / total_prof_ms,
-                      step_achieved=step_gbs, step_frac=step_gbs / world / peaks['hbm_gbs'],
+                      step_achieved=step_gbs, step_frac=step_gbs / peaks['hbm_gbs'],
                       kernels={k: dict(ms_total=v[0], launches=v[1]) for k, v in prof.items()}),
         e2e=dict(value=graphs / (ms_e2e / 1e3), unit='graphs/s',
                  h2d_bytes_per_step=sum(t.numel() * t.element_size() for t in host[0]),
                  d2h_bytes_per_step=grad_host.numel() * 4, ms_per_step=ms_e2e / args.steps),
         gpu_launches=int(launches), clocks=sampler.summary(),
     )
+    if train_line is not None:
+        line['training_step'] = train_line
+    if allreduce_check is not None:
+        line['allreduce_check'] = allreduce_check
     if cpu is not None:
         line['cpu_baseline'] = dict(value=cpu['value'], unit='graphs/s', cores=cpu['cores'], kind=cpu['kind'],
                                     sample=cpu['sample'])
@@ -397,6 +449,7 @@ def main():
     ap.add_argument('--cpu-budget', type=float, default=15.0)
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-graphs', action='store_true')
+    ap.add_argument('--no-train-line', action='store_true')
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == 'reference':

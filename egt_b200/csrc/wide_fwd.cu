@@ -58,9 +58,13 @@ wide_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
   static_assert(SM_TOTAL == C::FWD_SMEM, "host-side shared-memory size (wide_common.cuh) out of date");
   static_assert(NG * 128 * 2 * H * 4 <= SM_STAGE, "row-sum exchange must fit below the stages");
   // ---- tensor memory map (columns) ----
-  constexpr uint32_t TM_O = 0, TM_G = D, G_S = 0, G_EG = 16, G_AOP = 16 + C::EGN, G_EO = 32 + C::EGN;
-  constexpr uint32_t GC = 32 + C::EGN + C::DEP;
-  static_assert(D + NG * GC <= 512, "tensor memory budget");
+  // Q lives in tensor memory as the A operand of Q K^T (no shared-memory A read per key: a [128 x 16] shared-memory A
+  // tile is 4 KB per tcgen05.mma whatever N is, and with one S product per KEY that streaming was most of the kernel).
+  // A~ and H_hat are written over the S / EG columns the thread has just consumed; the issuer orders the product
+  // that reads them before the next key's S / EG by issue order.
+  constexpr uint32_t TM_O = 0, TM_Q = D, TM_G = D + D / 2, G_S = 0, G_EG = 16, G_A = 0, G_H = 16, G_EO = 16 + C::EGN;
+  constexpr uint32_t GC = 16 + C::EGN + C::DEP;
+  static_assert(TM_G + NG * GC <= 512, "tensor memory budget");
   struct Bars { uint64_t q_full, e_full[NS], tile_done[NS], ready[NG], done[NG]; uint32_t tmem_base; };
   static_assert(sizeof(Bars) <= 256, "barrier block");
 
@@ -152,12 +156,12 @@ wide_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
         const uint32_t tg = tmem + TM_G + q * GC;
         const uint32_t loK = desc_lo(sbase + SM_KVX + q * 3 * KV_MAT, 16);
 #pragma unroll
-        for (int at = 0; at < C::NQA; ++at) {              // k-steps over the channels: runs of <= 4 per 64-channel atom
+        for (int at = 0; at < C::NQA; ++at) {              // k-steps over the channels: runs of <= 4 per 64-channel atom of Kexp
           const int ks = C::DKS - 4 * at < 4 ? C::DKS - 4 * at : 4;
-          if (ks == 4) MmaChain<4>::ss(tg + G_S, loQ + at * 1024, HI_SW, loK + at * 128, HI_SW, ID_S, at > 0, 2, 2);
-          else if (ks == 3) MmaChain<3>::ss(tg + G_S, loQ + at * 1024, HI_SW, loK + at * 128, HI_SW, ID_S, at > 0, 2, 2);
-          else if (ks == 2) MmaChain<2>::ss(tg + G_S, loQ + at * 1024, HI_SW, loK + at * 128, HI_SW, ID_S, at > 0, 2, 2);
-          else if (ks == 1) MmaChain<1>::ss(tg + G_S, loQ + at * 1024, HI_SW, loK + at * 128, HI_SW, ID_S, at > 0, 2, 2);
+          if (ks == 4) MmaChain<4>::ts(tg + G_S, tmem + TM_Q + at * 32, loK + at * 128, HI_SW, ID_S, at > 0, 8, 2);
+          else if (ks == 3) MmaChain<3>::ts(tg + G_S, tmem + TM_Q + at * 32, loK + at * 128, HI_SW, ID_S, at > 0, 8, 2);
+          else if (ks == 2) MmaChain<2>::ts(tg + G_S, tmem + TM_Q + at * 32, loK + at * 128, HI_SW, ID_S, at > 0, 8, 2);
+          else if (ks == 1) MmaChain<1>::ts(tg + G_S, tmem + TM_Q + at * 32, loK + at * 128, HI_SW, ID_S, at > 0, 8, 2);
         }
         const uint32_t le = lo_e(st, kt);
         const uint32_t lw = loWeg + (DE >= 16 ? 0u : (uint32_t)(kt & 1) * (W_EG_SZ / 16));
@@ -168,13 +172,13 @@ wide_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
       auto issue_mma2 = [&](int q, int st, int kt, int vslot, bool first) {   // O += A~ Vexp ; e' = e I + H_hat W_r + b_r
         const uint32_t tg = tmem + TM_G + q * GC;
         const uint32_t loV = desc_lo(sbase + SM_KVX + (q * 3 + 1 + vslot) * KV_MAT, 2048);
-        MmaChain<1>::ts(tmem + TM_O, tg + G_AOP, loV, HI_SW, ID_PV, first ? 0u : 1u, 0, 0);
+        MmaChain<1>::ts(tmem + TM_O, tg + G_A, loV, HI_SW, ID_PV, first ? 0u : 1u, 0, 0);
         const uint32_t le = lo_e(st, kt);
         const uint32_t li = loI + (DE >= 16 ? 0u : (uint32_t)(kt & 1) * 32u);
 #pragma unroll
         for (int s = 0; s < C::DEP / 16; ++s)
           MmaChain<1>::ss(tg + G_EO + 16 * s, le + (DE >= 16 ? 2 * s : 0), HI_SW, li, HI_NONE, ID_S, 0, 0, 0);
-        MmaChain<1>::ts(tg + G_EO, tg + G_AOP + 8, loWr, HI_NONE, ID_EO, 1, 0, 0);
+        MmaChain<1>::ts(tg + G_EO, tg + G_H, loWr, HI_NONE, ID_EO, 1, 0, 0);
         MmaChain<1>::ss(tg + G_EO, loOnes, HI_NONE, loWb, HI_NONE, ID_EO, 1, 0, 0);
       };
       tc_fence_after();
@@ -328,8 +332,17 @@ wide_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
       uint32_t apack[4], hpack[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) { apack[i] = pack_bf16(av[2 * i], av[2 * i + 1]); hpack[i] = pack_bf16(hv[2 * i], hv[2 * i + 1]); }
-      tmem_st4(tg + G_AOP + 4 * half, apack);
-      tmem_st4(tg + G_AOP + 8 + 4 * half, hpack);
+      // operands over the consumed inputs: A~ half -> S columns 4*half.. (S half 0 is consumed in both cases), H_hat half
+      // -> EG columns 4*half.. (EG half 0 likewise); with h = 8 the upper half of the K = 16 operands is written as zeros
+      if (H == 8) {
+        const uint32_t a8[8] = {apack[0], apack[1], apack[2], apack[3], 0u, 0u, 0u, 0u};
+        const uint32_t h8[8] = {hpack[0], hpack[1], hpack[2], hpack[3], 0u, 0u, 0u, 0u};
+        tmem_st8(tg + G_A, a8);
+        tmem_st8(tg + G_H, h8);
+      } else {
+        tmem_st4(tg + G_A + 4 * half, apack);
+        tmem_st4(tg + G_H + 4 * half, hpack);
+      }
     }
   };
 
@@ -359,10 +372,17 @@ wide_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
   // ---- pipeline ----
   mbar_wait(bar_e0, 0);                                  // tile 0 (e, K rows, V rows) has landed
   build(0, q, 0);
-  if (H == 8) {   // the upper halves of the K = 16 A operands (A~, H_hat) are never written again: keep them zero
-    const uint32_t z[4] = {0u, 0u, 0u, 0u};
-    tmem_st4(tg + G_AOP + 4, z);
-    tmem_st4(tg + G_AOP + 12, z);
+  {   // Q tile: shared memory (TMA, 128B swizzle) -> tensor memory, packed bf16; this thread copies its share of row t
+    mbar_wait(smem_u32(&bars->q_full), 0);
+    constexpr int QCH = D / 8 / NG;                      // 16-byte chunks (8 channels) per thread
+    static_assert((D / 8) % NG == 0, "Q copy split");
+#pragma unroll
+    for (int c = 0; c < QCH; ++c) {
+      const uint32_t ch = (uint32_t)(q * QCH + c);
+      const uint4 v = *(const uint4 *)(smem + SM_Q + (ch >> 3) * 16384u + trow + (((ch & 7u) ^ tx7) << 4));
+      const uint32_t r4[4] = {v.x, v.y, v.z, v.w};
+      tmem_st4(tlane + TM_Q + 4 * ch, r4);
+    }
     tmem_st_wait();
   }
   fence_proxy_async_smem();

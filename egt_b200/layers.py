@@ -233,3 +233,70 @@ class EGTLayer(nn.Module):
         if self.ffn_edge is not None:
             e = self.ffn_edge(e)
         return h, e
+
+
+class EGTStack(nn.Module):
+    """``L`` EGT layers as the reference's layer loop chains them (graph_xformer_model_base.py:335-341:
+    ``for ii in range(model_height): h, e = edge_update(tag, h, e); h, e = ffn_block(tag, h, e)``) with EVERY weight
+    of every layer in ONE flat float32 parameter, so that data-parallel training is a single all-reduce on
+    ``self.flat.grad`` (``egt_b200.allreduce_flat_grads([stack])``; MirroredStrategy semantics,
+    lib/training/training_base.py:230-238).  Layer ``ii`` carries the reference's tag ``f'{ii:0>2d}'`` (weights load
+    by the reference's names); ``ffn=False`` builds the attention blocks only."""
+
+    def __init__(self, model_height, ffn=True, ffn_multiplier=2., activation='elu', seed=0, **block_kwargs):
+        super().__init__()
+        self.layers = nn.ModuleList()
+        for ii in range(model_height):
+            tag = f'{ii:0>2d}'
+            self.layers.append(EGTLayer(tag=tag, ffn_multiplier=ffn_multiplier, activation=activation, seed=seed + ii, **block_kwargs)
+                               if ffn else EGTBlock(tag=tag, seed=seed + ii, **block_kwargs))
+        # every module of every layer that owns a flat parameter, in execution order
+        self._owners = []
+        for layer in self.layers:
+            mods = [layer] if isinstance(layer, EGTBlock) else [layer.block, layer.ffn_node] + ([layer.ffn_edge] if layer.ffn_edge is not None else [])
+            self._owners.extend(mods)
+        self._spans, total = [], 0
+        for m in self._owners:
+            n = m.flat.numel()
+            self._spans.append((total, n))
+            total += (n + 3) // 4 * 4                    # 16-byte aligned slices (the kernels use vector accesses)
+        flat = torch.zeros(total, dtype=torch.float32)
+        for m, (off, n) in zip(self._owners, self._spans):
+            flat[off:off + n].copy_(m.flat.data)
+            del m._parameters['flat']                    # the module keeps working on a VIEW of the stack's parameter
+            m.flat = flat[off:off + n]
+        self.flat = nn.Parameter(flat)
+        self._bind()
+
+    def _bind(self):
+        """Re-create the per-module views (after ``.to(device)`` or before every forward: autograd must see them as
+        slices of the ONE parameter)."""
+        for m, (off, n) in zip(self._owners, self._spans):
+            m.flat = self.flat[off:off + n]
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._bind()
+        return out
+
+    def load_keras_weights(self, weights, strict=True):
+        with torch.no_grad():
+            self._bind()
+            for layer in self.layers:
+                layer.load_keras_weights(weights, strict)
+
+    def grad_view(self, index, field):
+        """Gradient of ``field`` of the ``index``-th flat-owning module (execution order), a view into ``self.flat.grad``."""
+        if self.flat.grad is None:
+            return None
+        m, (off, n) = self._owners[index], self._spans[index]
+        o, shape = m.layout[field]
+        return self.flat.grad[off + o:off + o + math.prod(shape)].view(shape)
+
+    def forward(self, h, e, mask=None, edge_mask=None, training=None):
+        self._bind()
+        if training is None:
+            training = self.training
+        for layer in self.layers:
+            h, e = layer(h, e, mask, edge_mask=edge_mask, training=training)
+        return h, e

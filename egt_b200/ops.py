@@ -31,6 +31,19 @@ def _need_cuda(*ts):
             raise RuntimeError('egt_b200 runs on CUDA tensors only (sm_100a); there is no CPU fallback')
 
 
+def _refuse_rng_capture(training, random_mask_prob, attn_dropout):
+    """The Philox (seed, offset) of the random key mask / attention dropout reach the kernels as launch ARGUMENTS.
+    A CUDA graph freezes its launch arguments, so every replay of a captured training step would draw the identical
+    mask -- silently different from the reference, which draws fresh noise per step (egt_layers.py:103-108,116-117).
+    Capture is therefore refused while that RNG is live; run such steps eagerly (bench.py does) or set
+    EGT_ALLOW_FROZEN_RNG=1 to accept a frozen mask (e.g. to time the kernels)."""
+    import os
+    if training and (random_mask_prob > 0 or attn_dropout > 0) and torch.cuda.is_current_stream_capturing() \
+            and os.environ.get('EGT_ALLOW_FROZEN_RNG', '0') != '1':
+        raise RuntimeError('egt_b200: refusing to capture a training step with random_mask_prob / attn_dropout > 0 into a '
+                           'CUDA graph: the RNG offset is a launch argument and every replay would reuse the same mask')
+
+
 def _mask_u8(mask, B, N):
     if mask is None:
         return None
@@ -144,6 +157,7 @@ def egt_attention(inputs, mask=None, training=False, *, spec: AttnSpec, seed=0, 
     M = inputs.pop(0) if spec.attn_mask else None
     B, N, _ = qkv.shape
     m8 = _mask_u8(mask, B, N)
+    _refuse_rng_capture(training, spec.random_mask_prob, spec.attn_dropout)
     out = _EGTAttnFn.apply(qkv, E, G, M, m8, spec, training, seed, offset, return_attn)
     if return_attn:
         return out
@@ -329,6 +343,7 @@ def egt_block(h, e, mask, flat, spec: BlockSpec, layout, edge_mask=None, trainin
             edge_mask = edge_mask[..., 0]
         adj = (edge_mask != 0).to(torch.uint8).contiguous()
     e_in = e if spec.has_edge else None
+    _refuse_rng_capture(training, spec.random_mask_prob, spec.attn_dropout)
     out = _EGTBlockFn.apply(h, e_in, flat, m8, adj, spec, layout, training, seed, offset)
     if spec.is_residual:
         return out

@@ -1,0 +1,52 @@
+"""EGTStack: the reference's layer loop (graph_xformer_model_base.py:335-341) with every weight of every layer in ONE
+flat parameter -- same numbers as the layers run one by one, and one gradient buffer for the all-reduce."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+@pytest.mark.parametrize('ffn', [False, True])
+def test_stack_equals_layers_and_has_one_gradient_buffer(ffn):
+    import egt_b200
+    torch.manual_seed(0)
+    B, N, d, de, nh, L = 3, 40, 64, 8, 8, 3
+    kw = dict(model_width=d, edge_width=de, num_heads=nh, scale_degree=True)
+    stack = egt_b200.EGTStack(L, ffn=ffn, **kw).to(DEV)
+    with torch.no_grad():
+        stack.flat.add_(0.02 * torch.randn_like(stack.flat))
+    singles = [(egt_b200.EGTLayer(tag=f'{i:0>2d}', **kw) if ffn else egt_b200.EGTBlock(tag=f'{i:0>2d}', **kw)).to(DEV) for i in range(L)]
+    # copy the stack's weights into stand-alone layers
+    k = 0
+    for sl in singles:
+        mods = [sl] if not ffn else [sl.block, sl.ffn_node, sl.ffn_edge]
+        for m in mods:
+            with torch.no_grad():
+                m.flat.copy_(stack._owners[k].flat)
+            k += 1
+    mask = (torch.arange(N)[None] < torch.tensor([40, 31, 7])[:, None]).to(DEV)
+    h = torch.randn(B, N, d, device=DEV).bfloat16()
+    e = torch.randn(B, N, N, de, device=DEV).bfloat16()
+    hs, es = h.clone().requires_grad_(True), e.clone().requires_grad_(True)
+    h2, e2 = stack(hs, es, mask)
+    hr, er = h.clone().requires_grad_(True), e.clone().requires_grad_(True)
+    x, y = hr, er
+    for sl in singles:
+        x, y = sl(x, y, mask)
+    assert torch.equal(h2, x) and torch.equal(e2, y)
+    dh, dE = torch.randn_like(h2), torch.randn_like(e2)
+    torch.autograd.backward([h2, e2], [dh, dE])
+    torch.autograd.backward([x, y], [dh, dE])
+    assert torch.equal(hs.grad, hr.grad) and torch.equal(es.grad, er.grad)
+    # ONE gradient buffer: every module's gradient is a slice of stack.flat.grad
+    assert stack.flat.grad is not None and sum(p.numel() for p in stack.parameters()) == stack.flat.numel()
+    k = 0
+    for sl in singles:
+        mods = [sl] if not ffn else [sl.block, sl.ffn_node, sl.ffn_edge]
+        for m in mods:
+            off, n = stack._spans[k]
+            ref = m.flat.grad
+            got = stack.flat.grad[off:off + n]
+            torch.testing.assert_close(got, ref, rtol=1e-3, atol=1e-3 * float(ref.abs().max()))   # atomics: summation order
+            k += 1
