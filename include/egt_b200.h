@@ -238,6 +238,13 @@ int egt_debug_umma_probe(int a_mode, int b_mode, int N, int ksteps, uint32_t a_l
                          uint32_t b_lbo, uint32_t b_sbo, const uint32_t *a_off_host, const uint32_t *b_off_host,
                          const void *A, const void *B, float *D, void *stream);
 
+/* Measurement hook behind DESIGN.md's cost model of small tcgen05.mma instructions (tools/mma_timing.py): issues
+ * `chains` k-chains of `ksteps` instructions (M = 128, K = 16, N as given; a_mode 0 = A from shared memory K-major,
+ * 1 = A from tensor memory, 2 = A from shared memory MN-major) rotating over `ndst` accumulators and writes
+ * {cycles from first issue to completion, cycles spent issuing} to cycles_host[2].  Allocates 16 bytes of device
+ * memory for the duration of the call (the only entry point that does). */
+int egt_debug_mma_timing(int a_mode, int N, int ksteps, int chains, int ndst, long long *cycles_host, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
