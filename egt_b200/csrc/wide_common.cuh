@@ -39,7 +39,7 @@ template <class G>
 struct WideFwdSmem {
   static constexpr int STAGE = (G::NBOX * 16384 + 2 * G::KV_ROWS + 1023) & ~1023;
   static constexpr int W = 2 * (2 * G::DEW * G::EGN * 2) + 2 * G::DEP * 32 + 1024;
-  static constexpr int TOTAL = G::NQA * 16384 + G::NG * 3 * G::NQA * 2048 + G::NS * STAGE + W + 4096 + 256 + 256 + 4096 + 64;
+  static constexpr int TOTAL = G::NQA * 16384 + G::NG * 3 * G::NQA * 2048 + G::NS * STAGE + W + 4096 + 256 + 256 + 4096 + 64 + 128 * G::H * 4;
 };
 
 struct WideFwdC5 : WideGeo<16, 8, 32, 4, 3> { static constexpr int FWD_SMEM = WideFwdSmem<WideGeo<16, 8, 32, 4, 3>>::TOTAL; };

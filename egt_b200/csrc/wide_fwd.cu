@@ -32,7 +32,12 @@ using namespace umma;
 
 namespace {
 
-template <class C, bool RAND>
+// MAXONLY: the row-maximum pre-pass of the softmax.  tf.nn.softmax (egt_layers.py:111) subtracts the row maximum; the
+// main pass instead exponentiates H_hat - ref with a reference that must be known BEFORE the key loop.  While the
+// data-independent bound of the logits (WidePrep::bound) is below the exponent budget, ref = 0 is exact in fp32 and
+// the pre-pass returns at once; above it, the pre-pass streams e once more (S and [E|G] products and the logit
+// arithmetic only -- no exp, no P V, no e' write) and leaves max_m H_hat[l, m, hh] over the live keys in lse[0].
+template <class C, bool RAND, bool MAXONLY>
 __global__ void __launch_bounds__(C::THREADS, 1)
 wide_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant__ CUtensorMap tm_eo,
                 const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
@@ -53,7 +58,8 @@ wide_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
   constexpr uint32_t SM_CONST = SM_ONES + 4096;                        // uE vE uG vG (4 x 16 floats)
   constexpr uint32_t SM_BAR = SM_CONST + 256;
   constexpr uint32_t SM_MASK = SM_BAR + 256;                           // key-valid bytes, zero padded
-  constexpr uint32_t SM_TOTAL = SM_MASK + 4096 + 64;
+  constexpr uint32_t SM_REF = SM_MASK + 4096 + 64;                     // -ref * log2(e) per (row, head), float32
+  constexpr uint32_t SM_TOTAL = SM_REF + 128 * H * 4;
   static_assert(SM_TOTAL + 1024 <= 232448, "shared memory budget");
   static_assert(SM_TOTAL == C::FWD_SMEM, "host-side shared-memory size (wide_common.cuh) out of date");
   static_assert(NG * 128 * 2 * H * 4 <= SM_STAGE, "row-sum exchange must fit below the stages");
@@ -76,6 +82,10 @@ wide_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
   const int b = blockIdx.y, l0 = blockIdx.x * 128;
   const int N = a.N;
   const int NT = (N + TK - 1) / TK, J = NT * KPG;        // tiles; keys per group (padded keys are masked)
+  if (MAXONLY) {
+    pdl_wait();
+    if (a.prep->bound <= kWideSoftmaxBudget) return;     // the whole grid agrees: nothing to do
+  }
 
   // ---------------------------------------- set-up ----------------------------------------
   if (warp == 4 * NG) {
@@ -194,7 +204,7 @@ wide_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
           mbar_wait(bar_done0 + 8 * q, j & 1);           // group q finished key j (its A~ / H_hat are in tensor memory)
           tc_fence_after();
           fence_proxy_async_smem();
-          issue_mma2(q, st, i * NG + q, j & 1, j == 0 && q == 0);
+          if (!MAXONLY) issue_mma2(q, st, i * NG + q, j & 1, j == 0 && q == 0);
           if (j + 1 < J) {
             if (i2 == 0 && q == 0) { mbar_wait(bar_e0 + 8 * st2, (T2 / NS) & 1); tc_fence_after(); }
             issue_mma1(q, st2, i2 * NG + q);
@@ -208,14 +218,16 @@ wide_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
       for (int T = 0; T < NT; ++T) {                     // store tile T when every group has written its e', refill the stage
         const int st = T % NS;
         mbar_wait(bar_td0 + 8 * st, (T / NS) & 1);
-        fence_proxy_async_smem();
+        if (!MAXONLY) {
+          fence_proxy_async_smem();
 #pragma unroll
-        for (int x = 0; x < C::NBOX; ++x)
-          tma_store_3d(&tm_eo, sbase + SM_STAGE + st * STAGE_BYTES + ST_E + x * 16384, T * TK * DE + 64 * x, l0, b);
-        tma_store_commit();
-        if (T + NS < NT) { tma_store_wait_read<0>(); load_tile(T + NS); }
+          for (int x = 0; x < C::NBOX; ++x)
+            tma_store_3d(&tm_eo, sbase + SM_STAGE + st * STAGE_BYTES + ST_E + x * 16384, T * TK * DE + 64 * x, l0, b);
+          tma_store_commit();
+        }
+        if (T + NS < NT) { if (!MAXONLY) tma_store_wait_read<0>(); load_tile(T + NS); }
       }
-      tma_store_wait_all<0>();
+      if (!MAXONLY) tma_store_wait_all<0>();
     }
     __syncwarp();
     __syncthreads();                                     // sync C: everything is stored
@@ -233,13 +245,14 @@ wide_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
   const float *cst = (const float *)(smem + SM_CONST);
   const uint8_t *smask = smem + SM_MASK;
   const float lo = a.clip_lo, hi = a.clip_hi, ln_eps = a.ln_eps;
-  const float sm_shift = fmaxf(a.prep->bound - kWideSoftmaxBudget, 0.f);   // exponent reference (see fused_fwd.cu)
-  const float nshift2 = -sm_shift * kLog2e;
+  // exponent reference of the softmax: 0 while the logits cannot overflow, else the row maximum of the pre-pass
+  const bool use_ref = !MAXONLY && a.prep->bound > kWideSoftmaxBudget;
+  float *sref = (float *)(smem + SM_REF) + t * H;
   const uint32_t trow = (uint32_t)t * 128u, tx7 = (uint32_t)(t & 7);
   const uint32_t bar_ready = bar_ready0 + 8 * q, bar_done = bar_done0 + 8 * q;
-  float psum[H], gsum[H];
+  float psum[H], gsum[H];                                // MAXONLY: psum holds the running maxima
 #pragma unroll
-  for (int i = 0; i < H; ++i) { psum[i] = 0.f; gsum[i] = 0.f; }
+  for (int i = 0; i < H; ++i) { psum[i] = MAXONLY ? -INFINITY : 0.f; gsum[i] = 0.f; }
 
   // expanded K / V operands of key kt of stage st: channel c = t of the key's row goes to row c % h of the 16 x d
   // operand, into the 16-byte chunk c / 8 at its own position c % 8; every other element of the operand stays zero
@@ -308,6 +321,11 @@ wide_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
         uG[4 * v4] = a2.x; uG[4 * v4 + 1] = a2.y; uG[4 * v4 + 2] = a2.z; uG[4 * v4 + 3] = a2.w;
         vG[4 * v4] = a3.x; vG[4 * v4 + 1] = a3.y; vG[4 * v4 + 2] = a3.z; vG[4 * v4 + 3] = a3.w;
       }
+      float nsh[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};             // -ref * log2(e) of this row's heads
+      if (use_ref) {
+        const float4 r0 = *(const float4 *)(sref + 8 * half), r1 = *(const float4 *)(sref + 8 * half + 4);
+        nsh[0] = r0.x; nsh[1] = r0.y; nsh[2] = r0.z; nsh[3] = r0.w; nsh[4] = r1.x; nsh[5] = r1.y; nsh[6] = r1.z; nsh[7] = r1.w;
+      }
       tmem_ld_wait();
       float av[8], hv[8];
 #pragma unroll
@@ -322,13 +340,19 @@ wide_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
           const uint32_t bits = (i & 1) ? (w >> 16) : (w & 0xFFFFu);
           live = live && !(bits < a.rand_thr);                             // :103-108
         }
-        const float pr = live ? ex2_approx(fmaf(Hh, kLog2e, nshift2)) : 0.f;   // :111 (un-normalised)
+        if (MAXONLY) {                                                     // row maximum over the live keys only
+          psum[8 * half + i] = fmaxf(psum[8 * half + i], live ? Hh : -INFINITY);
+          av[i] = hv[i] = G;                                               // (unused)
+          continue;
+        }
+        const float pr = live ? ex2_approx(fmaf(Hh, kLog2e, nsh[i])) : 0.f;    // :111 (un-normalised, relative to ref)
         const float gg = live ? sigmoid_fast(G) : 0.f;                     // :112
         psum[8 * half + i] += pr;
         gsum[8 * half + i] += gg;
         av[i] = pr * gg;                                                   // :113
         hv[i] = Hh;
       }
+      if (MAXONLY) continue;
       uint32_t apack[4], hpack[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) { apack[i] = pack_bf16(av[2 * i], av[2 * i + 1]); hpack[i] = pack_bf16(hv[2 * i], hv[2 * i + 1]); }
@@ -385,6 +409,11 @@ wide_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
     }
     tmem_st_wait();
   }
+  if (use_ref && q == 0) {   // row maxima of the pre-pass -> shared memory as -ref * log2(e) (every group reads them)
+    const size_t ps = ((size_t)b * N + (rowvalid ? l : 0)) * H;
+#pragma unroll
+    for (int i = 0; i < H; ++i) sref[i] = rowvalid ? -a.lse[ps + i] * kLog2e : 0.f;
+  }
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();                                       // sync B
@@ -395,11 +424,12 @@ wide_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
       const int kt = i * NG + q, m = T * TK + kt;
       mbar_wait(bar_ready, j & 1);                       // S / EG of key j are in tensor memory; so is e' of key j-1
       tc_fence_after();
-      if (j > 0) {
+      if (j > 0 && !MAXONLY) {
         phase_b(pst, pkt);
         if (plast) { fence_proxy_async_smem(); mbar_arrive(bar_td0 + 8 * pst); }
       }
       phase_a(m, st, kt);
+      if (MAXONLY && i == KPG - 1) mbar_arrive(bar_td0 + 8 * st);   // nothing is written back: the stage is free
       int T2 = T, i2 = i + 1, st2 = st;
       if (i2 == KPG) { i2 = 0; ++T2; if (++st2 == NS) st2 = 0; }
       if (j + 1 < J) {
@@ -415,9 +445,11 @@ wide_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
     }
     mbar_wait(bar_ready, J & 1);                         // e' of the last key
     tc_fence_after();
-    phase_b(pst, pkt);
-    fence_proxy_async_smem();
-    mbar_arrive(bar_td0 + 8 * pst);
+    if (!MAXONLY) {
+      phase_b(pst, pkt);
+      fence_proxy_async_smem();
+      mbar_arrive(bar_td0 + 8 * pst);
+    }
   }
   tc_fence_before();
   asm volatile("bar.sync 1, %0;" ::"n"(NG * 128) : "memory");   // every tcgen05.mma of the CTA has completed
@@ -433,6 +465,24 @@ wide_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
       *(float4 *)(mine + H + i) = make_float4(gsum[i], gsum[i + 1], gsum[i + 2], gsum[i + 3]);
     }
     asm volatile("bar.sync 1, %0;" ::"n"(NG * 128) : "memory");
+    if (MAXONLY) {   // row maxima over the groups' keys -> lse[0]; a row without a live key keeps the reference 0
+      if (q == 0) {
+#pragma unroll
+        for (int g2 = 1; g2 < NG; ++g2) {
+          const float *oth = xch + ((size_t)g2 * 128 + t) * (2 * H);
+#pragma unroll
+          for (int i = 0; i < H; ++i) psum[i] = fmaxf(psum[i], oth[i]);
+        }
+        if (rowvalid) {
+          const size_t ps = ((size_t)b * N + l) * H;
+#pragma unroll
+          for (int i = 0; i < H; ++i) a.lse[ps + i] = psum[i] > -INFINITY ? psum[i] : 0.f;
+        }
+      }
+      tc_fence_before();
+      __syncthreads();                                   // sync C
+      return;
+    }
 #pragma unroll
     for (int g2 = 1; g2 < NG; ++g2) {
       const float *oth = xch + ((size_t)((q + g2) % NG) * 128 + t) * (2 * H);
@@ -473,7 +523,7 @@ wide_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
         const size_t ps = ((size_t)b * N + l) * H, rs = (size_t)a.B * N * H;
 #pragma unroll
         for (int i = 0; i < H; ++i) {
-          a.lse[ps + i] = sm_shift;                                          // reference point of the exponent
+          if (!use_ref) a.lse[ps + i] = 0.f;                                 // reference point of the exponent (else: the pre-pass' row maximum)
           a.lse[rs + ps + i] = psum[i] > 0.f ? __logf(psum[i]) : 0.f;
           a.deg[ps + i] = gsum[i];
         }
@@ -496,14 +546,21 @@ int launch_cfg(const WideFwdArgs &a, const void *e, void *e_out, const void *qkv
   const int smem = C::FWD_SMEM + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    EGT_CHECK_CUDA(cudaFuncSetAttribute(wide_fwd_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    EGT_CHECK_CUDA(cudaFuncSetAttribute(wide_fwd_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    EGT_CHECK_CUDA(cudaFuncSetAttribute(wide_fwd_kernel<C, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    EGT_CHECK_CUDA(cudaFuncSetAttribute(wide_fwd_kernel<C, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    EGT_CHECK_CUDA(cudaFuncSetAttribute(wide_fwd_kernel<C, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    EGT_CHECK_CUDA(cudaFuncSetAttribute(wide_fwd_kernel<C, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
   dim3 grid((a.N + 127) / 128, a.B);
+  {   // row-maximum pre-pass: every CTA returns at once unless the logit bound exceeds the exponent budget
+    LaunchScope _ls("wide_fwd_rowmax_kernel", st);
+    if (a.rand_mask) EGT_CHECK_CUDA(launch_pdl(wide_fwd_kernel<C, true, true>, grid, dim3(C::THREADS), smem, st, tm_e, tm_eo, tm_q, tm_kv, a));
+    else EGT_CHECK_CUDA(launch_pdl(wide_fwd_kernel<C, false, true>, grid, dim3(C::THREADS), smem, st, tm_e, tm_eo, tm_q, tm_kv, a));
+  }
   LaunchScope _ls("wide_fwd_kernel", st);
-  if (a.rand_mask) EGT_CHECK_CUDA(launch_pdl(wide_fwd_kernel<C, true>, grid, dim3(C::THREADS), smem, st, tm_e, tm_eo, tm_q, tm_kv, a));
-  else EGT_CHECK_CUDA(launch_pdl(wide_fwd_kernel<C, false>, grid, dim3(C::THREADS), smem, st, tm_e, tm_eo, tm_q, tm_kv, a));
+  if (a.rand_mask) EGT_CHECK_CUDA(launch_pdl(wide_fwd_kernel<C, true, false>, grid, dim3(C::THREADS), smem, st, tm_e, tm_eo, tm_q, tm_kv, a));
+  else EGT_CHECK_CUDA(launch_pdl(wide_fwd_kernel<C, false, false>, grid, dim3(C::THREADS), smem, st, tm_e, tm_eo, tm_q, tm_kv, a));
   return EGT_OK;
 }
 
