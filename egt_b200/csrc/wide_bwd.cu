@@ -29,6 +29,7 @@
 #include "common.cuh"
 #include "wide.h"
 #include "wide_common.cuh"
+#include "wide_bwd_program.cuh"
 
 namespace egt {
 using namespace umma;
@@ -230,6 +231,33 @@ wide_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
         chain_rows(tmem + TM_W1 + wcol, loZ, HI_Z, desc_lo(win(st, kt, ST_E), 16384), HI_SW, ID_W, first_w ? 0u : 1u, ZSTEP, 128);
         chain_rows(tmem + TM_W2 + wcol, loZ, HI_Z, desc_lo(win(st, kt, ST_DE), 16384), HI_SW, ID_W, first_w ? 0u : 1u, ZSTEP, 128);
       };
+      // one handshake = ONE asm statement (wide_bwd_program.cuh): the products of key (st, kt), the inputs of the
+      // group's next key (st2, kt2) when there is one, and the commit
+      auto program = [&](int q, int st, int kt, int kslot, bool first, bool first_w, bool has_next, int st2, int kt2) {
+        const uint32_t tg = tmem + TM_G + q * GC, img = sbase + SM_IMG + q * IMG_G;
+        const uint32_t var = DE >= 16 ? 0u : (uint32_t)(kt & 1), var2 = DE >= 16 ? 0u : (uint32_t)(kt2 & 1);
+        const uint32_t wcol = DE >= 16 ? 0u : (uint32_t)(kt & 1) * DEP;
+        const uint32_t kx = sbase + SM_KVX + q * 3 * KV_MAT;
+        const uint32_t a_tg = tg, a_dq = tmem + TM_DQ, a_w1 = tmem + TM_W1 + wcol, a_w2 = tmem + TM_W2 + wcol;
+        const uint32_t a_kc = desc_lo(kx + kslot * KV_MAT, 2048), a_ldc = desc_lo(win(st, kt, ST_DE), 16);
+        const uint32_t a_i = loI + var * 32, a_s = desc_lo(img + C::ZBYTES, 128), a_a = desc_lo(img + C::ZBYTES + 4096, 128);
+        const uint32_t a_z = desc_lo(img, C::ZNONE ? 128u : IMG_G);
+        const uint32_t a_we = desc_lo(win(st, kt, ST_E), 16384), a_wd = desc_lo(win(st, kt, ST_DE), 16384);
+        const uint32_t a_kn = desc_lo(kx + (kslot ^ 1) * KV_MAT, 16), a_vn = desc_lo(kx + 2 * KV_MAT, 16);
+        const uint32_t a_len = desc_lo(win(st2, kt2, ST_E), 16), a_ldn = desc_lo(win(st2, kt2, ST_DE), 16);
+        const uint32_t a_weg = loWeg + var2 * (W_EG_SZ / 16), a_whx = loWhx + var2 * (W_HX_SZ / 16);
+        const uint32_t a_bar = bar_ready0 + 8 * q;
+        if constexpr (H == 16)
+          wide_bwd_program_c5(a_tg, a_dq, a_w1, a_w2, a_kc, a_ldc, loWdx, a_i, loQm, loDOm, a_s, a_a, a_z, a_we, a_wd, first, first_w,
+                              (uint32_t)KR, has_next, loQ, loDO, a_kn, a_vn, a_len, a_ldn, a_weg, a_whx, a_bar);
+        else if constexpr (DE == 8)
+          wide_bwd_program_c3(a_tg, a_dq, a_w1, a_w2, a_kc, a_ldc, loWdx, a_i, loQm, loDOm, a_s, a_a, a_z, a_we, a_wd, first, first_w,
+                              (uint32_t)KR, has_next, loQ, loDO, a_kn, a_vn, a_len, a_ldn, a_weg, a_whx, a_bar);
+        else
+          wide_bwd_program_c1(a_tg, a_dq, a_w1, a_w2, a_kc, a_ldc, loWdx, a_i, loQm, loDOm, a_s, a_a, a_z, a_we, a_wd, first, first_w,
+                              (uint32_t)KR, has_next, loQ, loDO, a_kn, a_vn, a_len, a_ldn, a_weg, a_whx, a_bar);
+      };
+      const bool use_program = true;
       tc_fence_after();
       mbar_wait(smem_u32(&bars->q_full), 0);
       mbar_wait(bar_e0, 0);
@@ -245,12 +273,14 @@ wide_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
           fence_proxy_async_smem();
           // d_e = 8: the first even and the first odd key start their own accumulators
           const bool first = j == 0 && q == 0, first_w = DE >= 16 ? first : (j == 0);
-          issue_mma2(q, st, i * NG + q, j & 1, first, first_w);
-          if (j + 1 < J) {
-            if (i2 == 0 && q == 0) { mbar_wait(bar_e0 + 8 * st2, (T2 / NS) & 1); tc_fence_after(); }
-            issue_mma1(q, st2, i2 * NG + q, (j + 1) & 1);
+          if (j + 1 < J && i2 == 0 && q == 0) { mbar_wait(bar_e0 + 8 * st2, (T2 / NS) & 1); tc_fence_after(); }
+          if (use_program) {
+            program(q, st, i * NG + q, j & 1, first, first_w, j + 1 < J, st2, i2 * NG + q);
+          } else {
+            issue_mma2(q, st, i * NG + q, j & 1, first, first_w);
+            if (j + 1 < J) issue_mma1(q, st2, i2 * NG + q, (j + 1) & 1);
+            mma_commit_w(bar_ready0 + 8 * q);
           }
-          mma_commit_w(bar_ready0 + 8 * q);
         }
         T = T2; i = i2; st = st2;
       }
