@@ -252,7 +252,7 @@ def test_block_forward_backward_vs_oracle(case, dtype):
         field = name.replace('/', '_')
         got = blk.grad_view(field)
         # weight gradients are sums over B*N^2 terms: compare relative to their own scale
-        tol = 2e-3 if dtype == torch.float32 else 3e-2
+        tol = 1e-3 if dtype == torch.float32 else 1e-2   # north_star: 1e-3 fp32 / 1e-2 bf16, relative to the tensor's own maximum
         # a bias gradient can be analytically ~0 (e.g. dense_edge_b/bias in 'bias' mode: softmax is
         # shift-invariant), so its error is measured against the scale of its kernel's gradient (a sum of
         # B*N^2 bf16-rounded terms carries the same absolute noise as the kernel's gradient does)
@@ -414,7 +414,7 @@ def test_fused_path_matches_staged_and_oracle(N, B, training, rmp):
         outs[force] = (h2, e2, gin)
     # weight gradients of the two paths agree to bf16 accumulation noise
     wa, wb = outs[0][2][2], outs[1][2][2]
-    assert float((wa - wb).abs().max()) <= 3e-2 * float(wb.abs().max())
+    assert float((wa - wb).abs().max()) <= 2e-2 * float(wb.abs().max())   # two bf16 paths: twice the 1e-2 of either against the oracle
 
 
 def test_block_step_replays_as_cuda_graph():

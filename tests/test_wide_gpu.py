@@ -68,8 +68,8 @@ def test_wide_path_matches_staged_and_oracle(width, N, B, training, rmp):
             floor = 1e-1 * float(dict(zip(pr, rin[2:]))[kname].abs().max()) if name.endswith('bias') and kname in pr else 0.
             denom = max(float(gr.abs().max()), floor, 1e-6)
             err = float((got.double().cpu() - gr).abs().max()) / denom
-            assert err < 2e-2, f'grad {name}: rel-to-max err {err:.3e} (force_staged={force})'
-    assert float((outs[0] - outs[1]).abs().max()) <= 3e-2 * float(outs[1].abs().max())
+            assert err < 1e-2, f'grad {name}: rel-to-max err {err:.3e} (force_staged={force})'
+    assert float((outs[0] - outs[1]).abs().max()) <= 2e-2 * float(outs[1].abs().max())
 
 
 @pytest.mark.parametrize('width', ['C0', 'C5', 'C1', 'C3'])
