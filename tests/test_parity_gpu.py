@@ -260,7 +260,10 @@ def test_block_forward_backward_vs_oracle(case, dtype):
         floor = 1e-1 * float(dict(zip(pr, rin[2:]))[kname].abs().max()) if name.endswith('bias') and kname in pr else 0.
         denom = max(float(gr.abs().max()), floor, 1e-6)
         err = float((got.double().cpu() - gr).abs().max()) / denom
-        assert err < tol, f'grad {name}: rel-to-max err {err:.3e}'
+        # when the floor is what the error is measured against (a gradient that is analytically ~0), the noise of
+        # the ~B*N^2 bf16-rounded terms is not relative to the tensor itself: twice the tolerance
+        tol_t = 2 * tol if floor > float(gr.abs().max()) else tol
+        assert err < tol_t, f'grad {name}: rel-to-max err {err:.3e}'
 
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
@@ -324,6 +327,20 @@ def test_block_full_size_vs_oracle_sample(N, d, de, nh, B):
     _close(e2[sel], e2r, torch.bfloat16, "e'")
     _close(gh[sel], ghr, torch.bfloat16, 'dh')
     _close(ge[sel], ger, torch.bfloat16, 'de')
+    # weight gradients at full size: the same two graphs as their own batch, every tensor against the oracle
+    pr = {k: v.double().clone().requires_grad_(True) for k, v in params.items() if not k.startswith('ffn')}
+    hr2 = _round(h[sel], torch.bfloat16)
+    er2 = _round(e[sel], torch.bfloat16)
+    h2w, e2w = O.egt_block(hr2, er2, mask[sel], pr, cfg)
+    wref = torch.autograd.grad([h2w, e2w], list(pr.values()), [dh[sel].double(), de_[sel].double()])
+    hs, es = h[sel].bfloat16().to(DEV).requires_grad_(True), e[sel].bfloat16().to(DEV).requires_grad_(True)
+    blk.flat.grad = None
+    h2s, e2s = blk(hs, es, mask[sel].to(DEV))
+    torch.autograd.backward([h2s, e2s], [dh[sel].to(DEV), de_[sel].to(DEV)])
+    for (name, _), gr in zip(pr.items(), wref):
+        got = blk.grad_view(name.replace('/', '_'))
+        err = float((got.double().cpu() - gr).abs().max()) / max(float(gr.abs().max()), 1e-6)
+        assert err < 1e-2, f'full-size weight gradient {name}: rel-to-max err {err:.3e}'
     # graphs are independent: permuting the batch permutes the outputs bit-exactly
     perm = torch.randperm(B, generator=g)
     h2p, e2p = blk(hg.detach()[perm], eg.detach()[perm], mask[perm].to(DEV))
