@@ -247,15 +247,17 @@ wide_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
         const uint32_t a_len = desc_lo(win(st2, kt2, ST_E), 16), a_ldn = desc_lo(win(st2, kt2, ST_DE), 16);
         const uint32_t a_weg = loWeg + var2 * (W_EG_SZ / 16), a_whx = loWhx + var2 * (W_HX_SZ / 16);
         const uint32_t a_bar = bar_ready0 + 8 * q;
-        if constexpr (H == 16)
-          wide_bwd_program_c5(a_tg, a_dq, a_w1, a_w2, a_kc, a_ldc, loWdx, a_i, loQm, loDOm, a_s, a_a, a_z, a_we, a_wd, first, first_w,
-                              (uint32_t)KR, has_next, loQ, loDO, a_kn, a_vn, a_len, a_ldn, a_weg, a_whx, a_bar);
-        else if constexpr (DE == 8)
-          wide_bwd_program_c3(a_tg, a_dq, a_w1, a_w2, a_kc, a_ldc, loWdx, a_i, loQm, loDOm, a_s, a_a, a_z, a_we, a_wd, first, first_w,
-                              (uint32_t)KR, has_next, loQ, loDO, a_kn, a_vn, a_len, a_ldn, a_weg, a_whx, a_bar);
-        else
-          wide_bwd_program_c1(a_tg, a_dq, a_w1, a_w2, a_kc, a_ldc, loWdx, a_i, loQm, loDOm, a_s, a_a, a_z, a_we, a_wd, first, first_w,
-                              (uint32_t)KR, has_next, loQ, loDO, a_kn, a_vn, a_len, a_ldn, a_weg, a_whx, a_bar);
+#define EGT_BWD_PROGRAM_ARGS a_kc, a_ldc, loWdx, a_i, loQm, loDOm, a_s, a_a, a_z, a_we, a_wd, first, first_w, (uint32_t)KR, has_next, \
+                             loQ, loDO, a_kn, a_vn, a_len, a_ldn, a_weg, a_whx, a_bar
+        (void)a_tg; (void)a_dq; (void)a_w1; (void)a_w2;   // tensor-memory addresses are literals inside the programs
+        if constexpr (H == 16) {
+          if (q == 0) wide_bwd_program_c5_g0(EGT_BWD_PROGRAM_ARGS); else wide_bwd_program_c5_g1(EGT_BWD_PROGRAM_ARGS);
+        } else if constexpr (DE == 8) {
+          if (q == 0) wide_bwd_program_c3_g0(wcol, EGT_BWD_PROGRAM_ARGS); else wide_bwd_program_c3_g1(wcol, EGT_BWD_PROGRAM_ARGS);
+        } else {
+          if (q == 0) wide_bwd_program_c1_g0(EGT_BWD_PROGRAM_ARGS); else wide_bwd_program_c1_g1(EGT_BWD_PROGRAM_ARGS);
+        }
+#undef EGT_BWD_PROGRAM_ARGS
       };
       const bool use_program = true;
       tc_fence_after();
