@@ -641,61 +641,61 @@ wide_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
   __syncthreads();                                       // sync C
 }
 
-// Column sums of the per-CTA partial rows: one thread per column, every CTA of the grid a slice of the columns.
-__global__ void __launch_bounds__(128) wide_bwd_colsum_kernel(const float *partials, int nparts, int PART, float *sums) {
-  const int col = blockIdx.x * 128 + threadIdx.x;
-  if (col >= PART) return;
-  const int per = (nparts + gridDim.y - 1) / gridDim.y, i0 = blockIdx.y * per, i1 = min(nparts, i0 + per);
-  float acc[8];
-#pragma unroll
-  for (int u = 0; u < 8; ++u) acc[u] = 0.f;
-  int i = i0;
-  for (; i + 8 <= i1; i += 8)
-#pragma unroll
-    for (int u = 0; u < 8; ++u) acc[u] += partials[(size_t)(i + u) * PART + col];
-  for (; i < i1; ++i) acc[0] += partials[(size_t)i * PART + col];
-  atomicAdd(sums + col, ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7])));
-}
-
 // Folds the per-CTA partial sums into the weight gradients (the library ADDS into them), see fused_prep.cuh.
 //   partial row layout: Mraw[j][c] (j = column of [E|G] in the order (hh/8, eg, hh%8)) | Wr[hh][c] | dbr[c] | sZ[(eg, hh)]
 //   sum x^_c dZ_j = Mraw[j][c] - mean_c' Mraw[j][c']        (x^ = r e - r mu, and sum_c' e_c' / d_e = mu)
-__global__ void __launch_bounds__(256) wide_bwd_finalize_kernel(const float *partials, int nparts, int H, int DE,
+// Phase 1 (every CTA of the 2-D grid): column sums of a slice of the partial rows, added to `sums`.  Phase 2 (the CTA
+// that finishes last, found with a counter behind `sums`): the fold.  `sums` and the counter are zeroed by the caller.
+__global__ void __launch_bounds__(128) wide_bwd_finalize_kernel(const float *partials, int nparts, int H, int DE, float *sums,
                                                                 egt_block_weights_t w, egt_block_grads_t g) {
   extern __shared__ float s[];
+  __shared__ int is_last;
   const int EGN = 2 * H, PART = EGN * DE + H * DE + DE + EGN;
-  const int tid = threadIdx.x;
-  for (int col = tid; col < PART; col += 256) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    int i = 0;
-    for (; i + 4 <= nparts; i += 4)
+  const int tid = threadIdx.x, nthr = 128;
+  {
+    const int col = blockIdx.x * 128 + tid;
+    if (col < PART) {
+      const int per = (nparts + gridDim.y - 1) / gridDim.y, i0 = blockIdx.y * per, i1 = min(nparts, i0 + per);
+      float acc[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) acc[u] += partials[(size_t)(i + u) * PART + col];
-    for (; i < nparts; ++i) acc[0] += partials[(size_t)i * PART + col];
-    s[col] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+      for (int u = 0; u < 8; ++u) acc[u] = 0.f;
+      int i = i0;
+      for (; i + 8 <= i1; i += 8)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] += partials[(size_t)(i + u) * PART + col];
+      for (; i < i1; ++i) acc[0] += partials[(size_t)i * PART + col];
+      atomicAdd(sums + col, ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7])));
+    }
   }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) is_last = atomicAdd((unsigned *)(sums + PART), 1u) == gridDim.x * gridDim.y - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (int col = tid; col < PART; col += nthr) s[col] = __ldcg(sums + col);
   __syncthreads();
   float *Mraw = s, *Wr = s + EGN * DE, *dbr = Wr + H * DE, *sZ = dbr + DE;
   float *mean = sZ + EGN;                                // [EGN]
-  for (int j = tid; j < EGN; j += 256) {
+  for (int j = tid; j < EGN; j += nthr) {
     float m = 0.f;
     for (int c = 0; c < DE; ++c) m += Mraw[j * DE + c];
     mean[j] = m / DE;
   }
   __syncthreads();
-  for (int idx = tid; idx < 2 * DE * H; idx += 256) {    // dW_E, dW_G
+  for (int idx = tid; idx < 2 * DE * H; idx += nthr) {   // dW_E, dW_G
     const int eg = idx / (DE * H), c = (idx / H) % DE, hh = idx % H;
     const int j = (hh >> 3) * 16 + eg * 8 + (hh & 7);
     const float M = Mraw[j * DE + c] - mean[j];
     float *dst = eg ? g.attention_gates_kernel : g.dense_edge_b_kernel;
     dst[c * H + hh] += w.norm_edge_gamma[c] * M + w.norm_edge_beta[c] * sZ[eg * H + hh];
   }
-  for (int idx = tid; idx < 2 * H; idx += 256) {         // db_E, db_G
+  for (int idx = tid; idx < 2 * H; idx += nthr) {        // db_E, db_G
     const int eg = idx / H, hh = idx % H;
     (eg ? g.attention_gates_bias : g.dense_edge_b_bias)[hh] += sZ[idx];
   }
-  for (int idx = tid; idx < H * DE; idx += 256) g.dense_edge_r_kernel[idx] += Wr[idx];
-  for (int c = tid; c < DE; c += 256) {
+  for (int idx = tid; idx < H * DE; idx += nthr) g.dense_edge_r_kernel[idx] += Wr[idx];
+  for (int c = tid; c < DE; c += nthr) {
     g.dense_edge_r_bias[c] += dbr[c];
     float dg = 0.f, db = 0.f;
     for (int hh = 0; hh < H; ++hh) {
@@ -742,7 +742,7 @@ bool wide_bwd_supported(const egt_block_cfg_t *cfg) {
 
 size_t wide_bwd_partials_floats(const egt_block_cfg_t *cfg) {
   const size_t H = cfg->attn.h, DE = cfg->d_e, EGN = 2 * H;
-  return ((size_t)cfg->attn.B * ((cfg->attn.N + 127) / 128) + 1) * (EGN * DE + H * DE + DE + EGN);   // + the row of column sums
+  return ((size_t)cfg->attn.B * ((cfg->attn.N + 127) / 128) + 1) * (EGN * DE + H * DE + DE + EGN) + 4;   // + the column sums and a counter
 }
 
 int wide_bwd_launch(const egt_block_cfg_t *cfg, const WideBwdArgs &a, const void *e, const void *de_out, void *de,
@@ -761,11 +761,10 @@ int wide_bwd_finalize_launch(const egt_block_cfg_t *cfg, const float *partials, 
   const int PART = EGN * DE + H * DE + DE + EGN;
   const size_t smem = (size_t)(PART + EGN) * sizeof(float);
   float *sums = const_cast<float *>(partials) + (size_t)nparts * PART;
-  LaunchScope _ls("wide_bwd_finalize_kernel", st);
-  EGT_CHECK_CUDA(cudaMemsetAsync(sums, 0, (size_t)PART * sizeof(float), st));
+  EGT_CHECK_CUDA(cudaMemsetAsync(sums, 0, (size_t)(PART + 1) * sizeof(float), st));
   const int ysplit = nparts >= 64 ? 16 : nparts >= 8 ? 4 : 1;
-  wide_bwd_colsum_kernel<<<dim3((PART + 127) / 128, ysplit), 128, 0, st>>>(partials, nparts, PART, sums);
-  wide_bwd_finalize_kernel<<<1, 256, smem, st>>>(sums, 1, H, DE, *w, *g);
+  LaunchScope _ls("wide_bwd_finalize_kernel", st);
+  wide_bwd_finalize_kernel<<<dim3((PART + 127) / 128, ysplit), 128, smem, st>>>(partials, nparts, H, DE, sums, *w, *g);
   EGT_CHECK_CUDA(cudaGetLastError());
   return EGT_OK;
 }

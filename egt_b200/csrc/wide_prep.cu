@@ -25,28 +25,39 @@ __device__ __forceinline__ int img(int n, int k, int N) { return (k >> 3) * (N *
 
 __global__ void __launch_bounds__(256) wide_prep_kernel(egt_block_weights_t w, int H, int DE, float clip_lo, float clip_hi,
                                                         WidePrep *out) {
-  __shared__ float wp[2][WMAXDE][WMAXH];
+  __shared__ float wp[2][WMAXDE][WMAXH], sW[2][WMAXDE][WMAXH], sgam[WMAXDE], sbet[WMAXDE], sbias[2][WMAXH];
   const int tid = threadIdx.x;
+  // every global load of the kernel is issued in this first phase (the rest works from shared memory: a dependent
+  // chain of L2 round trips per output is what made this one-CTA kernel take 13 us)
   for (int i = tid; i < 2 * DE * H; i += 256) {
     const int eg = i / (DE * H), c = (i / H) % DE, hh = i % H;
-    const float wv = (eg ? w.attention_gates_kernel : w.dense_edge_b_kernel)[c * H + hh];
-    const float full = w.norm_edge_gamma[c] * wv;
+    sW[eg][c][hh] = (eg ? w.attention_gates_kernel : w.dense_edge_b_kernel)[c * H + hh];
+  }
+  const bool cta0 = blockIdx.x == 0;                     // every CTA builds W' in shared memory; CTA 0 also writes the scalars
+  const int gtid = blockIdx.x * 256 + tid, gstride = gridDim.x * 256;
+  for (int c = tid; c < DE; c += 256) {
+    sgam[c] = w.norm_edge_gamma[c]; sbet[c] = w.norm_edge_beta[c];
+    if (cta0) out->br[c] = w.dense_edge_r_bias[c];
+  }
+  for (int i = tid; i < 2 * H; i += 256) sbias[i / H][i % H] = (i / H ? w.attention_gates_bias : w.dense_edge_b_bias)[i % H];
+  __syncthreads();
+  for (int i = tid; i < 2 * DE * H; i += 256) {
+    const int eg = i / (DE * H), c = (i / H) % DE, hh = i % H;
+    const float full = sgam[c] * sW[eg][c][hh];
     const float hi = __bfloat162float(__float2bfloat16_rn(full));
     const float v = hi + __bfloat162float(__float2bfloat16_rn(full - hi));   // what hi + lo represents
     wp[eg][c][hh] = v;
-    out->wp[eg][c][hh] = v;
+    if (cta0) out->wp[eg][c][hh] = v;
   }
-  for (int c = tid; c < DE; c += 256) out->br[c] = w.dense_edge_r_bias[c];
   __syncthreads();
-  if (tid < 32) {
+  if (cta0 && tid < 32) {
     const int eg = tid / 16, hh = tid % 16;
     float bnd = 0.f;
     if (hh < H) {
-      const float *W = eg ? w.attention_gates_kernel : w.dense_edge_b_kernel;
-      float u = 0.f, v = (eg ? w.attention_gates_bias : w.dense_edge_b_bias)[hh], n2 = 0.f;
+      float u = 0.f, v = sbias[eg][hh], n2 = 0.f;
       for (int c = 0; c < DE; ++c) {
         u += wp[eg][c][hh];
-        v += w.norm_edge_beta[c] * W[c * H + hh];
+        v += sbet[c] * sW[eg][c][hh];
         n2 += wp[eg][c][hh] * wp[eg][c][hh];
       }
       (eg ? out->uG : out->uE)[hh] = u;
@@ -60,7 +71,7 @@ __global__ void __launch_bounds__(256) wide_prep_kernel(egt_block_weights_t w, i
   const int EGN = 2 * H, DEP = DE < 16 ? 16 : DE, DEW = DEP;
   const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
   // column n of the [E|G] product <-> (eg, hh):  n = (hh/8)*16 + eg*8 + hh%8
-  for (int i = tid; i < 2 * EGN * DEW; i += 256) {         // w_eg[v]: hi part in k < DEW, lo part in DEW <= k < 2 DEW
+  for (int i = gtid; i < 2 * EGN * DEW; i += gstride) {         // w_eg[v]: hi part in k < DEW, lo part in DEW <= k < 2 DEW
     const int v = i / (EGN * DEW), n = (i / DEW) % EGN, k = i % DEW;
     const int eg = (n >> 3) & 1, hh = 8 * (n >> 4) + (n & 7);
     float x;
@@ -70,7 +81,7 @@ __global__ void __launch_bounds__(256) wide_prep_kernel(egt_block_weights_t w, i
     out->w_eg[v][img(n, k, EGN)] = hi;
     out->w_eg[v][img(n, DEW + k, EGN)] = __float2bfloat16_rn(x - __bfloat162float(hi));
   }
-  for (int i = tid; i < DEP * 16; i += 256) {              // w_r, b_r
+  for (int i = gtid; i < DEP * 16; i += gstride) {              // w_r, b_r
     const int n = i / 16, k = i % 16;
     out->w_r[img(n, k, DEP)] = (k < H && n < DE) ? __float2bfloat16_rn(w.dense_edge_r_kernel[k * DE + n]) : zero;
     float b = 0.f;
@@ -81,12 +92,12 @@ __global__ void __launch_bounds__(256) wide_prep_kernel(egt_block_weights_t w, i
     }
     out->b_r[img(n, k, DEP)] = __float2bfloat16_rn(b);
   }
-  for (int i = tid; i < 2 * 16 * 16; i += 256) {           // i16[v]
+  for (int i = gtid; i < 2 * 16 * 16; i += gstride) {           // i16[v]
     const int v = i / 256, n = (i / 16) % 16, k = i % 16;
     const bool one = DE >= 16 ? n == k : (n < 8 && k == n + 8 * v);
     out->i16[v][img(n, k, 16)] = __float2bfloat16_rn(one ? 1.f : 0.f);
   }
-  for (int i = tid; i < 2 * 16 * DEW; i += 256) {          // w_hx[v]: n = head, k = edge channel
+  for (int i = gtid; i < 2 * 16 * DEW; i += gstride) {          // w_hx[v]: n = head, k = edge channel
     const int v = i / (16 * DEW), n = (i / DEW) % 16, k = i % DEW;
     float x = 0.f;
     if (n < H) {
@@ -95,7 +106,7 @@ __global__ void __launch_bounds__(256) wide_prep_kernel(egt_block_weights_t w, i
     }
     out->w_hx[v][img(n, k, 16)] = __float2bfloat16_rn(x);
   }
-  for (int i = tid; i < DEP * EGN; i += 256) {             // w_dx: n = edge channel, k = column of [E|G]
+  for (int i = gtid; i < DEP * EGN; i += gstride) {             // w_dx: n = edge channel, k = column of [E|G]
     const int n = i / EGN, k = i % EGN;
     const int eg = (k >> 3) & 1, hh = 8 * (k >> 4) + (k & 7);
     out->w_dx[img(n, k, DEP)] = __float2bfloat16_rn(n < DE ? wp[eg][n][hh] : 0.f);
@@ -106,7 +117,7 @@ __global__ void __launch_bounds__(256) wide_prep_kernel(egt_block_weights_t w, i
 
 int wide_prep_launch(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, WidePrep *prep, cudaStream_t st) {
   LaunchScope _ls("wide_prep_kernel", st);
-  wide_prep_kernel<<<1, 256, 0, st>>>(*w, cfg->attn.h, cfg->d_e, cfg->attn.clip_lo, cfg->attn.clip_hi, prep);
+  wide_prep_kernel<<<8, 256, 0, st>>>(*w, cfg->attn.h, cfg->d_e, cfg->attn.clip_lo, cfg->attn.clip_hi, prep);
   EGT_CHECK_CUDA(cudaGetLastError());
   return EGT_OK;
 }
