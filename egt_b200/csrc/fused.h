@@ -17,6 +17,7 @@ constexpr int FH = 8, FDK = 8, FD = 64, FDE = 8;
 // exponent budget of the un-normalised softmax: exp(H_hat - max(bound - budget, 0)) <= e^75, and 4096 of them
 // still sum below FLT_MAX
 constexpr float kSoftmaxBudget = 75.f;
+constexpr float kLoThreshold = 16.f;    // logit bound above which W' is multiplied as hi + lo (FusedPrep::b_eg_lo)
 
 // Derived weights, rebuilt on the device at the start of every forward / backward call (the weights
 // change every optimiser step).  LayerNorm_e is folded into the projections:
@@ -30,6 +31,12 @@ struct FusedPrep {
   __nv_bfloat16 b_hx[2 * 16 * 8];     // dH_ext = de' W_r^T: N = 16 (g,key,hh4), K = 16 (key',c): W_r[hh,c]
   __nv_bfloat16 b_de[2][2 * 16 * 8];  // d x^ = dZ W'^T, one image per g: N = 16 (key',c), K = 16 (key,eg,hh4)
   __nv_bfloat16 b_wr[2 * 16 * 8];     // forward edge write-back H^ W_r: N = 16 (key',c), K = 16 (g,key,hh4): W_r[hh,c]
+  // second half of W'_eg = bf16 hi + bf16 lo (same layout as b_eg).  Used (use_lo != 0) only when the logit bound exceeds
+  // kLoThreshold: with one bf16 rounding of the weights a logit of magnitude |E| is off by |E| 2^-9, harmless at the
+  // usual |E| of a few units and whole units at |E| of several hundred.  wp / uE / uG always describe the weights the
+  // tensor core multiplies by (hi, or hi + lo).
+  __nv_bfloat16 b_eg_lo[2 * 32 * 8];
+  int use_lo;
   float uE[FH], vE[FH], uG[FH], vG[FH], br[FDE];
   float wp[2][FDE][FH];               // W'_E, W'_G as rounded to bf16 (for the weight-gradient epilogue)
   float bound;                        // sup |masked logit| over all inputs given these weights

@@ -49,8 +49,8 @@ constexpr uint32_t SM_STAGE = 32768;
 constexpr uint32_t ST_E = 0, ST_DE = 16384, ST_K = 32768, ST_V = 33792, STAGE_BYTES = 34816;
 constexpr uint32_t SM_KVX = SM_STAGE + NS * STAGE_BYTES;       // 4 slots x (Kexp 2048 | Vexp 2048)
 constexpr uint32_t SM_TR = SM_KVX + 4 * 4096;                  // dS^T 32768 | A~^T 32768  (16 keys x 128 rows)
-constexpr uint32_t SM_W = SM_TR + 65536;                       // b_eg 1024 | b_hx 512 | b_de 2 x 512
-constexpr uint32_t SM_CONST = SM_W + 2560;                     // uE vE uG vG (32 floats)
+constexpr uint32_t SM_W = SM_TR + 65536;                       // b_eg 1024 | b_hx 512 | b_de 2 x 512 | b_eg_lo 1024
+constexpr uint32_t SM_CONST = SM_W + 3584;                     // uE vE uG vG (32 floats)
 constexpr uint32_t SM_BAR = SM_CONST + 256;
 constexpr uint32_t SM_MASK = SM_BAR + 256;                       // key-valid bytes, zero padded (N <= 4096)
 constexpr uint32_t SM_TOTAL = SM_MASK + 4096 + 16;
@@ -112,6 +112,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
   } else if (warp < 8) {
     pdl_wait();                                        // prep / dV_att come from the preceding kernel
     if (tid < 160) ((uint4 *)(smem + SM_W))[tid] = ((const uint4 *)a.prep->b_eg)[tid];   // b_eg | b_hx | b_de
+    else if (tid < 224) ((uint4 *)(smem + SM_W + 2560))[tid - 160] = ((const uint4 *)a.prep->b_eg_lo)[tid - 160];
     if (tid < 32) ((float *)(smem + SM_CONST))[tid] = a.prep->uE[tid];                  // uE vE uG vG
     for (int i = tid; i < 2 * ((N + 1) / 2); i += 256)                                   // key-valid bytes
       smem[SM_MASK + i] = i < N ? (a.mask ? (uint8_t)(a.mask[(size_t)blockIdx.y * N + i] != 0) : (uint8_t)1) : (uint8_t)0;
@@ -146,6 +147,8 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     const uint32_t loE = desc_lo(sbase + SM_STAGE + ST_E, 16), loDE = desc_lo(sbase + SM_STAGE + ST_DE, 16);
     const uint32_t loWeg = desc_lo(sbase + SM_W, 512), loWhx = desc_lo(sbase + SM_W + 1024, 256);
     const uint32_t loWde = desc_lo(sbase + SM_W + 1536, 256);
+    const uint32_t loWegLo = desc_lo(sbase + SM_W + 2560, 512);
+    const bool use_lo = a.prep->use_lo != 0;           // W' = hi + lo only when the logits are large (fused.h)
     const uint32_t bar_e0 = smem_u32(&bars->e_full[0]), bar_m1 = smem_u32(&bars->mma1[0]), bar_m2 = smem_u32(&bars->mma2[0]);
     // tcgen05.mma is issued warp-collectively by warp 8 (umma.cuh): converged warp, one elected lane, k-chains in one
     // asm statement.  TMA stays with lane 0.
@@ -158,6 +161,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
       MmaChain<4>::ss(d + IN_S, loQ, HI_SW, k0, HI_SW, ID_N16, 0, 2, 2);
       MmaChain<4>::ss(d + IN_DA, loDO, HI_SW, v0, HI_SW, ID_N16, 0, 2, 2);
       MmaChain<1>::ss(d + IN_EG, loE + e0, HI_SW, loWeg, HI_NONE, ID_N32, 0, 0, 0);
+      if (use_lo) MmaChain<1>::ss(d + IN_EG, loE + e0, HI_SW, loWegLo, HI_NONE, ID_N32, 1, 0, 0);
       MmaChain<1>::ss(d + IN_HX, loDE + e0, HI_SW, loWhx, HI_NONE, ID_N16, 0, 0, 0);
     };
     auto issue_mma2 = [&](int p) {                     // dQ += dS Kexp ; d x^ = [dE|dG] W'^T   (operands / result: parity p & 1)

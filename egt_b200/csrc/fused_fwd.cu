@@ -21,11 +21,10 @@
 //     O  [128x64] += A~ [128x16] * Vexp       Vexp[(g,key,hh4), c] = V[key,c] * [c % 8 == hh]
 //     De [128x16]  = H_hat [128x16] * Wr blk  edge write-back of the two keys
 // e' = e + De + b_r is formed in place over the e stage and leaves by TMA store.
-// Softmax uses a data-INDEPENDENT reference instead of the row max: every logit satisfies |H_hat| <= bound
-// (FusedPrep::bound = clip + sqrt(d_e) ||W'_E|| + |v|, known before the loop), so exp(H_hat - shift) with
-// shift = max(bound - 75, 0) can never overflow fp32 (N <= 4096), and is exact for every row whose maximum
-// lies within ~155 of the bound.  shift is what the saved statistic lse[0] holds (tf.nn.softmax semantics,
-// egt_layers.py:111: the result does not depend on the reference point).
+// Softmax reference (tf.nn.softmax subtracts the row maximum, egt_layers.py:111): every logit satisfies
+// |H_hat| <= bound (FusedPrep::bound = clip + sqrt(d_e) ||W'_E|| + |v|, known before the loop).  While the bound is
+// below the fp32 exponent budget the reference 0 is exact; above it the MAXONLY pre-pass of this kernel leaves the row
+// maximum in lse[0] and the main pass exponentiates H_hat - max.  lse[0] is what the backward adds to the log row sum.
 //
 // There is no CTA-wide barrier in the main loop: compute threads arrive on an mbarrier when their part of a
 // step (4 keys) is done and the issuer waits for it.  The handshake compute -> issuer -> tensor core -> compute
@@ -46,8 +45,8 @@ constexpr uint32_t SM_Q = 0;                           // [128 x 128B] swizzled,
 constexpr uint32_t SM_STAGE = 16384;
 constexpr uint32_t ST_E = 0, ST_K = 16384, ST_V = 17408, STAGE_BYTES = 18432;
 constexpr uint32_t SM_KVX = SM_STAGE + NS * STAGE_BYTES;       // 8 slots (pair p & 7) x (Kexp 2048 | Vexp 2048)
-constexpr uint32_t SM_W = SM_KVX + 8 * 4096;                   // b_eg 1024 | b_wr 512
-constexpr uint32_t SM_CONST = SM_W + 1536;                     // uE vE uG vG br (40 floats)
+constexpr uint32_t SM_W = SM_KVX + 8 * 4096;                   // b_eg 1024 | b_wr 512 | b_eg_lo 1024
+constexpr uint32_t SM_CONST = SM_W + 2560;                     // uE vE uG vG br (40 floats)
 constexpr uint32_t SM_BAR = SM_CONST + 256;
 constexpr uint32_t SM_MASK = SM_BAR + 256;                       // key-valid bytes, zero padded (N <= 4096)
 constexpr uint32_t SM_WO = (SM_MASK + 4096 + 16 + 1023) & ~1023u;   // W_O operand image (MN-major, 8 KB) | b_O (64 floats)
@@ -67,7 +66,12 @@ struct Bars { uint64_t q_full, e_full[NS], mma1[2], mma2[2], step[2], oproj; uin
 
 }  // namespace
 
-template <bool RAND>
+// MAXONLY: the row-maximum pre-pass of the softmax (same scheme as wide_fwd.cu).  tf.nn.softmax (egt_layers.py:111)
+// subtracts the row maximum; the main pass needs its reference before the key loop.  While the data-independent bound of
+// the logits (FusedPrep::bound) is below the fp32 exponent budget the reference 0 is exact and every CTA of the pre-pass
+// returns at once; above it the pre-pass streams e once more (S and [E|G] products, logit arithmetic, no exp, no P V,
+// no e') and leaves max_m H_hat[l, m, hh] over the live keys in lse[0].
+template <bool RAND, bool MAXONLY>
 __global__ void __launch_bounds__(640, 1)
 fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant__ CUtensorMap tm_eo,
                  const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
@@ -82,6 +86,10 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
   const int NT = (N + 7) / 8, NQ = (N + 3) / 4;       // 8-key tiles, pipeline steps of 4 keys (two pairs)
 
   pdl_trigger();
+  if (MAXONLY) {
+    pdl_wait();
+    if (a.prep->bound <= kSoftmaxBudget) return;       // the whole grid agrees: nothing to do
+  }
   if (warp == 16) {
     if (lane == 0) {
       mbar_init(smem_u32(&bars->q_full), 1);
@@ -114,6 +122,7 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     pdl_wait();                                        // prep / qkv come from the preceding kernel
     if (tid < 64) ((uint4 *)(smem + SM_W))[tid] = ((const uint4 *)a.prep->b_eg)[tid];            // b_eg
     else if (tid < 96) ((uint4 *)(smem + SM_W + 1024))[tid - 64] = ((const uint4 *)a.prep->b_wr)[tid - 64];
+    else if (tid < 160) ((uint4 *)(smem + SM_W + 1536))[tid - 96] = ((const uint4 *)a.prep->b_eg_lo)[tid - 96];
     if (tid < 40) ((float *)(smem + SM_CONST))[tid] = a.prep->uE[tid];                            // uE vE uG vG br
     for (int i = tid; i < 4 * NQ; i += 512)                                                        // key-valid bytes
       smem[SM_MASK + i] = i < N ? (a.mask ? (uint8_t)(a.mask[(size_t)blockIdx.y * N + i] != 0) : (uint8_t)1) : (uint8_t)0;
@@ -142,6 +151,8 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     const uint32_t loQ = desc_lo(sbase + SM_Q, 16), loK = desc_lo(sbase + SM_KVX, 16);
     const uint32_t loV = desc_lo(sbase + SM_KVX + 2048, 2048), loE = desc_lo(sbase + SM_STAGE + ST_E, 16);
     const uint32_t loWeg = desc_lo(sbase + SM_W, 512), loWr = desc_lo(sbase + SM_W + 1024, 256);
+    const uint32_t loWegLo = desc_lo(sbase + SM_W + 1536, 512);
+    const bool use_lo = a.prep->use_lo != 0;           // W' = hi + lo only when the logits are large (fused.h)
     // tcgen05.mma is issued warp-collectively by warp 16 (umma.cuh: converged warp, one elected lane, k-chains in one
     // asm statement): issuing from inside `if (lane == 0)` costs > 100 cycles per instruction and was most of the
     // ~1700-cycle handshake measured in round 1.  TMA stays with lane 0.
@@ -150,6 +161,7 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
       const uint32_t d = tmem + TM_IN + buf * TM_IN_COLS + (p & 1) * TM_PAIR;
       MmaChain<4>::ss(d + IN_S, loQ, HI_SW, loK + slot * 256, HI_SW, ID_N16, 0, 2, 2);   // 4096 B per slot
       MmaChain<1>::ss(d + IN_EG, loE + st * (STAGE_BYTES / 16) + 2 * j, HI_SW, loWeg, HI_NONE, ID_N32, 0, 0, 0);
+      if (use_lo) MmaChain<1>::ss(d + IN_EG, loE + st * (STAGE_BYTES / 16) + 2 * j, HI_SW, loWegLo, HI_NONE, ID_N32, 1, 0, 0);
     };
     const uint32_t bar_e0 = smem_u32(&bars->e_full[0]), bar_m1 = smem_u32(&bars->mma1[0]), bar_m2 = smem_u32(&bars->mma2[0]);
     auto issue_mma1 = [&](int q) {                     // both pairs of step q -> input buffer q & 1
@@ -188,7 +200,7 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
       mbar_wait(bar_step + 8 * (it & 1), (it >> 1) & 1);   // all compute threads finished step it
       tc_fence_after();
       fence_proxy_async_smem();                        // the compute threads' shared-memory writes of step it
-      issue_mma2(it);                                  //  (ordered before this point by the mbarrier) -> async proxy
+      if (!MAXONLY) issue_mma2(it);                    //  (ordered before this point by the mbarrier) -> async proxy
       if (it + 2 < NQ) issue_mma1(it + 2);
       mma_commit_w(bar_m2 + 8 * (it & 1));             // ONE completion per handshake: products of step it and
                                                        // S / EG of step it+2, both consumed during step it+2
@@ -196,20 +208,22 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
         // step it contained the e' update of step it-2; tile T (steps 2T, 2T+1) is complete when it == 2T+3
         if (it >= 4 && (it & 1) == 0) {                // tile stored at the previous handshake: recycle its stage
           const int T = (it - 4) >> 1;
-          tma_store_wait_read<0>();
+          if (!MAXONLY) tma_store_wait_read<0>();
           if (T + NS < NT) load_tile(T + NS);
         }
         if (it >= 3 && (it & 1) == 1) {
           const int T = (it - 3) >> 1;
-          tma_store_3d(&tm_eo, sbase + SM_STAGE + (T % NS) * STAGE_BYTES + ST_E, T * 64, l0, b);
-          tma_store_commit();
+          if (!MAXONLY) {
+            tma_store_3d(&tm_eo, sbase + SM_STAGE + (T % NS) * STAGE_BYTES + ST_E, T * 64, l0, b);
+            tma_store_commit();
+          }
           next_store = T + 1;
         }
       }
       __syncwarp();
     }
     __syncthreads();                                   // sync #(NQ+1): every e' update is done
-    if (leader) {
+    if (leader && !MAXONLY) {
       for (int T = next_store; T < NT; ++T)
         tma_store_3d(&tm_eo, sbase + SM_STAGE + (T % NS) * STAGE_BYTES + ST_E, T * 64, l0, b);
       tma_store_commit();
@@ -246,8 +260,18 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
   float psum[4], gsum[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) { psum[i] = 0.f; gsum[i] = 0.f; }
-  const float sm_shift = fmaxf(a.prep->bound - kSoftmaxBudget, 0.f);   // reference point of the exponent
-  const float nshift2 = -sm_shift * kLog2e, ln_eps = a.ln_eps;
+  // exponent reference of the softmax: 0 while the logits cannot overflow, else the row maximum of the pre-pass
+  const bool use_ref = !MAXONLY && a.prep->bound > kSoftmaxBudget;
+  const float ln_eps = a.ln_eps;
+  float nsh[4] = {0.f, 0.f, 0.f, 0.f};                 // -ref * log2(e) of this thread's heads
+  if (use_ref && rowvalid) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) nsh[i] = -a.lse[((size_t)b * N + l) * FH + 4 * g + i] * kLog2e;
+  }
+  if (MAXONLY) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) psum[i] = -INFINITY;   // psum holds the running maxima
+  }
   const uint32_t trow = (uint32_t)t * 128u, tx7 = (uint32_t)(t & 7);
 
   // expanded K / V operands of pair p2 (stage st2) into slot p2 & 3: one 16-byte chunk per thread
@@ -319,7 +343,12 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
           const uint32_t bits = (i & 1) ? (w >> 16) : (w & 0xFFFFu);
           live = live && !(bits < a.rand_thr);                             // :103-108
         }
-        const float pr = live ? ex2_approx(fmaf(Hh, kLog2e, nshift2)) : 0.f;  // :111 (unnormalised)
+        if (MAXONLY) {                                                     // row maximum over the live keys only
+          psum[i] = fmaxf(psum[i], live ? Hh : -INFINITY);
+          av[i] = hv[i] = G;                                               // (unused)
+          continue;
+        }
+        const float pr = live ? ex2_approx(fmaf(Hh, kLog2e, nsh[i])) : 0.f;   // :111 (unnormalised, relative to ref)
         const float gg = live ? sigmoid_fast(G) : 0.f;                     // :112
         psum[i] += pr;
         gsum[i] += gg;
@@ -329,8 +358,10 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
       apack[kk * 2 + 0] = pack_bf16(av[0], av[1]); apack[kk * 2 + 1] = pack_bf16(av[2], av[3]);
       hpack[kk * 2 + 0] = pack_bf16(hv[0], hv[1]); hpack[kk * 2 + 1] = pack_bf16(hv[2], hv[3]);
     }
-    tmem_st4(tout + g * 4, apack);
-    tmem_st4(tout + 8 + g * 4, hpack);
+    if (!MAXONLY) {
+      tmem_st4(tout + g * 4, apack);
+      tmem_st4(tout + 8 + g * 4, hpack);
+    }
   };
 
   // ---- phase B: e' = e + H_hat W_r + b_r for key g of pair p, in place over the e stage ---------------
@@ -371,7 +402,7 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     else mbar_wait(bar_mma1 + ob8, 0);                 // steps 0, 1: issued before the loop
     tc_fence_after();
     phase_a(2 * it + kq, st_a);
-    if (it >= 2) phase_b(2 * (it - 2) + kq, st_b);
+    if (it >= 2 && !MAXONLY) phase_b(2 * (it - 2) + kq, st_b);
     if (it + 2 < NQ) {
       if ((it & 1) == 0) mbar_wait(bar_e + 8 * st_n, par_n);        // first step of tile (it+2)>>1
       build(2 * (it + 2) + kq, st_n);
@@ -389,7 +420,7 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
   for (int q = (NQ >= 2 ? NQ - 2 : 0); q < NQ; ++q) {  // e' updates of the last two steps
     mbar_wait(bar_mma2 + 8 * (q & 1), (q >> 1) & 1);
     tc_fence_after();
-    phase_b(2 * q + kq, (q >> 1) % NS);
+    if (!MAXONLY) phase_b(2 * q + kq, (q >> 1) % NS);
   }
   fence_proxy_async_smem();
   __syncthreads();                                     // sync #(NQ+1)
@@ -401,6 +432,15 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     *(float4 *)xch = make_float4(psum[0], psum[1], psum[2], psum[3]);
     *(float4 *)(xch + 4) = make_float4(gsum[0], gsum[1], gsum[2], gsum[3]);
     __syncthreads();                                   // partial row sums exchanged
+    if (MAXONLY) {   // row maxima over both key-pair parities -> lse[0]; a row without a live key keeps the reference 0
+      const float *oth = (const float *)(smem + SM_KVX) + (((kq ^ 1) * 2 + g) * 128 + t) * 8;
+      const float4 p4 = *(const float4 *)oth;
+      const float mx[4] = {fmaxf(psum[0], p4.x), fmaxf(psum[1], p4.y), fmaxf(psum[2], p4.z), fmaxf(psum[3], p4.w)};
+      if (kq == 0 && rowvalid) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a.lse[((size_t)b * N + l) * FH + 4 * g + i] = mx[i] > -INFINITY ? mx[i] : 0.f;
+      }
+    } else {
     {
       const float *oth = (const float *)(smem + SM_KVX) + (((kq ^ 1) * 2 + g) * 128 + t) * 8;
       const float4 p4 = *(const float4 *)oth, g4 = *(const float4 *)(oth + 4);
@@ -448,12 +488,13 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
         const size_t ps = ((size_t)b * N + l) * FH + 4 * g, rs = (size_t)a.B * N * FH;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          a.lse[ps + i] = sm_shift;                                        // reference point of the exponent
+          if (!use_ref) a.lse[ps + i] = 0.f;                               // reference point of the exponent (else: the pre-pass' row maximum)
           a.lse[rs + ps + i] = psum[i] > 0.f ? __logf(psum[i]) : 0.f;
           a.deg[ps + i] = gsum[i];
         }
       }
     }
+    }   // !MAXONLY
   }
   if (a.w_o) {   // h' = h + V_att W_O + b_O  (graph_xformer_model_base.py:136-140)
     fence_proxy_async_smem();
@@ -498,14 +539,23 @@ int fused_fwd_launch(const FusedFwdArgs &a, const void *e, void *e_out, const vo
   const int smem = SM_TOTAL + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    EGT_CHECK_CUDA(cudaFuncSetAttribute(fused_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    EGT_CHECK_CUDA(cudaFuncSetAttribute(fused_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    EGT_CHECK_CUDA(cudaFuncSetAttribute(fused_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    EGT_CHECK_CUDA(cudaFuncSetAttribute(fused_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    EGT_CHECK_CUDA(cudaFuncSetAttribute(fused_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    EGT_CHECK_CUDA(cudaFuncSetAttribute(fused_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
   dim3 grid((a.N + 127) / 128, a.B);
+  {   // row-maximum pre-pass: every CTA returns at once unless the logit bound exceeds the exponent budget
+    FusedFwdArgs m = a;
+    m.w_o = nullptr;
+    LaunchScope _ls("fused_fwd_rowmax_kernel", st);
+    if (a.rand_mask) EGT_CHECK_CUDA(launch_pdl(fused_fwd_kernel<true, true>, grid, dim3(640), smem, st, tm_e, tm_eo, tm_q, tm_kv, m));
+    else EGT_CHECK_CUDA(launch_pdl(fused_fwd_kernel<false, true>, grid, dim3(640), smem, st, tm_e, tm_eo, tm_q, tm_kv, m));
+  }
   LaunchScope _ls("fused_fwd_kernel", st);
-  if (a.rand_mask) EGT_CHECK_CUDA(launch_pdl(fused_fwd_kernel<true>, grid, dim3(640), smem, st, tm_e, tm_eo, tm_q, tm_kv, a));
-  else EGT_CHECK_CUDA(launch_pdl(fused_fwd_kernel<false>, grid, dim3(640), smem, st, tm_e, tm_eo, tm_q, tm_kv, a));
+  if (a.rand_mask) EGT_CHECK_CUDA(launch_pdl(fused_fwd_kernel<true, false>, grid, dim3(640), smem, st, tm_e, tm_eo, tm_q, tm_kv, a));
+  else EGT_CHECK_CUDA(launch_pdl(fused_fwd_kernel<false, false>, grid, dim3(640), smem, st, tm_e, tm_eo, tm_q, tm_kv, a));
   return EGT_OK;
 }
 

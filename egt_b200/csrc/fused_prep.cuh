@@ -28,35 +28,46 @@ __device__ __forceinline__ void fused_prep_body(const egt_block_weights_t &w, fl
   pdl_wait();                        // parameters were read above; everything below writes global memory
   prep_sync();
   if (tid < FDE) out->br[tid] = sbr[tid];
+  __shared__ float wlo[2][FDE][FH], sbound;
+  {   // bound of the logits from the full-precision W'_E (decides whether the lo half is needed)
+    if (tid < 8) {
+      const int hh = tid;
+      float n2 = 0.f, v = sbias[0][hh];
+      for (int c = 0; c < FDE; ++c) { const float f = sgam[c] * sW[0][c][hh]; n2 += f * f; v += sbet[c] * sW[0][c][hh]; }
+      // |LN(e)_c| has l2 norm <= sqrt(d_e)  =>  |E| <= sqrt(d_e) * ||W'[:,hh]|| + |v|
+      float bnd = fmaxf(fabsf(clip_lo), fabsf(clip_hi)) + sqrtf((float)FDE * n2) + fabsf(v);
+      for (int o = 4; o > 0; o >>= 1) bnd = fmaxf(bnd, __shfl_xor_sync(0xffu, bnd, o));
+      if (hh == 0) { sbound = bnd; out->bound = bnd; out->use_lo = bnd > kLoThreshold; }
+    }
+  }
+  prep_sync();
+  const bool use_lo = sbound > kLoThreshold;
   {
     int eg = tid / 64, c = (tid / 8) % 8, hh = tid % 8;
-    float v = __bfloat162float(__float2bfloat16_rn(sgam[c] * sW[eg][c][hh]));
-    wp[eg][c][hh] = v;
-    out->wp[eg][c][hh] = v;
+    const float full = sgam[c] * sW[eg][c][hh];
+    const float hi = __bfloat162float(__float2bfloat16_rn(full));
+    const float lo = use_lo ? __bfloat162float(__float2bfloat16_rn(full - hi)) : 0.f;
+    wp[eg][c][hh] = hi + lo;                           // what the tensor core multiplies by
+    wlo[eg][c][hh] = lo;
+    out->wp[eg][c][hh] = hi + lo;
   }
   prep_sync();
   if (tid < 16) {
     int eg = tid / 8, hh = tid % 8;
-    float u = 0.f, v = sbias[eg][hh], n2 = 0.f;
+    float u = 0.f, v = sbias[eg][hh];
     for (int c = 0; c < FDE; ++c) {
       u += wp[eg][c][hh];
       v += sbet[c] * sW[eg][c][hh];
-      n2 += wp[eg][c][hh] * wp[eg][c][hh];
     }
     (eg ? out->uG : out->uE)[hh] = u;
     (eg ? out->vG : out->vE)[hh] = v;
-    if (eg == 0) {
-      // |LN(e)_c| has l2 norm <= sqrt(d_e)  =>  |E| <= sqrt(d_e) * ||W'[:,hh]|| + |v|
-      float bnd = fmaxf(fabsf(clip_lo), fabsf(clip_hi)) + sqrtf((float)FDE * n2) + fabsf(v);
-      for (int o = 4; o > 0; o >>= 1) bnd = fmaxf(bnd, __shfl_xor_sync(0xffu, bnd, o));
-      if (hh == 0) out->bound = bnd;
-    }
   }
   // operand images (head-group ordered, fused.h)
   for (int i = tid; i < 32 * 16; i += 128) {      // b_eg
     int n = i / 16, k = i % 16;
     int g = n / 16, key = (n / 8) % 2, eg = (n / 4) % 2, hh = 4 * g + n % 4, key2 = k / 8, c = k % 8;
-    out->b_eg[(k / 8) * (32 * 8) + n * 8 + (k % 8)] = __float2bfloat16_rn(key == key2 ? wp[eg][c][hh] : 0.f);
+    out->b_eg[(k / 8) * (32 * 8) + n * 8 + (k % 8)] = __float2bfloat16_rn(key == key2 ? wp[eg][c][hh] - wlo[eg][c][hh] : 0.f);
+    out->b_eg_lo[(k / 8) * (32 * 8) + n * 8 + (k % 8)] = __float2bfloat16_rn(key == key2 ? wlo[eg][c][hh] : 0.f);
   }
   for (int i = tid; i < 16 * 16; i += 128) {      // b_hx, b_de[g]
     int n = i / 16, k = i % 16;

@@ -40,6 +40,7 @@ struct WidePrep {
   float br[WMAXDE];
   float wp[2][WMAXDE][WMAXH];               // W'_E, W'_G (float32; hi + lo is what the forward multiplies by)
   float bound;                              // sup |masked logit| given these weights (fused.h)
+  int use_lo;                               // bound > kLoThreshold: the lo half of w_eg is multiplied too (else it is zero)
 };
 
 struct WideFwdArgs {

@@ -198,6 +198,7 @@ wide_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
                             uint32_t astep, uint32_t bstep) {
         mma_chain8_n(dcol, loA, hiA, loB, hiB, idesc, acc, astep, bstep, (uint32_t)KR);
       };
+      const uint32_t use_lo = a.prep->use_lo != 0;       // W' = hi + lo only when the logits are large (wide.h)
       auto issue_mma1 = [&](int q, int st, int kt, int kslot) {   // inputs of the group's next key
         const uint32_t tg = tmem + TM_G + q * GC;
         chain_d(tg + G_S, loQ, desc_lo(sbase + SM_KVX + (q * 3 + kslot) * KV_MAT, 16));
@@ -206,7 +207,7 @@ wide_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
         const uint32_t var = DE >= 16 ? 0u : (uint32_t)(kt & 1);
         constexpr int EK = C::DEW / 16;                    // W' = hi + lo (wide.h): the e window is multiplied by both
         MmaChain<EK>::ss(tg + G_EG, le, HI_SW, loWeg + var * (W_EG_SZ / 16), HI_NONE, ID_EG, 0, 2, 2 * EGN);
-        MmaChain<EK>::ss(tg + G_EG, le, HI_SW, loWeg + var * (W_EG_SZ / 16) + 2 * EK * EGN, HI_NONE, ID_EG, 1, 2, 2 * EGN);
+        if (use_lo) MmaChain<EK>::ss(tg + G_EG, le, HI_SW, loWeg + var * (W_EG_SZ / 16) + 2 * EK * EGN, HI_NONE, ID_EG, 1, 2, 2 * EGN);
         MmaChain<EK>::ss(tg + G_HX, ld, HI_SW, loWhx + var * (W_HX_SZ / 16), HI_NONE, ID_N16, 0, 2, 32);
       };
       auto issue_mma2 = [&](int q, int st, int kt, int kslot, bool first, bool first_w) {
@@ -248,7 +249,7 @@ wide_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
         const uint32_t a_weg = loWeg + var2 * (W_EG_SZ / 16), a_whx = loWhx + var2 * (W_HX_SZ / 16);
         const uint32_t a_bar = bar_ready0 + 8 * q;
 #define EGT_BWD_PROGRAM_ARGS a_kc, a_ldc, loWdx, a_i, loQm, loDOm, a_s, a_a, a_z, a_we, a_wd, first, first_w, (uint32_t)KR, has_next, \
-                             loQ, loDO, a_kn, a_vn, a_len, a_ldn, a_weg, a_whx, a_bar
+                             loQ, loDO, a_kn, a_vn, a_len, a_ldn, a_weg, a_whx, use_lo, a_bar
         (void)a_tg; (void)a_dq; (void)a_w1; (void)a_w2;   // tensor-memory addresses are literals inside the programs
         if constexpr (H == 16) {
           if (q == 0) wide_bwd_program_c5_g0(EGT_BWD_PROGRAM_ARGS); else wide_bwd_program_c5_g1(EGT_BWD_PROGRAM_ARGS);

@@ -168,6 +168,7 @@ wide_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
         const int ch = DE >= 16 ? kt * DE : (kt & ~1) * DE;          // first channel of the K window inside the tile row
         return desc_lo(sbase + SM_STAGE + st * STAGE_BYTES + ST_E + (uint32_t)(ch >> 6) * 16384u + (uint32_t)(ch & 63) * 2u, 16);
       };
+      const bool use_lo = a.prep->use_lo != 0;           // W' = hi + lo only when the logits are large (wide.h)
       auto issue_mma1 = [&](int q, int st, int kt) {     // S and [E|G] of the group's next key
         const uint32_t tg = tmem + TM_G + q * GC;
         const uint32_t loK = desc_lo(sbase + SM_KVX + q * 3 * KV_MAT, 16);
@@ -183,7 +184,7 @@ wide_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
         const uint32_t lw = loWeg + (DE >= 16 ? 0u : (uint32_t)(kt & 1) * (W_EG_SZ / 16));
         constexpr int EK = C::DEW / 16;                    // W' = hi + lo (wide.h): the e window is multiplied by both
         MmaChain<EK>::ss(tg + G_EG, le, HI_SW, lw, HI_NONE, ID_EG, 0, 2, 2 * C::EGN);
-        MmaChain<EK>::ss(tg + G_EG, le, HI_SW, lw + 2 * EK * C::EGN, HI_NONE, ID_EG, 1, 2, 2 * C::EGN);
+        if (use_lo) MmaChain<EK>::ss(tg + G_EG, le, HI_SW, lw + 2 * EK * C::EGN, HI_NONE, ID_EG, 1, 2, 2 * C::EGN);
       };
       auto issue_mma2 = [&](int q, int st, int kt, int vslot, bool first) {   // O += A~ Vexp ; e' = e I + H_hat W_r + b_r
         const uint32_t tg = tmem + TM_G + q * GC;

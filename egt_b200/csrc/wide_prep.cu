@@ -6,6 +6,7 @@
 #include <math.h>
 #include "common.cuh"
 #include "wide.h"
+#include "fused.h"    // kLoThreshold
 
 namespace egt {
 
@@ -41,32 +42,40 @@ __global__ void __launch_bounds__(256) wide_prep_kernel(egt_block_weights_t w, i
   }
   for (int i = tid; i < 2 * H; i += 256) sbias[i / H][i % H] = (i / H ? w.attention_gates_bias : w.dense_edge_b_bias)[i % H];
   __syncthreads();
+  __shared__ float sbound;
+  if (tid < 32) {   // bound of the logits from the full-precision W'_E (decides whether the lo half of W' is needed)
+    float bnd = 0.f;
+    if (tid < H) {
+      float n2 = 0.f, v = sbias[0][tid];
+      for (int c = 0; c < DE; ++c) { const float f = sgam[c] * sW[0][c][tid]; n2 += f * f; v += sbet[c] * sW[0][c][tid]; }
+      // |LN(e)| has l2 norm <= sqrt(d_e)  =>  |E| <= sqrt(d_e) ||W'[:,hh]|| + |v|
+      bnd = fmaxf(fabsf(clip_lo), fabsf(clip_hi)) + sqrtf((float)DE * n2) + fabsf(v);
+    }
+    for (int o = 16; o > 0; o >>= 1) bnd = fmaxf(bnd, __shfl_xor_sync(0xffffffffu, bnd, o));
+    if (tid == 0) { sbound = bnd; if (cta0) { out->bound = bnd; out->use_lo = bnd > kLoThreshold; } }
+  }
+  __syncthreads();
+  const bool use_lo = sbound > kLoThreshold;
   for (int i = tid; i < 2 * DE * H; i += 256) {
     const int eg = i / (DE * H), c = (i / H) % DE, hh = i % H;
     const float full = sgam[c] * sW[eg][c][hh];
     const float hi = __bfloat162float(__float2bfloat16_rn(full));
-    const float v = hi + __bfloat162float(__float2bfloat16_rn(full - hi));   // what hi + lo represents
+    const float v = hi + (use_lo ? __bfloat162float(__float2bfloat16_rn(full - hi)) : 0.f);   // what the tensor core multiplies by
     wp[eg][c][hh] = v;
     if (cta0) out->wp[eg][c][hh] = v;
   }
   __syncthreads();
   if (cta0 && tid < 32) {
     const int eg = tid / 16, hh = tid % 16;
-    float bnd = 0.f;
     if (hh < H) {
-      float u = 0.f, v = sbias[eg][hh], n2 = 0.f;
+      float u = 0.f, v = sbias[eg][hh];
       for (int c = 0; c < DE; ++c) {
         u += wp[eg][c][hh];
         v += sbet[c] * sW[eg][c][hh];
-        n2 += wp[eg][c][hh] * wp[eg][c][hh];
       }
       (eg ? out->uG : out->uE)[hh] = u;
       (eg ? out->vG : out->vE)[hh] = v;
-      // |LN(e)| has l2 norm <= sqrt(d_e)  =>  |E| <= sqrt(d_e) ||W'[:,hh]|| + |v|
-      if (eg == 0) bnd = fmaxf(fabsf(clip_lo), fabsf(clip_hi)) + sqrtf((float)DE * n2) + fabsf(v);
     }
-    for (int o = 16; o > 0; o >>= 1) bnd = fmaxf(bnd, __shfl_xor_sync(0xffffffffu, bnd, o));
-    if (tid == 0) out->bound = bnd;
   }
   const int EGN = 2 * H, DEP = DE < 16 ? 16 : DE, DEW = DEP;
   const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);

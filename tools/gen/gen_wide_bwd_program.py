@@ -50,8 +50,8 @@ def gen(name, q, H, DK, DE, znone):
     loQm = o('loQm'); loDOm = o('loDOm'); loS = o('loS'); loA = o('loA'); loZ = o('loZ'); we = o('we'); wd = o('wd')
     first = o('first'); first_w = o('first_w'); KR = o('KR'); has_next = o('has_next')
     loQ = o('loQ'); loDO = o('loDO'); loKn = o('loKn'); loVn = o('loVn'); len_ = o('len'); ldn = o('ldn')
-    loWeg = o('loWeg'); loWhx = o('loWhx'); bar = o('bar')
-    e('.reg .pred pe, pn, pt, pz, pacc, paccw, pk;')
+    loWeg = o('loWeg'); loWhx = o('loWhx'); use_lo = o('use_lo'); bar = o('bar')
+    e('.reg .pred pe, pn, pt, pz, pacc, paccw, pk, plo;')
     e('.reg .b32 hsw, hno, hti, hz, iN16, iEG, iDX, iDQ, iT, iW, rd, ra;')
     e('.reg .b64 da, db;')
     e('elect.sync _|pe, 0xffffffff;')
@@ -61,6 +61,7 @@ def gen(name, q, H, DK, DE, znone):
     e(f'setp.ne.b32 pz, {KR}, {KR};')
     e(f'setp.eq.b32 pacc, {first}, 0;')
     e(f'setp.eq.b32 paccw, {first_w}, 0;')
+    e(f'setp.eq.b32 plo, {use_lo}, 0;')
     for reg, val in (('hsw', HI_SW), ('hno', HI_NONE), ('hti', HI_TIMG), ('hz', HI_TIMG if znone else HI_SW),
                      ('iN16', idesc(128, 16, 0, 0)), ('iEG', idesc(128, EGN, 0, 0)), ('iDX', idesc(128, DEP, 0, 0)),
                      ('iDQ', idesc(128, D, 0, 1)), ('iT', idesc(128, 16, 1, 1)), ('iW', idesc(128, DEP, 1, 1))):
@@ -134,7 +135,9 @@ def gen(name, q, H, DK, DE, znone):
             ss('rd', 'pz' if s == 0 else 'pt', 'iN16')
     e(f'mov.b32 rd, {tg + G_EG};')
     e(f'mov.b64 db, {{{loWeg}, hno}};')
-    for s in range(2 * EK):                               # W' = hi + lo
+    for s in range(2 * EK):                               # W' = hi (+ lo when the logits are large)
+        if s == EK:
+            e('@plo bra LEGDONE;')
         if s % EK == 0:
             e(f'mov.b64 da, {{{len_}, hsw}};')
         else:
@@ -142,6 +145,7 @@ def gen(name, q, H, DK, DE, znone):
         if s:
             e(f'add.u64 db, db, {2 * EGN};')
         ss('rd', 'pz' if s == 0 else 'pt', 'iEG')
+    e('LEGDONE:')
     e(f'mov.b32 rd, {tg + G_HX};')
     e(f'mov.b64 da, {{{ldn}, hsw}};')
     e(f'mov.b64 db, {{{loWhx}, hno}};')
