@@ -346,6 +346,60 @@ def run_ours(args, w):
         train_line = dict(random_mask_prob=0.1, training=True, cuda_graphs=False, ms_per_step=ms_train / args.steps,
                           value=B * world * args.steps / (ms_train / 1e3), unit='graphs/s',
                           eager_ms_per_step_without_mask=ms_eager / args.steps)
+    # ---- one FULL layer: attention block + node FFN + edge FFN, forward + backward, same inputs ----
+    # (graph_xformer_model_base.py:335-341: edge_update then ffn_block); CUDA graphs like the headline step
+    layer_line = None
+    if not args.no_layer_line and args.random_mask_prob == 0:
+        lay = egt_b200.EGTStack(1, ffn=True, model_width=d, edge_width=d_e, num_heads=h, scale_degree=bool(args.scale_degree),
+                                seed=3000 + rank).to(dev)
+        lay.train(False)
+
+        def layer_step(i):
+            hh, ee, mm = devs[i % nsets]
+            dh, de = ups[i % nsets]
+            hh = hh.detach().requires_grad_(True)
+            ee = ee.detach().requires_grad_(True)
+            lay.flat.grad = None
+            h2, e2 = lay(hh, ee, mm)
+            torch.autograd.backward([h2, e2], [dh, de])
+            egt_b200.allreduce_flat_grads([lay])
+            return hh.grad, ee.grad
+
+        for i in range(3):
+            layer_step(i)
+        torch.cuda.synchronize()
+        lgraphs, keep = [], []
+        if use_graphs:
+            try:
+                side = torch.cuda.Stream()             # warm up on a side stream first, as torch.cuda.graph asks
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for i in range(2):
+                        layer_step(i)
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                for i in range(nsets):
+                    g_ = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g_):
+                        keep.append((layer_step(i), lay.flat.grad))
+                    lgraphs.append(g_)
+                torch.cuda.synchronize()
+            except Exception as ex:
+                print(f'[bench] full-layer graph capture failed ({type(ex).__name__}: {ex}); timing eager launches', file=sys.stderr)
+                lgraphs = []
+                torch.cuda.synchronize()
+        run_layer = (lambda i: lgraphs[i % nsets].replay()) if lgraphs else layer_step
+        for i in range(3):
+            run_layer(i)
+        ms_layer = timed(run_layer, args.steps)
+        lib.egt_profile_enable(1)
+        timed(layer_step, args.steps)
+        lprof = L.profile_read()
+        lib.egt_profile_enable(0)
+        layer_line = dict(what='attention block + node FFN + edge FFN, forward + backward', cuda_graphs=bool(lgraphs),
+                          ms_per_step=ms_layer / args.steps, value=B * world * args.steps / (ms_layer / 1e3), unit='graphs/s',
+                          kernels_ms={k: v[0] / max(1, v[1]) for k, v in lprof.items()})
+        del lgraphs, keep
     allreduce_check = None
     # ---- self-check of the gradient all-reduce (N > 1): the peer-memory kernel against NCCL on the same buffer ----
     # (after every captured / timed region: NCCL work issued before a CUDA-graph capture was seen to invalidate it)
@@ -428,6 +482,8 @@ def run_ours(args, w):
     )
     if train_line is not None:
         line['training_step'] = train_line
+    if layer_line is not None:
+        line['full_layer'] = layer_line
     if allreduce_check is not None:
         line['allreduce_check'] = allreduce_check
     if cpu is not None:
@@ -451,6 +507,7 @@ def main():
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-graphs', action='store_true')
     ap.add_argument('--no-train-line', action='store_true')
+    ap.add_argument('--no-layer-line', action='store_true', help='skip the full-layer (block + FFN) measurement')
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == 'reference':

@@ -20,7 +20,7 @@ EXPORTS = ['egt_abi_version', 'egt_last_error', 'egt_last_path', 'egt_rng_unifor
            'egt_block_param_layout', 'egt_attn_fwd', 'egt_attn_bwd', 'egt_block_workspace_bytes',
            'egt_block_fwd', 'egt_block_bwd', 'egt_launch_count', 'egt_profile_enable', 'egt_profile_read',
            'egt_debug_umma_probe', 'egt_debug_mma_timing', 'egt_debug_force_staged', 'egt_peer_allreduce',
-           'egt_ffn_fwd', 'egt_ffn_bwd']
+           'egt_ffn_fwd', 'egt_ffn_bwd', 'egt_ffn_workspace_bytes', 'egt_ffn_fwd_ws', 'egt_ffn_bwd_ws']
 
 FFN_FIELDS = ['norm_gamma', 'norm_beta', 'lr1_kernel', 'lr1_bias', 'lr2_kernel', 'lr2_bias']
 
@@ -119,6 +119,12 @@ def load():
     lib.egt_ffn_fwd.argtypes = [C.POINTER(FfnCfg), C.POINTER(FfnWeights), vp, vp, vp]
     lib.egt_ffn_bwd.restype = C.c_int
     lib.egt_ffn_bwd.argtypes = [C.POINTER(FfnCfg), C.POINTER(FfnWeights), C.POINTER(FfnGrads), vp, vp, vp, vp]
+    lib.egt_ffn_workspace_bytes.restype = C.c_size_t
+    lib.egt_ffn_workspace_bytes.argtypes = [C.POINTER(FfnCfg)]
+    lib.egt_ffn_fwd_ws.restype = C.c_int
+    lib.egt_ffn_fwd_ws.argtypes = [C.POINTER(FfnCfg), C.POINTER(FfnWeights), vp, vp, vp, C.c_size_t, vp]
+    lib.egt_ffn_bwd_ws.restype = C.c_int
+    lib.egt_ffn_bwd_ws.argtypes = [C.POINTER(FfnCfg), C.POINTER(FfnWeights), C.POINTER(FfnGrads), vp, vp, vp, vp, C.c_size_t, vp]
     lib.egt_peer_allreduce.restype = C.c_int
     lib.egt_peer_allreduce.argtypes = [vp, vp, vp, C.c_int64, C.c_int, C.c_int, vp]
     lib.egt_launch_count.restype = C.c_long

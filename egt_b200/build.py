@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, 'lib')
 LIB = os.path.join(LIBDIR, 'libegt_b200.so')
 SOURCES = ['abi.cu', 'attn_staged.cu', 'attn_fast.cu', 'edge_kernels.cu', 'edge_fast.cu', 'node_kernels.cu', 'umma_probe.cu', 'mma_timing.cu', 'fused_prep.cu', 'fused_fwd.cu',
-           'fused_bwd.cu', 'wide_prep.cu', 'wide_fwd.cu', 'wide_bwd.cu', 'node_blas.cu', 'node_tc.cu', 'peer_allreduce.cu', 'ffn_kernels.cu']
+           'fused_bwd.cu', 'wide_prep.cu', 'wide_fwd.cu', 'wide_bwd.cu', 'node_blas.cu', 'node_tc.cu', 'peer_allreduce.cu', 'ffn_kernels.cu', 'ffn_tc.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xptxas', '-v']
 

@@ -12,6 +12,7 @@
 #include <string.h>
 #include "common.cuh"
 #include "kernels.h"
+#include "node_blas.h"
 
 namespace egt {
 
@@ -513,7 +514,8 @@ static int ffn_plan(FfnArgs &a, int backward, size_t &smem) {
 
 using namespace egt;
 
-extern "C" int egt_ffn_fwd(const egt_ffn_cfg_t *cfg, const egt_ffn_weights_t *w, const void *x, void *y, void *stream) {
+extern "C" int egt_ffn_fwd_ws(const egt_ffn_cfg_t *cfg, const egt_ffn_weights_t *w, const void *x, void *y, void *ws, size_t ws_bytes,
+                              void *stream) {
   EGT_REQUIRE(cfg && w && x && y, EGT_E_ARG, "ffn_fwd: NULL argument");
   EGT_REQUIRE(cfg->rows > 0 && cfg->width > 0 && cfg->hidden > 0, EGT_E_SHAPE, "ffn_fwd: rows, width, hidden must be positive");
   EGT_REQUIRE(cfg->dtype == EGT_F32 || cfg->dtype == EGT_BF16, EGT_E_DTYPE, "ffn_fwd: dtype must be EGT_F32 or EGT_BF16");
@@ -523,6 +525,13 @@ extern "C" int egt_ffn_fwd(const egt_ffn_cfg_t *cfg, const egt_ffn_weights_t *w,
   a.gamma = w->norm_gamma; a.beta = w->norm_beta; a.W1 = w->lr1_kernel; a.b1 = w->lr1_bias; a.W2 = w->lr2_kernel; a.b2 = w->lr2_bias;
   a.x = x; a.y = y;
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    const int rc = ffn_tc_fwd_launch(cfg, w, x, y, st);     // tensor-core path (ffn_tc.cu) when the shape is served
+    if (rc != 1) return rc;
+  }
+  if (ws && ffn_blas_supported(cfg) && ws_bytes >= ffn_blas_workspace_bytes(cfg) && ((uintptr_t)ws & 255) == 0 &&
+      ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0)
+    return ffn_blas_fwd(cfg, w, x, y, ws, st);             // cuBLAS path (node_blas.cu)
   if (a.w == E8W && a.hid == E8H && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0) {   // edge channel of the fused widths
     const long long nch = (a.rows + 127) / 128;
     const unsigned grid = (unsigned)(nch < 148 * 16 ? nch : 148 * 16);
@@ -547,8 +556,8 @@ extern "C" int egt_ffn_fwd(const egt_ffn_cfg_t *cfg, const egt_ffn_weights_t *w,
   return EGT_OK;
 }
 
-extern "C" int egt_ffn_bwd(const egt_ffn_cfg_t *cfg, const egt_ffn_weights_t *w, const egt_ffn_grads_t *g, const void *x,
-                           const void *dy, void *dx, void *stream) {
+extern "C" int egt_ffn_bwd_ws(const egt_ffn_cfg_t *cfg, const egt_ffn_weights_t *w, const egt_ffn_grads_t *g, const void *x,
+                              const void *dy, void *dx, void *ws, size_t ws_bytes, void *stream) {
   EGT_REQUIRE(cfg && w && g && x && dy && dx, EGT_E_ARG, "ffn_bwd: NULL argument");
   EGT_REQUIRE(cfg->rows > 0 && cfg->width > 0 && cfg->hidden > 0, EGT_E_SHAPE, "ffn_bwd: rows, width, hidden must be positive");
   EGT_REQUIRE(cfg->dtype == EGT_F32 || cfg->dtype == EGT_BF16, EGT_E_DTYPE, "ffn_bwd: dtype must be EGT_F32 or EGT_BF16");
@@ -559,6 +568,13 @@ extern "C" int egt_ffn_bwd(const egt_ffn_cfg_t *cfg, const egt_ffn_weights_t *w,
   a.g_gamma = g->norm_gamma; a.g_beta = g->norm_beta; a.g_W1 = g->lr1_kernel; a.g_b1 = g->lr1_bias; a.g_W2 = g->lr2_kernel; a.g_b2 = g->lr2_bias;
   a.x = x; a.dy = dy; a.dx = dx;
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    const int rc = ffn_tc_bwd_launch(cfg, w, g, x, dy, dx, st);
+    if (rc != 1) return rc;
+  }
+  if (ws && ffn_blas_supported(cfg) && ws_bytes >= ffn_blas_workspace_bytes(cfg) && ((uintptr_t)ws & 255) == 0 &&
+      ((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)dx & 15) == 0)
+    return ffn_blas_bwd(cfg, w, g, x, dy, dx, ws, st);
   if (a.w == E8W && a.hid == E8H && ((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)dx & 15) == 0) {
     const long long nch = (a.rows + 127) / 128;
     const unsigned grid = (unsigned)(nch < 148 * 8 ? nch : 148 * 8);
@@ -582,4 +598,18 @@ extern "C" int egt_ffn_bwd(const egt_ffn_cfg_t *cfg, const egt_ffn_weights_t *w,
   else ffn_bwd_kernel<__nv_bfloat16><<<grid, FT, smem, st>>>(a);
   EGT_CHECK_CUDA(cudaGetLastError());
   return EGT_OK;
+}
+
+extern "C" int egt_ffn_fwd(const egt_ffn_cfg_t *cfg, const egt_ffn_weights_t *w, const void *x, void *y, void *stream) {
+  return egt_ffn_fwd_ws(cfg, w, x, y, nullptr, 0, stream);
+}
+extern "C" int egt_ffn_bwd(const egt_ffn_cfg_t *cfg, const egt_ffn_weights_t *w, const egt_ffn_grads_t *g, const void *x,
+                           const void *dy, void *dx, void *stream) {
+  return egt_ffn_bwd_ws(cfg, w, g, x, dy, dx, nullptr, 0, stream);
+}
+// Bytes of device workspace egt_ffn_{fwd,bwd}_ws can use for this shape (0: none needed).
+extern "C" size_t egt_ffn_workspace_bytes(const egt_ffn_cfg_t *cfg) {
+  if (!cfg) return 0;
+  if (ffn_tc_serves(cfg)) return 0;
+  return ffn_blas_supported(cfg) ? ffn_blas_workspace_bytes(cfg) : 0;
 }

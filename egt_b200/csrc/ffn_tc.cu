@@ -1,0 +1,720 @@
+// ffn_tc.cu -- the feed-forward half of a layer on sm_100a tensor cores, bf16 activations:
+//
+//   y = x + Dense_w( act( Dense_2w( LayerNorm(x) ) ) )        graph_xformer_model_base.py:229-258, :309-324
+//
+// for channel widths w in {8, 16, 32, 64} with hidden = 2 w: the edge channel of every named configuration
+// (d_e = 8 / 32 / 64, rows = B N N) and the node channel at d = 64 (rows = B N).
+//
+// Data layout ("super-rows"): the [rows, w] tensor is read as [rows w / 64, 64] -- one 128-byte row holds
+// P = 64 / w consecutive pairs -- so that a TMA box of [128 x 128 B] is one 128B-swizzled tcgen05 operand whatever
+// the width.  Both dense layers become products against BLOCK-DIAGONAL weight images (P blocks):
+//
+//   pre [128 x 128] = x^ [128 x 64] * W1blk [64 x 128]        (LayerNorm affine folded: W1' = gamma (.) W1)
+//   out [128 x 64]  = hid [128 x 128] * W2blk [128 x 64]
+//
+// and the backward adds  dhid = dy * W2blk^T,  dx^ = dpre * W1blk'^T  and the row-contracted products
+// dpre^T x^ , hid^T dy (weight gradients: the diagonal blocks of a [128 x 64] accumulator that lives in tensor
+// memory across the CTA's tiles) plus two products against a tile of ones for the bias gradients.  The same two
+// shared-memory images serve all four dense products: an image read K-major for W is read MN-major for W^T.
+//
+// The thread arithmetic is the point-wise part only: LayerNorm statistics, bias + activation, LayerNorm backward.
+// Forward: two compute warpgroups (thread = super-row) with private tensor memory and a private issuing warp each.
+// Backward: one group of 256 threads (thread = super-row x column half), one issuing warp; the LayerNorm of the next
+// tile is computed while the tensor core works on dx^ of the current one.
+#include <stdlib.h>
+#include <string.h>
+#include "common.cuh"
+#include "fused.h"      // encode_tmap_3d
+#include "kernels.h"
+#include "umma.cuh"
+
+namespace egt {
+using namespace umma;
+
+namespace {
+
+constexpr uint32_t TILE = 16384;          // [128 rows x 128 B] swizzled tile
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct FfnTcArgs {
+  long long srows;                        // super-rows = rows * w / 64
+  int act; float eps;
+  const float *gamma, *beta, *W1, *b1, *W2, *b2;
+  float *g_gamma, *g_beta, *g_W1, *g_b1, *g_W2, *g_b2;
+};
+
+__device__ __forceinline__ void unpack8(const uint4 v, float *x) {
+  x[0] = bf16_lo(v.x); x[1] = bf16_hi(v.x); x[2] = bf16_lo(v.y); x[3] = bf16_hi(v.y);
+  x[4] = bf16_lo(v.z); x[5] = bf16_hi(v.z); x[6] = bf16_lo(v.w); x[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ uint4 pack8(const float *x) {
+  uint4 v;
+  v.x = pack_bf16(x[0], x[1]); v.y = pack_bf16(x[2], x[3]); v.z = pack_bf16(x[4], x[5]); v.w = pack_bf16(x[6], x[7]);
+  return v;
+}
+
+// ACT >= 0: compile-time activation; ACT < 0: the run-time code `act`
+template <int ACT>
+__device__ __forceinline__ float act_f(int act, float x) {
+  if (ACT == EGT_ACT_ELU) return x > 0.f ? x : ex2_approx(x * kLog2e) - 1.f;
+  return edge_act_fwd(ACT < 0 ? act : ACT, 0.2f, x);
+}
+// value and derivative from the pre-activation
+template <int ACT>
+__device__ __forceinline__ void act_fd(int act, float x, float &f, float &d) {
+  if (ACT == EGT_ACT_ELU) {
+    const float ex = ex2_approx(x * kLog2e);
+    f = x > 0.f ? x : ex - 1.f;
+    d = x > 0.f ? 1.f : ex;
+  } else {
+    f = edge_act_fwd(ACT < 0 ? act : ACT, 0.2f, x);
+    d = edge_act_bwd(ACT < 0 ? act : ACT, 0.2f, x);
+  }
+}
+
+// Block-diagonal operand images (bf16, 128 rows x 128 B, 128B swizzle; row = hidden index j of the super-row,
+// column = channel index c of the super-row):
+//   img1[j][c] = gamma[c'] W1[c'][j']     img2[j][c] = W2[j'][c']       (c' = c % W, j' = j % 2W; zero off the blocks)
+// img1 is the K-major B operand of x^ * W1blk and the MN-major B operand of dpre * W1blk^T;
+// img2 is the K-major B operand of dy * W2blk^T and the MN-major B operand of hid * W2blk.
+// sb1[j] = b1[j'] + sum_c beta[c] W1[c][j'] ;  sb2[c] = b2[c'].
+template <int W>
+__device__ __forceinline__ void build_images(uint8_t *img1, uint8_t *img2, float *sb1, float *sb2, const FfnTcArgs &a,
+                                             int tid, int nthr) {
+  constexpr int H = 2 * W;
+  for (int i = tid; i < 128 * 8; i += nthr) {
+    const int j = i >> 3, c0 = (i & 7) << 3;
+    uint4 v1 = make_uint4(0, 0, 0, 0), v2 = make_uint4(0, 0, 0, 0);
+    if (c0 / W == j / H) {
+      const int jh = j % H, cw0 = c0 % W;
+      float y1[8], y2[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        y1[u] = a.gamma[cw0 + u] * a.W1[(size_t)(cw0 + u) * H + jh];
+        y2[u] = a.W2[(size_t)jh * W + cw0 + u];
+      }
+      v1 = pack8(y1); v2 = pack8(y2);
+    }
+    *(uint4 *)(img1 + sw128_off(j, c0)) = v1;
+    *(uint4 *)(img2 + sw128_off(j, c0)) = v2;
+  }
+  for (int j = tid; j < 128; j += nthr) {
+    const int jh = j % H;
+    float s = a.b1[jh];
+    for (int c = 0; c < W; ++c) s = fmaf(a.beta[c], a.W1[(size_t)c * H + jh], s);
+    sb1[j] = s;
+  }
+  for (int c = tid; c < 64; c += nthr) sb2[c] = a.b2[c % W];
+}
+
+__device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {   // one arrival per warp (barrier count = warps)
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthr) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthr) : "memory"); }
+
+constexpr uint32_t HI_SW = desc_hi(1024, LAYOUT_SW128);
+
+// ------------------------------------------------------------------------------------------------------------------
+// forward
+constexpr int F_NS = 6;
+struct FwdBars {
+  uint64_t full[F_NS], tile_done[F_NS], ready1[2], done1[2], ready2[2], done2[2];
+  uint32_t tmem_base, pad;
+};
+constexpr int F_SMEM = 1024 + F_NS * TILE + 2 * TILE + 2 * TILE + (128 + 64) * 4 + sizeof(FwdBars);
+
+template <int W, int ACT>
+__global__ void __launch_bounds__(384, 1) ffn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x,
+                                                            const __grid_constant__ CUtensorMap tm_y, const FfnTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t *sStage = smem, *sA1 = smem + F_NS * TILE, *sImg1 = sA1 + 2 * TILE, *sImg2 = sImg1 + TILE;
+  float *sb1 = (float *)(sImg2 + TILE), *sb2 = sb1 + 128;
+  FwdBars *bars = (FwdBars *)(sb2 + 64);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long ntiles = (a.srows + 127) / 128;
+  const int nl = (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);     // tiles of this CTA
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int s = 0; s < F_NS; ++s) { mbar_init(smem_u32(&bars->full[s]), 1); mbar_init(smem_u32(&bars->tile_done[s]), 4); }
+      for (int q = 0; q < 2; ++q) {
+        mbar_init(smem_u32(&bars->ready1[q]), 4); mbar_init(smem_u32(&bars->done1[q]), 1);
+        mbar_init(smem_u32(&bars->ready2[q]), 4); mbar_init(smem_u32(&bars->done2[q]), 1);
+      }
+      mbar_fence_init();
+      tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_y);
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(&bars->tmem_base), 512);
+  }
+  build_images<W>(sImg1, sImg2, sb1, sb2, a, tid, 384);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+  constexpr uint32_t GC = 192, C_D1 = 0, C_D2 = 128;      // per group: pre -> hid (bf16, aliased) | out
+  constexpr int P = 64 / W;
+
+  if (warp < 8) {
+    // ---- compute group q: thread = super-row ----
+    const int q = warp >> 2, t = tid & 127;
+    const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16) + q * GC;
+    uint8_t *A1 = sA1 + q * TILE;
+    // x tile i -> LayerNorm -> A operand of the first product
+    auto layer_norm = [&](int i) {
+      const int s = i % F_NS;
+      const uint8_t *stg = sStage + s * TILE;
+      mbar_wait(smem_u32(&bars->full[s]), (i / F_NS) & 1);
+      float xs[64];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) unpack8(*(const uint4 *)(stg + sw128_off(t, 8 * j)), xs + 8 * j);
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        float mu = 0.f;
+#pragma unroll
+        for (int c = 0; c < W; ++c) mu += xs[p * W + c];
+        mu *= (1.f / W);
+        float var = 0.f;
+#pragma unroll
+        for (int c = 0; c < W; ++c) { xs[p * W + c] -= mu; var = fmaf(xs[p * W + c], xs[p * W + c], var); }
+        const float rs = rsqrtf(var * (1.f / W) + a.eps);
+#pragma unroll
+        for (int c = 0; c < W; ++c) xs[p * W + c] *= rs;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) *(uint4 *)(A1 + sw128_off(t, 8 * j)) = pack8(xs + 8 * j);
+      fence_proxy_async_smem();
+      warp_arrive(smem_u32(&bars->ready1[q]), lane);
+    };
+    // The LayerNorm of the group's next tile runs between the two products of the current one, so neither round trip
+    // to the tensor core is exposed.
+    if (q < nl) layer_norm(q);
+    for (int i = q, it = 0; i < nl; i += 2, ++it) {
+      const int s = i % F_NS;
+      uint8_t *stg = sStage + s * TILE;
+      mbar_wait(smem_u32(&bars->done1[q]), it & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {     // hid = act(pre + b1') -> bf16 A operand over the columns already read
+        uint32_t r[32], o[16];
+        tmem_ld32(tl + C_D1 + 32 * k, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const float v0 = act_f<ACT>(a.act, __uint_as_float(r[2 * c]) + sb1[32 * k + 2 * c]);
+          const float v1 = act_f<ACT>(a.act, __uint_as_float(r[2 * c + 1]) + sb1[32 * k + 2 * c + 1]);
+          o[c] = pack_bf16(v0, v1);
+        }
+        tmem_st16(tl + C_D1 + 16 * k, o);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      warp_arrive(smem_u32(&bars->ready2[q]), lane);
+      if (i + 2 < nl) layer_norm(i + 2);   // the first product of tile i is complete: its A operand may be overwritten
+      mbar_wait(smem_u32(&bars->done2[q]), it & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {     // y = x + out + b2, in place over the stage
+        uint32_t r[32];
+        tmem_ld32(tl + C_D2 + 32 * k, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = 4 * k + jj;
+          uint4 *p = (uint4 *)(stg + sw128_off(t, 8 * j));
+          float xin[8], y[8];
+          unpack8(*p, xin);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) y[c] = __uint_as_float(r[8 * jj + c]) + sb2[8 * j + c] + xin[c];
+          *p = pack8(y);
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      warp_arrive(smem_u32(&bars->tile_done[s]), lane);
+    }
+  } else if (warp == 8) {
+    // ---- TMA producer: load x tiles, store y tiles ----
+    if (lane == 0) {
+      for (int i = 0; i < nl; ++i) {
+        const int s = i % F_NS;
+        const uint32_t dst = smem_u32(sStage + s * TILE);
+        if (i >= F_NS) {
+          mbar_wait(smem_u32(&bars->tile_done[s]), ((i / F_NS) - 1) & 1);
+          tma_store_3d(&tm_y, dst, 0, (int)((blockIdx.x + (long long)(i - F_NS) * gridDim.x) * 128), 0);
+          tma_store_commit();
+          tma_store_wait_read<0>();
+        }
+        mbar_expect_tx(smem_u32(&bars->full[s]), TILE);
+        tma_load_3d(dst, &tm_x, smem_u32(&bars->full[s]), 0, (int)((blockIdx.x + (long long)i * gridDim.x) * 128), 0);
+      }
+      for (int i = nl > F_NS ? nl - F_NS : 0; i < nl; ++i) {
+        const int s = i % F_NS;
+        mbar_wait(smem_u32(&bars->tile_done[s]), (i / F_NS) & 1);
+        tma_store_3d(&tm_y, smem_u32(sStage + s * TILE), 0, (int)((blockIdx.x + (long long)i * gridDim.x) * 128), 0);
+        tma_store_commit();
+      }
+      tma_store_wait_all<0>();
+    }
+  } else if (warp == 9 || warp == 10) {
+    // ---- issuer of group q (warp-collective issue) ----
+    const int q = warp - 9;
+    const uint32_t td = tmem + q * GC;
+    const uint32_t loA1 = desc_lo(smem_u32(sA1 + q * TILE), 16), loI1 = desc_lo(smem_u32(sImg1), 16),
+                   loI2 = desc_lo(smem_u32(sImg2), TILE);
+    constexpr uint32_t ID_G1 = idesc_bf16(128, 128, 0, 0), ID_G2 = idesc_bf16(128, 64, 0, 1);
+    // order: G1(0) | G2(0) G1(1) | G2(1) G1(2) | ...   (G1 of the next tile overwrites the columns G2 reads its A
+    // operand from: the tensor core executes one thread's instructions in order)
+    if (q < nl) {
+      mbar_wait(smem_u32(&bars->ready1[q]), 0);
+      tc_fence_after();
+      MmaChain<4>::ss(td + C_D1, loA1, HI_SW, loI1, HI_SW, ID_G1, 0, 2, 2);
+      mma_commit_w(smem_u32(&bars->done1[q]));
+    }
+    for (int i = q, it = 0; i < nl; i += 2, ++it) {
+      mbar_wait(smem_u32(&bars->ready2[q]), it & 1);
+      tc_fence_after();
+      MmaChain<8>::ts(td + C_D2, td + C_D1, loI2, HI_SW, ID_G2, 0, 8, 128);
+      mma_commit_w(smem_u32(&bars->done2[q]));
+      if (i + 2 < nl) {
+        mbar_wait(smem_u32(&bars->ready1[q]), (it + 1) & 1);
+        tc_fence_after();
+        MmaChain<4>::ss(td + C_D1, loA1, HI_SW, loI1, HI_SW, ID_G1, 0, 2, 2);
+        mma_commit_w(smem_u32(&bars->done1[q]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// backward
+constexpr int B_NS = 3;
+struct BwdBars {
+  uint64_t full[B_NS], readyA, doneA, readyB, doneB, doneC, out_ready, out_free;
+  uint32_t tmem_base, pad;
+};
+// stages [dy | x] | out | hid (2 atoms) | dpre (2 atoms) | img1 | img2 | ones 4 KB | sb1 | xch[2][128][4] | sdg, sdb | bars
+constexpr int B_SMEM = 1024 + B_NS * 2 * TILE + TILE + 2 * TILE + 2 * TILE + 2 * TILE + 4096 + 128 * 4 + 2 * 128 * 4 * 4 +
+                       2 * 64 * 4 + sizeof(BwdBars);
+
+template <int W, int ACT>
+__global__ void __launch_bounds__(320, 1) ffn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_x,
+                                                            const __grid_constant__ CUtensorMap tm_dy,
+                                                            const __grid_constant__ CUtensorMap tm_dx, const FfnTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t *sStage = smem;                                   // per stage: dy tile | x tile (x^ after the LayerNorm)
+  uint8_t *sOut = sStage + B_NS * 2 * TILE;
+  uint8_t *sHid = sOut + TILE, *sDpre = sHid + 2 * TILE;
+  uint8_t *sImg1 = sDpre + 2 * TILE, *sImg2 = sImg1 + TILE, *sOnes = sImg2 + TILE;
+  float *sb1 = (float *)(sOnes + 4096);
+  float *xch = sb1 + 128;                                   // [2][128][4]
+  float *sdg = xch + 2 * 128 * 4, *sdb = sdg + 64;
+  BwdBars *bars = (BwdBars *)(sdb + 64);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long ntiles = (a.srows + 127) / 128;
+  const int nl = (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int s = 0; s < B_NS; ++s) mbar_init(smem_u32(&bars->full[s]), 1);
+      mbar_init(smem_u32(&bars->readyA), 8); mbar_init(smem_u32(&bars->doneA), 1);
+      mbar_init(smem_u32(&bars->readyB), 8); mbar_init(smem_u32(&bars->doneB), 1);
+      mbar_init(smem_u32(&bars->doneC), 1);
+      mbar_init(smem_u32(&bars->out_ready), 8); mbar_init(smem_u32(&bars->out_free), 1);
+      mbar_fence_init();
+      tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_dy); tma_prefetch_desc(&tm_dx);
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(&bars->tmem_base), 512);
+  }
+  {
+    float *dummy_b2 = sdg;      // build_images writes 64 floats of b2 here; zeroed below (the backward does not need b2)
+    build_images<W>(sImg1, sImg2, sb1, dummy_b2, a, tid, 320);
+  }
+  for (int i = tid; i < 4096 / 16; i += 320) ((uint4 *)sOnes)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+  __syncthreads();
+  if (tid < 128) sdg[tid] = 0.f;                            // sdg | sdb
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+  // tensor memory: pre 128 | dhid 128 | dx^ 64 | dW1 acc 64 | dW2 acc 64 | db1 acc 16 | db2 acc 16  = 480 columns
+  constexpr uint32_t C_D1 = 0, C_DH = 128, C_D3 = 256, C_W1 = 320, C_W2 = 384, C_B1 = 448, C_B2 = 464;
+  constexpr int PH = W >= 32 ? 1 : 32 / W;                  // LayerNorm groups inside a 32-channel half
+  constexpr int GW = W >= 32 ? 32 : W;                      // channels of a group that lie inside the half
+
+  if (warp < 8) {
+    // ---- compute: thread = (super-row t, column half g) ----
+    const int t = tid & 127, g = tid >> 7;
+    const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    float rs_cur[PH], rs_next[PH];
+
+    // LayerNorm of tile i (stage s): x -> x^ in place, 1/std kept
+    auto ln_fwd = [&](int i, float *rs) {
+      const int s = i % B_NS;
+      uint8_t *sx = sStage + s * 2 * TILE + TILE;
+      mbar_wait(smem_u32(&bars->full[s]), (i / B_NS) & 1);
+      float xs[32];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) unpack8(*(const uint4 *)(sx + sw128_off(t, 8 * (4 * g + j))), xs + 8 * j);
+      if (W == 64) {
+        float sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) sum += xs[c];
+        xch[(g * 128 + t) * 4 + 0] = sum;
+        named_bar_sync(1, 256);
+        const float mu = (xch[t * 4 + 0] + xch[(128 + t) * 4 + 0]) * (1.f / 64.f);
+        float var = 0.f;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) { xs[c] -= mu; var = fmaf(xs[c], xs[c], var); }
+        xch[(g * 128 + t) * 4 + 1] = var;
+        named_bar_sync(1, 256);
+        rs[0] = rsqrtf((xch[t * 4 + 1] + xch[(128 + t) * 4 + 1]) * (1.f / 64.f) + a.eps);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) xs[c] *= rs[0];
+      } else {
+#pragma unroll
+        for (int p = 0; p < PH; ++p) {
+          float mu = 0.f;
+#pragma unroll
+          for (int c = 0; c < GW; ++c) mu += xs[p * GW + c];
+          mu *= (1.f / GW);
+          float var = 0.f;
+#pragma unroll
+          for (int c = 0; c < GW; ++c) { xs[p * GW + c] -= mu; var = fmaf(xs[p * GW + c], xs[p * GW + c], var); }
+          rs[p] = rsqrtf(var * (1.f / GW) + a.eps);
+#pragma unroll
+          for (int c = 0; c < GW; ++c) xs[p * GW + c] *= rs[p];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) *(uint4 *)(sx + sw128_off(t, 8 * (4 * g + j))) = pack8(xs + 8 * j);
+      fence_proxy_async_smem();
+      warp_arrive(smem_u32(&bars->readyA), lane);
+    };
+
+    if (nl > 0) ln_fwd(0, rs_cur);
+    for (int i = 0; i < nl; ++i) {
+      const int s = i % B_NS;
+      const uint8_t *sdy = sStage + s * 2 * TILE, *sx = sdy + TILE;
+      // ---- T1: hid, dpre images ----
+      mbar_wait(smem_u32(&bars->doneA), i & 1);
+      tc_fence_after();
+      uint4 hq[8], dq[8];               // the thread's 64 columns of hid and dpre, bf16
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int col0 = 64 * g + 16 * k;
+        uint32_t r1[16], r2[16];
+        tmem_ld16(tl + C_D1 + col0, r1);
+        tmem_ld16(tl + C_DH + col0, r2);
+        tmem_ld_wait();
+        float hv[16], dv[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          float f, d;
+          act_fd<ACT>(a.act, __uint_as_float(r1[c]) + sb1[col0 + c], f, d);
+          hv[c] = f;
+          dv[c] = __uint_as_float(r2[c]) * d;
+        }
+        hq[2 * k] = pack8(hv); hq[2 * k + 1] = pack8(hv + 8);
+        dq[2 * k] = pack8(dv); dq[2 * k + 1] = pack8(dv + 8);
+      }
+      tc_fence_before();
+      // the images are written only now: the weight-gradient products of tile i-1, which read them, were issued BEHIND
+      // the products of this tile and ran while the arithmetic above did
+      if (i > 0) mbar_wait(smem_u32(&bars->doneC), (i - 1) & 1);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t off = (uint32_t)g * TILE + sw128_off(t, 8 * k);
+        *(uint4 *)(sHid + off) = hq[k];
+        *(uint4 *)(sDpre + off) = dq[k];
+      }
+      fence_proxy_async_smem();
+      warp_arrive(smem_u32(&bars->readyB), lane);
+      // ---- LayerNorm of the next tile while the tensor core computes dx^ ----
+      if (i + 1 < nl) ln_fwd(i + 1, rs_next);
+      // ---- T2: LayerNorm backward + residual -> dx tile ----
+      mbar_wait(smem_u32(&bars->doneB), i & 1);
+      tc_fence_after();
+      {
+        uint32_t r[32];
+        tmem_ld32(tl + C_D3 + 32 * g, r);
+        float xh[32], dyv[32];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          unpack8(*(const uint4 *)(sx + sw128_off(t, 8 * (4 * g + j))), xh + 8 * j);
+          unpack8(*(const uint4 *)(sdy + sw128_off(t, 8 * (4 * g + j))), dyv + 8 * j);
+        }
+        tmem_ld_wait();
+        float m1[PH], m2[PH];
+#pragma unroll
+        for (int p = 0; p < PH; ++p) {
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int c = 0; c < GW; ++c) {
+            const float d = __uint_as_float(r[p * GW + c]);
+            s1 += d;
+            s2 = fmaf(d, xh[p * GW + c], s2);
+          }
+          m1[p] = s1; m2[p] = s2;
+        }
+        if (W == 64) {
+          xch[(g * 128 + t) * 4 + 2] = m1[0];
+          xch[(g * 128 + t) * 4 + 3] = m2[0];
+          named_bar_sync(1, 256);
+          m1[0] = xch[t * 4 + 2] + xch[(128 + t) * 4 + 2];
+          m2[0] = xch[t * 4 + 3] + xch[(128 + t) * 4 + 3];
+        }
+        if (i > 0) mbar_wait(smem_u32(&bars->out_free), (i - 1) & 1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float y[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const int cc = 8 * j + c, p = cc / GW;
+            const float d = __uint_as_float(r[cc]);
+            y[c] = fmaf(rs_cur[p], d - (m1[p] + xh[cc] * m2[p]) * (1.f / W), dyv[cc]);
+          }
+          *(uint4 *)(sOut + sw128_off(t, 8 * (4 * g + j))) = pack8(y);
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      warp_arrive(smem_u32(&bars->out_ready), lane);
+#pragma unroll
+      for (int p = 0; p < PH; ++p) rs_cur[p] = rs_next[p];
+    }
+    // ---- flush the weight-gradient accumulators: tensor memory -> shared memory -> one atomic per entry and CTA ----
+    if (nl > 0) {
+      mbar_wait(smem_u32(&bars->doneC), (nl - 1) & 1);
+      tc_fence_after();
+      constexpr int H = 2 * W, P = 64 / W, LD = 65;
+      // scratch over the (now idle) stages: M1[128][65] | M2[128][65] | v1[128] | vb2[64] | Rg[256] | Rb[256]
+      float *M1 = (float *)sStage, *M2 = M1 + 128 * LD, *v1s = M2 + 128 * LD, *vb2 = v1s + 128, *Rg = vb2 + 64, *Rb = Rg + 256;
+      {
+        uint32_t rb[4], rb2[4], rw1[32], rw2[32];
+        tmem_ld4(tl + C_B1, rb);
+        tmem_ld4(tl + C_B2, rb2);
+        tmem_ld32(tl + C_W1 + 32 * g, rw1);
+        tmem_ld32(tl + C_W2 + 32 * g, rw2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          M1[t * LD + 32 * g + c] = __uint_as_float(rw1[c]);     // sum_rows dpre[:, j = t] x^[:, c]
+          M2[t * LD + 32 * g + c] = __uint_as_float(rw2[c]);     // sum_rows hid[:, j = t] dy[:, c]
+        }
+        if (g == 0) v1s[t] = __uint_as_float(rb[0]);             // sum_rows dpre[:, j = t]
+        if (g == 1 && t < 64) vb2[t] = __uint_as_float(rb2[0]);  // sum_rows dy[:, c = t]
+      }
+      named_bar_sync(1, 256);
+      // dW1[c'][j'] += gamma[c'] M + beta[c'] db1[j'] ,  dW2[j'][c'] += M2   (M, M2: sums of the P diagonal blocks)
+      const int rot = (int)(blockIdx.x * 64u) % (W * H);          // CTAs start at different entries: less contention
+      for (int e0 = tid; e0 < W * H; e0 += 256) {
+        const int e = (e0 + rot) % (W * H);
+        {
+          const int cw = e / H, jh = e % H;
+          float M = 0.f, db1 = 0.f;
+#pragma unroll
+          for (int p = 0; p < P; ++p) { M += M1[(p * H + jh) * LD + p * W + cw]; db1 += v1s[p * H + jh]; }
+          atomicAdd(a.g_W1 + e, fmaf(a.gamma[cw], M, a.beta[cw] * db1));
+        }
+        {
+          const int jh = e / W, cw = e % W;
+          float M = 0.f;
+#pragma unroll
+          for (int p = 0; p < P; ++p) M += M2[(p * H + jh) * LD + p * W + cw];
+          atomicAdd(a.g_W2 + e, M);
+        }
+      }
+      {   // dgamma[c'] = sum_j' M W1[c'][j'] ,  dbeta[c'] = sum_j' W1[c'][j'] db1[j']: 256 / W partial sums per channel
+        constexpr int NP = 256 / W;
+        const int cw = tid % W, part = tid / W;
+        float dg = 0.f, db = 0.f;
+        for (int jh = part; jh < H; jh += NP) {
+          float M = 0.f, db1 = 0.f;
+#pragma unroll
+          for (int p = 0; p < P; ++p) { M += M1[(p * H + jh) * LD + p * W + cw]; db1 += v1s[p * H + jh]; }
+          const float w1 = a.W1[(size_t)cw * H + jh];
+          dg = fmaf(M, w1, dg);
+          db = fmaf(w1, db1, db);
+        }
+        Rg[part * W + cw] = dg;
+        Rb[part * W + cw] = db;
+      }
+      named_bar_sync(1, 256);
+      if (tid < W) {
+        constexpr int NP = 256 / W;
+        float dg = 0.f, db = 0.f, d2 = 0.f;
+        for (int q = 0; q < NP; ++q) { dg += Rg[q * W + tid]; db += Rb[q * W + tid]; }
+#pragma unroll
+        for (int p = 0; p < P; ++p) d2 += vb2[p * W + tid];
+        atomicAdd(a.g_gamma + tid, dg);
+        atomicAdd(a.g_beta + tid, db);
+        atomicAdd(a.g_b2 + tid, d2);
+      } else if (tid >= 64 && tid < 64 + H) {
+        const int jh = tid - 64;
+        float d1 = 0.f;
+#pragma unroll
+        for (int p = 0; p < P; ++p) d1 += v1s[p * H + jh];
+        atomicAdd(a.g_b1 + jh, d1);
+      }
+    }
+  } else if (warp == 8) {
+    // ---- TMA producer ----
+    if (lane == 0) {
+      auto load = [&](int i) {
+        const int s = i % B_NS;
+        const int row = (int)((blockIdx.x + (long long)i * gridDim.x) * 128);
+        mbar_expect_tx(smem_u32(&bars->full[s]), 2 * TILE);
+        tma_load_3d(smem_u32(sStage + s * 2 * TILE), &tm_dy, smem_u32(&bars->full[s]), 0, row, 0);
+        tma_load_3d(smem_u32(sStage + s * 2 * TILE + TILE), &tm_x, smem_u32(&bars->full[s]), 0, row, 0);
+      };
+      for (int i = 0; i < nl && i < B_NS; ++i) load(i);
+      for (int i = 0; i < nl; ++i) {
+        mbar_wait(smem_u32(&bars->out_ready), i & 1);
+        tma_store_3d(&tm_dx, smem_u32(sOut), 0, (int)((blockIdx.x + (long long)i * gridDim.x) * 128), 0);
+        tma_store_commit();
+        tma_store_wait_read<0>();
+        mbar_arrive(smem_u32(&bars->out_free));
+        mbar_wait(smem_u32(&bars->doneC), i & 1);           // the tensor core has read the stage too
+        if (i + B_NS < nl) load(i + B_NS);
+      }
+      tma_store_wait_all<0>();
+    }
+  } else if (warp == 9) {
+    // ---- issuer ----
+    const uint32_t loI1 = desc_lo(smem_u32(sImg1), TILE), loI2 = desc_lo(smem_u32(sImg2), 16);
+    const uint32_t loHid = desc_lo(smem_u32(sHid), TILE), loDpre_k = desc_lo(smem_u32(sDpre), 16),
+                   loDpre_mn = desc_lo(smem_u32(sDpre), TILE);
+    const uint32_t loOnes = desc_lo(smem_u32(sOnes), 128);
+    constexpr uint32_t HI_ONES = desc_hi(256, LAYOUT_NONE);
+    constexpr uint32_t ID_A = idesc_bf16(128, 128, 0, 0), ID_D3 = idesc_bf16(128, 64, 0, 1), ID_T = idesc_bf16(128, 64, 1, 1),
+                       ID_B = idesc_bf16(128, 16, 1, 0);
+    auto issue_A = [&](int i) {          // pre = x^ W1blk ; dhid = dy W2blk^T
+      const uint32_t dy_addr = smem_u32(sStage + (i % B_NS) * 2 * TILE), x_addr = dy_addr + TILE;
+      mbar_wait(smem_u32(&bars->readyA), i & 1);
+      tc_fence_after();
+      MmaChain<4>::ss(tmem + C_D1, desc_lo(x_addr, 16), HI_SW, desc_lo(smem_u32(sImg1), 16), HI_SW, ID_A, 0, 2, 2);
+      MmaChain<4>::ss(tmem + C_DH, desc_lo(dy_addr, 16), HI_SW, loI2, HI_SW, ID_A, 0, 2, 2);
+      mma_commit_w(smem_u32(&bars->doneA));
+    };
+    // order: A(0) | D3(0) A(1) wgrad(0) | D3(1) A(2) wgrad(1) | ...  -- the products the threads wait for go first
+    if (nl > 0) issue_A(0);
+    for (int i = 0; i < nl; ++i) {
+      const uint32_t dy_addr = smem_u32(sStage + (i % B_NS) * 2 * TILE), x_addr = dy_addr + TILE;
+      mbar_wait(smem_u32(&bars->readyB), i & 1);
+      tc_fence_after();
+      MmaChain<4>::ss(tmem + C_D3, loDpre_k, HI_SW, loI1, HI_SW, ID_D3, 0, 2, 128);                                   // dx^ = dpre W1blk^T
+      MmaChain<4>::ss(tmem + C_D3, loDpre_k + (TILE >> 4), HI_SW, loI1 + 4 * 128, HI_SW, ID_D3, 1, 2, 128);
+      mma_commit_w(smem_u32(&bars->doneB));
+      if (i + 1 < nl) issue_A(i + 1);
+      const uint32_t acc = i > 0;
+      MmaChain<8>::ss(tmem + C_W1, loDpre_mn, HI_SW, desc_lo(x_addr, TILE), HI_SW, ID_T, acc, 128, 128);              // dpre^T x^
+      MmaChain<8>::ss(tmem + C_W2, loHid, HI_SW, desc_lo(dy_addr, TILE), HI_SW, ID_T, acc, 128, 128);                 // hid^T dy
+      MmaChain<8>::ss(tmem + C_B1, loDpre_mn, HI_SW, loOnes, HI_ONES, ID_B, acc, 128, 32);                            // dpre^T 1
+      MmaChain<8>::ss(tmem + C_B2, desc_lo(dy_addr, TILE), HI_SW, loOnes, HI_ONES, ID_B, acc, 128, 32);               // [dy | x^]^T 1
+      mma_commit_w(smem_u32(&bars->doneC));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+bool ffn_tc_enabled() {     // read on every call: the parity tests switch between the two implementations
+  const char *e = getenv("EGT_FFN_TC");
+  return !(e && e[0] == '0');
+}
+
+bool ffn_tc_supported(const egt_ffn_cfg_t *cfg, const void *p0, const void *p1, const void *p2) {
+  if (!ffn_tc_enabled() || cfg->dtype != EGT_BF16) return false;
+  // activations with a discontinuous derivative stay on the fp32 kernels: with bf16 operands the sign of a
+  // pre-activation near zero can differ from the reference's, which flips relu' between 0 and 1 for that element
+  if (cfg->activation == EGT_ACT_RELU || cfg->activation == EGT_ACT_LRELU) return false;
+  const int w = cfg->width;
+  if (!(w == 8 || w == 16 || w == 32 || w == 64) || cfg->hidden != 2 * w) return false;
+  if ((cfg->rows * w) % 64 != 0) return false;
+  if (cfg->rows * w / 64 > 0x7fffffffll - 256) return false;
+  if ((((uintptr_t)p0 | (uintptr_t)p1 | (uintptr_t)p2) & 15) != 0) return false;
+  return true;
+}
+
+void fill_args(FfnTcArgs &a, const egt_ffn_cfg_t *cfg, const egt_ffn_weights_t *w, const egt_ffn_grads_t *g) {
+  memset(&a, 0, sizeof(a));
+  a.srows = cfg->rows * cfg->width / 64; a.act = cfg->activation; a.eps = cfg->ln_eps;
+  a.gamma = w->norm_gamma; a.beta = w->norm_beta; a.W1 = w->lr1_kernel; a.b1 = w->lr1_bias; a.W2 = w->lr2_kernel; a.b2 = w->lr2_bias;
+  if (g) { a.g_gamma = g->norm_gamma; a.g_beta = g->norm_beta; a.g_W1 = g->lr1_kernel; a.g_b1 = g->lr1_bias; a.g_W2 = g->lr2_kernel; a.g_b2 = g->lr2_bias; }
+}
+
+template <int W, int ACT>
+int fwd_launch_t(const CUtensorMap &mx, const CUtensorMap &my, const FfnTcArgs &a, unsigned grid, cudaStream_t st) {
+  EGT_CHECK_CUDA(cudaFuncSetAttribute(ffn_tc_fwd_kernel<W, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
+  LaunchScope _ls("ffn_tc_fwd_kernel", st);
+  ffn_tc_fwd_kernel<W, ACT><<<grid, 384, F_SMEM, st>>>(mx, my, a);
+  EGT_CHECK_CUDA(cudaGetLastError());
+  return EGT_OK;
+}
+template <int W, int ACT>
+int bwd_launch_t(const CUtensorMap &mx, const CUtensorMap &mdy, const CUtensorMap &mdx, const FfnTcArgs &a, unsigned grid,
+                 cudaStream_t st) {
+  EGT_CHECK_CUDA(cudaFuncSetAttribute(ffn_tc_bwd_kernel<W, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
+  LaunchScope _ls("ffn_tc_bwd_kernel", st);
+  ffn_tc_bwd_kernel<W, ACT><<<grid, 320, B_SMEM, st>>>(mx, mdy, mdx, a);
+  EGT_CHECK_CUDA(cudaGetLastError());
+  return EGT_OK;
+}
+
+#define FFN_TC_DISPATCH(FN, ...)                                                                   \
+  do {                                                                                             \
+    const bool elu = cfg->activation == EGT_ACT_ELU;                                               \
+    switch (cfg->width) {                                                                          \
+      case 8: return elu ? FN<8, EGT_ACT_ELU>(__VA_ARGS__) : FN<8, -1>(__VA_ARGS__);               \
+      case 16: return elu ? FN<16, EGT_ACT_ELU>(__VA_ARGS__) : FN<16, -1>(__VA_ARGS__);            \
+      case 32: return elu ? FN<32, EGT_ACT_ELU>(__VA_ARGS__) : FN<32, -1>(__VA_ARGS__);            \
+      default: return elu ? FN<64, EGT_ACT_ELU>(__VA_ARGS__) : FN<64, -1>(__VA_ARGS__);            \
+    }                                                                                              \
+  } while (0)
+
+}  // namespace
+
+bool ffn_tc_serves(const egt_ffn_cfg_t *cfg) { return ffn_tc_supported(cfg, nullptr, nullptr, nullptr); }
+
+// Returns 1 when the shape is not served by the tensor-core path (the caller then uses ffn_kernels.cu).
+int ffn_tc_fwd_launch(const egt_ffn_cfg_t *cfg, const egt_ffn_weights_t *w, const void *x, void *y, cudaStream_t st) {
+  if (!ffn_tc_supported(cfg, x, y, nullptr)) return 1;
+  FfnTcArgs a;
+  fill_args(a, cfg, w, nullptr);
+  CUtensorMap mx, my;
+  int rc = encode_tmap_3d(&mx, x, 64, (uint64_t)a.srows, 1, 128, (uint64_t)a.srows * 128, 64, 128, 1, 1);
+  if (rc) return rc;
+  rc = encode_tmap_3d(&my, y, 64, (uint64_t)a.srows, 1, 128, (uint64_t)a.srows * 128, 64, 128, 1, 1);
+  if (rc) return rc;
+  const long long ntiles = (a.srows + 127) / 128;
+  const unsigned grid = (unsigned)(ntiles < 148 ? ntiles : 148);
+  FFN_TC_DISPATCH(fwd_launch_t, mx, my, a, grid, st);
+}
+
+int ffn_tc_bwd_launch(const egt_ffn_cfg_t *cfg, const egt_ffn_weights_t *w, const egt_ffn_grads_t *g, const void *x,
+                      const void *dy, void *dx, cudaStream_t st) {
+  if (!ffn_tc_supported(cfg, x, dy, dx)) return 1;
+  FfnTcArgs a;
+  fill_args(a, cfg, w, g);
+  CUtensorMap mx, mdy, mdx;
+  int rc = encode_tmap_3d(&mx, x, 64, (uint64_t)a.srows, 1, 128, (uint64_t)a.srows * 128, 64, 128, 1, 1);
+  if (rc) return rc;
+  rc = encode_tmap_3d(&mdy, dy, 64, (uint64_t)a.srows, 1, 128, (uint64_t)a.srows * 128, 64, 128, 1, 1);
+  if (rc) return rc;
+  rc = encode_tmap_3d(&mdx, dx, 64, (uint64_t)a.srows, 1, 128, (uint64_t)a.srows * 128, 64, 128, 1, 1);
+  if (rc) return rc;
+  const long long ntiles = (a.srows + 127) / 128;
+  const unsigned grid = (unsigned)(ntiles < 148 ? ntiles : 148);
+  FFN_TC_DISPATCH(bwd_launch_t, mx, mdy, mdx, a, grid, st);
+}
+
+}  // namespace egt

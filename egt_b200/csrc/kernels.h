@@ -98,4 +98,11 @@ int edge_proj_bwd_launch(const EdgeParams &p, int dtype, cudaStream_t st);
 // shape-specialised versions (edge_fast.cu); kind 0..3 in the order above; returns 1 when the shape is not covered
 int edge_fast_launch(int kind, const EdgeParams &p, int dtype, cudaStream_t st);
 
+// feed-forward half on tensor cores (ffn_tc.cu): bf16, width 8/16/32/64, hidden = 2 width; returns 1 when the shape is
+// not served (the caller falls back to the CUDA-core kernels of ffn_kernels.cu); EGT_FFN_TC=0 switches it off
+bool ffn_tc_serves(const egt_ffn_cfg_t *cfg);   // shape / dtype / activation served (pointer alignment checked at launch)
+int ffn_tc_fwd_launch(const egt_ffn_cfg_t *cfg, const egt_ffn_weights_t *w, const void *x, void *y, cudaStream_t st);
+int ffn_tc_bwd_launch(const egt_ffn_cfg_t *cfg, const egt_ffn_weights_t *w, const egt_ffn_grads_t *g, const void *x,
+                      const void *dy, void *dx, cudaStream_t st);
+
 }  // namespace egt

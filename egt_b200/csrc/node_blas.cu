@@ -243,4 +243,179 @@ int node_blas_bwd2(const void *h, const float *d_qkv, const egt_block_weights_t 
   return gemm_rm(hd, false, true, R, d, 3 * d, c.dqkv_bf, 3 * d, c.w_qkv, 3 * d, dhn, CUDA_R_32F, d, 0.f);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Feed-forward half of a layer for the channel widths the tcgen05 kernels of ffn_tc.cu do not serve (node channel at
+// d = 96 / 128, any hidden width): the same cuBLAS + element-wise-kernel pattern.
+//   reference: ffnlr1 / ffnact / ffnlr2, ffn_block (lib/models/graph_xformer_model_base.py:229-258, :309-324)
+namespace {
+
+// w1_aug [w+8, hid] = [W1 ; b1 ; 0], w1 [w, hid], w2 [hid, w]   (bf16 operand copies)
+__global__ void __launch_bounds__(256) fb_prep_kernel(const float *W1, const float *b1, const float *W2, int w, int hid,
+                                                      __nv_bfloat16 *w1_aug, __nv_bfloat16 *w1, __nv_bfloat16 *w2) {
+  const int tot_aug = (w + 8) * hid;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < tot_aug; i += gridDim.x * 256) {
+    const int r = i / hid, c = i % hid;
+    const float v = r < w ? W1[i] : r == w ? b1[c] : 0.f;
+    w1_aug[i] = __float2bfloat16_rn(v);
+    if (r < w && w1) w1[i] = __float2bfloat16_rn(v);
+  }
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < hid * w; i += gridDim.x * 256) w2[i] = __float2bfloat16_rn(W2[i]);
+}
+
+// hid = act(pre)   (pre already carries the bias)
+__global__ void __launch_bounds__(256) fb_act_kernel(const __nv_bfloat16 *pre, __nv_bfloat16 *hid, size_t n, int act) {
+  for (size_t i = ((size_t)blockIdx.x * 256 + threadIdx.x) * 2; i < n; i += (size_t)gridDim.x * 512) {   // n even
+    const __nv_bfloat162 p = *(const __nv_bfloat162 *)(pre + i);
+    *(__nv_bfloat162 *)(hid + i) = __floats2bfloat162_rn(edge_act_fwd(act, 0.2f, __bfloat162float(p.x)),
+                                                         edge_act_fwd(act, 0.2f, __bfloat162float(p.y)));
+  }
+}
+// dpre = dhid * act'(pre), in place over dhid
+__global__ void __launch_bounds__(256) fb_dact_kernel(const __nv_bfloat16 *pre, __nv_bfloat16 *dhid, size_t n, int act) {
+  for (size_t i = ((size_t)blockIdx.x * 256 + threadIdx.x) * 2; i < n; i += (size_t)gridDim.x * 512) {
+    const __nv_bfloat162 p = *(const __nv_bfloat162 *)(pre + i), d = *(const __nv_bfloat162 *)(dhid + i);
+    *(__nv_bfloat162 *)(dhid + i) = __floats2bfloat162_rn(__bfloat162float(d.x) * edge_act_bwd(act, 0.2f, __bfloat162float(p.x)),
+                                                          __bfloat162float(d.y) * edge_act_bwd(act, 0.2f, __bfloat162float(p.y)));
+  }
+}
+
+struct FfnCarve {
+  __nv_bfloat16 *xe_aug, *pre, *hid, *w1_aug, *w1, *w2;
+  float *tmp;
+  void *blas_ws;
+};
+FfnCarve ffn_carve(void *base, size_t R, int w, int hid) {
+  char *p = (char *)base;
+  FfnCarve c;
+  auto take = [&](size_t bytes) { char *q = p; p += al(bytes); return q; };
+  c.xe_aug = (__nv_bfloat16 *)take(R * (w + 8) * 2);
+  c.pre = (__nv_bfloat16 *)take(R * hid * 2);
+  c.hid = (__nv_bfloat16 *)take(R * hid * 2);
+  c.w1_aug = (__nv_bfloat16 *)take((size_t)(w + 8) * hid * 2);
+  c.w1 = (__nv_bfloat16 *)take((size_t)w * hid * 2);
+  c.w2 = (__nv_bfloat16 *)take((size_t)hid * w * 2);
+  c.tmp = (float *)take(R * w * 4);
+  c.blas_ws = take(kBlasWs);
+  return c;
+}
+int ffn_begin(cublasHandle_t *h, void *blas_ws, cudaStream_t st) {
+  int rc = get_handle(h);
+  if (rc) return rc;
+  cublasStatus_t s = cublasSetStream(*h, st);
+  EGT_REQUIRE(s == CUBLAS_STATUS_SUCCESS, EGT_E_CUDA, "cublasSetStream failed with status %d", (int)s);
+  s = cublasSetWorkspace(*h, blas_ws, kBlasWs);
+  EGT_REQUIRE(s == CUBLAS_STATUS_SUCCESS, EGT_E_CUDA, "cublasSetWorkspace failed with status %d", (int)s);
+  return EGT_OK;
+}
+unsigned ew_grid(size_t n, int per_thread) {
+  const size_t b = (n / per_thread + 255) / 256;
+  return (unsigned)(b < 1 ? 1 : b < 4096 ? b : 4096);
+}
+
+}  // namespace
+
+// bf16, smooth activations (the derivative of relu / lrelu flips with the bf16 rounding of a pre-activation near
+// zero), widths that are multiples of 8, enough rows for a GEMM to pay
+bool ffn_blas_supported(const egt_ffn_cfg_t *cfg) {
+  static const bool off = getenv("EGT_FFN_BLAS") && atoi(getenv("EGT_FFN_BLAS")) == 0;
+  return !off && cfg->dtype == EGT_BF16 && cfg->activation != EGT_ACT_RELU && cfg->activation != EGT_ACT_LRELU &&
+         cfg->width % 8 == 0 && cfg->hidden % 8 == 0 && cfg->width <= 256 && cfg->rows >= 512 && cfg->rows < (1ll << 31);
+}
+
+size_t ffn_blas_workspace_bytes(const egt_ffn_cfg_t *cfg) {
+  const size_t R = (size_t)cfg->rows, w = cfg->width, hid = cfg->hidden;
+  return al(R * (w + 8) * 2) + 2 * al(R * hid * 2) + al((w + 8) * hid * 2) + 2 * al(w * hid * 2) + al(R * w * 4) + al(kBlasWs);
+}
+
+int ffn_blas_fwd(const egt_ffn_cfg_t *cfg, const egt_ffn_weights_t *wt, const void *x, void *y, void *ws, cudaStream_t st) {
+  const int R = (int)cfg->rows, w = cfg->width, hid = cfg->hidden;
+  const FfnCarve c = ffn_carve(ws, R, w, hid);
+  cublasHandle_t hd;
+  int rc = ffn_begin(&hd, c.blas_ws, st);
+  if (rc) return rc;
+  {
+    LaunchScope _ls("fb_prep_kernel", st);
+    fb_prep_kernel<<<64, 256, 0, st>>>(wt->lr1_kernel, wt->lr1_bias, wt->lr2_kernel, w, hid, c.w1_aug, nullptr, c.w2);
+  }
+  {
+    LaunchScope _ls("nb_ln_aug_kernel", st);
+    nb_ln_aug_kernel<<<(R + 7) / 8, 256, 0, st>>>((const __nv_bfloat16 *)x, wt->norm_gamma, wt->norm_beta, cfg->ln_eps, R, w, c.xe_aug);
+  }
+  EGT_CHECK_CUDA(cudaGetLastError());
+  {
+    LaunchScope _ls("cublas_gemm", st);
+    if ((rc = gemm_rm(hd, false, false, R, hid, w + 8, c.xe_aug, w + 8, c.w1_aug, hid, c.pre, CUDA_R_16BF, hid, 0.f))) return rc;
+  }
+  const size_t nh = (size_t)R * hid, nw = (size_t)R * w;
+  {
+    LaunchScope _ls("fb_act_kernel", st);
+    fb_act_kernel<<<ew_grid(nh, 2), 256, 0, st>>>(c.pre, c.pre, nh, cfg->activation);
+  }
+  EGT_CHECK_CUDA(cudaGetLastError());
+  {
+    LaunchScope _ls("cublas_gemm", st);
+    if ((rc = gemm_rm(hd, false, false, R, w, hid, c.pre, hid, c.w2, w, c.tmp, CUDA_R_32F, w, 0.f))) return rc;
+  }
+  LaunchScope _ls("nb_out_epilogue_kernel", st);
+  nb_out_epilogue_kernel<<<ew_grid(nw, 4) < 2048 ? ew_grid(nw, 4) : 2048, 256, 0, st>>>((const __nv_bfloat16 *)x, c.tmp, wt->lr2_bias, nw, w,
+                                                                                          (__nv_bfloat16 *)y);
+  EGT_CHECK_CUDA(cudaGetLastError());
+  return EGT_OK;
+}
+
+int ffn_blas_bwd(const egt_ffn_cfg_t *cfg, const egt_ffn_weights_t *wt, const egt_ffn_grads_t *g, const void *x, const void *dy,
+                 void *dx, void *ws, cudaStream_t st) {
+  const int R = (int)cfg->rows, w = cfg->width, hid = cfg->hidden;
+  const FfnCarve c = ffn_carve(ws, R, w, hid);
+  cublasHandle_t hd;
+  int rc = ffn_begin(&hd, c.blas_ws, st);
+  if (rc) return rc;
+  const size_t nh = (size_t)R * hid;
+  {
+    LaunchScope _ls("fb_prep_kernel", st);
+    fb_prep_kernel<<<64, 256, 0, st>>>(wt->lr1_kernel, wt->lr1_bias, wt->lr2_kernel, w, hid, c.w1_aug, c.w1, c.w2);
+  }
+  {
+    LaunchScope _ls("nb_ln_aug_kernel", st);
+    nb_ln_aug_kernel<<<(R + 7) / 8, 256, 0, st>>>((const __nv_bfloat16 *)x, wt->norm_gamma, wt->norm_beta, cfg->ln_eps, R, w, c.xe_aug);
+  }
+  {
+    LaunchScope _ls("nb_colsum_kernel", st);
+    nb_colsum_kernel<__nv_bfloat16><<<(R + 63) / 64, 256, 0, st>>>((const __nv_bfloat16 *)dy, R, w, g->lr2_bias, nullptr);
+  }
+  EGT_CHECK_CUDA(cudaGetLastError());
+  {
+    LaunchScope _ls("cublas_gemm", st);
+    if ((rc = gemm_rm(hd, false, false, R, hid, w + 8, c.xe_aug, w + 8, c.w1_aug, hid, c.pre, CUDA_R_16BF, hid, 0.f))) return rc;   // pre
+  }
+  {
+    LaunchScope _ls("fb_act_kernel", st);
+    fb_act_kernel<<<ew_grid(nh, 2), 256, 0, st>>>(c.pre, c.hid, nh, cfg->activation);
+  }
+  EGT_CHECK_CUDA(cudaGetLastError());
+  {
+    LaunchScope _ls("cublas_gemm", st);
+    if ((rc = gemm_rm(hd, true, false, hid, w, R, c.hid, hid, dy, w, g->lr2_kernel, CUDA_R_32F, w, 1.f))) return rc;       // dW2 += hid^T dy
+    if ((rc = gemm_rm(hd, false, true, R, hid, w, dy, w, c.w2, w, c.hid, CUDA_R_16BF, hid, 0.f))) return rc;              // dhid = dy W2^T
+  }
+  {
+    LaunchScope _ls("fb_dact_kernel", st);
+    fb_dact_kernel<<<ew_grid(nh, 2), 256, 0, st>>>(c.pre, c.hid, nh, cfg->activation);                                    // dpre
+  }
+  {
+    LaunchScope _ls("nb_colsum_kernel", st);
+    nb_colsum_kernel<__nv_bfloat16><<<(R + 63) / 64, 256, 0, st>>>(c.hid, R, hid, g->lr1_bias, nullptr);
+  }
+  EGT_CHECK_CUDA(cudaGetLastError());
+  {
+    LaunchScope _ls("cublas_gemm", st);
+    if ((rc = gemm_rm(hd, true, false, w, hid, R, c.xe_aug, w + 8, c.hid, hid, g->lr1_kernel, CUDA_R_32F, hid, 1.f))) return rc;   // dW1 += LN(x)^T dpre
+    if ((rc = gemm_rm(hd, false, true, R, w, hid, c.hid, hid, c.w1, hid, c.tmp, CUDA_R_32F, w, 0.f))) return rc;                  // d LN(x) = dpre W1^T
+  }
+  LnBwdArgs lb;
+  lb.x = x; lb.dy = c.tmp; lb.dres = dy; lb.gamma = wt->norm_gamma; lb.eps = cfg->ln_eps; lb.dx = dx;
+  lb.dgamma = g->norm_gamma; lb.dbeta = g->norm_beta; lb.R = R; lb.D = w;
+  return ln_bwd_launch(lb, EGT_BF16, st);
+}
+
 }  // namespace egt

@@ -18,4 +18,11 @@ int node_blas_bwd1(const void *dh_out, const void *v_att, const egt_block_weight
 int node_blas_bwd2(const void *h, const float *d_qkv, const egt_block_weights_t *w, const egt_block_grads_t *g, float eps,
                    float *dhn, int R, int d, void *ws, cudaStream_t st);
 
+// feed-forward half of a layer on cuBLAS (widths / hidden sizes ffn_tc.cu does not serve); EGT_FFN_BLAS=0 turns it off
+bool ffn_blas_supported(const egt_ffn_cfg_t *cfg);
+size_t ffn_blas_workspace_bytes(const egt_ffn_cfg_t *cfg);
+int ffn_blas_fwd(const egt_ffn_cfg_t *cfg, const egt_ffn_weights_t *w, const void *x, void *y, void *ws, cudaStream_t st);
+int ffn_blas_bwd(const egt_ffn_cfg_t *cfg, const egt_ffn_weights_t *w, const egt_ffn_grads_t *g, const void *x, const void *dy,
+                 void *dx, void *ws, cudaStream_t st);
+
 }  // namespace egt

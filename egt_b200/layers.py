@@ -271,6 +271,10 @@ class EGTStack(nn.Module):
     def _bind(self):
         """Re-create the per-module views (after ``.to(device)`` or before every forward: autograd must see them as
         slices of the ONE parameter)."""
+        # drop the previous views first: they keep the autograd node of self.flat from an earlier call alive (on
+        # whatever stream that call ran), which breaks CUDA-graph capture of a later call
+        for m in self._owners:
+            m.flat = None
         for m, (off, n) in zip(self._owners, self._spans):
             m.flat = self.flat[off:off + n]
 

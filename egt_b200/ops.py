@@ -380,7 +380,9 @@ class _EGTFfnFn(torch.autograd.Function):
         w = L.FfnWeights()
         for f in L.FFN_FIELDS:
             setattr(w, f, flat.data_ptr() + 4 * layout[f][0])
-        L.check(lib.egt_ffn_fwd(C.byref(cfg), C.byref(w), _ptr(x), _ptr(y), _stream()))
+        nws = int(lib.egt_ffn_workspace_bytes(C.byref(cfg)))
+        ws = torch.empty(nws, dtype=torch.uint8, device=x.device) if nws else None
+        L.check(lib.egt_ffn_fwd_ws(C.byref(cfg), C.byref(w), _ptr(x), _ptr(y), _ptr(ws) if nws else None, nws, _stream()))
         ctx.save_for_backward(x, flat)
         ctx.cfg, ctx.layout = cfg, layout
         return y
@@ -397,7 +399,10 @@ class _EGTFfnFn(torch.autograd.Function):
         for f in L.FFN_FIELDS:
             setattr(w, f, flat.data_ptr() + 4 * layout[f][0])
             setattr(g, f, dflat.data_ptr() + 4 * layout[f][0])
-        L.check(lib.egt_ffn_bwd(C.byref(cfg), C.byref(w), C.byref(g), _ptr(x), _ptr(dy), _ptr(dx), _stream()))
+        nws = int(lib.egt_ffn_workspace_bytes(C.byref(cfg)))
+        ws = torch.empty(nws, dtype=torch.uint8, device=x.device) if nws else None
+        L.check(lib.egt_ffn_bwd_ws(C.byref(cfg), C.byref(w), C.byref(g), _ptr(x), _ptr(dy), _ptr(dx), _ptr(ws) if nws else None, nws,
+                                   _stream()))
         return dx, dflat, None, None, None, None, None
 
 

@@ -210,6 +210,15 @@ typedef struct egt_ffn_grads {             /* accumulators: the library ADDS int
 int egt_ffn_fwd(const egt_ffn_cfg_t *cfg, const egt_ffn_weights_t *w, const void *x, void *y, void *stream);
 int egt_ffn_bwd(const egt_ffn_cfg_t *cfg, const egt_ffn_weights_t *w, const egt_ffn_grads_t *g, const void *x,
                 const void *dy, void *dx, void *stream);
+/* The same two calls with a caller-owned device workspace of egt_ffn_workspace_bytes(cfg) bytes (256-byte aligned).
+ * With a workspace, channel shapes that neither tensor-core kernel serves (node channel at d = 96 / 128) run as cuBLAS
+ * GEMMs with element-wise kernels around them instead of the CUDA-core kernels; egt_ffn_workspace_bytes returns 0 when
+ * the shape does not use one (ws may then be NULL). */
+size_t egt_ffn_workspace_bytes(const egt_ffn_cfg_t *cfg);
+int egt_ffn_fwd_ws(const egt_ffn_cfg_t *cfg, const egt_ffn_weights_t *w, const void *x, void *y, void *ws, size_t ws_bytes,
+                   void *stream);
+int egt_ffn_bwd_ws(const egt_ffn_cfg_t *cfg, const egt_ffn_weights_t *w, const egt_ffn_grads_t *g, const void *x,
+                   const void *dy, void *dx, void *ws, size_t ws_bytes, void *stream);
 
 /* ---- data parallelism: the single gradient all-reduce of MirroredStrategy (training_base.py:230-238) --- */
 /* One-shot SUM all-reduce of `grad` (n float32, n % 4 == 0) over peer-mapped memory (NVLink / NVSwitch).

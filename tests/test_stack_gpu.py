@@ -50,3 +50,42 @@ def test_stack_equals_layers_and_has_one_gradient_buffer(ffn):
             got = stack.flat.grad[off:off + n]
             torch.testing.assert_close(got, ref, rtol=1e-3, atol=1e-3 * float(ref.abs().max()))   # atomics: summation order
             k += 1
+
+
+def test_full_layer_step_replays_from_a_cuda_graph():
+    """One full layer (attention block + node FFN + edge FFN) forward + backward captured after eager warm-up steps:
+    the replay reproduces the eager gradients (bench.py's full_layer leg relies on this)."""
+    import egt_b200
+    torch.manual_seed(0)
+    B, N, d, de = 2, 48, 64, 8
+    lay = egt_b200.EGTStack(1, ffn=True, model_width=d, edge_width=de, num_heads=8).to(DEV)
+    lay.train(False)
+    h = torch.randn(B, N, d, device=DEV).bfloat16()
+    e = torch.randn(B, N, N, de, device=DEV).bfloat16()
+    m = torch.ones(B, N, dtype=torch.bool, device=DEV)
+    dh, de_ = torch.randn_like(h), torch.randn_like(e)
+
+    def step():
+        hh, ee = h.detach().requires_grad_(True), e.detach().requires_grad_(True)
+        lay.flat.grad = None
+        h2, e2 = lay(hh, ee, m)
+        torch.autograd.backward([h2, e2], [dh, de_])
+        return hh.grad, ee.grad, lay.flat.grad
+
+    for _ in range(2):
+        ref = [t.clone() for t in step()]          # eager, on the default stream
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = step()
+    for _ in range(2):
+        g.replay()
+    torch.cuda.synchronize()
+    for got, want in zip(out, ref):
+        scale = float(want.float().abs().max())
+        assert float((got.float() - want.float()).abs().max()) <= 2e-3 * scale   # weight gradients: atomics, order differs

@@ -17,9 +17,10 @@ try:
     d = json.loads(open(f'gpurun_out/sweep_{sys.argv[1]}.json').read())
     k = d['roofline']['kernels']
     t = d.get('training_step') or {}
+    fl = d.get('full_layer') or {}
     print(d['config']['workload'], d['config'].get('path'), round(d['value']), 'graphs/s', round(d['ms_per_step'], 4), 'ms',
           'step_frac', round(d['roofline']['step_frac'], 3), 'e2e', round(d['e2e']['value']),
-          'train', round(t.get('value', 0)),
+          'train', round(t.get('value', 0)), 'layer_ms', round(fl.get('ms_per_step', 0), 4),
           ' '.join(f"{n.replace('_kernel', '')}={v['ms_total'] / v['launches'] * 1000:.0f}" for n, v in k.items()))
 except Exception as ex:
     print(sys.argv[1], 'FAILED', ex)
