@@ -18,9 +18,10 @@
 // shared-memory images serve all four dense products: an image read K-major for W is read MN-major for W^T.
 //
 // The thread arithmetic is the point-wise part only: LayerNorm statistics, bias + activation, LayerNorm backward.
-// Forward: two compute warpgroups (thread = super-row) with private tensor memory and a private issuing warp each.
-// Backward: one group of 256 threads (thread = super-row x column half), one issuing warp; the LayerNorm of the next
-// tile is computed while the tensor core works on dx^ of the current one.
+// Forward: two compute groups of 256 threads (thread = super-row x column half) with private tensor memory and a
+// private issuing warp each; biases and the residual are accumulated by the tensor core as well.
+// Backward: one group of 512 threads (thread = super-row x channel quarter), one issuing warp; the LayerNorm of the
+// next tile is computed while the tensor core works on dx^ of the current one.
 #include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
@@ -80,7 +81,7 @@ __device__ __forceinline__ void act_fd(int act, float x, float &f, float &d) {
 // sb1[j] = b1[j'] + sum_c beta[c] W1[c][j'] ;  sb2[c] = b2[c'].
 template <int W>
 __device__ __forceinline__ void build_images(uint8_t *img1, uint8_t *img2, float *sb1, float *sb2, const FfnTcArgs &a,
-                                             int tid, int nthr) {
+                                             int tid, int nthr, float sc1 = 1.f) {
   constexpr int H = 2 * W;
   for (int i = tid; i < 128 * 8; i += nthr) {
     const int j = i >> 3, c0 = (i & 7) << 3;
@@ -90,7 +91,7 @@ __device__ __forceinline__ void build_images(uint8_t *img1, uint8_t *img2, float
       float y1[8], y2[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        y1[u] = a.gamma[cw0 + u] * a.W1[(size_t)(cw0 + u) * H + jh];
+        y1[u] = a.gamma[cw0 + u] * a.W1[(size_t)(cw0 + u) * H + jh] * sc1;
         y2[u] = a.W2[(size_t)jh * W + cw0 + u];
       }
       v1 = pack8(y1); v2 = pack8(y2);
@@ -117,30 +118,82 @@ constexpr uint32_t HI_SW = desc_hi(1024, LAYOUT_SW128);
 
 // ------------------------------------------------------------------------------------------------------------------
 // forward
+//
+// Two compute groups of 256 threads (thread = super-row x 32-channel half) with private tensor memory
+// (pre 128 | hid 64 | out 64 columns) and a private issuing warp each.  Everything that is linear runs on the tensor
+// core, including the biases (a constant A tile whose columns 0 / 1 are ones against a B image holding bias hi / lo
+// in k-rows 0 / 1) and the residual (x * I accumulated into the second product), so the threads only normalise,
+// apply the activation and convert.  For elu the first layer is pre-multiplied by log2(e): the exponential is one
+// ex2 of the accumulator.
 constexpr int F_NS = 6;
 struct FwdBars {
   uint64_t full[F_NS], tile_done[F_NS], ready1[2], done1[2], ready2[2], done2[2];
   uint32_t tmem_base, pad;
 };
-constexpr int F_SMEM = 1024 + F_NS * TILE + 2 * TILE + 2 * TILE + (128 + 64) * 4 + sizeof(FwdBars);
+// stages | A1 x 2 | img1 | img2 | ones A | identity 8 KB | bias1 image 4 KB | bias2 image 2 KB | xch 2 x [2][128][2] | bars
+constexpr int F_SMEM = 1024 + F_NS * TILE + 2 * TILE + 2 * TILE + TILE + 8192 + 4096 + 2048 + 2 * 2 * 128 * 2 * 4 + sizeof(FwdBars);
+constexpr int F_THREADS = 19 * 32;     // 16 compute warps, TMA producer, two issuers
+
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t v) { return make_float2(bf16_lo(v), bf16_hi(v)); }
+__device__ __forceinline__ void fmul2(float2 &acc, const float2 a) {
+  unsigned long long &c = reinterpret_cast<unsigned long long &>(acc);
+  asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(c) : "l"(reinterpret_cast<const unsigned long long &>(a)));
+}
+
+// 32 channels of one super-row (16 float2) -> normalised in place; GW channels per LayerNorm group inside the half.
+// W == 64: the two halves of a row exchange their partial sums through xch (named barrier `bar_id` over `bar_n` threads).
+template <int W>
+__device__ __forceinline__ void ln_half(float2 *x, float eps, float *xch, int t, int half, int bar_id, int bar_n, float *rs_out) {
+  constexpr int GW = W >= 32 ? 32 : W, PH = 32 / GW;
+#pragma unroll
+  for (int p = 0; p < PH; ++p) {
+    float2 s2 = x[p * GW / 2];
+#pragma unroll
+    for (int c = 1; c < GW / 2; ++c) fadd2(s2, x[p * GW / 2 + c]);
+    float sum = s2.x + s2.y;
+    if (W == 64) {
+      xch[(half * 128 + t) * 2] = sum;
+      named_bar_sync(bar_id, bar_n);
+      sum = xch[t * 2] + xch[(128 + t) * 2];
+    }
+    const float mu = sum * (1.f / W);
+    const float2 nm = make_float2(-mu, -mu);
+    float2 v2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < GW / 2; ++c) { fadd2(x[p * GW / 2 + c], nm); ffma2(v2, x[p * GW / 2 + c], x[p * GW / 2 + c]); }
+    float var = v2.x + v2.y;
+    if (W == 64) {
+      xch[(half * 128 + t) * 2 + 1] = var;
+      named_bar_sync(bar_id, bar_n);
+      var = xch[t * 2 + 1] + xch[(128 + t) * 2 + 1];
+    }
+    const float rs = rsqrtf(var * (1.f / W) + eps);
+    const float2 r2 = make_float2(rs, rs);
+#pragma unroll
+    for (int c = 0; c < GW / 2; ++c) fmul2(x[p * GW / 2 + c], r2);
+    if (rs_out) rs_out[p] = rs;
+  }
+}
 
 template <int W, int ACT>
-__global__ void __launch_bounds__(384, 1) ffn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x,
-                                                            const __grid_constant__ CUtensorMap tm_y, const FfnTcArgs a) {
+__global__ void __launch_bounds__(F_THREADS, 1) ffn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x,
+                                                                  const __grid_constant__ CUtensorMap tm_y, const FfnTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t *sStage = smem, *sA1 = smem + F_NS * TILE, *sImg1 = sA1 + 2 * TILE, *sImg2 = sImg1 + TILE;
-  float *sb1 = (float *)(sImg2 + TILE), *sb2 = sb1 + 128;
-  FwdBars *bars = (FwdBars *)(sb2 + 64);
+  uint8_t *sStage = smem, *sA1 = smem + F_NS * TILE, *sImg1 = sA1 + 2 * TILE, *sImg2 = sImg1 + TILE, *sOnes = sImg2 + TILE;
+  uint8_t *sIdent = sOnes + TILE, *sBb1 = sIdent + 8192, *sBb2 = sBb1 + 4096;
+  float *xch = (float *)(sBb2 + 2048);
+  FwdBars *bars = (FwdBars *)(xch + 2 * 2 * 128 * 2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long ntiles = (a.srows + 127) / 128;
   const int nl = (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);     // tiles of this CTA
+  constexpr float SC = ACT == EGT_ACT_ELU ? kLog2e : 1.f;                      // scale folded into the first layer
   if (warp == 0) {
     if (lane == 0) {
-      for (int s = 0; s < F_NS; ++s) { mbar_init(smem_u32(&bars->full[s]), 1); mbar_init(smem_u32(&bars->tile_done[s]), 4); }
+      for (int s = 0; s < F_NS; ++s) { mbar_init(smem_u32(&bars->full[s]), 1); mbar_init(smem_u32(&bars->tile_done[s]), 8); }
       for (int q = 0; q < 2; ++q) {
-        mbar_init(smem_u32(&bars->ready1[q]), 4); mbar_init(smem_u32(&bars->done1[q]), 1);
-        mbar_init(smem_u32(&bars->ready2[q]), 4); mbar_init(smem_u32(&bars->done2[q]), 1);
+        mbar_init(smem_u32(&bars->ready1[q]), 8); mbar_init(smem_u32(&bars->done1[q]), 1);
+        mbar_init(smem_u32(&bars->ready2[q]), 8); mbar_init(smem_u32(&bars->done2[q]), 1);
       }
       mbar_fence_init();
       tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_y);
@@ -148,43 +201,79 @@ __global__ void __launch_bounds__(384, 1) ffn_tc_fwd_kernel(const __grid_constan
     __syncwarp();
     tmem_alloc(smem_u32(&bars->tmem_base), 512);
   }
-  build_images<W>(sImg1, sImg2, sb1, sb2, a, tid, 384);
+  {
+    float *sb1 = (float *)sStage, *sb2 = sb1 + 128;     // bias vectors, staged in the first stage until the images are built
+    build_images<W>(sImg1, sImg2, sb1, sb2, a, tid, F_THREADS, SC);
+    // constant operands: ones A tile (columns 0 and 1), identity
+    for (int i = tid; i < 128 * 8; i += F_THREADS) {
+      const int r = i >> 3, ch = i & 7;
+      *(uint4 *)(sOnes + sw128_off(r, 8 * ch)) = ch == 0 ? make_uint4(0x3F803F80u, 0, 0, 0) : make_uint4(0, 0, 0, 0);
+    }
+    for (int i = tid; i < 64 * 8; i += F_THREADS) {
+      const int r = i >> 3, ch = i & 7;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (ch == (r >> 3)) {
+        const uint32_t one = (r & 1) ? 0x3F800000u : 0x00003F80u;
+        const int wsel = (r & 7) >> 1;
+        v.x = wsel == 0 ? one : 0; v.y = wsel == 1 ? one : 0; v.z = wsel == 2 ? one : 0; v.w = wsel == 3 ? one : 0;
+      }
+      *(uint4 *)(sIdent + sw128_off(r, 8 * ch)) = v;
+    }
+    __syncthreads();
+    // bias images, MN-major: k-row 0 = hi, k-row 1 = lo, k-rows 2..15 zero
+    for (int i = tid; i < 16 * 16; i += F_THREADS) {          // bias 1: 16 k-rows x 16 chunks of 8 hidden columns
+      const int k = i >> 4, n0 = (i & 15) << 3;
+      float y[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float b = sb1[n0 + u] * SC, hi = __bfloat162float(__float2bfloat16_rn(b));
+        y[u] = k == 0 ? hi : k == 1 ? b - hi : 0.f;
+      }
+      *(uint4 *)(sBb1 + (uint32_t)(n0 >> 6) * 2048u + (uint32_t)(k >> 3) * 1024u + (uint32_t)(k & 7) * 128u +
+                 ((uint32_t)((((n0 & 63) >> 3) ^ k) & 7) << 4)) = pack8(y);
+    }
+    for (int i = tid; i < 16 * 8; i += F_THREADS) {           // bias 2: 16 k-rows x 8 chunks of 8 channels
+      const int k = i >> 3, n0 = (i & 7) << 3;
+      float y[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float b = sb2[n0 + u], hi = __bfloat162float(__float2bfloat16_rn(b));
+        y[u] = k == 0 ? hi : k == 1 ? b - hi : 0.f;
+      }
+      *(uint4 *)(sBb2 + (uint32_t)(k >> 3) * 1024u + (uint32_t)(k & 7) * 128u + ((uint32_t)(((n0 >> 3) ^ k) & 7) << 4)) = pack8(y);
+    }
+  }
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
-  constexpr uint32_t GC = 192, C_D1 = 0, C_D2 = 128;      // per group: pre -> hid (bf16, aliased) | out
-  constexpr int P = 64 / W;
+  constexpr uint32_t GC = 256, C_D1 = 0, C_HID = 128, C_D2 = 192;      // per group: pre | hid (bf16) | out
 
-  if (warp < 8) {
-    // ---- compute group q: thread = super-row ----
-    const int q = warp >> 2, t = tid & 127;
+  if (warp < 16) {
+    // ---- compute group q: thread = (super-row t, channel half) ----
+    const int q = warp >> 3, half = (warp >> 2) & 1, t = tid & 127;
     const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16) + q * GC;
     uint8_t *A1 = sA1 + q * TILE;
-    // x tile i -> LayerNorm -> A operand of the first product
+    float *xq = xch + q * (2 * 128 * 2);
     auto layer_norm = [&](int i) {
       const int s = i % F_NS;
       const uint8_t *stg = sStage + s * TILE;
       mbar_wait(smem_u32(&bars->full[s]), (i / F_NS) & 1);
-      float xs[64];
+      float2 x[16];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) unpack8(*(const uint4 *)(stg + sw128_off(t, 8 * j)), xs + 8 * j);
-#pragma unroll
-      for (int p = 0; p < P; ++p) {
-        float mu = 0.f;
-#pragma unroll
-        for (int c = 0; c < W; ++c) mu += xs[p * W + c];
-        mu *= (1.f / W);
-        float var = 0.f;
-#pragma unroll
-        for (int c = 0; c < W; ++c) { xs[p * W + c] -= mu; var = fmaf(xs[p * W + c], xs[p * W + c], var); }
-        const float rs = rsqrtf(var * (1.f / W) + a.eps);
-#pragma unroll
-        for (int c = 0; c < W; ++c) xs[p * W + c] *= rs;
+      for (int j = 0; j < 4; ++j) {
+        const uint4 v = *(const uint4 *)(stg + sw128_off(t, 8 * (4 * half + j)));
+        x[4 * j] = bf2_to_f2(v.x); x[4 * j + 1] = bf2_to_f2(v.y); x[4 * j + 2] = bf2_to_f2(v.z); x[4 * j + 3] = bf2_to_f2(v.w);
       }
+      ln_half<W>(x, a.eps, xq, t, half, 1 + q, 256, nullptr);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) *(uint4 *)(A1 + sw128_off(t, 8 * j)) = pack8(xs + 8 * j);
+      for (int j = 0; j < 4; ++j) {
+        uint4 v;
+        v.x = pack_bf16(x[4 * j].x, x[4 * j].y); v.y = pack_bf16(x[4 * j + 1].x, x[4 * j + 1].y);
+        v.z = pack_bf16(x[4 * j + 2].x, x[4 * j + 2].y); v.w = pack_bf16(x[4 * j + 3].x, x[4 * j + 3].y);
+        *(uint4 *)(A1 + sw128_off(t, 8 * (4 * half + j))) = v;
+      }
       fence_proxy_async_smem();
       warp_arrive(smem_u32(&bars->ready1[q]), lane);
     };
@@ -197,17 +286,24 @@ __global__ void __launch_bounds__(384, 1) ffn_tc_fwd_kernel(const __grid_constan
       mbar_wait(smem_u32(&bars->done1[q]), it & 1);
       tc_fence_after();
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {     // hid = act(pre + b1') -> bf16 A operand over the columns already read
+      for (int k = 0; k < 2; ++k) {     // hid = act(pre) -> bf16 A operand of the second product
         uint32_t r[32], o[16];
-        tmem_ld32(tl + C_D1 + 32 * k, r);
+        tmem_ld32(tl + C_D1 + 64 * half + 32 * k, r);
         tmem_ld_wait();
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
-          const float v0 = act_f<ACT>(a.act, __uint_as_float(r[2 * c]) + sb1[32 * k + 2 * c]);
-          const float v1 = act_f<ACT>(a.act, __uint_as_float(r[2 * c + 1]) + sb1[32 * k + 2 * c + 1]);
+          float v0 = __uint_as_float(r[2 * c]), v1 = __uint_as_float(r[2 * c + 1]);
+          if (ACT == EGT_ACT_ELU) {     // accumulator = log2(e) * pre
+            const float e0 = ex2_approx(v0) - 1.f, e1 = ex2_approx(v1) - 1.f;
+            v0 = v0 > 0.f ? v0 * (1.f / kLog2e) : e0;
+            v1 = v1 > 0.f ? v1 * (1.f / kLog2e) : e1;
+          } else {
+            v0 = act_f<ACT>(a.act, v0);
+            v1 = act_f<ACT>(a.act, v1);
+          }
           o[c] = pack_bf16(v0, v1);
         }
-        tmem_st16(tl + C_D1 + 16 * k, o);
+        tmem_st16(tl + C_HID + 32 * half + 16 * k, o);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -215,27 +311,25 @@ __global__ void __launch_bounds__(384, 1) ffn_tc_fwd_kernel(const __grid_constan
       if (i + 2 < nl) layer_norm(i + 2);   // the first product of tile i is complete: its A operand may be overwritten
       mbar_wait(smem_u32(&bars->done2[q]), it & 1);
       tc_fence_after();
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {     // y = x + out + b2, in place over the stage
+      {                                  // y = out (bias and residual are already in the accumulator), in place over x
         uint32_t r[32];
-        tmem_ld32(tl + C_D2 + 32 * k, r);
+        tmem_ld32(tl + C_D2 + 32 * half, r);
         tmem_ld_wait();
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const int j = 4 * k + jj;
-          uint4 *p = (uint4 *)(stg + sw128_off(t, 8 * j));
-          float xin[8], y[8];
-          unpack8(*p, xin);
-#pragma unroll
-          for (int c = 0; c < 8; ++c) y[c] = __uint_as_float(r[8 * jj + c]) + sb2[8 * j + c] + xin[c];
-          *p = pack8(y);
+        for (int j = 0; j < 4; ++j) {
+          uint4 v;
+          v.x = pack_bf16(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1]));
+          v.y = pack_bf16(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
+          v.z = pack_bf16(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
+          v.w = pack_bf16(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
+          *(uint4 *)(stg + sw128_off(t, 8 * (4 * half + j))) = v;
         }
       }
       tc_fence_before();
       fence_proxy_async_smem();
       warp_arrive(smem_u32(&bars->tile_done[s]), lane);
     }
-  } else if (warp == 8) {
+  } else if (warp == 16) {
     // ---- TMA producer: load x tiles, store y tiles ----
     if (lane == 0) {
       for (int i = 0; i < nl; ++i) {
@@ -258,32 +352,32 @@ __global__ void __launch_bounds__(384, 1) ffn_tc_fwd_kernel(const __grid_constan
       }
       tma_store_wait_all<0>();
     }
-  } else if (warp == 9 || warp == 10) {
+  } else {
     // ---- issuer of group q (warp-collective issue) ----
-    const int q = warp - 9;
+    const int q = warp - 17;
     const uint32_t td = tmem + q * GC;
     const uint32_t loA1 = desc_lo(smem_u32(sA1 + q * TILE), 16), loI1 = desc_lo(smem_u32(sImg1), 16),
-                   loI2 = desc_lo(smem_u32(sImg2), TILE);
-    constexpr uint32_t ID_G1 = idesc_bf16(128, 128, 0, 0), ID_G2 = idesc_bf16(128, 64, 0, 1);
-    // order: G1(0) | G2(0) G1(1) | G2(1) G1(2) | ...   (G1 of the next tile overwrites the columns G2 reads its A
-    // operand from: the tensor core executes one thread's instructions in order)
-    if (q < nl) {
-      mbar_wait(smem_u32(&bars->ready1[q]), 0);
+                   loI2 = desc_lo(smem_u32(sImg2), TILE), loOnes = desc_lo(smem_u32(sOnes), 16),
+                   loId = desc_lo(smem_u32(sIdent), 16), loB1 = desc_lo(smem_u32(sBb1), 2048), loB2 = desc_lo(smem_u32(sBb2), 2048);
+    constexpr uint32_t ID_G1 = idesc_bf16(128, 128, 0, 0), ID_B1 = idesc_bf16(128, 128, 0, 1), ID_G2 = idesc_bf16(128, 64, 0, 1),
+                       ID_RES = idesc_bf16(128, 64, 0, 0);
+    auto issue_g1 = [&](int it) {        // pre = x^ W1blk + 1 b1'
+      mbar_wait(smem_u32(&bars->ready1[q]), it & 1);
       tc_fence_after();
       MmaChain<4>::ss(td + C_D1, loA1, HI_SW, loI1, HI_SW, ID_G1, 0, 2, 2);
+      MmaChain<1>::ss(td + C_D1, loOnes, HI_SW, loB1, HI_SW, ID_B1, 1, 0, 0);
       mma_commit_w(smem_u32(&bars->done1[q]));
-    }
+    };
+    // order: G1(0) | G2(0) G1(1) | G2(1) G1(2) | ...
+    if (q < nl) issue_g1(0);
     for (int i = q, it = 0; i < nl; i += 2, ++it) {
       mbar_wait(smem_u32(&bars->ready2[q]), it & 1);
       tc_fence_after();
-      MmaChain<8>::ts(td + C_D2, td + C_D1, loI2, HI_SW, ID_G2, 0, 8, 128);
+      MmaChain<8>::ts(td + C_D2, td + C_HID, loI2, HI_SW, ID_G2, 0, 8, 128);                                        // hid W2blk
+      MmaChain<4>::ss(td + C_D2, desc_lo(smem_u32(sStage + (i % F_NS) * TILE), 16), HI_SW, loId, HI_SW, ID_RES, 1, 2, 2);   // + x
+      MmaChain<1>::ss(td + C_D2, loOnes, HI_SW, loB2, HI_SW, ID_G2, 1, 0, 0);                                       // + b2
       mma_commit_w(smem_u32(&bars->done2[q]));
-      if (i + 2 < nl) {
-        mbar_wait(smem_u32(&bars->ready1[q]), (it + 1) & 1);
-        tc_fence_after();
-        MmaChain<4>::ss(td + C_D1, loA1, HI_SW, loI1, HI_SW, ID_G1, 0, 2, 2);
-        mma_commit_w(smem_u32(&bars->done1[q]));
-      }
+      if (i + 2 < nl) issue_g1(it + 1);
     }
   }
   tc_fence_before();
@@ -293,19 +387,28 @@ __global__ void __launch_bounds__(384, 1) ffn_tc_fwd_kernel(const __grid_constan
 
 // ------------------------------------------------------------------------------------------------------------------
 // backward
+//
+// One compute group of 512 threads (thread = super-row x 16-channel quarter), one issuing warp.  Per tile:
+//   A:  pre = x^ W1blk , dhid = dy W2blk^T           -> threads: hid, dpre = dhid act'(pre) as bf16 images
+//   B:  dx^ = dpre W1blk^T                            -> threads: LayerNorm backward + residual -> dx tile
+//   C:  dW1 += dpre^T x^ , dW2 += hid^T dy , db1 += dpre^T 1 , db2 += dy^T 1     (accumulators stay in tensor memory)
+// Issue order  B(i) A(i+1) C(i): the products the threads wait for go first; the threads compute tile i+1's images in
+// registers while C(i) still reads tile i's, and the LayerNorm of tile i+1 runs while the tensor core does B(i).
 constexpr int B_NS = 3;
+constexpr int B_NQ = 4;                 // threads per super-row
+constexpr int B_THREADS = (4 * B_NQ + 2) * 32;
 struct BwdBars {
   uint64_t full[B_NS], readyA, doneA, readyB, doneB, doneC, out_ready, out_free;
   uint32_t tmem_base, pad;
 };
-// stages [dy | x] | out | hid (2 atoms) | dpre (2 atoms) | img1 | img2 | ones 4 KB | sb1 | xch[2][128][4] | sdg, sdb | bars
-constexpr int B_SMEM = 1024 + B_NS * 2 * TILE + TILE + 2 * TILE + 2 * TILE + 2 * TILE + 4096 + 128 * 4 + 2 * 128 * 4 * 4 +
+// stages [dy | x] | out | hid (2 atoms) | dpre (2 atoms) | img1 | img2 | ones 4 KB | sb1 | xch[4][128][4] | sdg, sdb | bars
+constexpr int B_SMEM = 1024 + B_NS * 2 * TILE + TILE + 2 * TILE + 2 * TILE + 2 * TILE + 4096 + 128 * 4 + B_NQ * 128 * 4 * 4 +
                        2 * 64 * 4 + sizeof(BwdBars);
 
 template <int W, int ACT>
-__global__ void __launch_bounds__(320, 1) ffn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_x,
-                                                            const __grid_constant__ CUtensorMap tm_dy,
-                                                            const __grid_constant__ CUtensorMap tm_dx, const FfnTcArgs a) {
+__global__ void __launch_bounds__(B_THREADS, 1) ffn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_x,
+                                                                  const __grid_constant__ CUtensorMap tm_dy,
+                                                                  const __grid_constant__ CUtensorMap tm_dx, const FfnTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t *sStage = smem;                                   // per stage: dy tile | x tile (x^ after the LayerNorm)
@@ -313,19 +416,20 @@ __global__ void __launch_bounds__(320, 1) ffn_tc_bwd_kernel(const __grid_constan
   uint8_t *sHid = sOut + TILE, *sDpre = sHid + 2 * TILE;
   uint8_t *sImg1 = sDpre + 2 * TILE, *sImg2 = sImg1 + TILE, *sOnes = sImg2 + TILE;
   float *sb1 = (float *)(sOnes + 4096);
-  float *xch = sb1 + 128;                                   // [2][128][4]
-  float *sdg = xch + 2 * 128 * 4, *sdb = sdg + 64;
+  float *xch = sb1 + 128;                                   // [B_NQ][128][4]
+  float *sdg = xch + B_NQ * 128 * 4, *sdb = sdg + 64;
   BwdBars *bars = (BwdBars *)(sdb + 64);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long ntiles = (a.srows + 127) / 128;
   const int nl = (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  constexpr int NCW = 4 * B_NQ, NCT = 128 * B_NQ;           // compute warps / threads
   if (warp == 0) {
     if (lane == 0) {
       for (int s = 0; s < B_NS; ++s) mbar_init(smem_u32(&bars->full[s]), 1);
-      mbar_init(smem_u32(&bars->readyA), 8); mbar_init(smem_u32(&bars->doneA), 1);
-      mbar_init(smem_u32(&bars->readyB), 8); mbar_init(smem_u32(&bars->doneB), 1);
+      mbar_init(smem_u32(&bars->readyA), NCW); mbar_init(smem_u32(&bars->doneA), 1);
+      mbar_init(smem_u32(&bars->readyB), NCW); mbar_init(smem_u32(&bars->doneB), 1);
       mbar_init(smem_u32(&bars->doneC), 1);
-      mbar_init(smem_u32(&bars->out_ready), 8); mbar_init(smem_u32(&bars->out_free), 1);
+      mbar_init(smem_u32(&bars->out_ready), NCW); mbar_init(smem_u32(&bars->out_free), 1);
       mbar_fence_init();
       tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_dy); tma_prefetch_desc(&tm_dx);
     }
@@ -334,9 +438,9 @@ __global__ void __launch_bounds__(320, 1) ffn_tc_bwd_kernel(const __grid_constan
   }
   {
     float *dummy_b2 = sdg;      // build_images writes 64 floats of b2 here; zeroed below (the backward does not need b2)
-    build_images<W>(sImg1, sImg2, sb1, dummy_b2, a, tid, 320);
+    build_images<W>(sImg1, sImg2, sb1, dummy_b2, a, tid, B_THREADS);
   }
-  for (int i = tid; i < 4096 / 16; i += 320) ((uint4 *)sOnes)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+  for (int i = tid; i < 4096 / 16; i += B_THREADS) ((uint4 *)sOnes)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
   __syncthreads();
   if (tid < 128) sdg[tid] = 0.f;                            // sdg | sdb
   fence_proxy_async_smem();
@@ -346,55 +450,52 @@ __global__ void __launch_bounds__(320, 1) ffn_tc_bwd_kernel(const __grid_constan
   const uint32_t tmem = bars->tmem_base;
   // tensor memory: pre 128 | dhid 128 | dx^ 64 | dW1 acc 64 | dW2 acc 64 | db1 acc 16 | db2 acc 16  = 480 columns
   constexpr uint32_t C_D1 = 0, C_DH = 128, C_D3 = 256, C_W1 = 320, C_W2 = 384, C_B1 = 448, C_B2 = 464;
-  constexpr int PH = W >= 32 ? 1 : 32 / W;                  // LayerNorm groups inside a 32-channel half
-  constexpr int GW = W >= 32 ? 32 : W;                      // channels of a group that lie inside the half
+  constexpr int CH = 64 / B_NQ;                             // channels of a super-row one thread owns (16)
+  constexpr int HC = 128 / B_NQ;                            // hidden columns one thread owns (32)
+  constexpr int GW = W >= CH ? CH : W;                      // channels of a LayerNorm group inside the thread's part
+  constexpr int PH = CH / GW;                               // LayerNorm groups inside the thread's part
+  constexpr int NX = W > CH ? W / CH : 1;                   // threads that share one LayerNorm group
 
-  if (warp < 8) {
-    // ---- compute: thread = (super-row t, column half g) ----
-    const int t = tid & 127, g = tid >> 7;
+  if (warp < NCW) {
+    // ---- compute: thread = (super-row t, channel quarter qq) ----
+    const int t = tid & 127, qq = tid >> 7;
+    const int xbase = (qq / NX) * NX;                       // first quarter of this thread's LayerNorm group
     const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     float rs_cur[PH], rs_next[PH];
+    auto xsum = [&](int slot, float v) {                    // sum over the NX threads of a LayerNorm group
+      xch[(qq * 128 + t) * 4 + slot] = v;
+      named_bar_sync(1, NCT);
+      float s = 0.f;
+#pragma unroll
+      for (int u = 0; u < NX; ++u) s += xch[((xbase + u) * 128 + t) * 4 + slot];
+      return s;
+    };
 
     // LayerNorm of tile i (stage s): x -> x^ in place, 1/std kept
     auto ln_fwd = [&](int i, float *rs) {
       const int s = i % B_NS;
       uint8_t *sx = sStage + s * 2 * TILE + TILE;
       mbar_wait(smem_u32(&bars->full[s]), (i / B_NS) & 1);
-      float xs[32];
+      float xs[CH];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) unpack8(*(const uint4 *)(sx + sw128_off(t, 8 * (4 * g + j))), xs + 8 * j);
-      if (W == 64) {
-        float sum = 0.f;
+      for (int j = 0; j < CH / 8; ++j) unpack8(*(const uint4 *)(sx + sw128_off(t, CH * qq + 8 * j)), xs + 8 * j);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) sum += xs[c];
-        xch[(g * 128 + t) * 4 + 0] = sum;
-        named_bar_sync(1, 256);
-        const float mu = (xch[t * 4 + 0] + xch[(128 + t) * 4 + 0]) * (1.f / 64.f);
+      for (int p = 0; p < PH; ++p) {
+        float mu = 0.f;
+#pragma unroll
+        for (int c = 0; c < GW; ++c) mu += xs[p * GW + c];
+        if (NX > 1) mu = xsum(0, mu);
+        mu *= (1.f / W);
         float var = 0.f;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) { xs[c] -= mu; var = fmaf(xs[c], xs[c], var); }
-        xch[(g * 128 + t) * 4 + 1] = var;
-        named_bar_sync(1, 256);
-        rs[0] = rsqrtf((xch[t * 4 + 1] + xch[(128 + t) * 4 + 1]) * (1.f / 64.f) + a.eps);
+        for (int c = 0; c < GW; ++c) { xs[p * GW + c] -= mu; var = fmaf(xs[p * GW + c], xs[p * GW + c], var); }
+        if (NX > 1) var = xsum(1, var);
+        rs[p] = rsqrtf(var * (1.f / W) + a.eps);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) xs[c] *= rs[0];
-      } else {
-#pragma unroll
-        for (int p = 0; p < PH; ++p) {
-          float mu = 0.f;
-#pragma unroll
-          for (int c = 0; c < GW; ++c) mu += xs[p * GW + c];
-          mu *= (1.f / GW);
-          float var = 0.f;
-#pragma unroll
-          for (int c = 0; c < GW; ++c) { xs[p * GW + c] -= mu; var = fmaf(xs[p * GW + c], xs[p * GW + c], var); }
-          rs[p] = rsqrtf(var * (1.f / GW) + a.eps);
-#pragma unroll
-          for (int c = 0; c < GW; ++c) xs[p * GW + c] *= rs[p];
-        }
+        for (int c = 0; c < GW; ++c) xs[p * GW + c] *= rs[p];
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) *(uint4 *)(sx + sw128_off(t, 8 * (4 * g + j))) = pack8(xs + 8 * j);
+      for (int j = 0; j < CH / 8; ++j) *(uint4 *)(sx + sw128_off(t, CH * qq + 8 * j)) = pack8(xs + 8 * j);
       fence_proxy_async_smem();
       warp_arrive(smem_u32(&bars->readyA), lane);
     };
@@ -406,21 +507,27 @@ __global__ void __launch_bounds__(320, 1) ffn_tc_bwd_kernel(const __grid_constan
       // ---- T1: hid, dpre images ----
       mbar_wait(smem_u32(&bars->doneA), i & 1);
       tc_fence_after();
-      uint4 hq[8], dq[8];               // the thread's 64 columns of hid and dpre, bf16
+      uint4 hq[HC / 8], dq[HC / 8];     // the thread's columns of hid and dpre, bf16
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int col0 = 64 * g + 16 * k;
+      for (int k = 0; k < HC / 16; ++k) {
+        const int col0 = HC * qq + 16 * k;
         uint32_t r1[16], r2[16];
         tmem_ld16(tl + C_D1 + col0, r1);
         tmem_ld16(tl + C_DH + col0, r2);
         tmem_ld_wait();
         float hv[16], dv[16];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          float f, d;
-          act_fd<ACT>(a.act, __uint_as_float(r1[c]) + sb1[col0 + c], f, d);
-          hv[c] = f;
-          dv[c] = __uint_as_float(r2[c]) * d;
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const float4 b = *(const float4 *)(sb1 + col0 + 4 * c4);
+          const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int c = 4 * c4 + u;
+            float f, d;
+            act_fd<ACT>(a.act, __uint_as_float(r1[c]) + bb[u], f, d);
+            hv[c] = f;
+            dv[c] = __uint_as_float(r2[c]) * d;
+          }
         }
         hq[2 * k] = pack8(hv); hq[2 * k + 1] = pack8(hv + 8);
         dq[2 * k] = pack8(dv); dq[2 * k + 1] = pack8(dv + 8);
@@ -430,8 +537,9 @@ __global__ void __launch_bounds__(320, 1) ffn_tc_bwd_kernel(const __grid_constan
       // the products of this tile and ran while the arithmetic above did
       if (i > 0) mbar_wait(smem_u32(&bars->doneC), (i - 1) & 1);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const uint32_t off = (uint32_t)g * TILE + sw128_off(t, 8 * k);
+      for (int k = 0; k < HC / 8; ++k) {
+        const int col = HC * qq + 8 * k;
+        const uint32_t off = (uint32_t)(col >> 6) * TILE + sw128_off(t, col & 63);
         *(uint4 *)(sHid + off) = hq[k];
         *(uint4 *)(sDpre + off) = dq[k];
       }
@@ -443,13 +551,13 @@ __global__ void __launch_bounds__(320, 1) ffn_tc_bwd_kernel(const __grid_constan
       mbar_wait(smem_u32(&bars->doneB), i & 1);
       tc_fence_after();
       {
-        uint32_t r[32];
-        tmem_ld32(tl + C_D3 + 32 * g, r);
-        float xh[32], dyv[32];
+        uint32_t r[CH];
+        tmem_ld16(tl + C_D3 + CH * qq, r);
+        float xh[CH], dyv[CH];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          unpack8(*(const uint4 *)(sx + sw128_off(t, 8 * (4 * g + j))), xh + 8 * j);
-          unpack8(*(const uint4 *)(sdy + sw128_off(t, 8 * (4 * g + j))), dyv + 8 * j);
+        for (int j = 0; j < CH / 8; ++j) {
+          unpack8(*(const uint4 *)(sx + sw128_off(t, CH * qq + 8 * j)), xh + 8 * j);
+          unpack8(*(const uint4 *)(sdy + sw128_off(t, CH * qq + 8 * j)), dyv + 8 * j);
         }
         tmem_ld_wait();
         float m1[PH], m2[PH];
@@ -464,16 +572,18 @@ __global__ void __launch_bounds__(320, 1) ffn_tc_bwd_kernel(const __grid_constan
           }
           m1[p] = s1; m2[p] = s2;
         }
-        if (W == 64) {
-          xch[(g * 128 + t) * 4 + 2] = m1[0];
-          xch[(g * 128 + t) * 4 + 3] = m2[0];
-          named_bar_sync(1, 256);
-          m1[0] = xch[t * 4 + 2] + xch[(128 + t) * 4 + 2];
-          m2[0] = xch[t * 4 + 3] + xch[(128 + t) * 4 + 3];
+        if (NX > 1) {
+          xch[(qq * 128 + t) * 4 + 2] = m1[0];
+          xch[(qq * 128 + t) * 4 + 3] = m2[0];
+          named_bar_sync(1, NCT);
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int u = 0; u < NX; ++u) { s1 += xch[((xbase + u) * 128 + t) * 4 + 2]; s2 += xch[((xbase + u) * 128 + t) * 4 + 3]; }
+          m1[0] = s1; m2[0] = s2;
         }
         if (i > 0) mbar_wait(smem_u32(&bars->out_free), (i - 1) & 1);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < CH / 8; ++j) {
           float y[8];
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
@@ -481,7 +591,7 @@ __global__ void __launch_bounds__(320, 1) ffn_tc_bwd_kernel(const __grid_constan
             const float d = __uint_as_float(r[cc]);
             y[c] = fmaf(rs_cur[p], d - (m1[p] + xh[cc] * m2[p]) * (1.f / W), dyv[cc]);
           }
-          *(uint4 *)(sOut + sw128_off(t, 8 * (4 * g + j))) = pack8(y);
+          *(uint4 *)(sOut + sw128_off(t, CH * qq + 8 * j)) = pack8(y);
         }
       }
       tc_fence_before();
@@ -495,27 +605,27 @@ __global__ void __launch_bounds__(320, 1) ffn_tc_bwd_kernel(const __grid_constan
       mbar_wait(smem_u32(&bars->doneC), (nl - 1) & 1);
       tc_fence_after();
       constexpr int H = 2 * W, P = 64 / W, LD = 65;
-      // scratch over the (now idle) stages: M1[128][65] | M2[128][65] | v1[128] | vb2[64] | Rg[256] | Rb[256]
-      float *M1 = (float *)sStage, *M2 = M1 + 128 * LD, *v1s = M2 + 128 * LD, *vb2 = v1s + 128, *Rg = vb2 + 64, *Rb = Rg + 256;
+      // scratch over the (now idle) stages: M1[128][65] | M2[128][65] | v1[128] | vb2[64] | Rg[NCT] | Rb[NCT]
+      float *M1 = (float *)sStage, *M2 = M1 + 128 * LD, *v1s = M2 + 128 * LD, *vb2 = v1s + 128, *Rg = vb2 + 64, *Rb = Rg + NCT;
       {
-        uint32_t rb[4], rb2[4], rw1[32], rw2[32];
+        uint32_t rb[4], rb2[4], rw1[CH], rw2[CH];
         tmem_ld4(tl + C_B1, rb);
         tmem_ld4(tl + C_B2, rb2);
-        tmem_ld32(tl + C_W1 + 32 * g, rw1);
-        tmem_ld32(tl + C_W2 + 32 * g, rw2);
+        tmem_ld16(tl + C_W1 + CH * qq, rw1);
+        tmem_ld16(tl + C_W2 + CH * qq, rw2);
         tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          M1[t * LD + 32 * g + c] = __uint_as_float(rw1[c]);     // sum_rows dpre[:, j = t] x^[:, c]
-          M2[t * LD + 32 * g + c] = __uint_as_float(rw2[c]);     // sum_rows hid[:, j = t] dy[:, c]
+        for (int c = 0; c < CH; ++c) {
+          M1[t * LD + CH * qq + c] = __uint_as_float(rw1[c]);     // sum_rows dpre[:, j = t] x^[:, c]
+          M2[t * LD + CH * qq + c] = __uint_as_float(rw2[c]);     // sum_rows hid[:, j = t] dy[:, c]
         }
-        if (g == 0) v1s[t] = __uint_as_float(rb[0]);             // sum_rows dpre[:, j = t]
-        if (g == 1 && t < 64) vb2[t] = __uint_as_float(rb2[0]);  // sum_rows dy[:, c = t]
+        if (qq == 0) v1s[t] = __uint_as_float(rb[0]);             // sum_rows dpre[:, j = t]
+        if (qq == 1 && t < 64) vb2[t] = __uint_as_float(rb2[0]);  // sum_rows dy[:, c = t]
       }
-      named_bar_sync(1, 256);
+      named_bar_sync(1, NCT);
       // dW1[c'][j'] += gamma[c'] M + beta[c'] db1[j'] ,  dW2[j'][c'] += M2   (M, M2: sums of the P diagonal blocks)
       const int rot = (int)(blockIdx.x * 64u) % (W * H);          // CTAs start at different entries: less contention
-      for (int e0 = tid; e0 < W * H; e0 += 256) {
+      for (int e0 = tid; e0 < W * H; e0 += NCT) {
         const int e = (e0 + rot) % (W * H);
         {
           const int cw = e / H, jh = e % H;
@@ -532,8 +642,8 @@ __global__ void __launch_bounds__(320, 1) ffn_tc_bwd_kernel(const __grid_constan
           atomicAdd(a.g_W2 + e, M);
         }
       }
-      {   // dgamma[c'] = sum_j' M W1[c'][j'] ,  dbeta[c'] = sum_j' W1[c'][j'] db1[j']: 256 / W partial sums per channel
-        constexpr int NP = 256 / W;
+      {   // dgamma[c'] = sum_j' M W1[c'][j'] ,  dbeta[c'] = sum_j' W1[c'][j'] db1[j']: NCT / W partial sums per channel
+        constexpr int NP = NCT / W;
         const int cw = tid % W, part = tid / W;
         float dg = 0.f, db = 0.f;
         for (int jh = part; jh < H; jh += NP) {
@@ -547,9 +657,9 @@ __global__ void __launch_bounds__(320, 1) ffn_tc_bwd_kernel(const __grid_constan
         Rg[part * W + cw] = dg;
         Rb[part * W + cw] = db;
       }
-      named_bar_sync(1, 256);
+      named_bar_sync(1, NCT);
       if (tid < W) {
-        constexpr int NP = 256 / W;
+        constexpr int NP = NCT / W;
         float dg = 0.f, db = 0.f, d2 = 0.f;
         for (int q = 0; q < NP; ++q) { dg += Rg[q * W + tid]; db += Rb[q * W + tid]; }
 #pragma unroll
@@ -565,7 +675,7 @@ __global__ void __launch_bounds__(320, 1) ffn_tc_bwd_kernel(const __grid_constan
         atomicAdd(a.g_b1 + jh, d1);
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == NCW) {
     // ---- TMA producer ----
     if (lane == 0) {
       auto load = [&](int i) {
@@ -587,7 +697,7 @@ __global__ void __launch_bounds__(320, 1) ffn_tc_bwd_kernel(const __grid_constan
       }
       tma_store_wait_all<0>();
     }
-  } else if (warp == 9) {
+  } else if (warp == NCW + 1) {
     // ---- issuer ----
     const uint32_t loI1 = desc_lo(smem_u32(sImg1), TILE), loI2 = desc_lo(smem_u32(sImg2), 16);
     const uint32_t loHid = desc_lo(smem_u32(sHid), TILE), loDpre_k = desc_lo(smem_u32(sDpre), 16),
@@ -656,7 +766,7 @@ template <int W, int ACT>
 int fwd_launch_t(const CUtensorMap &mx, const CUtensorMap &my, const FfnTcArgs &a, unsigned grid, cudaStream_t st) {
   EGT_CHECK_CUDA(cudaFuncSetAttribute(ffn_tc_fwd_kernel<W, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
   LaunchScope _ls("ffn_tc_fwd_kernel", st);
-  ffn_tc_fwd_kernel<W, ACT><<<grid, 384, F_SMEM, st>>>(mx, my, a);
+  ffn_tc_fwd_kernel<W, ACT><<<grid, F_THREADS, F_SMEM, st>>>(mx, my, a);
   EGT_CHECK_CUDA(cudaGetLastError());
   return EGT_OK;
 }
@@ -665,7 +775,7 @@ int bwd_launch_t(const CUtensorMap &mx, const CUtensorMap &mdy, const CUtensorMa
                  cudaStream_t st) {
   EGT_CHECK_CUDA(cudaFuncSetAttribute(ffn_tc_bwd_kernel<W, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
   LaunchScope _ls("ffn_tc_bwd_kernel", st);
-  ffn_tc_bwd_kernel<W, ACT><<<grid, 320, B_SMEM, st>>>(mx, mdy, mdx, a);
+  ffn_tc_bwd_kernel<W, ACT><<<grid, B_THREADS, B_SMEM, st>>>(mx, mdy, mdx, a);
   EGT_CHECK_CUDA(cudaGetLastError());
   return EGT_OK;
 }
