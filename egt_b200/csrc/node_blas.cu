@@ -102,16 +102,23 @@ __global__ void __launch_bounds__(256) nb_out_epilogue_kernel(const __nv_bfloat1
   }
 }
 
-// db[c] += sum_r Y[r, c] and, optionally, a bf16 copy of a float32 Y.  CTA = 64 rows x all columns.
+// db[c] += sum_r Y[r, c] and, optionally, a bf16 copy of a float32 Y.  CTA = 32 rows x all columns; a thread owns one
+// column and keeps 8 row loads in flight (the loop is latency-bound otherwise).
+constexpr int kColsumRows = 32;
 template <typename T>
 __global__ void __launch_bounds__(256) nb_colsum_kernel(const T *Y, int R, int C, float *db, __nv_bfloat16 *copy) {
-  const int r0 = blockIdx.x * 64, r1 = min(R, r0 + 64);
+  const int r0 = blockIdx.x * kColsumRows, r1 = min(R, r0 + kColsumRows);
   for (int c = threadIdx.x; c < C; c += 256) {
     float acc = 0.f;
-    for (int r = r0; r < r1; ++r) {
-      const float v = ldf(Y + (size_t)r * C + c);
-      acc += v;
-      if (copy) copy[(size_t)r * C + c] = __float2bfloat16_rn(v);
+    for (int r = r0; r < r1; r += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = r + u < r1 ? ldf(Y + (size_t)(r + u) * C + c) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        acc += v[u];
+        if (copy && r + u < r1) copy[(size_t)(r + u) * C + c] = __float2bfloat16_rn(v[u]);
+      }
     }
     atomicAdd(db + c, acc);
   }
@@ -213,7 +220,7 @@ int node_blas_bwd1(const void *dh_out, const void *v_att, const egt_block_weight
   }
   {
     LaunchScope _ls("nb_colsum_kernel", st);
-    nb_colsum_kernel<__nv_bfloat16><<<(R + 63) / 64, 256, 0, st>>>((const __nv_bfloat16 *)dh_out, R, d, g->dense_mha_bias, nullptr);
+    nb_colsum_kernel<__nv_bfloat16><<<(R + kColsumRows - 1) / kColsumRows, 256, 0, st>>>((const __nv_bfloat16 *)dh_out, R, d, g->dense_mha_bias, nullptr);
   }
   EGT_CHECK_CUDA(cudaGetLastError());
   LaunchScope _ls("cublas_gemm", st);
@@ -231,7 +238,7 @@ int node_blas_bwd2(const void *h, const float *d_qkv, const egt_block_weights_t 
   if (rc) return rc;
   {
     LaunchScope _ls("nb_colsum_kernel", st);
-    nb_colsum_kernel<float><<<(R + 63) / 64, 256, 0, st>>>(d_qkv, R, 3 * d, g->dense_qkv_bias, c.dqkv_bf);
+    nb_colsum_kernel<float><<<(R + kColsumRows - 1) / kColsumRows, 256, 0, st>>>(d_qkv, R, 3 * d, g->dense_qkv_bias, c.dqkv_bf);
   }
   {
     LaunchScope _ls("nb_ln_aug_kernel", st);
@@ -381,7 +388,7 @@ int ffn_blas_bwd(const egt_ffn_cfg_t *cfg, const egt_ffn_weights_t *wt, const eg
   }
   {
     LaunchScope _ls("nb_colsum_kernel", st);
-    nb_colsum_kernel<__nv_bfloat16><<<(R + 63) / 64, 256, 0, st>>>((const __nv_bfloat16 *)dy, R, w, g->lr2_bias, nullptr);
+    nb_colsum_kernel<__nv_bfloat16><<<(R + kColsumRows - 1) / kColsumRows, 256, 0, st>>>((const __nv_bfloat16 *)dy, R, w, g->lr2_bias, nullptr);
   }
   EGT_CHECK_CUDA(cudaGetLastError());
   {
@@ -404,7 +411,7 @@ int ffn_blas_bwd(const egt_ffn_cfg_t *cfg, const egt_ffn_weights_t *wt, const eg
   }
   {
     LaunchScope _ls("nb_colsum_kernel", st);
-    nb_colsum_kernel<__nv_bfloat16><<<(R + 63) / 64, 256, 0, st>>>(c.hid, R, hid, g->lr1_bias, nullptr);
+    nb_colsum_kernel<__nv_bfloat16><<<(R + kColsumRows - 1) / kColsumRows, 256, 0, st>>>(c.hid, R, hid, g->lr1_bias, nullptr);
   }
   EGT_CHECK_CUDA(cudaGetLastError());
   {

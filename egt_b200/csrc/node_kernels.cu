@@ -365,8 +365,9 @@ int xty_launch(const XtyArgs &a, int dtype, cudaStream_t st) {
 }
 
 // ---- LayerNorm backward + residual gradient ----------------------------------------------
-// one warp per row; dgamma/dbeta reduced per CTA in smem then atomically added.
-template <typename T>
+// One warp per row, lane l owns channels l, l + 32, ... (NPL of them, in registers); dgamma / dbeta are summed per lane
+// over the warp's rows in registers, then once per CTA through shared memory and once per CTA into global memory.
+template <typename T, int NPL>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(LnBwdArgs a, int rows_per_cta) {
   extern __shared__ float sm[];   // dg[D], db[D]
   float *sdg = sm, *sdb = sm + a.D;
@@ -375,39 +376,60 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(LnBwdArgs a, int rows_per_c
   __syncthreads();
   const int rbeg = blockIdx.x * rows_per_cta;
   const int rend = min(a.R, rbeg + rows_per_cta);
+  const float inv_d = 1.f / a.D;
+  float gam[NPL], dg[NPL], db[NPL];
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) {
+    const int k = lane + 32 * i;
+    gam[i] = k < a.D ? __ldg(a.gamma + k) : 0.f;
+    dg[i] = 0.f; db[i] = 0.f;
+  }
   for (int r = rbeg + warp; r < rend; r += 8) {
     const T *x = (const T *)a.x + (size_t)r * a.D;
     const float *dy = a.dy + (size_t)r * a.D;
+    const T *res = a.dres ? (const T *)a.dres + (size_t)r * a.D : nullptr;
+    float xv[NPL], g[NPL], rv[NPL];
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+      const int k = lane + 32 * i;
+      const bool ok = k < a.D;
+      xv[i] = ok ? ldf(x + k) : 0.f;
+      g[i] = ok ? dy[k] : 0.f;
+      rv[i] = ok && res ? ldf(res + k) : 0.f;
+    }
     float s = 0.f;
-    for (int k = lane; k < a.D; k += 32) s += ldf(x + k);
-    s = warp_sum(s);
-    float mu = s / a.D;
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) s += xv[i];
+    const float mu = warp_sum(s) * inv_d;
     float var = 0.f;
-    for (int k = lane; k < a.D; k += 32) {
-      float t = ldf(x + k) - mu;
-      var += t * t;
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+      xv[i] = lane + 32 * i < a.D ? xv[i] - mu : 0.f;
+      var = fmaf(xv[i], xv[i], var);
     }
-    var = warp_sum(var);
-    float rstd = rsqrtf(var / a.D + a.eps);
+    const float rstd = rsqrtf(warp_sum(var) * inv_d + a.eps);
     float m1 = 0.f, m2 = 0.f;
-    for (int k = lane; k < a.D; k += 32) {
-      float xn = (ldf(x + k) - mu) * rstd;
-      float g = dy[k];
-      float dxh = g * __ldg(a.gamma + k);
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+      xv[i] *= rstd;                                   // x^
+      const float dxh = g[i] * gam[i];
       m1 += dxh;
-      m2 += dxh * xn;
-      atomicAdd(sdg + k, g * xn);
-      atomicAdd(sdb + k, g);
+      m2 = fmaf(dxh, xv[i], m2);
+      dg[i] = fmaf(g[i], xv[i], dg[i]);
+      db[i] += g[i];
     }
-    m1 = warp_sum(m1) / a.D;
-    m2 = warp_sum(m2) / a.D;
-    for (int k = lane; k < a.D; k += 32) {
-      float xn = (ldf(x + k) - mu) * rstd;
-      float dxh = dy[k] * __ldg(a.gamma + k);
-      float v = rstd * (dxh - m1 - xn * m2);
-      if (a.dres) v += ldf((const T *)a.dres + (size_t)r * a.D + k);
-      stf((T *)a.dx + (size_t)r * a.D + k, v);
+    m1 = warp_sum(m1) * inv_d;
+    m2 = warp_sum(m2) * inv_d;
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+      const int k = lane + 32 * i;
+      if (k < a.D) stf((T *)a.dx + (size_t)r * a.D + k, fmaf(rstd, g[i] * gam[i] - m1 - xv[i] * m2, rv[i]));
     }
+  }
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) {
+    const int k = lane + 32 * i;
+    if (k < a.D) { atomicAdd(sdg + k, dg[i]); atomicAdd(sdb + k, db[i]); }
   }
   __syncthreads();
   for (int k = tid; k < a.D; k += 256) {
@@ -416,15 +438,27 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(LnBwdArgs a, int rows_per_c
   }
 }
 
+template <int NPL>
+static void ln_bwd_launch_t(const LnBwdArgs &a, int dtype, unsigned grid, size_t smem, int rows_per_cta, cudaStream_t st) {
+  if (dtype == EGT_F32) ln_bwd_kernel<float, NPL><<<grid, 256, smem, st>>>(a, rows_per_cta);
+  else ln_bwd_kernel<__nv_bfloat16, NPL><<<grid, 256, smem, st>>>(a, rows_per_cta);
+}
+
 int ln_bwd_launch(const LnBwdArgs &a, int dtype, cudaStream_t st) {
-  int ctas = 148 * 2;
+  EGT_REQUIRE(a.D > 0 && a.D <= 512, EGT_E_SHAPE, "ln_bwd: width %d not in 1..512", a.D);
+  int ctas = 148 * 4;
   int rows_per_cta = (a.R + ctas - 1) / ctas;
   if (rows_per_cta < 8) rows_per_cta = 8;
   unsigned grid = (a.R + rows_per_cta - 1) / rows_per_cta;
   size_t smem = 2 * (size_t)a.D * sizeof(float);
   LaunchScope _ls("ln_bwd_kernel", st);
-  if (dtype == EGT_F32) ln_bwd_kernel<float><<<grid, 256, smem, st>>>(a, rows_per_cta);
-  else ln_bwd_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(a, rows_per_cta);
+  const int npl = (a.D + 31) / 32;
+  if (npl <= 1) ln_bwd_launch_t<1>(a, dtype, grid, smem, rows_per_cta, st);
+  else if (npl <= 2) ln_bwd_launch_t<2>(a, dtype, grid, smem, rows_per_cta, st);
+  else if (npl <= 3) ln_bwd_launch_t<3>(a, dtype, grid, smem, rows_per_cta, st);
+  else if (npl <= 4) ln_bwd_launch_t<4>(a, dtype, grid, smem, rows_per_cta, st);
+  else if (npl <= 8) ln_bwd_launch_t<8>(a, dtype, grid, smem, rows_per_cta, st);
+  else ln_bwd_launch_t<16>(a, dtype, grid, smem, rows_per_cta, st);
   EGT_CHECK_CUDA(cudaGetLastError());
   return EGT_OK;
 }
