@@ -7,7 +7,7 @@ import subprocess
 import sys
 
 LIB = 'egt_b200/lib/libegt_b200.so'
-pat = re.compile(sys.argv[1] if len(sys.argv) > 1 else r'fused_(fwd|bwd)_kernel|wide_(fwd|bwd)_kernel|node_(qkv|out|bwd1|bwd2)_kernel|peer_allreduce')
+pat = re.compile(sys.argv[1] if len(sys.argv) > 1 else r'fused_(fwd|bwd)_kernel|wide_(fwd|bwd)_kernel|node_(qkv|out|bwd1|bwd2)_kernel|ffn_tc_(fwd|bwd)_kernel|peer_allreduce')
 KEY = ['UTCHMMA', 'UTCBAR', 'LDTM', 'STTM', 'UTMALDG', 'UTMASTG', 'UTMACCTL', 'SYNCS', 'ELECT', 'R2UR', 'MUFU', 'FFMA', 'FFMA2', 'HMMA',
        'LDS', 'STS', 'LDG', 'STG', 'RED', 'ATOMG', 'BAR']
 out = subprocess.run(['cuobjdump', '-sass', LIB], capture_output=True, text=True).stdout
