@@ -349,7 +349,7 @@ def run_ours(args, w):
     # ---- one FULL layer: attention block + node FFN + edge FFN, forward + backward, same inputs ----
     # (graph_xformer_model_base.py:335-341: edge_update then ffn_block); CUDA graphs like the headline step
     layer_line = None
-    if not args.no_layer_line and args.random_mask_prob == 0:
+    if not args.no_layer_line and args.random_mask_prob == 0 and world == 1:   # a single-GPU diagnostic line
         lay = egt_b200.EGTStack(1, ffn=True, model_width=d, edge_width=d_e, num_heads=h, scale_degree=bool(args.scale_degree),
                                 seed=3000 + rank).to(dev)
         lay.train(False)
@@ -362,7 +362,6 @@ def run_ours(args, w):
             lay.flat.grad = None
             h2, e2 = lay(hh, ee, mm)
             torch.autograd.backward([h2, e2], [dh, de])
-            egt_b200.allreduce_flat_grads([lay])
             return hh.grad, ee.grad
 
         for i in range(3):
