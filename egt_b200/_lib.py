@@ -19,7 +19,7 @@ EGT_E_SHAPE, EGT_E_DTYPE, EGT_E_ALIGN, EGT_E_ARCH, EGT_E_CUDA, EGT_E_ARG = -1, -
 EXPORTS = ['egt_abi_version', 'egt_last_error', 'egt_last_path', 'egt_rng_uniform_host',
            'egt_block_param_layout', 'egt_attn_fwd', 'egt_attn_bwd', 'egt_block_workspace_bytes',
            'egt_block_fwd', 'egt_block_bwd', 'egt_launch_count', 'egt_profile_enable', 'egt_profile_read',
-           'egt_debug_umma_probe', 'egt_debug_mma_timing', 'egt_debug_force_staged', 'egt_peer_allreduce',
+           'egt_debug_umma_probe', 'egt_debug_mma_timing', 'egt_debug_force_staged', 'egt_peer_allreduce', 'egt_peer_allreduce_push', 'egt_peer_allreduce_push_floats',
            'egt_ffn_fwd', 'egt_ffn_bwd', 'egt_ffn_workspace_bytes', 'egt_ffn_fwd_ws', 'egt_ffn_bwd_ws']
 
 FFN_FIELDS = ['norm_gamma', 'norm_beta', 'lr1_kernel', 'lr1_bias', 'lr2_kernel', 'lr2_bias']
@@ -127,6 +127,10 @@ def load():
     lib.egt_ffn_bwd_ws.argtypes = [C.POINTER(FfnCfg), C.POINTER(FfnWeights), C.POINTER(FfnGrads), vp, vp, vp, vp, C.c_size_t, vp]
     lib.egt_peer_allreduce.restype = C.c_int
     lib.egt_peer_allreduce.argtypes = [vp, vp, vp, C.c_int64, C.c_int, C.c_int, vp]
+    lib.egt_peer_allreduce_push.restype = C.c_int
+    lib.egt_peer_allreduce_push.argtypes = [vp, vp, vp, C.c_int64, C.c_int64, C.c_int, C.c_int, vp]
+    lib.egt_peer_allreduce_push_floats.restype = C.c_int64
+    lib.egt_peer_allreduce_push_floats.argtypes = [C.c_int64, C.c_int]
     lib.egt_launch_count.restype = C.c_long
     lib.egt_profile_enable.argtypes = [C.c_int]
     lib.egt_profile_read.restype = C.c_int

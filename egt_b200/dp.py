@@ -21,17 +21,24 @@ def shard_batch(t: torch.Tensor, rank: int, world: int) -> torch.Tensor:
 
 
 class _PeerAllReduce:
-    """One-shot all-reduce over NVLink peer memory (csrc/peer_allreduce.cu): every rank publishes its
-    gradient in a symmetric buffer and sums all peers' buffers with direct loads.  The payload is a few
-    tens of KB, so this is a latency play: one small kernel instead of a ring / tree through NCCL."""
+    """One-shot all-reduce over NVLink peer memory (csrc/peer_allreduce.cu).  The payload is a few tens of KB, so this
+    is a latency play.  Default protocol ``push``: every rank stores its gradient, with the call number inside every
+    8-byte word, straight into a receive slot of every peer and adds the slots of its own buffer -- no fence, no flag
+    round trip, no remote load.  ``EGT_PEER_PROTOCOL=pull`` selects the first version (publish, flag exchange, remote
+    loads), which measured 37 us per call on 8 GPUs against NCCL's 29."""
 
     def __init__(self, numel: int, device: torch.device):
         import ctypes as C
+        import os
         import torch.distributed._symmetric_memory as symm
         from . import _lib as L
         self._C, self._L = C, L
         self.numel = numel
-        self.buf = symm.empty(2 * numel, dtype=torch.float32, device=device)
+        world = dist.get_world_size()
+        self.push = os.environ.get('EGT_PEER_PROTOCOL', 'push') != 'pull' and numel % 2 == 0
+        lib = L.load()
+        self.buf_floats = int(lib.egt_peer_allreduce_push_floats(numel, world)) if self.push else 2 * numel
+        self.buf = symm.empty(self.buf_floats, dtype=torch.float32, device=device)
         self.hdl = symm.rendezvous(self.buf, dist.group.WORLD)
         assert self.hdl.signal_pad_size >= 4 * (32 * 8 + 32), 'signal pad too small'
         self.buf.zero_()
@@ -41,9 +48,14 @@ class _PeerAllReduce:
     def __call__(self, grad: torch.Tensor):
         C, L = self._C, self._L
         lib = L.load()
-        L.check(lib.egt_peer_allreduce(C.c_void_p(self.hdl.buffer_ptrs_dev), C.c_void_p(self.hdl.signal_pad_ptrs_dev),
-                                       C.c_void_p(grad.data_ptr()), self.numel, self.hdl.rank, self.hdl.world_size,
-                                       C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        if self.push:
+            L.check(lib.egt_peer_allreduce_push(C.c_void_p(self.hdl.buffer_ptrs_dev), C.c_void_p(self.hdl.signal_pad_ptrs_dev),
+                                                C.c_void_p(grad.data_ptr()), self.numel, self.buf_floats, self.hdl.rank,
+                                                self.hdl.world_size, stream))
+        else:
+            L.check(lib.egt_peer_allreduce(C.c_void_p(self.hdl.buffer_ptrs_dev), C.c_void_p(self.hdl.signal_pad_ptrs_dev),
+                                           C.c_void_p(grad.data_ptr()), self.numel, self.hdl.rank, self.hdl.world_size, stream))
 
 
 _peer_cache = {}

@@ -227,6 +227,13 @@ int egt_ffn_bwd_ws(const egt_ffn_cfg_t *cfg, const egt_ffn_weights_t *w, const e
  * Stream-ordered, no host synchronisation, CUDA-graph capturable; all ranks must call it equally often. */
 int egt_peer_allreduce(const uint64_t *buffer_ptrs_dev, const uint64_t *signal_pad_ptrs_dev, float *grad,
                        int64_t n, int rank, int world, void *stream);
+/* The same collective as STORES with the flag inside every 8-byte word (no fence, no flag round trip, no remote load):
+ * each rank writes {x0, flag, x1, flag} into slot [rank] of every peer's symmetric buffer and adds the slots of its own
+ * buffer in rank order.  buffer_floats = size of every rank's symmetric buffer, at least
+ * egt_peer_allreduce_push_floats(n, world) = 4 n world float32, zero-filled before the first call; n % 2 == 0. */
+int64_t egt_peer_allreduce_push_floats(int64_t n, int world);
+int egt_peer_allreduce_push(const uint64_t *buffer_ptrs_dev, const uint64_t *signal_pad_ptrs_dev, float *grad, int64_t n,
+                            int64_t buffer_floats, int rank, int world, void *stream);
 
 /* Counter-based uniform in (0,1) used for the random key mask / dropout (testing hook; host code).
  * stream_id 0 = random mask, 1 = attention dropout.  idx is the RNG element index: Philox call idx >> 3, 16-bit

@@ -50,6 +50,32 @@ for it in range(5):
     ok &= err < 1e-5
     if rank == 0:
         print(f'graph replay {it}: max |peer - nccl| = {err:.2e}', flush=True)
+# latency: 50 back-to-back calls per graph replay (ranks stay within one call of each other), CUDA events, max over ranks
+gl = torch.cuda.CUDAGraph()
+with torch.cuda.graph(gl):
+    for _ in range(50):
+        peer(buf)
+for _ in range(3):
+    gl.replay()
+torch.cuda.synchronize()
+dist.barrier()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(20):
+    gl.replay()
+e1.record()
+torch.cuda.synchronize()
+us = torch.tensor([e0.elapsed_time(e1) / 1000 * 1e3], device=dev)
+dist.all_reduce(us, op=dist.ReduceOp.MAX)
+e0.record()
+for _ in range(200):
+    dist.all_reduce(buf)
+e1.record()
+torch.cuda.synchronize()
+us_nccl = torch.tensor([e0.elapsed_time(e1) / 200 * 1e3], device=dev)
+dist.all_reduce(us_nccl, op=dist.ReduceOp.MAX)
+if rank == 0:
+    print(f'latency of one {n}-float all-reduce on {world} GPUs: peer kernel {float(us):.1f} us (graph replay), NCCL {float(us_nccl):.1f} us (eager)', flush=True)
 t = torch.tensor([int(ok)], device=dev)
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
