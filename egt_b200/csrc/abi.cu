@@ -57,6 +57,42 @@ bool pdl_enabled() {
   return on;
 }
 
+// ---- a side stream for the small kernels that depend on the weights only (wide_prep) or feed nothing downstream
+// (wide_bwd_finalize): they run next to the node kernels of the same call instead of between them.  Fork / join with
+// events, so a call captured into a CUDA graph records parallel branches.  Created on the first call of a device that
+// is not being captured (stream creation is not allowed inside a global-mode capture); EGT_SIDE_STREAM=0 turns it off.
+struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; bool ok = false; };
+static SideStream g_side[16];
+static SideStream *side_stream(cudaStream_t st) {
+  static const bool off = getenv("EGT_SIDE_STREAM") && atoi(getenv("EGT_SIDE_STREAM")) == 0;
+  if (off) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  SideStream &x = g_side[dev];
+  if (!x.ok) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return nullptr;
+    if (cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    x.ok = true;
+  }
+  return &x;
+}
+// side waits for everything issued on st so far; returns the stream to launch the branch on (st itself when off)
+static cudaStream_t side_fork(SideStream *x, cudaStream_t st) {
+  if (!x) return st;
+  if (cudaEventRecord(x->fork, st) != cudaSuccess || cudaStreamWaitEvent(x->s, x->fork, 0) != cudaSuccess) return st;
+  return x->s;
+}
+// st waits for the branch
+static int side_join(SideStream *x, cudaStream_t st, cudaStream_t branch) {
+  if (!x || branch == st) return EGT_OK;
+  EGT_CHECK_CUDA(cudaEventRecord(x->join, branch));
+  EGT_CHECK_CUDA(cudaStreamWaitEvent(st, x->join, 0));
+  return EGT_OK;
+}
+
 static size_t esize(int dtype) { return dtype == EGT_F32 ? 4 : 2; }
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -338,6 +374,10 @@ int egt_block_fwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
   const bool wide = !fused && wide_supported(cfg, a.dtype) && !g_force_staged;
   if (wide) {    // width-generic fused path (wide_fwd.cu); Q is stored pre-scaled by dk^-0.5
     const bool node_tc = d == 64 && a.h == 8;          // the tcgen05 node kernels (node_tc.cu) serve model width 64
+    SideStream *side = side_stream(st);
+    // the folded weights depend on the weights only: their kernel runs next to the node kernels, not in front of them
+    cudaStream_t sb = side_fork(side, st);
+    if ((rc = wide_prep_launch(cfg, w, (WidePrep *)ws.prep, sb))) return rc;
     if (node_tc) {
       if ((rc = node_qkv_launch(io->h, w->norm_mha_gamma, w->norm_mha_beta, cfg->ln_eps, w->dense_qkv_kernel,
                                 w->dense_qkv_bias, 1.0f / sqrtf((float)a.dk), io->qkv, R, w, a.clip_lo, a.clip_hi, nullptr, st))) return rc;
@@ -352,7 +392,7 @@ int egt_block_fwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
       lq.R = R; lq.din = d; lq.dout = 3 * d;
       if ((rc = linear_launch(lq, a.dtype, st))) return rc;
     }
-    if ((rc = wide_prep_launch(cfg, w, (WidePrep *)ws.prep, st))) return rc;
+    if ((rc = side_join(side, st, sb))) return rc;
     g_last_path = 1;
     WideFwdArgs fa;
     memset(&fa, 0, sizeof(fa));
@@ -452,6 +492,9 @@ int egt_block_bwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
 
   if (wide_bwd) {   // width-generic fused backward (wide_bwd.cu); node side on node_tc.cu (d = 64) or the staged kernels
     const bool node_tc = d == 64 && a.h == 8;
+    SideStream *side = side_stream(st);
+    cudaStream_t sb = side_fork(side, st);             // folded weights next to the first node kernel
+    if ((rc = wide_prep_launch(cfg, w, (WidePrep *)ws.prep, sb))) return rc;
     if (node_tc) {
       if ((rc = node_bwd1_launch(io->dh_out, io->v_att, w->dense_mha_kernel, ws.d_v_att, g->dense_mha_kernel,
                                  g->dense_mha_bias, R, w, a.clip_lo, a.clip_hi, nullptr, st))) return rc;
@@ -467,7 +510,7 @@ int egt_block_bwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
       x1.X = io->v_att; x1.Y = io->dh_out; x1.dW = g->dense_mha_kernel; x1.db = g->dense_mha_bias; x1.R = R; x1.dx = d; x1.dy = d;
       if ((rc = xty_launch(x1, a.dtype, st))) return rc;
     }
-    if ((rc = wide_prep_launch(cfg, w, (WidePrep *)ws.prep, st))) return rc;
+    if ((rc = side_join(side, st, sb))) return rc;
     const int tiles = (a.N + 127) / 128;
     if (tiles > 1) EGT_CHECK_CUDA(cudaMemsetAsync(ws.d_qkv_f32, 0, (size_t)R * 3 * d * sizeof(float), st));
     WideBwdArgs fb;
@@ -481,11 +524,16 @@ int egt_block_bwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
     fb.rand_thr = (uint32_t)ceilf(a.random_mask_prob * 65536.0f - 0.5f);
     fb.seed = a.seed; fb.offset = a.offset;
     if ((rc = wide_bwd_launch(cfg, fb, io->e, io->de_out, io->de, io->qkv, st))) return rc;
-    if ((rc = wide_bwd_finalize_launch(cfg, ws.partials, w, g, (const WidePrep *)ws.prep, st))) return rc;
-    if (node_tc)
-      return node_bwd2_launch(io->h, io->dh_out, ws.d_qkv_f32, w->norm_mha_gamma, w->norm_mha_beta, cfg->ln_eps,
-                              w->dense_qkv_kernel, io->dh, g->dense_qkv_kernel, g->dense_qkv_bias, g->norm_mha_gamma,
-                              g->norm_mha_beta, R, nullptr, 0, w, g, st);
+    // the fold of the edge-side weight gradients feeds nothing downstream: next to the last node kernels (it writes the
+    // edge weights' gradients, they write the node weights')
+    sb = side_fork(side, st);
+    if ((rc = wide_bwd_finalize_launch(cfg, ws.partials, w, g, (const WidePrep *)ws.prep, sb))) return rc;
+    if (node_tc) {
+      if ((rc = node_bwd2_launch(io->h, io->dh_out, ws.d_qkv_f32, w->norm_mha_gamma, w->norm_mha_beta, cfg->ln_eps,
+                                 w->dense_qkv_kernel, io->dh, g->dense_qkv_kernel, g->dense_qkv_bias, g->norm_mha_gamma,
+                                 g->norm_mha_beta, R, nullptr, 0, w, g, st))) return rc;
+      return side_join(side, st, sb);
+    }
     // node side: hn = LN(h); dW_qkv += hn^T dqkv; dhn = dqkv W_qkv^T; dh = LN_bwd(dhn) + dh'
     if (ws.nblas) {
       if ((rc = node_blas_bwd2(io->h, ws.d_qkv_f32, w, g, cfg->ln_eps, ws.dhn, R, d, ws.nblas, st))) return rc;
@@ -493,8 +541,10 @@ int egt_block_bwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
       memset(&lb, 0, sizeof(lb));
       lb.x = io->h; lb.dy = ws.dhn; lb.dres = io->dh_out; lb.gamma = w->norm_mha_gamma; lb.eps = cfg->ln_eps;
       lb.dx = io->dh; lb.dgamma = g->norm_mha_gamma; lb.dbeta = g->norm_mha_beta; lb.R = R; lb.D = d;
-      return ln_bwd_launch(lb, a.dtype, st);
+      if ((rc = ln_bwd_launch(lb, a.dtype, st))) return rc;
+      return side_join(side, st, sb);
     }
+    if ((rc = side_join(side, st, sb))) return rc;     // staged node kernels below: keep them behind the fold
     LinearArgs l2;
     memset(&l2, 0, sizeof(l2));
     l2.x = io->h; l2.ln_gamma = w->norm_mha_gamma; l2.ln_beta = w->norm_mha_beta; l2.ln_eps = cfg->ln_eps;
