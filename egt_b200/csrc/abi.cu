@@ -61,7 +61,7 @@ bool pdl_enabled() {
 // (wide_bwd_finalize): they run next to the node kernels of the same call instead of between them.  Fork / join with
 // events, so a call captured into a CUDA graph records parallel branches.  Created on the first call of a device that
 // is not being captured (stream creation is not allowed inside a global-mode capture); EGT_SIDE_STREAM=0 turns it off.
-struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; bool ok = false; };
+struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr, aux = nullptr; bool ok = false; };
 static SideStream g_side[16];
 static SideStream *side_stream(cudaStream_t st) {
   static const bool off = getenv("EGT_SIDE_STREAM") && atoi(getenv("EGT_SIDE_STREAM")) == 0;
@@ -75,6 +75,7 @@ static SideStream *side_stream(cudaStream_t st) {
     if (cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&x.aux, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     x.ok = true;
   }
   return &x;
@@ -85,12 +86,21 @@ static cudaStream_t side_fork(SideStream *x, cudaStream_t st) {
   if (cudaEventRecord(x->fork, st) != cudaSuccess || cudaStreamWaitEvent(x->s, x->fork, 0) != cudaSuccess) return st;
   return x->s;
 }
-// st waits for the branch
-static int side_join(SideStream *x, cudaStream_t st, cudaStream_t branch) {
+// mark: remember what the branch has been given so far; wait: st waits for the marked work only (the branch may already
+// have been given more, which keeps running next to st); join = mark + wait
+static int side_mark(SideStream *x, cudaStream_t st, cudaStream_t branch) {
   if (!x || branch == st) return EGT_OK;
   EGT_CHECK_CUDA(cudaEventRecord(x->join, branch));
+  return EGT_OK;
+}
+static int side_wait(SideStream *x, cudaStream_t st, cudaStream_t branch) {
+  if (!x || branch == st) return EGT_OK;
   EGT_CHECK_CUDA(cudaStreamWaitEvent(st, x->join, 0));
   return EGT_OK;
+}
+static int side_join(SideStream *x, cudaStream_t st, cudaStream_t branch) {
+  int rc = side_mark(x, st, branch);
+  return rc ? rc : side_wait(x, st, branch);
 }
 
 static size_t esize(int dtype) { return dtype == EGT_F32 ? 4 : 2; }
@@ -495,11 +505,12 @@ int egt_block_bwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
     SideStream *side = side_stream(st);
     cudaStream_t sb = side_fork(side, st);             // folded weights next to the first node kernel
     if ((rc = wide_prep_launch(cfg, w, (WidePrep *)ws.prep, sb))) return rc;
+    if ((rc = side_mark(side, st, sb))) return rc;     // what wide_bwd has to wait for
     if (node_tc) {
       if ((rc = node_bwd1_launch(io->dh_out, io->v_att, w->dense_mha_kernel, ws.d_v_att, g->dense_mha_kernel,
                                  g->dense_mha_bias, R, w, a.clip_lo, a.clip_hi, nullptr, st))) return rc;
     } else if (ws.nblas) {
-      if ((rc = node_blas_bwd1(io->dh_out, io->v_att, w, g, ws.d_v_att, R, d, ws.nblas, st))) return rc;
+      if ((rc = node_blas_bwd1(io->dh_out, io->v_att, w, g, ws.d_v_att, R, d, ws.nblas, st, sb))) return rc;   // dW_O, db_O: side
     } else {
       LinearArgs l1;  // dV_att = dh' W_O^T ; dW_O += V_att^T dh' ; db_O += colsum(dh')
       memset(&l1, 0, sizeof(l1));
@@ -510,7 +521,7 @@ int egt_block_bwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
       x1.X = io->v_att; x1.Y = io->dh_out; x1.dW = g->dense_mha_kernel; x1.db = g->dense_mha_bias; x1.R = R; x1.dx = d; x1.dy = d;
       if ((rc = xty_launch(x1, a.dtype, st))) return rc;
     }
-    if ((rc = side_join(side, st, sb))) return rc;
+    if ((rc = side_wait(side, st, sb))) return rc;
     const int tiles = (a.N + 127) / 128;
     if (tiles > 1) EGT_CHECK_CUDA(cudaMemsetAsync(ws.d_qkv_f32, 0, (size_t)R * 3 * d * sizeof(float), st));
     WideBwdArgs fb;
@@ -536,7 +547,7 @@ int egt_block_bwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
     }
     // node side: hn = LN(h); dW_qkv += hn^T dqkv; dhn = dqkv W_qkv^T; dh = LN_bwd(dhn) + dh'
     if (ws.nblas) {
-      if ((rc = node_blas_bwd2(io->h, ws.d_qkv_f32, w, g, cfg->ln_eps, ws.dhn, R, d, ws.nblas, st))) return rc;
+      if ((rc = node_blas_bwd2(io->h, ws.d_qkv_f32, w, g, cfg->ln_eps, ws.dhn, R, d, ws.nblas, st, sb, side ? side->aux : nullptr))) return rc;
       LnBwdArgs lb;
       memset(&lb, 0, sizeof(lb));
       lb.x = io->h; lb.dy = ws.dhn; lb.dres = io->dh_out; lb.gamma = w->norm_mha_gamma; lb.eps = cfg->ln_eps;

@@ -21,19 +21,19 @@ namespace egt {
 
 namespace {
 
-cublasHandle_t g_handle[16] = {};
+cublasHandle_t g_handle[2][16] = {};   // [1]: GEMMs issued on the side stream (own workspace)
 std::mutex g_handle_mu;
 
-int get_handle(cublasHandle_t *out) {
+int get_handle(cublasHandle_t *out, int which = 0) {
   int dev = 0;
   EGT_CHECK_CUDA(cudaGetDevice(&dev));
   EGT_REQUIRE(dev >= 0 && dev < 16, EGT_E_ARG, "node_blas: device index %d out of range", dev);
   std::lock_guard<std::mutex> lk(g_handle_mu);
-  if (!g_handle[dev]) {
-    cublasStatus_t s = cublasCreate(&g_handle[dev]);
+  if (!g_handle[which][dev]) {
+    cublasStatus_t s = cublasCreate(&g_handle[which][dev]);
     EGT_REQUIRE(s == CUBLAS_STATUS_SUCCESS, EGT_E_CUDA, "cublasCreate failed with status %d", (int)s);
   }
-  *out = g_handle[dev];
+  *out = g_handle[which][dev];
   return EGT_OK;
 }
 
@@ -129,7 +129,7 @@ size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 struct Carve {
   __nv_bfloat16 *hn_aug, *w_aug, *w_qkv, *w_o, *dqkv_bf;
   float *tmp;
-  void *blas_ws;
+  void *blas_ws, *blas_ws2;
 };
 constexpr size_t kBlasWs = 32u << 20;
 
@@ -144,15 +144,17 @@ Carve carve(void *base, int R, int d) {
   c.dqkv_bf = (__nv_bfloat16 *)take((size_t)R * 3 * d * 2);
   c.tmp = (float *)take((size_t)R * d * 4);
   c.blas_ws = take(kBlasWs);
+  c.blas_ws2 = take(kBlasWs);
   return c;
 }
 
-int begin(cublasHandle_t *h, const Carve &c, cudaStream_t st) {
-  int rc = get_handle(h);
+// which = 1: the handle of the side stream (its own cuBLAS workspace: its GEMMs run next to those of handle 0)
+int begin(cublasHandle_t *h, const Carve &c, cudaStream_t st, int which = 0) {
+  int rc = get_handle(h, which);
   if (rc) return rc;
   cublasStatus_t s = cublasSetStream(*h, st);
   EGT_REQUIRE(s == CUBLAS_STATUS_SUCCESS, EGT_E_CUDA, "cublasSetStream failed with status %d", (int)s);
-  s = cublasSetWorkspace(*h, c.blas_ws, kBlasWs);
+  s = cublasSetWorkspace(*h, which ? c.blas_ws2 : c.blas_ws, kBlasWs);
   EGT_REQUIRE(s == CUBLAS_STATUS_SUCCESS, EGT_E_CUDA, "cublasSetWorkspace failed with status %d", (int)s);
   return EGT_OK;
 }
@@ -166,7 +168,7 @@ bool node_blas_supported(int d) {
 
 size_t node_blas_workspace_bytes(int R, int d) {
   return al((size_t)R * (d + 8) * 2) + al((size_t)(d + 8) * 3 * d * 2) + al((size_t)d * 3 * d * 2) + al((size_t)d * d * 2) +
-         al((size_t)R * 3 * d * 2) + al((size_t)R * d * 4) + al(kBlasWs);
+         al((size_t)R * 3 * d * 2) + al((size_t)R * d * 4) + 2 * al(kBlasWs);
 }
 
 int node_blas_qkv(const void *h, const egt_block_weights_t *w, float eps, float qscale, void *qkv, int R, int d, void *ws,
@@ -207,35 +209,42 @@ int node_blas_out(const void *v_att, const void *h, const egt_block_weights_t *w
   return EGT_OK;
 }
 
-// dV_att = dh' W_O^T ; dW_O += V_att^T dh' ; db_O += colsum(dh')
+// dV_att = dh' W_O^T ; dW_O += V_att^T dh' ; db_O += colsum(dh').  The two weight-gradient kernels feed nothing in the
+// backward pass: they go to `side` (== st: same stream), where they run next to the fused backward kernel.
 int node_blas_bwd1(const void *dh_out, const void *v_att, const egt_block_weights_t *w, const egt_block_grads_t *g, void *d_v_att,
-                   int R, int d, void *ws, cudaStream_t st) {
+                   int R, int d, void *ws, cudaStream_t st, cudaStream_t side) {
   const Carve c = carve(ws, R, d);
-  cublasHandle_t hd;
+  cublasHandle_t hd, hs;
   int rc = begin(&hd, c, st);
   if (rc) return rc;
+  if ((rc = begin(&hs, c, side, 1))) return rc;
+  {
+    LaunchScope _ls("nb_colsum_kernel", side);
+    nb_colsum_kernel<__nv_bfloat16><<<(R + kColsumRows - 1) / kColsumRows, 256, 0, side>>>((const __nv_bfloat16 *)dh_out, R, d, g->dense_mha_bias, nullptr);
+  }
+  {
+    LaunchScope _ls("cublas_gemm", side);
+    if ((rc = gemm_rm(hs, true, false, d, d, R, v_att, d, dh_out, d, g->dense_mha_kernel, CUDA_R_32F, d, 1.f))) return rc;
+  }
   {
     LaunchScope _ls("nb_prep_kernel", st);
     nb_prep_kernel<<<64, 256, 0, st>>>(w->dense_qkv_kernel, w->dense_qkv_bias, w->dense_mha_kernel, d, 1.f, c.w_aug, c.w_qkv, c.w_o);
   }
-  {
-    LaunchScope _ls("nb_colsum_kernel", st);
-    nb_colsum_kernel<__nv_bfloat16><<<(R + kColsumRows - 1) / kColsumRows, 256, 0, st>>>((const __nv_bfloat16 *)dh_out, R, d, g->dense_mha_bias, nullptr);
-  }
   EGT_CHECK_CUDA(cudaGetLastError());
   LaunchScope _ls("cublas_gemm", st);
-  if ((rc = gemm_rm(hd, false, true, R, d, d, dh_out, d, c.w_o, d, d_v_att, CUDA_R_16BF, d, 0.f))) return rc;
-  return gemm_rm(hd, true, false, d, d, R, v_att, d, dh_out, d, g->dense_mha_kernel, CUDA_R_32F, d, 1.f);
+  return gemm_rm(hd, false, true, R, d, d, dh_out, d, c.w_o, d, d_v_att, CUDA_R_16BF, d, 0.f);
 }
 
 // dW_qkv += LN(h)^T dqkv ; db_qkv += colsum(dqkv) ; dhn = dqkv W_qkv^T (float32, for ln_bwd_kernel)
-// (w_qkv was converted by node_blas_bwd1 of the same backward call)
+// (w_qkv was converted by node_blas_bwd1 of the same backward call).  The weight-gradient GEMM goes to `side` once its
+// operands exist (fork / join through the two events; side == st: everything on one stream).
 int node_blas_bwd2(const void *h, const float *d_qkv, const egt_block_weights_t *w, const egt_block_grads_t *g, float eps,
-                   float *dhn, int R, int d, void *ws, cudaStream_t st) {
+                   float *dhn, int R, int d, void *ws, cudaStream_t st, cudaStream_t side, cudaEvent_t ev_operands) {
   const Carve c = carve(ws, R, d);
-  cublasHandle_t hd;
+  cublasHandle_t hd, hs;
   int rc = begin(&hd, c, st);
   if (rc) return rc;
+  if ((rc = begin(&hs, c, side, 1))) return rc;
   {
     LaunchScope _ls("nb_colsum_kernel", st);
     nb_colsum_kernel<float><<<(R + kColsumRows - 1) / kColsumRows, 256, 0, st>>>(d_qkv, R, 3 * d, g->dense_qkv_bias, c.dqkv_bf);
@@ -245,8 +254,15 @@ int node_blas_bwd2(const void *h, const float *d_qkv, const egt_block_weights_t 
     nb_ln_aug_kernel<<<(R + 7) / 8, 256, 0, st>>>((const __nv_bfloat16 *)h, w->norm_mha_gamma, w->norm_mha_beta, eps, R, d, c.hn_aug);
   }
   EGT_CHECK_CUDA(cudaGetLastError());
+  if (side != st) {
+    EGT_CHECK_CUDA(cudaEventRecord(ev_operands, st));
+    EGT_CHECK_CUDA(cudaStreamWaitEvent(side, ev_operands, 0));
+  }
+  {
+    LaunchScope _ls("cublas_gemm", side);
+    if ((rc = gemm_rm(hs, true, false, d, 3 * d, R, c.hn_aug, d + 8, c.dqkv_bf, 3 * d, g->dense_qkv_kernel, CUDA_R_32F, 3 * d, 1.f))) return rc;
+  }
   LaunchScope _ls("cublas_gemm", st);
-  if ((rc = gemm_rm(hd, true, false, d, 3 * d, R, c.hn_aug, d + 8, c.dqkv_bf, 3 * d, g->dense_qkv_kernel, CUDA_R_32F, 3 * d, 1.f))) return rc;
   return gemm_rm(hd, false, true, R, d, 3 * d, c.dqkv_bf, 3 * d, c.w_qkv, 3 * d, dhn, CUDA_R_32F, d, 0.f);
 }
 

@@ -13,10 +13,12 @@ int node_blas_qkv(const void *h, const egt_block_weights_t *w, float eps, float 
                   cudaStream_t st);
 int node_blas_out(const void *v_att, const void *h, const egt_block_weights_t *w, void *h_out, int R, int d, void *ws,
                   cudaStream_t st);
+// side: stream for the weight-gradient kernels that feed nothing downstream (pass st to keep everything on one stream);
+// the caller makes `side` wait for the inputs before the call and joins it before it returns
 int node_blas_bwd1(const void *dh_out, const void *v_att, const egt_block_weights_t *w, const egt_block_grads_t *g, void *d_v_att,
-                   int R, int d, void *ws, cudaStream_t st);
+                   int R, int d, void *ws, cudaStream_t st, cudaStream_t side);
 int node_blas_bwd2(const void *h, const float *d_qkv, const egt_block_weights_t *w, const egt_block_grads_t *g, float eps,
-                   float *dhn, int R, int d, void *ws, cudaStream_t st);
+                   float *dhn, int R, int d, void *ws, cudaStream_t st, cudaStream_t side, cudaEvent_t ev_operands);
 
 // feed-forward half of a layer on cuBLAS (widths / hidden sizes ffn_tc.cu does not serve); EGT_FFN_BLAS=0 turns it off
 bool ffn_blas_supported(const egt_ffn_cfg_t *cfg);
