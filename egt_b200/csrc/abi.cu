@@ -507,8 +507,9 @@ int egt_block_bwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
     if ((rc = wide_prep_launch(cfg, w, (WidePrep *)ws.prep, sb))) return rc;
     if ((rc = side_mark(side, st, sb))) return rc;     // what wide_bwd has to wait for
     if (node_tc) {
+      const bool idle_sms = a.B * ((a.N + 127) / 128) + 20 <= 148;      // the fused kernel's grid leaves SMs for the side launch
       if ((rc = node_bwd1_launch(io->dh_out, io->v_att, w->dense_mha_kernel, ws.d_v_att, g->dense_mha_kernel,
-                                 g->dense_mha_bias, R, w, a.clip_lo, a.clip_hi, nullptr, st))) return rc;
+                                 g->dense_mha_bias, R, w, a.clip_lo, a.clip_hi, nullptr, st, idle_sms ? sb : st))) return rc;
     } else if (ws.nblas) {
       if ((rc = node_blas_bwd1(io->dh_out, io->v_att, w, g, ws.d_v_att, R, d, ws.nblas, st, sb))) return rc;   // dW_O, db_O: side
     } else {
@@ -579,8 +580,14 @@ int egt_block_bwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
   }
 
   if (fused_bwd) {
+    // dW_O / db_O feed nothing in the backward pass: a second small launch on the side stream, next to the fused backward
+    // kernel (whose 128-CTA grid leaves SMs idle at the headline shape); joined before the call returns
+    // -- only when that grid really leaves 20 SMs idle: otherwise the second launch competes with it
+    const int bwd_ctas = a.B * ((a.N + 127) / 128);
+    SideStream *side = bwd_ctas + 20 <= 148 ? side_stream(st) : nullptr;
+    cudaStream_t sb = side_fork(side, st);
     if ((rc = node_bwd1_launch(io->dh_out, io->v_att, w->dense_mha_kernel, ws.d_v_att, g->dense_mha_kernel,
-                               g->dense_mha_bias, R, w, a.clip_lo, a.clip_hi, (FusedPrep *)ws.prep, st))) return rc;
+                               g->dense_mha_bias, R, w, a.clip_lo, a.clip_hi, (FusedPrep *)ws.prep, st, sb))) return rc;
     // N x N part in one kernel (fused_bwd.cu): de, dQ|dK|dV and the edge-side weight-gradient partial sums
     const int tiles = (a.N + 127) / 128;
     if (tiles > 1) EGT_CHECK_CUDA(cudaMemsetAsync(ws.d_qkv_f32, 0, (size_t)R * 3 * d * sizeof(float), st));
@@ -595,9 +602,10 @@ int egt_block_bwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
     fb.rand_thr = (uint32_t)ceilf(a.random_mask_prob * 65536.0f - 0.5f);
     fb.seed = a.seed; fb.offset = a.offset;
     if ((rc = fused_bwd_launch(fb, io->e, io->de_out, io->de, io->qkv, st))) return rc;
-    return node_bwd2_launch(io->h, io->dh_out, ws.d_qkv_f32, w->norm_mha_gamma, w->norm_mha_beta, cfg->ln_eps,
-                            w->dense_qkv_kernel, io->dh, g->dense_qkv_kernel, g->dense_qkv_bias, g->norm_mha_gamma,
-                            g->norm_mha_beta, R, ws.partials, a.B * tiles, w, g, st);
+    if ((rc = node_bwd2_launch(io->h, io->dh_out, ws.d_qkv_f32, w->norm_mha_gamma, w->norm_mha_beta, cfg->ln_eps,
+                               w->dense_qkv_kernel, io->dh, g->dense_qkv_kernel, g->dense_qkv_bias, g->norm_mha_gamma,
+                               g->norm_mha_beta, R, ws.partials, a.B * tiles, w, g, st))) return rc;
+    return side_join(side, st, sb);
   }
 
   // dV_att = dh' W_O^T ; dW_O += V_att^T dh' ; db_O += colsum(dh')

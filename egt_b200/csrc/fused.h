@@ -96,7 +96,8 @@ int node_qkv_launch(const void *h, const float *gamma, const float *beta, float 
 int node_out_launch(const void *v_att, const void *h, const float *W, const float *bias, void *h_out, int R,
                     cudaStream_t st);
 int node_bwd1_launch(const void *dh_out, const void *v_att, const float *W, void *d_v_att, float *dW, float *db, int R,
-                     const egt_block_weights_t *w, float clip_lo, float clip_hi, FusedPrep *prep_out, cudaStream_t st);
+                     const egt_block_weights_t *w, float clip_lo, float clip_hi, FusedPrep *prep_out, cudaStream_t st,
+                     cudaStream_t side);   // side != st: dW_O / db_O as a second small launch on `side`
 int node_bwd2_launch(const void *h, const void *dh_out, const float *dqkv, const float *gamma, const float *beta,
                      float eps, const float *W, void *dh, float *dW, float *db, float *dgamma, float *dbeta, int R,
                      const float *partials, int nparts, const egt_block_weights_t *w, const egt_block_grads_t *g,

@@ -292,6 +292,7 @@ struct NodeBwd1Args {
   const __nv_bfloat16 *dh_out, *v_att; const float *W;       // W_O [64,64]
   __nv_bfloat16 *d_v_att; float *dW, *db; int R;
   egt_block_weights_t w; float clip_lo, clip_hi; FusedPrep *prep_out;   // extra CTA: fused_prep_body (NULL = off)
+  int parts;   // bit 0: dV_att (what the fused backward waits for) ; bit 1: dW_O, db_O (can run next to it on a few SMs)
 };
 
 __global__ void __launch_bounds__(128) node_bwd1_kernel(const NodeBwd1Args a) {
@@ -303,9 +304,10 @@ __global__ void __launch_bounds__(128) node_bwd1_kernel(const NodeBwd1Args a) {
   const int nwork = a.prep_out ? gridDim.x - 1 : gridDim.x;
   pdl_trigger();
   if ((int)blockIdx.x == nwork) { fused_prep_body(a.w, a.clip_lo, a.clip_hi, a.prep_out, t); return; }
+  const bool do_dx = a.parts & 1, do_dw = a.parts & 2;
   node_setup(bars, t, 128);
-  build_wt_k(sW, a.W, ND, ND, t, 128);
-  fill_ones(sOnes, t, 128);
+  if (do_dx) build_wt_k(sW, a.W, ND, ND, t, 128);
+  if (do_dw) fill_ones(sOnes, t, 128);
   pdl_wait();
   tc_fence_before();
   __syncthreads();
@@ -320,10 +322,12 @@ __global__ void __launch_bounds__(128) node_bwd1_kernel(const NodeBwd1Args a) {
     const int r = tile * 128 + t;
     {
       uint4 v[8];
-      const uint4 *sx = (const uint4 *)(a.v_att + (size_t)(r < a.R ? r : 0) * ND);
+      if (do_dw) {
+        const uint4 *sx = (const uint4 *)(a.v_att + (size_t)(r < a.R ? r : 0) * ND);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = r < a.R ? sx[j] : make_uint4(0, 0, 0, 0);
-      put_row(sX, t, v);
+        for (int j = 0; j < 8; ++j) v[j] = r < a.R ? sx[j] : make_uint4(0, 0, 0, 0);
+        put_row(sX, t, v);
+      }
       const uint4 *sy = (const uint4 *)(a.dh_out + (size_t)(r < a.R ? r : 0) * ND);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = r < a.R ? sy[j] : make_uint4(0, 0, 0, 0);
@@ -334,14 +338,18 @@ __global__ void __launch_bounds__(128) node_bwd1_kernel(const NodeBwd1Args a) {
     __syncthreads();
     if (t == 0) {
       tc_fence_after();
+      if (do_dx) {
 #pragma unroll
-      for (int s = 0; s < 4; ++s)      // dV_att = dh' W_O^T
-        mma_ss(tmem + TM_D1, smem_desc(smem_u32(sY) + 32 * s, 16, 1024, LAYOUT_SW128),
-               smem_desc(smem_u32(sW) + 32 * s, 16, 1024, LAYOUT_SW128), ID_MAIN, s > 0);
+        for (int s = 0; s < 4; ++s)      // dV_att = dh' W_O^T
+          mma_ss(tmem + TM_D1, smem_desc(smem_u32(sY) + 32 * s, 16, 1024, LAYOUT_SW128),
+                 smem_desc(smem_u32(sW) + 32 * s, 16, 1024, LAYOUT_SW128), ID_MAIN, s > 0);
+      }
+      if (do_dw) {
 #pragma unroll
-      for (int s = 0; s < 8; ++s)      // [V_att | 1]^T dh'
-        mma_ss(tmem + TM_D2, smem_desc(smem_u32(sX) + 2048 * s, TILE, 1024, LAYOUT_SW128),
-               smem_desc(smem_u32(sY) + 2048 * s, TILE, 1024, LAYOUT_SW128), ID_T, !(first && s == 0));
+        for (int s = 0; s < 8; ++s)      // [V_att | 1]^T dh'
+          mma_ss(tmem + TM_D2, smem_desc(smem_u32(sX) + 2048 * s, TILE, 1024, LAYOUT_SW128),
+                 smem_desc(smem_u32(sY) + 2048 * s, TILE, 1024, LAYOUT_SW128), ID_T, !(first && s == 0));
+      }
       mma_commit(smem_u32(&bars->bar));
     }
     first = false;
@@ -349,7 +357,7 @@ __global__ void __launch_bounds__(128) node_bwd1_kernel(const NodeBwd1Args a) {
     phase ^= 1;
     tc_fence_after();
 #pragma unroll 1
-    for (int ch = 0; ch < 2; ++ch) {
+    for (int ch = 0; ch < (do_dx ? 2 : 0); ++ch) {
       uint32_t o[32];
       tmem_ld32(tlane + TM_D1 + 32 * ch, o);
       tmem_ld_wait();
@@ -367,7 +375,7 @@ __global__ void __launch_bounds__(128) node_bwd1_kernel(const NodeBwd1Args a) {
     tc_fence_before();
     __syncthreads();
   }
-  if (!first) {   // flush dW_O (rows 0-63) and db_O (row 64)
+  if (!first && do_dw) {   // flush dW_O (rows 0-63) and db_O (row 64)
 #pragma unroll 1
     for (int ch = 0; ch < 2; ++ch) {
       uint32_t o[32];
@@ -593,12 +601,26 @@ int node_out_launch(const void *v_att, const void *h, const float *W, const floa
   return EGT_OK;
 }
 
+// side != st: the weight-gradient half (dW_O, db_O) runs as a second launch of at most 20 CTAs on `side` -- next to the
+// dV_att half and then next to the fused backward kernel, on the SMs its 128-CTA grid leaves idle.  The caller forks
+// `side` from `st` before the call and joins it before it returns.
 int node_bwd1_launch(const void *dh_out, const void *v_att, const float *W, void *d_v_att, float *dW, float *db, int R,
-                     const egt_block_weights_t *w, float clip_lo, float clip_hi, FusedPrep *prep_out, cudaStream_t st) {
-  NodeBwd1Args a{(const __nv_bfloat16 *)dh_out, (const __nv_bfloat16 *)v_att, W, (__nv_bfloat16 *)d_v_att, dW, db, R, *w, clip_lo, clip_hi, prep_out};
+                     const egt_block_weights_t *w, float clip_lo, float clip_hi, FusedPrep *prep_out, cudaStream_t st,
+                     cudaStream_t side) {
+  NodeBwd1Args a{(const __nv_bfloat16 *)dh_out, (const __nv_bfloat16 *)v_att, W, (__nv_bfloat16 *)d_v_att, dW, db, R, *w, clip_lo, clip_hi, prep_out, 3};
   const int smem = 3 * TILE + 8192 + 64 + 1024;
   static bool once = false;
   if (!once) { int rc = set_smem(node_bwd1_kernel, smem); if (rc) return rc; once = true; }
+  if (side != st) {
+    NodeBwd1Args b = a;
+    b.parts = 2; b.prep_out = nullptr;
+    const int tiles = node_grid(R);
+    {
+      LaunchScope _ls("node_bwd1w_kernel", side);
+      EGT_CHECK_CUDA(launch_pdl(node_bwd1_kernel, dim3(tiles < 20 ? tiles : 20), dim3(128), smem, side, b));
+    }
+    a.parts = 1;
+  }
   LaunchScope _ls("node_bwd1_kernel", st);
   EGT_CHECK_CUDA(launch_pdl(node_bwd1_kernel, dim3(node_grid(R) + (prep_out ? 1 : 0)), dim3(128), smem, st, a));
   return EGT_OK;
