@@ -543,7 +543,7 @@ int egt_block_bwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
     if (node_tc) {
       if ((rc = node_bwd2_launch(io->h, io->dh_out, ws.d_qkv_f32, w->norm_mha_gamma, w->norm_mha_beta, cfg->ln_eps,
                                  w->dense_qkv_kernel, io->dh, g->dense_qkv_kernel, g->dense_qkv_bias, g->norm_mha_gamma,
-                                 g->norm_mha_beta, R, nullptr, 0, w, g, st))) return rc;
+                                 g->norm_mha_beta, R, nullptr, 0, w, g, st, st))) return rc;   // the side stream is busy with the fold
       return side_join(side, st, sb);
     }
     // node side: hn = LN(h); dW_qkv += hn^T dqkv; dhn = dqkv W_qkv^T; dh = LN_bwd(dhn) + dh'
@@ -602,9 +602,11 @@ int egt_block_bwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
     fb.rand_thr = (uint32_t)ceilf(a.random_mask_prob * 65536.0f - 0.5f);
     fb.seed = a.seed; fb.offset = a.offset;
     if ((rc = fused_bwd_launch(fb, io->e, io->de_out, io->de, io->qkv, st))) return rc;
+    // (splitting this kernel into its dh half and its weight-gradient half on two streams was measured: the dh half alone
+    // takes as long as the whole kernel -- 26 us, the float32 -> bf16 staging of dqkv -- and the step got 2 % slower)
     if ((rc = node_bwd2_launch(io->h, io->dh_out, ws.d_qkv_f32, w->norm_mha_gamma, w->norm_mha_beta, cfg->ln_eps,
                                w->dense_qkv_kernel, io->dh, g->dense_qkv_kernel, g->dense_qkv_bias, g->norm_mha_gamma,
-                               g->norm_mha_beta, R, ws.partials, a.B * tiles, w, g, st))) return rc;
+                               g->norm_mha_beta, R, ws.partials, a.B * tiles, w, g, st, st))) return rc;
     return side_join(side, st, sb);
   }
 

@@ -101,7 +101,8 @@ int node_bwd1_launch(const void *dh_out, const void *v_att, const float *W, void
 int node_bwd2_launch(const void *h, const void *dh_out, const float *dqkv, const float *gamma, const float *beta,
                      float eps, const float *W, void *dh, float *dW, float *db, float *dgamma, float *dbeta, int R,
                      const float *partials, int nparts, const egt_block_weights_t *w, const egt_block_grads_t *g,
-                     cudaStream_t st);   // partials != NULL: one extra CTA folds the fused backward's partial sums
+                     cudaStream_t st, cudaStream_t side);   // partials != NULL: one extra CTA folds the fused backward's partial
+                                                            // sums; side != st: weight-gradient half as a second launch on `side`
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda at link time)
 int encode_tmap_3d(CUtensorMap *out, const void *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,

@@ -401,23 +401,38 @@ struct NodeBwd2Args {
   const float *W;                                            // W_qkv [64,192]
   __nv_bfloat16 *dh; float *dW, *db, *dgamma, *dbeta; int R;
   const float *partials; int nparts; egt_block_weights_t w; egt_block_grads_t g;   // extra CTA: finalize (NULL = off)
+  int parts;   // bit 0: dh (+ dgamma, dbeta) ; bit 1: dW_qkv, db_qkv.  Launched as two kernels, the halves share an SM.
 };
+
+// shared-memory map; the two halves of a split launch only ask for what they use so that their CTAs fit one SM together
+__host__ __device__ inline int node_bwd2_smem(int parts) {
+  int b = 3 * (int)TILE;                                   // dqkv tiles
+  if (parts & 2) b += 2 * (int)TILE;                       // LN(h) | 1
+  if (parts & 1) b += 24576 + 128 * 65 * 4;                // W_qkv^T image | transpose scratch
+  return b + 2 * ND * 4 + 64;
+}
 
 __global__ void __launch_bounds__(128) node_bwd2_kernel(const NodeBwd2Args a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t *sX = smem, *sOnes = smem + TILE, *sY = smem + 2 * TILE;   // LN(h) | 1 | dqkv (3 tiles)
-  uint8_t *sW = smem + 5 * TILE;                                      // W_qkv^T image: 3 k-atoms x 8 KB
-  float *sred = (float *)(smem + 5 * TILE + 24576);                   // [128][65] float32 transpose scratch
-  float *sgb = sred + 128 * 65;                                       // gamma, beta
+  const bool do_dx = a.parts & 1, do_dw = a.parts & 2;
+  uint8_t *p = smem;
+  uint8_t *sX = p, *sOnes = p + TILE;                                 // LN(h) | 1   (adjacent: one MN-major operand)
+  if (do_dw) p += 2 * TILE;
+  uint8_t *sY = p;                                                    // dqkv (3 tiles)
+  p += 3 * TILE;
+  uint8_t *sW = p;                                                    // W_qkv^T image: 3 k-atoms x 8 KB
+  float *sred = (float *)(p + 24576);                                 // [128][65] float32 transpose scratch
+  if (do_dx) p += 24576 + 128 * 65 * 4;
+  float *sgb = (float *)p;                                            // gamma, beta
   NodeBars *bars = (NodeBars *)(sgb + 2 * ND);
   const int t = threadIdx.x;
   const int nwork = a.partials ? gridDim.x - 1 : gridDim.x;
   pdl_trigger();
   if ((int)blockIdx.x == nwork) { pdl_wait(); fused_bwd_finalize_body(a.partials, a.nparts, a.w, a.g, t, 128); return; }
-  node_setup(bars, t, 256);
-  build_wt_k(sW, a.W, ND, 3 * ND, t, 128);
-  fill_ones(sOnes, t, 128);
+  node_setup(bars, t, do_dw ? 256 : 64);
+  if (do_dx) build_wt_k(sW, a.W, ND, 3 * ND, t, 128);
+  if (do_dw) fill_ones(sOnes, t, 128);
   if (t < ND) { sgb[t] = a.gamma[t]; sgb[ND + t] = a.beta[t]; }
   pdl_wait();
   tc_fence_before();
@@ -454,7 +469,7 @@ __global__ void __launch_bounds__(128) node_bwd2_kernel(const NodeBwd2Args a) {
           xh[8 * j + c] *= rs;
           y[c] = valid ? fmaf(xh[8 * j + c], sgb[8 * j + c], sgb[ND + 8 * j + c]) : 0.f;
         }
-        *(uint4 *)(sX + sw128_off(t, 8 * j)) = pack8(y);
+        if (do_dw) *(uint4 *)(sX + sw128_off(t, 8 * j)) = pack8(y);
       }
     }
     {   // dqkv tile (float32 [128,192], rows contiguous) -> three bf16 tiles; coalesced: 24 threads per row
@@ -479,21 +494,25 @@ __global__ void __launch_bounds__(128) node_bwd2_kernel(const NodeBwd2Args a) {
     __syncthreads();
     if (t == 0) {
       tc_fence_after();
+      if (do_dx) {
 #pragma unroll
-      for (int s = 0; s < 12; ++s)     // dhn = dqkv W_qkv^T   (K = 192)
-        mma_ss(tmem + TM_D1, smem_desc(smem_u32(sY) + (uint32_t)(s >> 2) * TILE + 32 * (s & 3), 16, 1024, LAYOUT_SW128),
-               smem_desc(smem_u32(sW) + (uint32_t)(s >> 2) * 8192 + 32 * (s & 3), 16, 1024, LAYOUT_SW128), ID_MAIN, s > 0);
+        for (int s = 0; s < 12; ++s)     // dhn = dqkv W_qkv^T   (K = 192)
+          mma_ss(tmem + TM_D1, smem_desc(smem_u32(sY) + (uint32_t)(s >> 2) * TILE + 32 * (s & 3), 16, 1024, LAYOUT_SW128),
+                 smem_desc(smem_u32(sW) + (uint32_t)(s >> 2) * 8192 + 32 * (s & 3), 16, 1024, LAYOUT_SW128), ID_MAIN, s > 0);
+      }
+      if (do_dw) {
 #pragma unroll
-      for (int s = 0; s < 8; ++s)      // [LN(h) | 1]^T dqkv
-        mma_ss(tmem + TM_D2, smem_desc(smem_u32(sX) + 2048 * s, TILE, 1024, LAYOUT_SW128),
-               smem_desc(smem_u32(sY) + 2048 * s, TILE, 1024, LAYOUT_SW128), ID_T, !(first && s == 0));
+        for (int s = 0; s < 8; ++s)      // [LN(h) | 1]^T dqkv
+          mma_ss(tmem + TM_D2, smem_desc(smem_u32(sX) + 2048 * s, TILE, 1024, LAYOUT_SW128),
+                 smem_desc(smem_u32(sY) + 2048 * s, TILE, 1024, LAYOUT_SW128), ID_T, !(first && s == 0));
+      }
       mma_commit(smem_u32(&bars->bar));
     }
     first = false;
     mbar_wait(smem_u32(&bars->bar), phase);
     phase ^= 1;
     tc_fence_after();
-    {   // LayerNorm backward + residual for this thread's row
+    if (do_dx) {   // LayerNorm backward + residual for this thread's row
       float dy[64];
       uint32_t o[32];
       tmem_ld32(tlane + TM_D1, o);
@@ -547,9 +566,11 @@ __global__ void __launch_bounds__(128) node_bwd2_kernel(const NodeBwd2Args a) {
     tc_fence_before();
     __syncthreads();
   }
-  if (!first) {
+  if (!first && do_dx) {
     if (t < ND) atomicAdd(a.dgamma + t, dg_acc);
     else atomicAdd(a.dbeta + (t - ND), db_acc);
+  }
+  if (!first && do_dw) {
 #pragma unroll 1
     for (int ch = 0; ch < 6; ++ch) {   // dW_qkv (rows 0-63), db_qkv (row 64)
       uint32_t o[32];
@@ -565,7 +586,7 @@ __global__ void __launch_bounds__(128) node_bwd2_kernel(const NodeBwd2Args a) {
   }
   tc_fence_before();
   __syncthreads();
-  if (t < 32) tmem_dealloc(tmem, 256);
+  if (t < 32) tmem_dealloc(tmem, do_dw ? 256 : 64);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -626,17 +647,30 @@ int node_bwd1_launch(const void *dh_out, const void *v_att, const float *W, void
   return EGT_OK;
 }
 
+// side != st: two launches, the dh half on st and the weight-gradient half (+ the finalize CTA) on `side`; their CTAs
+// share the SMs (106 + 80 KB of shared memory, 64 + 256 tensor-memory columns), so the two latency chains overlap.
 int node_bwd2_launch(const void *h, const void *dh_out, const float *dqkv, const float *gamma, const float *beta,
                      float eps, const float *W, void *dh, float *dW, float *db, float *dgamma, float *dbeta, int R,
                      const float *partials, int nparts, const egt_block_weights_t *w, const egt_block_grads_t *g,
-                     cudaStream_t st) {
+                     cudaStream_t st, cudaStream_t side) {
   NodeBwd2Args a{(const __nv_bfloat16 *)h, (const __nv_bfloat16 *)dh_out, dqkv, gamma, beta, eps, W,
-                 (__nv_bfloat16 *)dh, dW, db, dgamma, dbeta, R, partials, nparts, *w, *g};
-  const int smem = 5 * TILE + 24576 + 128 * 65 * 4 + 2 * ND * 4 + 64 + 1024;
+                 (__nv_bfloat16 *)dh, dW, db, dgamma, dbeta, R, partials, nparts, *w, *g, 3};
   static bool once = false;
-  if (!once) { int rc = set_smem(node_bwd2_kernel, smem); if (rc) return rc; once = true; }
+  if (!once) { int rc = set_smem(node_bwd2_kernel, node_bwd2_smem(3) + 1024); if (rc) return rc; once = true; }
+  if (side != st) {
+    NodeBwd2Args b = a;
+    b.parts = 2;
+    {
+      LaunchScope _ls("node_bwd2w_kernel", side);
+      EGT_CHECK_CUDA(launch_pdl(node_bwd2_kernel, dim3(node_grid(R) + (partials ? 1 : 0)), dim3(128), node_bwd2_smem(2) + 1024, side, b));
+    }
+    a.parts = 1; a.partials = nullptr;
+    LaunchScope _ls("node_bwd2_kernel", st);
+    EGT_CHECK_CUDA(launch_pdl(node_bwd2_kernel, dim3(node_grid(R)), dim3(128), node_bwd2_smem(1) + 1024, st, a));
+    return EGT_OK;
+  }
   LaunchScope _ls("node_bwd2_kernel", st);
-  EGT_CHECK_CUDA(launch_pdl(node_bwd2_kernel, dim3(node_grid(R) + (partials ? 1 : 0)), dim3(128), smem, st, a));
+  EGT_CHECK_CUDA(launch_pdl(node_bwd2_kernel, dim3(node_grid(R) + (partials ? 1 : 0)), dim3(128), node_bwd2_smem(3) + 1024, st, a));
   return EGT_OK;
 }
 
