@@ -412,7 +412,9 @@ __host__ __device__ inline int node_bwd2_smem(int parts) {
   return b + 2 * ND * 4 + 64;
 }
 
-__global__ void __launch_bounds__(128) node_bwd2_kernel(const NodeBwd2Args a) {
+// 256 threads: threads 0-127 own the rows (= TMEM lanes); threads 128-255 only help with the staging (weight image,
+// float32 -> bf16 tiles of dqkv), which is 40 % of the kernel's latency chain with 128 threads.
+__global__ void __launch_bounds__(256) node_bwd2_kernel(const NodeBwd2Args a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const bool do_dx = a.parts & 1, do_dw = a.parts & 2;
@@ -426,30 +428,31 @@ __global__ void __launch_bounds__(128) node_bwd2_kernel(const NodeBwd2Args a) {
   if (do_dx) p += 24576 + 128 * 65 * 4;
   float *sgb = (float *)p;                                            // gamma, beta
   NodeBars *bars = (NodeBars *)(sgb + 2 * ND);
-  const int t = threadIdx.x;
+  const int tid = threadIdx.x, t = tid & 127;
+  const bool rowthr = tid < 128;
   const int nwork = a.partials ? gridDim.x - 1 : gridDim.x;
   pdl_trigger();
-  if ((int)blockIdx.x == nwork) { pdl_wait(); fused_bwd_finalize_body(a.partials, a.nparts, a.w, a.g, t, 128); return; }
-  node_setup(bars, t, do_dw ? 256 : 64);
-  if (do_dx) build_wt_k(sW, a.W, ND, 3 * ND, t, 128);
-  if (do_dw) fill_ones(sOnes, t, 128);
-  if (t < ND) { sgb[t] = a.gamma[t]; sgb[ND + t] = a.beta[t]; }
+  if ((int)blockIdx.x == nwork) { pdl_wait(); fused_bwd_finalize_body(a.partials, a.nparts, a.w, a.g, tid, 256); return; }
+  node_setup(bars, tid, do_dw ? 256 : 64);
+  if (do_dx) build_wt_k(sW, a.W, ND, 3 * ND, tid, 256);
+  if (do_dw) fill_ones(sOnes, tid, 256);
+  if (tid < ND) { sgb[tid] = a.gamma[tid]; sgb[ND + tid] = a.beta[tid]; }
   pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
-  const uint32_t tlane = tmem + ((uint32_t)((t >> 5) * 32) << 16);
+  const uint32_t tlane = tmem + ((uint32_t)(((tid >> 5) & 3) * 32) << 16);
   constexpr uint32_t ID_MAIN = idesc_bf16(128, 64, 0, 0), ID_T = idesc_bf16(128, 192, 1, 1);
   constexpr uint32_t TM_D1 = 0, TM_D2 = 64;
   uint32_t phase = 0;
   bool first = true;
-  float dg_acc = 0.f, db_acc = 0.f;     // thread c < 64: dgamma[c]; thread 64 + c: dbeta[c]
+  float dg_acc = 0.f, db_acc = 0.f;     // partial dgamma / dbeta of column tid & 63 over the row quarter tid >> 6
   for (int tile = blockIdx.x; tile * 128 < a.R; tile += nwork) {
     const int r = tile * 128 + t;
     const bool valid = r < a.R;
-    float xh[64], rs;
-    {   // x^ = (h - mu) rstd ; LN(h) -> X tile
+    float xh[64], rs = 0.f;
+    if (rowthr) {   // x^ = (h - mu) rstd ; LN(h) -> X tile
       const uint4 *src = (const uint4 *)(a.h + (size_t)(valid ? r : 0) * ND);
 #pragma unroll
       for (int j = 0; j < 8; ++j) unpack8(valid ? src[j] : make_uint4(0, 0, 0, 0), xh + 8 * j);
@@ -476,7 +479,7 @@ __global__ void __launch_bounds__(128) node_bwd2_kernel(const NodeBwd2Args a) {
       const float *base = a.dqkv + (size_t)tile * 128 * (3 * ND);
       const int rows_here = a.R - tile * 128 < 128 ? a.R - tile * 128 : 128;
 #pragma unroll 4
-      for (int i = t; i < 128 * 24; i += 128) {
+      for (int i = tid; i < 128 * 24; i += 256) {
         const int rr = i / 24, j = i % 24;
         float y[8];
         if (rr < rows_here) {
@@ -492,7 +495,7 @@ __global__ void __launch_bounds__(128) node_bwd2_kernel(const NodeBwd2Args a) {
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
-    if (t == 0) {
+    if (tid == 0) {
       tc_fence_after();
       if (do_dx) {
 #pragma unroll
@@ -514,52 +517,58 @@ __global__ void __launch_bounds__(128) node_bwd2_kernel(const NodeBwd2Args a) {
     tc_fence_after();
     if (do_dx) {   // LayerNorm backward + residual for this thread's row
       float dy[64];
-      uint32_t o[32];
-      tmem_ld32(tlane + TM_D1, o);
-      tmem_ld_wait();
+      if (rowthr) {
+        uint32_t o[32];
+        tmem_ld32(tlane + TM_D1, o);
+        tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 32; ++c) dy[c] = __uint_as_float(o[c]);
-      tmem_ld32(tlane + TM_D1 + 32, o);
-      tmem_ld_wait();
+        for (int c = 0; c < 32; ++c) dy[c] = __uint_as_float(o[c]);
+        tmem_ld32(tlane + TM_D1 + 32, o);
+        tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 32; ++c) dy[32 + c] = __uint_as_float(o[c]);
-      float m1 = 0.f, m2 = 0.f;
+        for (int c = 0; c < 32; ++c) dy[32 + c] = __uint_as_float(o[c]);
+        float m1 = 0.f, m2 = 0.f;
 #pragma unroll
-      for (int c = 0; c < 64; ++c) {
-        const float dxh = dy[c] * sgb[c];
-        m1 += dxh;
-        m2 = fmaf(dxh, xh[c], m2);
-        sred[t * 65 + c] = dy[c] * xh[c];          // -> dgamma (column sums below)
-      }
-      m1 *= (1.f / 64.f); m2 *= (1.f / 64.f);
-      if (valid) {
-        const uint4 *res = (const uint4 *)(a.dh_out + (size_t)r * ND);
-        uint4 *dst = (uint4 *)(a.dh + (size_t)r * ND);
+        for (int c = 0; c < 64; ++c) {
+          const float dxh = dy[c] * sgb[c];
+          m1 += dxh;
+          m2 = fmaf(dxh, xh[c], m2);
+          sred[t * 65 + c] = dy[c] * xh[c];          // -> dgamma (column sums below)
+        }
+        m1 *= (1.f / 64.f); m2 *= (1.f / 64.f);
+        if (valid) {
+          const uint4 *res = (const uint4 *)(a.dh_out + (size_t)r * ND);
+          uint4 *dst = (uint4 *)(a.dh + (size_t)r * ND);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float y[8], hr[8];
-          unpack8(res[j], hr);
+          for (int j = 0; j < 8; ++j) {
+            float y[8], hr[8];
+            unpack8(res[j], hr);
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            y[c] = fmaf(rs, fmaf(dy[8 * j + c], sgb[8 * j + c], -fmaf(xh[8 * j + c], m2, m1)), hr[c]);
-          dst[j] = pack8(y);
+            for (int c = 0; c < 8; ++c)
+              y[c] = fmaf(rs, fmaf(dy[8 * j + c], sgb[8 * j + c], -fmaf(xh[8 * j + c], m2, m1)), hr[c]);
+            dst[j] = pack8(y);
+          }
         }
       }
+      // column sums over the tile's rows: thread (column tid & 63, row quarter tid >> 6), summed over tiles in registers
+      const int cc = tid & 63, r0 = (tid >> 6) * 32;
       __syncthreads();
-      if (t < ND) {
+      {
         float s = 0.f;
 #pragma unroll 8
-        for (int rr = 0; rr < 128; ++rr) s += sred[rr * 65 + t];
+        for (int rr = 0; rr < 32; ++rr) s += sred[(r0 + rr) * 65 + cc];
         dg_acc += s;
       }
       __syncthreads();
+      if (rowthr) {
 #pragma unroll
-      for (int c = 0; c < 64; ++c) sred[t * 65 + c] = dy[c];   // -> dbeta
+        for (int c = 0; c < 64; ++c) sred[t * 65 + c] = dy[c];   // -> dbeta
+      }
       __syncthreads();
-      if (t >= ND) {
+      {
         float s = 0.f;
 #pragma unroll 8
-        for (int rr = 0; rr < 128; ++rr) s += sred[rr * 65 + (t - ND)];
+        for (int rr = 0; rr < 32; ++rr) s += sred[(r0 + rr) * 65 + cc];
         db_acc += s;
       }
     }
@@ -567,10 +576,10 @@ __global__ void __launch_bounds__(128) node_bwd2_kernel(const NodeBwd2Args a) {
     __syncthreads();
   }
   if (!first && do_dx) {
-    if (t < ND) atomicAdd(a.dgamma + t, dg_acc);
-    else atomicAdd(a.dbeta + (t - ND), db_acc);
+    atomicAdd(a.dgamma + (tid & 63), dg_acc);
+    atomicAdd(a.dbeta + (tid & 63), db_acc);
   }
-  if (!first && do_dw) {
+  if (!first && do_dw && rowthr) {
 #pragma unroll 1
     for (int ch = 0; ch < 6; ++ch) {   // dW_qkv (rows 0-63), db_qkv (row 64)
       uint32_t o[32];
@@ -586,7 +595,7 @@ __global__ void __launch_bounds__(128) node_bwd2_kernel(const NodeBwd2Args a) {
   }
   tc_fence_before();
   __syncthreads();
-  if (t < 32) tmem_dealloc(tmem, do_dw ? 256 : 64);
+  if (tid < 32) tmem_dealloc(tmem, do_dw ? 256 : 64);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -662,15 +671,15 @@ int node_bwd2_launch(const void *h, const void *dh_out, const float *dqkv, const
     b.parts = 2;
     {
       LaunchScope _ls("node_bwd2w_kernel", side);
-      EGT_CHECK_CUDA(launch_pdl(node_bwd2_kernel, dim3(node_grid(R) + (partials ? 1 : 0)), dim3(128), node_bwd2_smem(2) + 1024, side, b));
+      EGT_CHECK_CUDA(launch_pdl(node_bwd2_kernel, dim3(node_grid(R) + (partials ? 1 : 0)), dim3(256), node_bwd2_smem(2) + 1024, side, b));
     }
     a.parts = 1; a.partials = nullptr;
     LaunchScope _ls("node_bwd2_kernel", st);
-    EGT_CHECK_CUDA(launch_pdl(node_bwd2_kernel, dim3(node_grid(R)), dim3(128), node_bwd2_smem(1) + 1024, st, a));
+    EGT_CHECK_CUDA(launch_pdl(node_bwd2_kernel, dim3(node_grid(R)), dim3(256), node_bwd2_smem(1) + 1024, st, a));
     return EGT_OK;
   }
   LaunchScope _ls("node_bwd2_kernel", st);
-  EGT_CHECK_CUDA(launch_pdl(node_bwd2_kernel, dim3(node_grid(R) + (partials ? 1 : 0)), dim3(128), node_bwd2_smem(3) + 1024, st, a));
+  EGT_CHECK_CUDA(launch_pdl(node_bwd2_kernel, dim3(node_grid(R) + (partials ? 1 : 0)), dim3(256), node_bwd2_smem(3) + 1024, st, a));
   return EGT_OK;
 }
 
