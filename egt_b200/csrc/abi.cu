@@ -159,6 +159,7 @@ struct BlockWs {
   char *prep;                                 // FusedPrep (fused path only)
   char *nblas;                                // node_blas.cu scratch (wide path, d != 64)
   float *d_qkv_f32, *partials;                // fused backward: [R,3d] f32, [ctas,FPART] f32
+  char *d_qkv_bf;                             // fused backward, N <= 128 (one row tile per graph): [R,3d] bf16 instead
   size_t total;
 };
 static BlockWs carve(const egt_block_cfg_t *c, int backward, void *base, bool has_de_out = true) {
@@ -180,6 +181,7 @@ static BlockWs carve(const egt_block_cfg_t *c, int backward, void *base, bool ha
   if (fused && backward && has_de_out && (!wide || wide_bwd_supported(c))) {      // fused backward: nothing of shape [pairs,h] is materialised
     w.d_v_att = take(R * d * es);
     w.d_qkv_f32 = (float *)take(R * 3 * d * sizeof(float));
+    if (!wide && a.N <= 128) w.d_qkv_bf = take(R * 3 * d * 2);
     w.partials = (float *)take(wide ? wide_bwd_partials_floats(c) * sizeof(float)
                                     : (size_t)a.B * ((a.N + 127) / 128) * FPART * sizeof(float));
     w.hn = (float *)take(R * d * sizeof(float));
@@ -541,7 +543,7 @@ int egt_block_bwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
     sb = side_fork(side, st);
     if ((rc = wide_bwd_finalize_launch(cfg, ws.partials, w, g, (const WidePrep *)ws.prep, sb))) return rc;
     if (node_tc) {
-      if ((rc = node_bwd2_launch(io->h, io->dh_out, ws.d_qkv_f32, w->norm_mha_gamma, w->norm_mha_beta, cfg->ln_eps,
+      if ((rc = node_bwd2_launch(io->h, io->dh_out, ws.d_qkv_f32, nullptr, w->norm_mha_gamma, w->norm_mha_beta, cfg->ln_eps,
                                  w->dense_qkv_kernel, io->dh, g->dense_qkv_kernel, g->dense_qkv_bias, g->norm_mha_gamma,
                                  g->norm_mha_beta, R, nullptr, 0, w, g, st, st))) return rc;   // the side stream is busy with the fold
       return side_join(side, st, sb);
@@ -596,6 +598,9 @@ int egt_block_bwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
     fb.B = a.B; fb.N = a.N; fb.mask = io->mask; fb.prep = (const FusedPrep *)ws.prep;
     fb.v_att = (const __nv_bfloat16 *)io->v_att; fb.d_v_att = (const __nv_bfloat16 *)ws.d_v_att;
     fb.lse = io->lse; fb.deg = io->deg; fb.d_qkv = ws.d_qkv_f32; fb.partials = ws.partials;
+    // one row tile per graph: every dQ / dK / dV element has exactly one writer, so the kernel writes bf16 -- what the
+    // node kernel's tensor-core products consume -- and node_bwd2 loads its tiles by TMA instead of converting float32
+    fb.d_qkv_bf = (__nv_bfloat16 *)ws.d_qkv_bf;
     fb.clip_lo = a.clip_lo; fb.clip_hi = a.clip_hi; fb.dq_scale = 1.0f / sqrtf((float)a.dk); fb.ln_eps = cfg->ln_eps;
     fb.scale_degree = a.scale_degree; fb.scaler_type = a.scaler_type; fb.num_virtual_nodes = a.num_virtual_nodes;
     fb.rand_mask = a.training && a.random_mask_prob > 0.f;
@@ -604,7 +609,7 @@ int egt_block_bwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
     if ((rc = fused_bwd_launch(fb, io->e, io->de_out, io->de, io->qkv, st))) return rc;
     // (splitting this kernel into its dh half and its weight-gradient half on two streams was measured: the dh half alone
     // takes as long as the whole kernel -- 26 us, the float32 -> bf16 staging of dqkv -- and the step got 2 % slower)
-    if ((rc = node_bwd2_launch(io->h, io->dh_out, ws.d_qkv_f32, w->norm_mha_gamma, w->norm_mha_beta, cfg->ln_eps,
+    if ((rc = node_bwd2_launch(io->h, io->dh_out, ws.d_qkv_f32, ws.d_qkv_bf, w->norm_mha_gamma, w->norm_mha_beta, cfg->ln_eps,
                                w->dense_qkv_kernel, io->dh, g->dense_qkv_kernel, g->dense_qkv_bias, g->norm_mha_gamma,
                                g->norm_mha_beta, R, ws.partials, a.B * tiles, w, g, st, st))) return rc;
     return side_join(side, st, sb);

@@ -69,6 +69,7 @@ struct FusedBwdArgs {
   const __nv_bfloat16 *v_att, *d_v_att;   // [B,N,64] saved forward output / its upstream gradient
   const float *lse, *deg;             // [2,B,N,8] (reference point | log row sum), [B,N,8]
   float *d_qkv;                       // [B,N,192] float32: dQ | dK | dV
+  __nv_bfloat16 *d_qkv_bf;            // non-NULL and one row tile per graph: the same as bf16 here instead
   float *partials;                    // [gridDim.x * gridDim.y][FPART]
   float clip_lo, clip_hi, dq_scale, ln_eps;
   int scale_degree, scaler_type, num_virtual_nodes;
@@ -98,7 +99,7 @@ int node_out_launch(const void *v_att, const void *h, const float *W, const floa
 int node_bwd1_launch(const void *dh_out, const void *v_att, const float *W, void *d_v_att, float *dW, float *db, int R,
                      const egt_block_weights_t *w, float clip_lo, float clip_hi, FusedPrep *prep_out, cudaStream_t st,
                      cudaStream_t side);   // side != st: dW_O / db_O as a second small launch on `side`
-int node_bwd2_launch(const void *h, const void *dh_out, const float *dqkv, const float *gamma, const float *beta,
+int node_bwd2_launch(const void *h, const void *dh_out, const float *dqkv, const void *dqkv_bf, const float *gamma, const float *beta,
                      float eps, const float *W, void *dh, float *dW, float *db, float *dgamma, float *dbeta, int R,
                      const float *partials, int nparts, const egt_block_weights_t *w, const egt_block_grads_t *g,
                      cudaStream_t st, cudaStream_t side);   // partials != NULL: one extra CTA folds the fused backward's partial

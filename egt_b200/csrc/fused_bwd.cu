@@ -310,9 +310,11 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
 
     // dK / dV of the 16-key block kb: lane t = (key, hh) picks the block diagonal
     const bool single_tile = gridDim.x == 1;
+    const bool bf_out = single_tile && a.d_qkv_bf != nullptr;
     auto t_epilogue = [&](int kb) {
       const int m = 16 * kb + (t >> 3), hh = t & 7;
       float *dst = a.d_qkv + ((size_t)b * N + (m < N ? m : 0)) * (3 * FD) + FD + hh;
+      __nv_bfloat16 *dst_bf = a.d_qkv_bf + ((size_t)b * N + (m < N ? m : 0)) * (3 * FD) + FD + hh;
 #pragma unroll
       for (int which = 0; which < 2; ++which) {
 #pragma unroll
@@ -325,7 +327,8 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
             for (int q = 0; q < 4; ++q) {
               const float v = sel8(o + 8 * q, hh);
               float *pd = dst + which * FD + (half * 4 + q) * 8;
-              if (single_tile) *pd = v;
+              if (bf_out) dst_bf[which * FD + (half * 4 + q) * 8] = __float2bfloat16_rn(v);
+              else if (single_tile) *pd = v;
               else atomicAdd(pd, v);
             }
           }
@@ -615,7 +618,18 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     uint32_t o[32];
     tmem_ld32(tlane + TM_DQ + g * 32, o);              // warp-collective: never inside a divergent branch
     tmem_ld_wait();
-    if (rowvalid) {
+    if (rowvalid && gridDim.x == 1 && a.d_qkv_bf) {
+      uint4 *dq = (uint4 *)(a.d_qkv_bf + ((size_t)b * N + l) * (3 * FD) + g * 32);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 v;
+        v.x = pack_bf16(__uint_as_float(o[8 * q]) * a.dq_scale, __uint_as_float(o[8 * q + 1]) * a.dq_scale);
+        v.y = pack_bf16(__uint_as_float(o[8 * q + 2]) * a.dq_scale, __uint_as_float(o[8 * q + 3]) * a.dq_scale);
+        v.z = pack_bf16(__uint_as_float(o[8 * q + 4]) * a.dq_scale, __uint_as_float(o[8 * q + 5]) * a.dq_scale);
+        v.w = pack_bf16(__uint_as_float(o[8 * q + 6]) * a.dq_scale, __uint_as_float(o[8 * q + 7]) * a.dq_scale);
+        dq[q] = v;
+      }
+    } else if (rowvalid) {
       float4 *dq = (float4 *)(a.d_qkv + ((size_t)b * N + l) * (3 * FD) + g * 32);
 #pragma unroll
       for (int q = 0; q < 8; ++q)

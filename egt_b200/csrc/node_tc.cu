@@ -13,6 +13,7 @@
 // the accumulator hold dW and row 64 holds the column sum (the bias gradient); they accumulate in TMEM
 // over the CTA's tiles and are flushed once with atomics.
 #include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 #include "fused.h"
 #include "umma.cuh"
@@ -26,7 +27,7 @@ namespace {
 constexpr int ND = 64;            // model width served by these kernels
 constexpr uint32_t TILE = 16384;  // [128 rows x 128 B] swizzled tile
 
-struct NodeBars { uint64_t bar; uint32_t tmem_base; uint32_t pad; };
+struct NodeBars { uint64_t bar; uint32_t tmem_base; uint32_t pad; uint64_t bar_tma; };
 
 // thread t's row of 64 bf16 (8 x 16 B) -> swizzled tile
 __device__ __forceinline__ void put_row(uint8_t *tile, int t, const uint4 *v) {
@@ -397,6 +398,7 @@ __global__ void __launch_bounds__(128) node_bwd1_kernel(const NodeBwd1Args a) {
 // ------------------------------------------------------------------------------------------------
 struct NodeBwd2Args {
   const __nv_bfloat16 *h, *dh_out; const float *dqkv;       // dqkv [R,192] float32
+  int dqkv_is_bf16;                                          // the tiles come by TMA from a bf16 [R,192] tensor instead
   const float *gamma, *beta; float eps;
   const float *W;                                            // W_qkv [64,192]
   __nv_bfloat16 *dh; float *dW, *db, *dgamma, *dbeta; int R;
@@ -414,7 +416,7 @@ __host__ __device__ inline int node_bwd2_smem(int parts) {
 
 // 256 threads: threads 0-127 own the rows (= TMEM lanes); threads 128-255 only help with the staging (weight image,
 // float32 -> bf16 tiles of dqkv), which is 40 % of the kernel's latency chain with 128 threads.
-__global__ void __launch_bounds__(256) node_bwd2_kernel(const NodeBwd2Args a) {
+__global__ void __launch_bounds__(256) node_bwd2_kernel(const __grid_constant__ CUtensorMap tm_y, const NodeBwd2Args a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const bool do_dx = a.parts & 1, do_dw = a.parts & 2;
@@ -434,6 +436,7 @@ __global__ void __launch_bounds__(256) node_bwd2_kernel(const NodeBwd2Args a) {
   pdl_trigger();
   if ((int)blockIdx.x == nwork) { pdl_wait(); fused_bwd_finalize_body(a.partials, a.nparts, a.w, a.g, tid, 256); return; }
   node_setup(bars, tid, do_dw ? 256 : 64);
+  if (tid == 0 && a.dqkv_is_bf16) { mbar_init(smem_u32(&bars->bar_tma), 1); mbar_fence_init(); tma_prefetch_desc(&tm_y); }
   if (do_dx) build_wt_k(sW, a.W, ND, 3 * ND, tid, 256);
   if (do_dw) fill_ones(sOnes, tid, 256);
   if (tid < ND) { sgb[tid] = a.gamma[tid]; sgb[ND + tid] = a.beta[tid]; }
@@ -475,7 +478,13 @@ __global__ void __launch_bounds__(256) node_bwd2_kernel(const NodeBwd2Args a) {
         if (do_dw) *(uint4 *)(sX + sw128_off(t, 8 * j)) = pack8(y);
       }
     }
-    {   // dqkv tile (float32 [128,192], rows contiguous) -> three bf16 tiles; coalesced: 24 threads per row
+    if (a.dqkv_is_bf16) {   // dqkv tile: three [128 x 64] bf16 boxes by TMA (rows beyond R are zero-filled)
+      if (tid == 0) {
+        const uint32_t bar = smem_u32(&bars->bar_tma);
+        mbar_expect_tx(bar, 3 * TILE);
+        for (int j = 0; j < 3; ++j) tma_load_3d(smem_u32(sY) + j * TILE, &tm_y, bar, 64 * j, tile * 128, 0);
+      }
+    } else {   // dqkv tile (float32 [128,192], rows contiguous) -> three bf16 tiles; coalesced: 24 threads per row
       const float *base = a.dqkv + (size_t)tile * 128 * (3 * ND);
       const int rows_here = a.R - tile * 128 < 128 ? a.R - tile * 128 : 128;
 #pragma unroll 4
@@ -496,6 +505,7 @@ __global__ void __launch_bounds__(256) node_bwd2_kernel(const NodeBwd2Args a) {
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
+      if (a.dqkv_is_bf16) mbar_wait(smem_u32(&bars->bar_tma), phase);     // same parity as the MMA barrier: one use per tile
       tc_fence_after();
       if (do_dx) {
 #pragma unroll
@@ -658,12 +668,18 @@ int node_bwd1_launch(const void *dh_out, const void *v_att, const float *W, void
 
 // side != st: two launches, the dh half on st and the weight-gradient half (+ the finalize CTA) on `side`; their CTAs
 // share the SMs (106 + 80 KB of shared memory, 64 + 256 tensor-memory columns), so the two latency chains overlap.
-int node_bwd2_launch(const void *h, const void *dh_out, const float *dqkv, const float *gamma, const float *beta,
+int node_bwd2_launch(const void *h, const void *dh_out, const float *dqkv, const void *dqkv_bf, const float *gamma, const float *beta,
                      float eps, const float *W, void *dh, float *dW, float *db, float *dgamma, float *dbeta, int R,
                      const float *partials, int nparts, const egt_block_weights_t *w, const egt_block_grads_t *g,
                      cudaStream_t st, cudaStream_t side) {
-  NodeBwd2Args a{(const __nv_bfloat16 *)h, (const __nv_bfloat16 *)dh_out, dqkv, gamma, beta, eps, W,
+  NodeBwd2Args a{(const __nv_bfloat16 *)h, (const __nv_bfloat16 *)dh_out, dqkv, dqkv_bf ? 1 : 0, gamma, beta, eps, W,
                  (__nv_bfloat16 *)dh, dW, db, dgamma, dbeta, R, partials, nparts, *w, *g, 3};
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));
+  if (dqkv_bf) {   // [R, 192] bf16, boxes of [128 rows x 64 channels], 128B swizzle
+    int rc = encode_tmap_3d(&tm, dqkv_bf, 3 * ND, (uint64_t)R, 1, 3 * ND * 2, (uint64_t)R * 3 * ND * 2, 64, 128, 1, 1);
+    if (rc) return rc;
+  }
   static bool once = false;
   if (!once) { int rc = set_smem(node_bwd2_kernel, node_bwd2_smem(3) + 1024); if (rc) return rc; once = true; }
   if (side != st) {
@@ -671,15 +687,15 @@ int node_bwd2_launch(const void *h, const void *dh_out, const float *dqkv, const
     b.parts = 2;
     {
       LaunchScope _ls("node_bwd2w_kernel", side);
-      EGT_CHECK_CUDA(launch_pdl(node_bwd2_kernel, dim3(node_grid(R) + (partials ? 1 : 0)), dim3(256), node_bwd2_smem(2) + 1024, side, b));
+      EGT_CHECK_CUDA(launch_pdl(node_bwd2_kernel, dim3(node_grid(R) + (partials ? 1 : 0)), dim3(256), node_bwd2_smem(2) + 1024, side, tm, b));
     }
     a.parts = 1; a.partials = nullptr;
     LaunchScope _ls("node_bwd2_kernel", st);
-    EGT_CHECK_CUDA(launch_pdl(node_bwd2_kernel, dim3(node_grid(R)), dim3(256), node_bwd2_smem(1) + 1024, st, a));
+    EGT_CHECK_CUDA(launch_pdl(node_bwd2_kernel, dim3(node_grid(R)), dim3(256), node_bwd2_smem(1) + 1024, st, tm, a));
     return EGT_OK;
   }
   LaunchScope _ls("node_bwd2_kernel", st);
-  EGT_CHECK_CUDA(launch_pdl(node_bwd2_kernel, dim3(node_grid(R) + (partials ? 1 : 0)), dim3(256), node_bwd2_smem(3) + 1024, st, a));
+  EGT_CHECK_CUDA(launch_pdl(node_bwd2_kernel, dim3(node_grid(R) + (partials ? 1 : 0)), dim3(256), node_bwd2_smem(3) + 1024, st, tm, a));
   return EGT_OK;
 }
 
