@@ -526,7 +526,7 @@ int egt_block_bwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
     }
     if ((rc = side_wait(side, st, sb))) return rc;
     const int tiles = (a.N + 127) / 128;
-    if (tiles > 1) EGT_CHECK_CUDA(cudaMemsetAsync(ws.d_qkv_f32, 0, (size_t)R * 3 * d * sizeof(float), st));
+    if (tiles > 1 || wide_bwd_splits(cfg) > 1) EGT_CHECK_CUDA(cudaMemsetAsync(ws.d_qkv_f32, 0, (size_t)R * 3 * d * sizeof(float), st));
     WideBwdArgs fb;
     memset(&fb, 0, sizeof(fb));
     fb.B = a.B; fb.N = a.N; fb.mask = io->mask; fb.prep = (const WidePrep *)ws.prep;

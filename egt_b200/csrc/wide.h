@@ -79,6 +79,8 @@ int wide_bwd_launch(const egt_block_cfg_t *cfg, const WideBwdArgs &a, const void
                     const void *qkv, cudaStream_t st);
 bool wide_bwd_supported(const egt_block_cfg_t *cfg);   // shapes wide_bwd.cu instantiates (others pair with the staged backward)
 size_t wide_bwd_partials_floats(const egt_block_cfg_t *cfg);
+int wide_bwd_key_splits(int B, int N, int TK);
+int wide_bwd_splits(const egt_block_cfg_t *cfg);       // CTAs that share the keys of one (graph, row tile); > 1: d_qkv must be zero-filled
 int wide_bwd_finalize_launch(const egt_block_cfg_t *cfg, const float *partials, const egt_block_weights_t *w,
                              const egt_block_grads_t *g, const WidePrep *prep, cudaStream_t st);
 

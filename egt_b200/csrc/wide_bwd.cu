@@ -103,7 +103,12 @@ wide_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y, l0 = blockIdx.x * 128;
   const int N = a.N;
-  const int NT = (N + TK - 1) / TK, J = NT * KPG;
+  // gridDim.z > 1: the keys of a graph are split over gridDim.z CTAs (wave quantisation: 256 CTAs of equal length on 148
+  // SMs take two full waves, 1024 quarter-length CTAs take 7 / 4 of one); T, kt below are LOCAL tile / key-in-tile
+  // indices, T0 turns them into positions in the graph.  dQ is then accumulated across the CTAs with vector atomics.
+  const int NTall = (N + TK - 1) / TK;
+  const int per_split = (NTall + (int)gridDim.z - 1) / (int)gridDim.z, T0 = (int)blockIdx.z * per_split;
+  const int NT = NTall - T0 < per_split ? NTall - T0 : per_split, J = NT * KPG;   // the launcher guarantees NT >= 1
 
   // ---------------------------------------- set-up ----------------------------------------
   if (warp == 4 * NG) {
@@ -131,7 +136,7 @@ wide_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
     for (int i = tid; i < 64; i += nthr) ((uint4 *)(smem + SM_W + W_I))[i] = ((const uint4 *)pp->i16[0])[i];
     for (int i = tid; i < 64; i += nthr) ((float *)(smem + SM_CONST))[i] = pp->uE[i];
     for (int i = tid; i < 32; i += nthr) ((float *)(smem + SM_RED))[i] = 0.f;
-    for (int i = tid; i < NT * TK; i += nthr)
+    for (int i = tid; i < NTall * TK; i += nthr)
       smem[SM_MASK + i] = i < N ? (a.mask ? (uint8_t)(a.mask[(size_t)b * N + i] != 0) : (uint8_t)1) : (uint8_t)0;
   }
   tc_fence_before();
@@ -153,11 +158,11 @@ wide_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
       mbar_expect_tx(bar, TX_BYTES);
 #pragma unroll
       for (int x = 0; x < C::NBOX; ++x) {
-        tma_load_3d(dst + ST_E + x * 16384, &tm_e, bar, T * TK * DE + 64 * x, l0, b);
-        tma_load_3d(dst + ST_DE + x * 16384, &tm_dei, bar, T * TK * DE + 64 * x, l0, b);
+        tma_load_3d(dst + ST_E + x * 16384, &tm_e, bar, (T0 + T) * TK * DE + 64 * x, l0, b);
+        tma_load_3d(dst + ST_DE + x * 16384, &tm_dei, bar, (T0 + T) * TK * DE + 64 * x, l0, b);
       }
-      tma_load_3d(dst + ST_K, &tm_kv, bar, D, T * TK, b);
-      tma_load_3d(dst + ST_V, &tm_kv, bar, 2 * D, T * TK, b);
+      tma_load_3d(dst + ST_K, &tm_kv, bar, D, (T0 + T) * TK, b);
+      tma_load_3d(dst + ST_V, &tm_kv, bar, 2 * D, (T0 + T) * TK, b);
     };
     if (warp == 4 * NG + 1 && lane == 0) {
       mbar_expect_tx(smem_u32(&bars->q_full), C::NQA * 16384);
@@ -295,7 +300,7 @@ wide_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
         fence_proxy_async_smem();
 #pragma unroll
         for (int x = 0; x < C::NBOX; ++x)
-          tma_store_3d(&tm_de, sbase + SM_STAGE + st * STAGE_BYTES + ST_DE + x * 16384, T * TK * DE + 64 * x, l0, b);
+          tma_store_3d(&tm_de, sbase + SM_STAGE + st * STAGE_BYTES + ST_DE + x * 16384, (T0 + T) * TK * DE + 64 * x, l0, b);
         tma_store_commit();
         if (T + NS < NT) { tma_store_wait_read<0>(); load_tile(T + NS); }
       }
@@ -552,7 +557,7 @@ wide_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
     int pst = 0, pkt = 0, pm = 0, plast = 0;
     float pcoef = 0.f, pk0 = 0.f;
     for (int j = 0; j < J; ++j) {
-      const int kt = i * NG + q, m = T * TK + kt;
+      const int kt = i * NG + q, m = (T0 + T) * TK + kt;
       mbar_wait(bar_ready, j & 1);
       tc_fence_after();
       if (j > 0) {
@@ -593,15 +598,24 @@ wide_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
     for (int j = 0; j < CW / 8; ++j) tmem_ld8(tlane + TM_DQ + q * CW + 8 * j, o + 8 * j);
     tmem_ld_wait();
     if (rowvalid) {
-      float4 *dq = (float4 *)(a.d_qkv + ((size_t)b * N + l) * (3 * D) + q * CW);
+      float *dqf = a.d_qkv + ((size_t)b * N + l) * (3 * D) + q * CW;
+      float4 *dq = (float4 *)dqf;
+      if (gridDim.z > 1) {         // key split: the launcher zero-filled d_qkv
 #pragma unroll
-      for (int j = 0; j < CW / 4; ++j)
-        dq[j] = make_float4(__uint_as_float(o[4 * j]) * a.dq_scale, __uint_as_float(o[4 * j + 1]) * a.dq_scale,
-                            __uint_as_float(o[4 * j + 2]) * a.dq_scale, __uint_as_float(o[4 * j + 3]) * a.dq_scale);
+        for (int j = 0; j < CW / 4; ++j)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dqf + 4 * j), "f"(__uint_as_float(o[4 * j]) * a.dq_scale),
+                       "f"(__uint_as_float(o[4 * j + 1]) * a.dq_scale), "f"(__uint_as_float(o[4 * j + 2]) * a.dq_scale),
+                       "f"(__uint_as_float(o[4 * j + 3]) * a.dq_scale) : "memory");
+      } else {
+#pragma unroll
+        for (int j = 0; j < CW / 4; ++j)
+          dq[j] = make_float4(__uint_as_float(o[4 * j]) * a.dq_scale, __uint_as_float(o[4 * j + 1]) * a.dq_scale,
+                              __uint_as_float(o[4 * j + 2]) * a.dq_scale, __uint_as_float(o[4 * j + 3]) * a.dq_scale);
+      }
     }
   }
   // ---- weight-gradient partial sums of this CTA ----
-  float *part = a.partials + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * C::PART;
+  float *part = a.partials + (size_t)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * C::PART;
   {
     float *red = (float *)(smem + SM_RED);
 #pragma unroll
@@ -727,7 +741,7 @@ int launch_cfg(const WideBwdArgs &a, const void *e, const void *de_out, void *de
     EGT_CHECK_CUDA(cudaFuncSetAttribute(wide_bwd_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  dim3 grid((a.N + 127) / 128, a.B);
+  dim3 grid((a.N + 127) / 128, a.B, wide_bwd_key_splits(a.B, a.N, C::TK));
   LaunchScope _ls("wide_bwd_kernel", st);
   if (a.rand_mask) EGT_CHECK_CUDA(launch_pdl(wide_bwd_kernel<C, true>, grid, dim3(384), smem, st, tm_e, tm_dei, tm_de, tm_q, tm_kv, a));
   else EGT_CHECK_CUDA(launch_pdl(wide_bwd_kernel<C, false>, grid, dim3(384), smem, st, tm_e, tm_dei, tm_de, tm_q, tm_kv, a));
@@ -736,6 +750,34 @@ int launch_cfg(const WideBwdArgs &a, const void *e, const void *de_out, void *de
 
 }  // namespace
 
+// How many CTAs share the keys of one (graph, row tile): the count in {1, 2, 4, 8} that minimises full waves / count on
+// 148 SMs, with at least 64 keys per CTA (its prologue -- Q, dO, the row statistics -- is paid per CTA) and no empty split.
+int wide_bwd_key_splits(int B, int N, int TK) {
+  const char *fe = getenv("EGT_WIDE_KSPLIT");            // read per call: the parity tests force a split
+  const int forced = fe ? atoi(fe) : 0;
+  const int base = B * ((N + 127) / 128), NT = (N + TK - 1) / TK;
+  int best = 1;
+  double cost = (double)((base + 147) / 148);
+  for (int ks = 2; ks <= 8; ks *= 2) {
+    const int per = (NT + ks - 1) / ks;
+    if (per * (ks - 1) >= NT || per * TK < 64) continue;
+    const double c = (double)((base * ks + 147) / 148) / ks + 0.01 * ks;
+    if (c < cost - 1e-9) { cost = c; best = ks; }
+  }
+  if (forced > 0) {
+    const int per = (NT + forced - 1) / forced;
+    if (forced <= 8 && per * (forced - 1) < NT) best = forced;
+  }
+  return best;
+}
+static int wide_bwd_tk(const egt_block_cfg_t *cfg) {
+  const int h = cfg->attn.h, dk = cfg->attn.dk, de = cfg->d_e;
+  if (h == 16 && dk == 8 && de == 32) return WideBwdC5::TK;
+  if (h == 8 && dk == 12 && de == 8) return WideBwdC3::TK;
+  return WideBwdC1::TK;
+}
+int wide_bwd_splits(const egt_block_cfg_t *cfg) { return wide_bwd_key_splits(cfg->attn.B, cfg->attn.N, wide_bwd_tk(cfg)); }
+
 bool wide_bwd_supported(const egt_block_cfg_t *cfg) {
   const int h = cfg->attn.h, dk = cfg->attn.dk, de = cfg->d_e;
   return (h == 16 && dk == 8 && de == 32) || (h == 8 && dk == 12 && de == 8) || (h == 8 && dk == 8 && de == 64);
@@ -743,7 +785,7 @@ bool wide_bwd_supported(const egt_block_cfg_t *cfg) {
 
 size_t wide_bwd_partials_floats(const egt_block_cfg_t *cfg) {
   const size_t H = cfg->attn.h, DE = cfg->d_e, EGN = 2 * H;
-  return ((size_t)cfg->attn.B * ((cfg->attn.N + 127) / 128) + 1) * (EGN * DE + H * DE + DE + EGN) + 4;   // + the column sums and a counter
+  return ((size_t)cfg->attn.B * ((cfg->attn.N + 127) / 128) * wide_bwd_splits(cfg) + 1) * (EGN * DE + H * DE + DE + EGN) + 4;   // + the column sums and a counter
 }
 
 int wide_bwd_launch(const egt_block_cfg_t *cfg, const WideBwdArgs &a, const void *e, const void *de_out, void *de,
@@ -758,7 +800,7 @@ int wide_bwd_launch(const egt_block_cfg_t *cfg, const WideBwdArgs &a, const void
 int wide_bwd_finalize_launch(const egt_block_cfg_t *cfg, const float *partials, const egt_block_weights_t *w,
                              const egt_block_grads_t *g, const WidePrep *, cudaStream_t st) {
   const int H = cfg->attn.h, DE = cfg->d_e, EGN = 2 * H;
-  const int nparts = cfg->attn.B * ((cfg->attn.N + 127) / 128);
+  const int nparts = cfg->attn.B * ((cfg->attn.N + 127) / 128) * wide_bwd_splits(cfg);
   const int PART = EGN * DE + H * DE + DE + EGN;
   const size_t smem = (size_t)(PART + EGN) * sizeof(float);
   float *sums = const_cast<float *>(partials) + (size_t)nparts * PART;

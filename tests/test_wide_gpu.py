@@ -84,3 +84,44 @@ def test_fused_large_edge_logits(width):
     _close(e2, e2r, torch.bfloat16, "e'")
     _close(gin[0], rin[0], torch.bfloat16, 'dh')
     _close(gin[1], rin[1], torch.bfloat16, 'de')
+
+
+@pytest.mark.parametrize('N,d,de,nh,B,ks', [(512, 128, 32, 16, 2, 4), (512, 128, 32, 16, 2, 8), (190, 96, 8, 8, 2, 2),
+                                            (300, 64, 64, 8, 2, 4)])
+def test_wide_backward_key_split(N, d, de, nh, B, ks, monkeypatch):
+    """The wide backward splits the keys of a (graph, row tile) over several CTAs when that fills the last wave of the grid
+    (csrc/wide_bwd.cu: wide_bwd_key_splits; dQ is then accumulated with atomics).  Forced here with EGT_WIDE_KSPLIT: every
+    gradient equals the unsplit kernel's, and the oracle's on the sampled graphs."""
+    from tests.test_parity_gpu import test_block_full_size_vs_oracle_sample, _spec_kwargs
+    import egt_b200
+    from oracle import egt_oracle as O
+    cfg = O.BlockConfig(model_width=d, edge_width=de, num_heads=nh, scale_degree=True)
+    params = O.init_block_params(cfg, dtype=torch.float64)
+    h, e, mask = O.synthetic_batch(B, N, d, de, ragged=True, dtype=torch.float32)
+    blk = egt_b200.EGTBlock(**_spec_kwargs(cfg))
+    blk.load_keras_weights(params)
+    blk = blk.to(DEV)
+    g = torch.Generator().manual_seed(3)
+    dh = torch.randn(B, N, d, generator=g).bfloat16().to(DEV)
+    de_ = torch.randn(B, N, N, de, generator=g).bfloat16().to(DEV)
+
+    def run():
+        hg, eg = h.bfloat16().to(DEV).requires_grad_(True), e.bfloat16().to(DEV).requires_grad_(True)
+        blk.flat.grad = None
+        h2, e2 = blk(hg, eg, mask.to(DEV))
+        torch.autograd.backward([h2, e2], [dh, de_])
+        return hg.grad.clone(), eg.grad.clone(), blk.flat.grad.clone()
+
+    monkeypatch.setenv('EGT_WIDE_KSPLIT', '1')
+    ref = run()
+    monkeypatch.setenv('EGT_WIDE_KSPLIT', str(ks))
+    got = run()
+    assert torch.equal(got[1], ref[1])                       # de: per (row, key), untouched by the split
+    for a_, b_, what in zip(got, ref, ('dh', 'de', 'weight gradients')):
+        scale = float(b_.float().abs().max())
+        err = float((a_.float() - b_.float()).abs().max())
+        # summation order differs (atomics): float32 weight gradients to 2e-3, bf16 dh to one bf16 step of its largest values
+        tol = 8e-3 if a_.dtype == torch.bfloat16 else 2e-3
+        assert err <= tol * scale, f'{what}: {err:.3e} vs scale {scale:.3e}'
+    # and the split kernel against the oracle, through the shared full-size check
+    test_block_full_size_vs_oracle_sample(N, d, de, nh, B)
