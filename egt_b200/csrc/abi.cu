@@ -181,9 +181,9 @@ static BlockWs carve(const egt_block_cfg_t *c, int backward, void *base, bool ha
   if (fused && backward && has_de_out && (!wide || wide_bwd_supported(c))) {      // fused backward: nothing of shape [pairs,h] is materialised
     w.d_v_att = take(R * d * es);
     w.d_qkv_f32 = (float *)take(R * 3 * d * sizeof(float));
-    if (!wide && a.N <= 128) w.d_qkv_bf = take(R * 3 * d * 2);
+    if (!wide && a.N <= 128 && fused_bwd_key_splits(a.B, a.N) == 1) w.d_qkv_bf = take(R * 3 * d * 2);
     w.partials = (float *)take(wide ? wide_bwd_partials_floats(c) * sizeof(float)
-                                    : (size_t)a.B * ((a.N + 127) / 128) * FPART * sizeof(float));
+                                    : (size_t)a.B * ((a.N + 127) / 128) * fused_bwd_key_splits(a.B, a.N) * FPART * sizeof(float));
     w.hn = (float *)take(R * d * sizeof(float));
     w.dhn = (float *)take(R * d * sizeof(float));
     w.total = off;
@@ -585,14 +585,14 @@ int egt_block_bwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
     // dW_O / db_O feed nothing in the backward pass: a second small launch on the side stream, next to the fused backward
     // kernel (whose 128-CTA grid leaves SMs idle at the headline shape); joined before the call returns
     // -- only when that grid really leaves 20 SMs idle: otherwise the second launch competes with it
-    const int bwd_ctas = a.B * ((a.N + 127) / 128);
+    const int bwd_ctas = a.B * ((a.N + 127) / 128) * fused_bwd_key_splits(a.B, a.N);
     SideStream *side = bwd_ctas + 20 <= 148 ? side_stream(st) : nullptr;
     cudaStream_t sb = side_fork(side, st);
     if ((rc = node_bwd1_launch(io->dh_out, io->v_att, w->dense_mha_kernel, ws.d_v_att, g->dense_mha_kernel,
                                g->dense_mha_bias, R, w, a.clip_lo, a.clip_hi, (FusedPrep *)ws.prep, st, sb))) return rc;
     // N x N part in one kernel (fused_bwd.cu): de, dQ|dK|dV and the edge-side weight-gradient partial sums
-    const int tiles = (a.N + 127) / 128;
-    if (tiles > 1) EGT_CHECK_CUDA(cudaMemsetAsync(ws.d_qkv_f32, 0, (size_t)R * 3 * d * sizeof(float), st));
+    const int tiles = (a.N + 127) / 128, ksplit = fused_bwd_key_splits(a.B, a.N);
+    if (tiles > 1 || ksplit > 1) EGT_CHECK_CUDA(cudaMemsetAsync(ws.d_qkv_f32, 0, (size_t)R * 3 * d * sizeof(float), st));
     FusedBwdArgs fb;
     memset(&fb, 0, sizeof(fb));
     fb.B = a.B; fb.N = a.N; fb.mask = io->mask; fb.prep = (const FusedPrep *)ws.prep;
@@ -611,7 +611,7 @@ int egt_block_bwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
     // takes as long as the whole kernel -- 26 us, the float32 -> bf16 staging of dqkv -- and the step got 2 % slower)
     if ((rc = node_bwd2_launch(io->h, io->dh_out, ws.d_qkv_f32, ws.d_qkv_bf, w->norm_mha_gamma, w->norm_mha_beta, cfg->ln_eps,
                                w->dense_qkv_kernel, io->dh, g->dense_qkv_kernel, g->dense_qkv_bias, g->norm_mha_gamma,
-                               g->norm_mha_beta, R, ws.partials, a.B * tiles, w, g, st, st))) return rc;
+                               g->norm_mha_beta, R, ws.partials, a.B * tiles * ksplit, w, g, st, st))) return rc;
     return side_join(side, st, sb);
   }
 

@@ -86,6 +86,7 @@ int fused_fwd_launch(const FusedFwdArgs &a, const void *e, void *e_out, const vo
 // accumulated with atomics across the row tiles of a graph).
 int fused_bwd_launch(const FusedBwdArgs &a, const void *e, const void *de_out, void *de, const void *qkv,
                      cudaStream_t st);
+int fused_bwd_key_splits(int B, int N);   // CTAs per (graph, row tile) of fused_bwd; > 1: d_qkv must be zero-filled, one partial row per CTA
 int fused_bwd_finalize_launch(const float *partials, int nparts, const egt_block_weights_t *w,
                               const egt_block_grads_t *g, cudaStream_t st);
 

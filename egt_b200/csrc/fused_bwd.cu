@@ -32,6 +32,7 @@
 // key pair is done and the issuer waits for it.  Every dependency spans TWO pairs (same structure as
 // fused_fwd.cu): the S / dA / EG / dHx products of pair it+2 are issued when pair it is done, and the de
 // update of pair it (which needs the d x^ product issued when pair it is done) runs during pair it+2.
+#include <stdlib.h>
 #include "common.cuh"
 #include "fused.h"
 #include "umma.cuh"
@@ -90,7 +91,13 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y, l0 = blockIdx.x * 128;
   const int N = a.N;
-  const int NT = (N + 7) / 8, NP = (N + 1) / 2;       // 8-key tiles, key pairs
+  // gridDim.z > 1: the keys of a graph are split over gridDim.z CTAs in runs of a multiple of 16 keys (wave quantisation,
+  // see wide_bwd.cu).  Pair / tile / key indices below are LOCAL to the run [K0, K0 + NK); K0 turns them into positions
+  // in the graph where global memory is addressed (TMA coordinates, mask, dK / dV rows, random-mask counters).
+  const int per_split = (((N + (int)gridDim.z - 1) / (int)gridDim.z) + 15) & ~15;
+  const int K0 = (int)blockIdx.z * per_split;
+  const int NK = N - K0 < per_split ? N - K0 : per_split;          // the launcher guarantees NK >= 1
+  const int NT = (NK + 7) / 8, NP = (NK + 1) / 2;     // 8-key tiles, key pairs
 
   pdl_trigger();
   if (warp == 8) {
@@ -114,8 +121,8 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     if (tid < 160) ((uint4 *)(smem + SM_W))[tid] = ((const uint4 *)a.prep->b_eg)[tid];   // b_eg | b_hx | b_de
     else if (tid < 224) ((uint4 *)(smem + SM_W + 2560))[tid - 160] = ((const uint4 *)a.prep->b_eg_lo)[tid - 160];
     if (tid < 32) ((float *)(smem + SM_CONST))[tid] = a.prep->uE[tid];                  // uE vE uG vG
-    for (int i = tid; i < 2 * ((N + 1) / 2); i += 256)                                   // key-valid bytes
-      smem[SM_MASK + i] = i < N ? (a.mask ? (uint8_t)(a.mask[(size_t)blockIdx.y * N + i] != 0) : (uint8_t)1) : (uint8_t)0;
+    for (int i = tid; i < 2 * ((NK + 1) / 2); i += 256)                                  // key-valid bytes
+      smem[SM_MASK + i] = i < NK ? (a.mask ? (uint8_t)(a.mask[(size_t)blockIdx.y * N + K0 + i] != 0) : (uint8_t)1) : (uint8_t)0;
     fence_proxy_async_smem();
   } else if (warp >= 12) {
     pdl_wait();                                        // the helper adds into d_qkv, zeroed earlier on the stream
@@ -134,10 +141,10 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
       const uint32_t bar = smem_u32(&bars->e_full[st]);
       const uint32_t dst = sbase + SM_STAGE + st * STAGE_BYTES;
       mbar_expect_tx(bar, STAGE_BYTES);
-      tma_load_3d(dst + ST_E, &tm_e, bar, T * 64, l0, b);
-      tma_load_3d(dst + ST_DE, &tm_dei, bar, T * 64, l0, b);
-      tma_load_3d(dst + ST_K, &tm_kv, bar, FD, T * 8, b);
-      tma_load_3d(dst + ST_V, &tm_kv, bar, 2 * FD, T * 8, b);
+      tma_load_3d(dst + ST_E, &tm_e, bar, K0 * 8 + T * 64, l0, b);
+      tma_load_3d(dst + ST_DE, &tm_dei, bar, K0 * 8 + T * 64, l0, b);
+      tma_load_3d(dst + ST_K, &tm_kv, bar, FD, K0 + T * 8, b);
+      tma_load_3d(dst + ST_V, &tm_kv, bar, 2 * FD, K0 + T * 8, b);
     };
     // descriptor low words (address | LBO); the high words are compile-time constants
     constexpr uint32_t HI_SW = desc_hi(1024, LAYOUT_SW128), HI_NONE = desc_hi(128, LAYOUT_NONE);
@@ -212,7 +219,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
         }
         if (it >= 5 && ((it - 5) & 3) == 0) {
           const int T = (it - 5) >> 2;
-          tma_store_3d(&tm_de, sbase + SM_STAGE + (T % NS) * STAGE_BYTES + ST_DE, T * 64, l0, b);
+          tma_store_3d(&tm_de, sbase + SM_STAGE + (T % NS) * STAGE_BYTES + ST_DE, K0 * 8 + T * 64, l0, b);
           tma_store_commit();
           next_store = T + 1;
         }
@@ -222,7 +229,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     __syncthreads();                                   // sync #(NP+1): every de update is done
     if (leader) {
       for (int T = next_store; T < NT; ++T)
-        tma_store_3d(&tm_de, sbase + SM_STAGE + (T % NS) * STAGE_BYTES + ST_DE, T * 64, l0, b);
+        tma_store_3d(&tm_de, sbase + SM_STAGE + (T % NS) * STAGE_BYTES + ST_DE, K0 * 8 + T * 64, l0, b);
       tma_store_commit();
       tma_store_wait_all<0>();
     }
@@ -310,9 +317,9 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
 
     // dK / dV of the 16-key block kb: lane t = (key, hh) picks the block diagonal
     const bool single_tile = gridDim.x == 1;
-    const bool bf_out = single_tile && a.d_qkv_bf != nullptr;
+    const bool bf_out = single_tile && gridDim.z == 1 && a.d_qkv_bf != nullptr;
     auto t_epilogue = [&](int kb) {
-      const int m = 16 * kb + (t >> 3), hh = t & 7;
+      const int m = K0 + 16 * kb + (t >> 3), hh = t & 7;
       float *dst = a.d_qkv + ((size_t)b * N + (m < N ? m : 0)) * (3 * FD) + FD + hh;
       __nv_bfloat16 *dst_bf = a.d_qkv_bf + ((size_t)b * N + (m < N ? m : 0)) * (3 * FD) + FD + hh;
 #pragma unroll
@@ -505,7 +512,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     uint32_t sreg2[2][4], dareg2[2][4], egreg2[2][8], hxreg2[2][4];
     uint32_t rbw[4] = {0u, 0u, 0u, 0u};
     if (RAND) {   // one Philox call = this thread's 2 keys x 4 heads (rng_elem_index, common.cuh)
-      const uint64_t qd = rng_elem_index((uint64_t)b, (uint64_t)l, (uint64_t)(2 * p), 4u * (uint32_t)g, (uint64_t)N, FH) >> 3;
+      const uint64_t qd = rng_elem_index((uint64_t)b, (uint64_t)l, (uint64_t)(K0 + 2 * p), 4u * (uint32_t)g, (uint64_t)N, FH) >> 3;
       const Philox4 ph = philox4x32_10((uint32_t)qd, (uint32_t)(qd >> 32), (uint32_t)a.offset,
                                        (uint32_t)(a.offset >> 32), (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
       rbw[0] = ph.x; rbw[1] = ph.y; rbw[2] = ph.z; rbw[3] = ph.w;          // key kk, head 4g+i: 16-bit lane 4kk+i
@@ -618,7 +625,14 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     uint32_t o[32];
     tmem_ld32(tlane + TM_DQ + g * 32, o);              // warp-collective: never inside a divergent branch
     tmem_ld_wait();
-    if (rowvalid && gridDim.x == 1 && a.d_qkv_bf) {
+    if (rowvalid && gridDim.z > 1) {                     // key split: the launcher zero-filled d_qkv
+      float *dqf = a.d_qkv + ((size_t)b * N + l) * (3 * FD) + g * 32;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dqf + 4 * q), "f"(__uint_as_float(o[4 * q]) * a.dq_scale),
+                     "f"(__uint_as_float(o[4 * q + 1]) * a.dq_scale), "f"(__uint_as_float(o[4 * q + 2]) * a.dq_scale),
+                     "f"(__uint_as_float(o[4 * q + 3]) * a.dq_scale) : "memory");
+    } else if (rowvalid && gridDim.x == 1 && a.d_qkv_bf) {
       uint4 *dq = (uint4 *)(a.d_qkv_bf + ((size_t)b * N + l) * (3 * FD) + g * 32);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -665,7 +679,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
       }
   }
   __syncthreads();                                     // partial sums complete
-  if (tid < FPART) a.partials[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * FPART + tid] = red[tid];
+  if (tid < FPART) a.partials[(size_t)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * FPART + tid] = red[tid];
   tc_fence_before();
   __syncthreads();                                     // final
 }
@@ -692,11 +706,25 @@ int fused_bwd_launch(const FusedBwdArgs &a, const void *e, const void *de_out, v
     EGT_CHECK_CUDA(cudaFuncSetAttribute(fused_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  dim3 grid((a.N + 127) / 128, a.B);
+  dim3 grid((a.N + 127) / 128, a.B, fused_bwd_key_splits(a.B, a.N));
   LaunchScope _ls("fused_bwd_kernel", st);
   if (a.rand_mask) EGT_CHECK_CUDA(launch_pdl(fused_bwd_kernel<true>, grid, dim3(512), smem, st, tm_e, tm_dei, tm_de, tm_q, tm_kv, a));
   else EGT_CHECK_CUDA(launch_pdl(fused_bwd_kernel<false>, grid, dim3(512), smem, st, tm_e, tm_dei, tm_de, tm_q, tm_kv, a));
   return EGT_OK;
+}
+
+// CTAs that share the keys of one (graph, row tile), in runs of a multiple of 16 keys (see wide_bwd_key_splits,
+// wide_bwd.cu).  Measured with the count the wide kernel's rule picks: S256 (64 keys per CTA) 405 -> 483 us, S512 (128 keys
+// per CTA) 742 -> 776 us -- this kernel's per-CTA prologue and epilogue (row statistics, the 104 weight-gradient sums of
+// every thread, dQ) cost more than the last wave wastes -- so the split is off unless EGT_FUSED_KSPLIT forces a count
+// (the parity tests do).
+int fused_bwd_key_splits(int B, int N) {
+  (void)B;
+  const char *fe = getenv("EGT_FUSED_KSPLIT");
+  const int forced = fe ? atoi(fe) : 0;
+  auto run = [&](int ks) { return (((N + ks - 1) / ks) + 15) & ~15; };
+  if (forced > 1 && forced <= 8 && run(forced) * (forced - 1) < N) return forced;
+  return 1;
 }
 
 int fused_bwd_finalize_launch(const float *partials, int nparts, const egt_block_weights_t *w,

@@ -125,3 +125,44 @@ def test_wide_backward_key_split(N, d, de, nh, B, ks, monkeypatch):
         assert err <= tol * scale, f'{what}: {err:.3e} vs scale {scale:.3e}'
     # and the split kernel against the oracle, through the shared full-size check
     test_block_full_size_vs_oracle_sample(N, d, de, nh, B)
+
+
+@pytest.mark.parametrize('N,B,ks,rmp', [(256, 3, 4, 0.0), (188, 4, 2, 0.0), (512, 2, 8, 0.0), (300, 2, 4, 0.1)])
+def test_fused_backward_key_split(N, B, ks, rmp, monkeypatch):
+    """Same for the d_e = 8 kernels (csrc/fused_bwd.cu: fused_bwd_key_splits, forced with EGT_FUSED_KSPLIT), including a
+    training step with random key masks: the counters of the mask are positions in the graph, not in the CTA's run."""
+    from tests.test_parity_gpu import test_block_full_size_vs_oracle_sample, _spec_kwargs
+    import egt_b200
+    from oracle import egt_oracle as O
+    d, de, nh = 64, 8, 8
+    cfg = O.BlockConfig(model_width=d, edge_width=de, num_heads=nh, scale_degree=True, random_mask_prob=rmp)
+    params = O.init_block_params(cfg, dtype=torch.float64)
+    h, e, mask = O.synthetic_batch(B, N, d, de, ragged=True, dtype=torch.float32)
+    blk = egt_b200.EGTBlock(**_spec_kwargs(cfg))
+    blk.load_keras_weights(params)
+    blk = blk.to(DEV)
+    blk.train(rmp > 0)
+    g = torch.Generator().manual_seed(5)
+    dh = torch.randn(B, N, d, generator=g).bfloat16().to(DEV)
+    de_ = torch.randn(B, N, N, de, generator=g).bfloat16().to(DEV)
+
+    def run():
+        blk.rng.offset = 41                                  # the same random mask in both runs
+        hg, eg = h.bfloat16().to(DEV).requires_grad_(True), e.bfloat16().to(DEV).requires_grad_(True)
+        blk.flat.grad = None
+        h2, e2 = blk(hg, eg, mask.to(DEV))
+        torch.autograd.backward([h2, e2], [dh, de_])
+        return hg.grad.clone(), eg.grad.clone(), blk.flat.grad.clone()
+
+    monkeypatch.setenv('EGT_FUSED_KSPLIT', '1')
+    ref = run()
+    monkeypatch.setenv('EGT_FUSED_KSPLIT', str(ks))
+    got = run()
+    assert torch.equal(got[1], ref[1])                       # de: per (row, key), untouched by the split
+    for a_, b_, what in zip(got, ref, ('dh', 'de', 'weight gradients')):
+        scale = float(b_.float().abs().max())
+        err = float((a_.float() - b_.float()).abs().max())
+        tol = 8e-3 if a_.dtype == torch.bfloat16 else 2e-3
+        assert err <= tol * scale, f'{what}: {err:.3e} vs scale {scale:.3e}'
+    if rmp == 0:
+        test_block_full_size_vs_oracle_sample(N, d, de, nh, B)
