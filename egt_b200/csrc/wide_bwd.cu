@@ -617,12 +617,21 @@ wide_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
   // ---- weight-gradient partial sums of this CTA ----
   float *part = a.partials + (size_t)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * C::PART;
   {
+    // transpose-reduce over the warp (see fused_bwd.cu): value k, summed over the 32 lanes, ends in lane k
     float *red = (float *)(smem + SM_RED);
+    float v[32];
 #pragma unroll
-    for (int i = 0; i < EGN; ++i) {
-      const float v = warp_sum(sZ[i]);
-      if (lane == 0) atomicAdd(red + i, v);
+    for (int i = 0; i < 32; ++i) v[i] = i < EGN ? sZ[i] : 0.f;
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+      const bool up = (lane & s) != 0;
+#pragma unroll
+      for (int i = 0; i < s; ++i) {
+        const float send = up ? v[i] : v[i + s], keep = up ? v[i + s] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+      }
     }
+    if (lane < EGN) atomicAdd(red + lane, v[0]);
   }
   if (q == 0 && warp < 2) {   // lanes 0 .. 63 of the accumulators: rows [r dZ (EGN) | H_hat (H) | 1] of Z_img
     const int row = t;                                   // warp 0: lanes 0-31, warp 1: lanes 32-63
