@@ -760,7 +760,7 @@ int launch_cfg(const WideBwdArgs &a, const void *e, const void *de_out, void *de
 }  // namespace
 
 // How many CTAs share the keys of one (graph, row tile): the count in {1, 2, 4, 8} that minimises full waves / count on
-// 148 SMs, with at least 64 keys per CTA (its prologue -- Q, dO, the row statistics -- is paid per CTA) and no empty split.
+// 148 SMs, with enough keys per CTA (its prologue -- Q, dO, the row statistics -- is paid per CTA) and no empty split.
 int wide_bwd_key_splits(int B, int N, int TK) {
   const char *fe = getenv("EGT_WIDE_KSPLIT");            // read per call: the parity tests force a split
   const int forced = fe ? atoi(fe) : 0;
@@ -769,7 +769,8 @@ int wide_bwd_key_splits(int B, int N, int TK) {
   double cost = (double)((base + 147) / 148);
   for (int ks = 2; ks <= 8; ks *= 2) {
     const int per = (NT + ks - 1) / ks;
-    if (per * (ks - 1) >= NT || per * TK < 64) continue;
+    // at least 64 keys per CTA; 32 when every CTA still runs in the first wave (an under-filled grid: the split only adds SMs)
+    if (per * (ks - 1) >= NT || per * TK < (base * ks <= 148 ? 32 : 64)) continue;
     const double c = (double)((base * ks + 147) / 148) / ks + 0.01 * ks;
     if (c < cost - 1e-9) { cost = c; best = ks; }
   }
