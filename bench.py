@@ -332,8 +332,9 @@ def run_ours(args, w):
     ms_e2e = timed_e2e(args.steps)
 
     # ---- the shipped training setting (every reference config: random_mask_prob = 0.1, training = True) ----
-    # timed with eager launches: the key mask's Philox offset is a launch argument, so a replayed CUDA graph would
-    # draw the same mask every step (egt_b200.ops refuses that capture)
+    # The key mask's Philox offset = a launch argument + a device counter the captured step bumps (egt_b200.layers), so
+    # the step replays from a CUDA graph and still draws a new mask every time; the eager time is reported next to it.
+    # (N > 1: eager only -- NCCL work issued before a capture was seen to invalidate it, and the timed regions above use NCCL.)
     train_line = None
     if args.random_mask_prob == 0 and not args.no_train_line:
         blk_t = egt_b200.EGTBlock(model_width=d, edge_width=d_e, num_heads=h, scale_degree=bool(args.scale_degree),
@@ -342,10 +343,34 @@ def run_ours(args, w):
         for i in range(3):
             step(i, block=blk_t)
         ms_eager = timed(lambda i: step(i), args.steps)
-        ms_train = timed(lambda i: step(i, block=blk_t), args.steps)
-        train_line = dict(random_mask_prob=0.1, training=True, cuda_graphs=False, ms_per_step=ms_train / args.steps,
+        ms_train_eager = timed(lambda i: step(i, block=blk_t), args.steps)
+        ms_train, tgraphs, tkeep = ms_train_eager, [], []
+        if use_graphs and world == 1:
+            try:
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for i in range(2):
+                        step(i, block=blk_t)
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                for i in range(nsets):
+                    g_ = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g_):
+                        tkeep.append((step(i, block=blk_t), blk_t.flat.grad))
+                    tgraphs.append(g_)
+                for i in range(3):
+                    tgraphs[i % nsets].replay()
+                ms_train = timed(lambda i: tgraphs[i % nsets].replay(), args.steps)
+            except Exception as ex:
+                print(f'[bench] training-step graph capture failed ({type(ex).__name__}: {ex}); eager time reported', file=sys.stderr)
+                tgraphs = []
+                torch.cuda.synchronize()
+        train_line = dict(random_mask_prob=0.1, training=True, cuda_graphs=bool(tgraphs), ms_per_step=ms_train / args.steps,
                           value=B * world * args.steps / (ms_train / 1e3), unit='graphs/s',
+                          eager_ms_per_step=ms_train_eager / args.steps,
                           eager_ms_per_step_without_mask=ms_eager / args.steps)
+        del tgraphs, tkeep
     # ---- one FULL layer: attention block + node FFN + edge FFN, forward + backward, same inputs ----
     # (graph_xformer_model_base.py:335-341: edge_update then ffn_block); CUDA graphs like the headline step
     layer_line = None

@@ -52,7 +52,7 @@ class AttnCfg(C.Structure):
                 ('clip_hi', C.c_float), ('scale_degree', C.c_int32), ('scaler_type', C.c_int32),
                 ('num_virtual_nodes', C.c_int32), ('training', C.c_int32),
                 ('random_mask_prob', C.c_float), ('attn_dropout', C.c_float),
-                ('seed', C.c_uint64), ('offset', C.c_uint64)]
+                ('seed', C.c_uint64), ('offset', C.c_uint64), ('offset_dev', C.c_void_p)]
 
 
 class BlockCfg(C.Structure):

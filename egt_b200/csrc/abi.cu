@@ -135,7 +135,7 @@ static AttnParams make_attn_params(const egt_attn_cfg_t *c) {
   P.rand_mask = c->training && c->random_mask_prob > 0.f;
   P.dropout = c->training && c->attn_dropout > 0.f;
   P.random_mask_prob = c->random_mask_prob; P.attn_dropout = c->attn_dropout;
-  P.seed = c->seed; P.offset = c->offset;
+  P.seed = c->seed; P.offset = c->offset; P.offset_dev = c->offset_dev;
   P.dq_scale = 1.0f;
   return P;
 }
@@ -414,7 +414,7 @@ int egt_block_fwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
     fa.scale_degree = a.scale_degree; fa.scaler_type = a.scaler_type; fa.num_virtual_nodes = a.num_virtual_nodes;
     fa.rand_mask = a.training && a.random_mask_prob > 0.f;
     fa.rand_thr = (uint32_t)ceilf(a.random_mask_prob * 65536.0f - 0.5f);
-    fa.seed = a.seed; fa.offset = a.offset;
+    fa.seed = a.seed; fa.offset = a.offset; fa.offset_dev = a.offset_dev;
     if ((rc = wide_fwd_launch(cfg, fa, io->e, io->e_out, io->qkv, st))) return rc;
     if (node_tc) return node_out_launch(io->v_att, io->h, w->dense_mha_kernel, w->dense_mha_bias, io->h_out, R, st);
     if (ws.nblas) return node_blas_out(io->v_att, io->h, w, io->h_out, R, d, ws.nblas, st);
@@ -448,7 +448,7 @@ int egt_block_fwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
     fa.scale_degree = a.scale_degree; fa.scaler_type = a.scaler_type; fa.num_virtual_nodes = a.num_virtual_nodes;
     fa.rand_mask = a.training && a.random_mask_prob > 0.f;
     fa.rand_thr = (uint32_t)ceilf(a.random_mask_prob * 65536.0f - 0.5f);
-    fa.seed = a.seed; fa.offset = a.offset;
+    fa.seed = a.seed; fa.offset = a.offset; fa.offset_dev = a.offset_dev;
     // the output projection + residual runs in the same kernel (V_att goes from registers to the tensor core)
     fa.w_o = w->dense_mha_kernel; fa.b_o = w->dense_mha_bias;
     fa.h = (const __nv_bfloat16 *)io->h; fa.h_out = (__nv_bfloat16 *)io->h_out;
@@ -536,7 +536,7 @@ int egt_block_bwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
     fb.scale_degree = a.scale_degree; fb.scaler_type = a.scaler_type; fb.num_virtual_nodes = a.num_virtual_nodes;
     fb.rand_mask = a.training && a.random_mask_prob > 0.f;
     fb.rand_thr = (uint32_t)ceilf(a.random_mask_prob * 65536.0f - 0.5f);
-    fb.seed = a.seed; fb.offset = a.offset;
+    fb.seed = a.seed; fb.offset = a.offset; fb.offset_dev = a.offset_dev;
     if ((rc = wide_bwd_launch(cfg, fb, io->e, io->de_out, io->de, io->qkv, st))) return rc;
     // the fold of the edge-side weight gradients feeds nothing downstream: next to the last node kernels (it writes the
     // edge weights' gradients, they write the node weights')
@@ -605,7 +605,7 @@ int egt_block_bwd(const egt_block_cfg_t *cfg, const egt_block_weights_t *w, cons
     fb.scale_degree = a.scale_degree; fb.scaler_type = a.scaler_type; fb.num_virtual_nodes = a.num_virtual_nodes;
     fb.rand_mask = a.training && a.random_mask_prob > 0.f;
     fb.rand_thr = (uint32_t)ceilf(a.random_mask_prob * 65536.0f - 0.5f);
-    fb.seed = a.seed; fb.offset = a.offset;
+    fb.seed = a.seed; fb.offset = a.offset; fb.offset_dev = a.offset_dev;
     if ((rc = fused_bwd_launch(fb, io->e, io->de_out, io->de, io->qkv, st))) return rc;
     // (splitting this kernel into its dh half and its weight-gradient half on two streams was measured: the dh half alone
     // takes as long as the whole kernel -- 26 us, the float32 -> bf16 staging of dqkv -- and the step got 2 % slower)

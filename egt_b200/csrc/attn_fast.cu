@@ -95,12 +95,12 @@ __device__ __forceinline__ Elem eval_elem(const AttnParams &P, float dot, float 
       e.x += neg; e.gin += neg;
     }
     if (P.rand_mask) {                                            // :103-108
-      const float u = rng_uniform(P.seed, P.offset, 0u, rng_elem_index(b, l, m, hh, P.N, P.h));
+      const float u = rng_uniform(P.seed, P.offset + (P.offset_dev ? *P.offset_dev : 0ull), 0u, rng_elem_index(b, l, m, hh, P.N, P.h));
       const float neg = u < P.random_mask_prob ? -kNegMask : 0.f;
       e.x += neg; e.gin += neg;
     }
     if (P.dropout) {
-      const float u = rng_uniform(P.seed, P.offset, 1u, rng_elem_index(b, l, m, hh, P.N, P.h));
+      const float u = rng_uniform(P.seed, P.offset + (P.offset_dev ? *P.offset_dev : 0ull), 1u, rng_elem_index(b, l, m, hh, P.N, P.h));
       e.keep = u >= P.attn_dropout ? 1.f / (1.f - P.attn_dropout) : 0.f;
     }
   }

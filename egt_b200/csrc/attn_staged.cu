@@ -48,13 +48,13 @@ struct LogitCtx {
       x += neg; gin += neg;
     }
     if (P.rand_mask) {                                       // :103-108 (same noise for H_hat and G)
-      float u = rng_uniform(P.seed, P.offset, 0u, rng_elem_index(b, l, m, hh, P.N, P.h));
+      float u = rng_uniform(P.seed, P.offset + (P.offset_dev ? *P.offset_dev : 0ull), 0u, rng_elem_index(b, l, m, hh, P.N, P.h));
       float neg = u < P.random_mask_prob ? -kNegMask : 0.f;
       x += neg; gin += neg;
     }
     keep = 1.f;
     if (P.dropout) {                                         // :116-117 tf.nn.dropout
-      float u = rng_uniform(P.seed, P.offset, 1u, rng_elem_index(b, l, m, hh, P.N, P.h));
+      float u = rng_uniform(P.seed, P.offset + (P.offset_dev ? *P.offset_dev : 0ull), 1u, rng_elem_index(b, l, m, hh, P.N, P.h));
       keep = u >= P.attn_dropout ? 1.f / (1.f - P.attn_dropout) : 0.f;
     }
     return Hh;

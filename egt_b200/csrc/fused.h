@@ -52,6 +52,7 @@ struct FusedFwdArgs {
   int scale_degree, scaler_type, num_virtual_nodes;
   int rand_mask; uint32_t rand_thr;   // mask element when its 16 random bits < rand_thr
   uint64_t seed, offset;
+  const uint64_t *offset_dev;         // device word added to offset at run time (NULL: none)
   // output projection fused behind the attention (graph_xformer_model_base.py:136-140); w_o == NULL = off
   const float *w_o, *b_o;             // dense_mha kernel [64,64], bias [64]
   const __nv_bfloat16 *h;             // [B,N,64] residual input
@@ -75,6 +76,7 @@ struct FusedBwdArgs {
   int scale_degree, scaler_type, num_virtual_nodes;
   int rand_mask; uint32_t rand_thr;
   uint64_t seed, offset;
+  const uint64_t *offset_dev;         // device word added to offset at run time (NULL: none)
 };
 
 bool fused_supported(const egt_block_cfg_t *cfg, int dtype);

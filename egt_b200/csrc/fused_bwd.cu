@@ -513,8 +513,9 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     uint32_t rbw[4] = {0u, 0u, 0u, 0u};
     if (RAND) {   // one Philox call = this thread's 2 keys x 4 heads (rng_elem_index, common.cuh)
       const uint64_t qd = rng_elem_index((uint64_t)b, (uint64_t)l, (uint64_t)(K0 + 2 * p), 4u * (uint32_t)g, (uint64_t)N, FH) >> 3;
-      const Philox4 ph = philox4x32_10((uint32_t)qd, (uint32_t)(qd >> 32), (uint32_t)a.offset,
-                                       (uint32_t)(a.offset >> 32), (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+      const uint64_t roff = a.offset + (a.offset_dev ? *a.offset_dev : 0ull);
+      const Philox4 ph = philox4x32_10((uint32_t)qd, (uint32_t)(qd >> 32), (uint32_t)roff,
+                                       (uint32_t)(roff >> 32), (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
       rbw[0] = ph.x; rbw[1] = ph.y; rbw[2] = ph.z; rbw[3] = ph.w;          // key kk, head 4g+i: 16-bit lane 4kk+i
     }
 #pragma unroll

@@ -318,8 +318,9 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant
     }
     if (RAND) {   // one Philox call = this thread's 2 keys x 4 heads (rng_elem_index, common.cuh)
       const uint64_t qd = rng_elem_index((uint64_t)b, (uint64_t)l, (uint64_t)(2 * p), 4u * (uint32_t)g, (uint64_t)N, FH) >> 3;
-      const Philox4 ph = philox4x32_10((uint32_t)qd, (uint32_t)(qd >> 32), (uint32_t)a.offset,
-                                       (uint32_t)(a.offset >> 32), (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+      const uint64_t roff = a.offset + (a.offset_dev ? *a.offset_dev : 0ull);
+      const Philox4 ph = philox4x32_10((uint32_t)qd, (uint32_t)(qd >> 32), (uint32_t)roff,
+                                       (uint32_t)(roff >> 32), (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
       rb[0][0] = ph.x; rb[0][1] = ph.y; rb[1][0] = ph.z; rb[1][1] = ph.w;   // key kk, head 4g+i: 16-bit lane 4kk+i
     }
     const float4 uE4 = *(const float4 *)(cst + 4 * g), vE4 = *(const float4 *)(cst + 8 + 4 * g);

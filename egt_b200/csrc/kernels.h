@@ -15,6 +15,7 @@ struct AttnParams {
   int rand_mask, dropout;            // already gated on `training`
   float random_mask_prob, attn_dropout;
   uint64_t seed, offset;
+  const uint64_t *offset_dev;        // device word added to offset at run time (NULL: none)
   const void *qkv, *E, *G, *M;
   const uint8_t *mask;
   void *v_att, *h_hat, *a_tild;

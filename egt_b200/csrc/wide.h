@@ -53,6 +53,7 @@ struct WideFwdArgs {
   int scale_degree, scaler_type, num_virtual_nodes;
   int rand_mask; uint32_t rand_thr;   // mask element when its 16 random bits < rand_thr
   uint64_t seed, offset;
+  const uint64_t *offset_dev;         // device word added to offset at run time (NULL: none)
 };
 
 struct WideBwdArgs {
@@ -67,6 +68,7 @@ struct WideBwdArgs {
   int scale_degree, scaler_type, num_virtual_nodes;
   int rand_mask; uint32_t rand_thr;
   uint64_t seed, offset;
+  const uint64_t *offset_dev;         // device word added to offset at run time (NULL: none)
 };
 
 // shape gate: which (h, dk, d_e) have an instantiation; flags as fused_supported()

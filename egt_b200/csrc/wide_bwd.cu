@@ -434,7 +434,8 @@ wide_bwd_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
 #pragma unroll
         for (int q4 = 0; q4 < 2; ++q4) {
           const uint64_t qd = rng_elem_index((uint64_t)b, (uint64_t)l, (uint64_t)(m & ~1), (uint32_t)(8 * half + 4 * q4), (uint64_t)N, H) >> 3;
-          const Philox4 ph = philox4x32_10((uint32_t)qd, (uint32_t)(qd >> 32), (uint32_t)a.offset, (uint32_t)(a.offset >> 32),
+          const uint64_t roff = a.offset + (a.offset_dev ? *a.offset_dev : 0ull);
+          const Philox4 ph = philox4x32_10((uint32_t)qd, (uint32_t)(qd >> 32), (uint32_t)roff, (uint32_t)(roff >> 32),
                                            (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
           rb[2 * q4] = (m & 1) ? ph.z : ph.x; rb[2 * q4 + 1] = (m & 1) ? ph.w : ph.y;
         }

@@ -36,6 +36,19 @@ class _RngState:
         return self.seed, self.offset
 
 
+def _rng_args(module, training, live):
+    """(seed, offset, offset_dev) of one call.  Eager calls advance the host offset.  A call that is being captured into
+    a CUDA graph with live RNG (random key mask / attention dropout) also takes a snapshot of the module's DEVICE counter
+    and bumps it, both as captured work: the kernels add the snapshot to the (frozen) host offset, so every replay of the
+    graph draws new noise, and the backward of the call reuses the forward's snapshot."""
+    if not training:
+        return 0, 0, None
+    seed, offset = module.rng.next()
+    if live and module._rng_counter.is_cuda and torch.cuda.is_current_stream_capturing():
+        return seed, offset, ops.graph_safe_offset(module._rng_counter)
+    return seed, offset, None
+
+
 class EGT(nn.Module):
     """Drop-in for the reference Keras layer ``EGT`` (egt_layers.py:4-40).  No weights.
 
@@ -55,6 +68,7 @@ class EGT(nn.Module):
         self.spec.validate()
         self.return_attn = return_attn
         self.rng = _RngState(seed)
+        self.register_buffer('_rng_counter', torch.zeros(1, dtype=torch.int64), persistent=False)   # see _rng_args
 
     def get_config(self):
         """Same keys as egt_layers.py:42-55, plus ``attn_dropout`` which the reference forgets."""
@@ -70,9 +84,9 @@ class EGT(nn.Module):
     def forward(self, inputs, mask=None, training=None):
         if training is None:                                                 # egt_layers.py:58-59
             training = self.training
-        seed, offset = self.rng.next() if training else (0, 0)
+        seed, offset, offset_dev = _rng_args(self, training, self.spec.random_mask_prob > 0 or self.spec.attn_dropout > 0)
         return ops.egt_attention(inputs, mask, training, spec=self.spec, seed=seed, offset=offset,
-                                 return_attn=self.return_attn)
+                                 return_attn=self.return_attn, offset_dev=offset_dev)
 
 
 class EGTBlock(nn.Module):
@@ -93,6 +107,7 @@ class EGTBlock(nn.Module):
         total, self.layout = ops.param_layout(self.spec)
         self.flat = nn.Parameter(torch.zeros(total, dtype=torch.float32))
         self.rng = _RngState(seed)
+        self.register_buffer('_rng_counter', torch.zeros(1, dtype=torch.int64), persistent=False)   # see _rng_args
         self.reset_parameters()
 
     # -- parameters ---------------------------------------------------------------------
@@ -142,9 +157,9 @@ class EGTBlock(nn.Module):
     def forward(self, h, e, mask=None, edge_mask=None, training=None):
         if training is None:
             training = self.training
-        seed, offset = self.rng.next() if training else (0, 0)
+        seed, offset, offset_dev = _rng_args(self, training, self.spec.random_mask_prob > 0 or self.spec.attn_dropout > 0)
         return ops.egt_block(h, e, mask, self.flat, self.spec, self.layout, edge_mask=edge_mask,
-                             training=training, seed=seed, offset=offset)
+                             training=training, seed=seed, offset=offset, offset_dev=offset_dev)
 
 
 class EGTFFN(nn.Module):

@@ -31,17 +31,28 @@ def _need_cuda(*ts):
             raise RuntimeError('egt_b200 runs on CUDA tensors only (sm_100a); there is no CPU fallback')
 
 
-def _refuse_rng_capture(training, random_mask_prob, attn_dropout):
+def _refuse_rng_capture(training, random_mask_prob, attn_dropout, offset_dev=None):
     """The Philox (seed, offset) of the random key mask / attention dropout reach the kernels as launch ARGUMENTS.
     A CUDA graph freezes its launch arguments, so every replay of a captured training step would draw the identical
     mask -- silently different from the reference, which draws fresh noise per step (egt_layers.py:103-108,116-117).
-    Capture is therefore refused while that RNG is live; run such steps eagerly (bench.py does) or set
-    EGT_ALLOW_FROZEN_RNG=1 to accept a frozen mask (e.g. to time the kernels)."""
+    With ``offset_dev`` (a device word the kernels add to the offset when they run; the layers of egt_b200.layers keep
+    one per module and bump it inside the captured step) a replay draws new noise and capture is fine.  Without it
+    capture is refused while that RNG is live; EGT_ALLOW_FROZEN_RNG=1 accepts a frozen mask (e.g. to time the kernels)."""
     import os
-    if training and (random_mask_prob > 0 or attn_dropout > 0) and torch.cuda.is_current_stream_capturing() \
-            and os.environ.get('EGT_ALLOW_FROZEN_RNG', '0') != '1':
+    if training and (random_mask_prob > 0 or attn_dropout > 0) and offset_dev is None \
+            and torch.cuda.is_current_stream_capturing() and os.environ.get('EGT_ALLOW_FROZEN_RNG', '0') != '1':
         raise RuntimeError('egt_b200: refusing to capture a training step with random_mask_prob / attn_dropout > 0 into a '
-                           'CUDA graph: the RNG offset is a launch argument and every replay would reuse the same mask')
+                           'CUDA graph without a device-side RNG offset: every replay would reuse the same mask')
+
+
+def graph_safe_offset(counter: torch.Tensor):
+    """For a step that is being captured into a CUDA graph: returns a snapshot of the module's device RNG counter (an
+    int64 tensor of one element that must exist BEFORE the capture) and bumps the counter -- both as captured work, so
+    every replay sees the next value.  The snapshot is what the forward AND the backward kernels of this call add to
+    their Philox offset."""
+    snap = counter.clone()
+    counter.add_(1)
+    return snap
 
 
 def _mask_u8(mask, B, N):
@@ -77,7 +88,7 @@ class AttnSpec:
         if self.scaler_type not in ('log', 'linear'):                       # :23-24
             raise ValueError('scaler_type must be log or linear')
 
-    def c_cfg(self, B, N, dk, dtype, training, seed, offset, mask_kind=None) -> L.AttnCfg:
+    def c_cfg(self, B, N, dk, dtype, training, seed, offset, mask_kind=None, offset_dev=None) -> L.AttnCfg:
         c = L.AttnCfg()
         c.B, c.N, c.h, c.dk, c.dtype = B, N, self.num_heads, dk, dtype
         c.edge_input, c.gate_input = int(self.edge_input), int(self.gate_input)
@@ -91,12 +102,13 @@ class AttnSpec:
         c.training = int(bool(training))
         c.random_mask_prob, c.attn_dropout = float(self.random_mask_prob), float(self.attn_dropout)
         c.seed, c.offset = int(seed) & (2**64 - 1), int(offset) & (2**64 - 1)
+        c.offset_dev = None if offset_dev is None else offset_dev.data_ptr()
         return c
 
 
 class _EGTAttnFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, qkv, E, G, M, mask_u8, spec: AttnSpec, training, seed, offset, want_attn):
+    def forward(ctx, qkv, E, G, M, mask_u8, spec: AttnSpec, training, seed, offset, want_attn, offset_dev=None):
         lib = L.load()
         _need_cuda(qkv, E, G, M, mask_u8)
         B, N, C3 = qkv.shape
@@ -111,7 +123,8 @@ class _EGTAttnFn(torch.autograd.Function):
         for t, nm in ((E, 'E'), (G, 'G'), (M, 'M')):
             if t is not None:
                 assert t.shape == (B, N, N, h) and t.dtype == qkv.dtype, f'{nm} must be [B,N,N,h] {qkv.dtype}'
-        cfg = spec.c_cfg(B, N, dk, _dtype_code(qkv), training, seed, offset)
+        cfg = spec.c_cfg(B, N, dk, _dtype_code(qkv), training, seed, offset, offset_dev=offset_dev)
+        ctx.offset_dev = offset_dev                      # keeps the snapshot alive until the backward has used it
         v_att = torch.empty(B, N, d, dtype=qkv.dtype, device=qkv.device)
         h_hat = torch.empty(B, N, N, h, dtype=qkv.dtype, device=qkv.device)
         a_tild = torch.empty(B, N, N, h, dtype=qkv.dtype, device=qkv.device) if want_attn else None
@@ -143,10 +156,10 @@ class _EGTAttnFn(torch.autograd.Function):
         L.check(lib.egt_attn_bwd(C.byref(cfg), _ptr(qkv), _ptr(E), _ptr(G), _ptr(M), _ptr(mask_u8),
                                  _ptr(lse), _ptr(deg), _ptr(d_v_att), _ptr(d_h_hat), _ptr(d_qkv),
                                  _ptr(dE), _ptr(dG), _ptr(row_ws), _stream()))
-        return d_qkv, dE, dG, None, None, None, None, None, None, None
+        return d_qkv, dE, dG, None, None, None, None, None, None, None, None
 
 
-def egt_attention(inputs, mask=None, training=False, *, spec: AttnSpec, seed=0, offset=0, return_attn=False):
+def egt_attention(inputs, mask=None, training=False, *, spec: AttnSpec, seed=0, offset=0, return_attn=False, offset_dev=None):
     """``EGT.call``: ([QKV, E?, G?, M?], mask, training) -> (V_att, H_hat, A_tild | None)
     (egt_layers.py:57-143 / :145-213).  Positional input order as in egt_layers.py:62-65."""
     spec.validate()
@@ -157,8 +170,8 @@ def egt_attention(inputs, mask=None, training=False, *, spec: AttnSpec, seed=0, 
     M = inputs.pop(0) if spec.attn_mask else None
     B, N, _ = qkv.shape
     m8 = _mask_u8(mask, B, N)
-    _refuse_rng_capture(training, spec.random_mask_prob, spec.attn_dropout)
-    out = _EGTAttnFn.apply(qkv, E, G, M, m8, spec, training, seed, offset, return_attn)
+    _refuse_rng_capture(training, spec.random_mask_prob, spec.attn_dropout, offset_dev)
+    out = _EGTAttnFn.apply(qkv, E, G, M, m8, spec, training, seed, offset, return_attn, offset_dev)
     if return_attn:
         return out
     return out[0], out[1], None
@@ -221,7 +234,7 @@ class BlockSpec:
             raise ValueError(f'unsupported edge_activation {a!r}')
         return _ACT[key], 0.
 
-    def c_cfg(self, B, N, dtype, training, seed, offset) -> L.BlockCfg:
+    def c_cfg(self, B, N, dtype, training, seed, offset, offset_dev=None) -> L.BlockCfg:
         c = L.BlockCfg()
         a = c.attn
         a.B, a.N, a.h, a.dk, a.dtype = B, N, self.num_heads, self.model_width // self.num_heads, dtype
@@ -234,6 +247,7 @@ class BlockSpec:
         a.training = int(bool(training))
         a.random_mask_prob, a.attn_dropout = float(self.random_mask_prob), float(self.attn_dropout)
         a.seed, a.offset = int(seed) & (2**64 - 1), int(offset) & (2**64 - 1)
+        a.offset_dev = None if offset_dev is None else offset_dev.data_ptr()
         c.d_e = self.edge_width
         c.edge_channel_type = _ECT[self.edge_channel_type]
         c.gate_attention = int(self.gate_attention)
@@ -267,7 +281,7 @@ def _fill_ptrs(struct, flat: torch.Tensor, layout):
 
 class _EGTBlockFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, h, e, flat, mask_u8, adj_u8, spec: BlockSpec, layout, training, seed, offset):
+    def forward(ctx, h, e, flat, mask_u8, adj_u8, spec: BlockSpec, layout, training, seed, offset, offset_dev=None):
         lib = L.load()
         _need_cuda(h, e, flat, mask_u8, adj_u8)
         B, N, d = h.shape
@@ -277,7 +291,8 @@ class _EGTBlockFn(torch.autograd.Function):
         if spec.has_edge:
             assert e is not None and e.shape == (B, N, N, spec.edge_width) and e.dtype == h.dtype
             e = e.contiguous()
-        cfg = spec.c_cfg(B, N, _dtype_code(h), training, seed, offset)
+        cfg = spec.c_cfg(B, N, _dtype_code(h), training, seed, offset, offset_dev)
+        ctx.offset_dev = offset_dev                      # keeps the snapshot alive until the backward has used it
         dev = h.device
         io = L.BlockFwdIO()
         h_out = torch.empty_like(h)
@@ -327,10 +342,10 @@ class _EGTBlockFn(torch.autograd.Function):
         w = _fill_ptrs(L.BlockWeights(), flat, layout)
         g = _fill_ptrs(L.BlockGrads(), dflat, layout)
         L.check(lib.egt_block_bwd(C.byref(cfg), C.byref(w), C.byref(g), C.byref(io), _stream()))
-        return dh, de, dflat, None, None, None, None, None, None, None
+        return dh, de, dflat, None, None, None, None, None, None, None, None
 
 
-def egt_block(h, e, mask, flat, spec: BlockSpec, layout, edge_mask=None, training=False, seed=0, offset=0):
+def egt_block(h, e, mask, flat, spec: BlockSpec, layout, edge_mask=None, training=False, seed=0, offset=0, offset_dev=None):
     """``edge_update(tag, h, e) -> (h, e)`` (graph_xformer_model_base.py:164-223, :328-339)."""
     spec.validate()
     B, N, _ = h.shape
@@ -343,8 +358,8 @@ def egt_block(h, e, mask, flat, spec: BlockSpec, layout, edge_mask=None, trainin
             edge_mask = edge_mask[..., 0]
         adj = (edge_mask != 0).to(torch.uint8).contiguous()
     e_in = e if spec.has_edge else None
-    _refuse_rng_capture(training, spec.random_mask_prob, spec.attn_dropout)
-    out = _EGTBlockFn.apply(h, e_in, flat, m8, adj, spec, layout, training, seed, offset)
+    _refuse_rng_capture(training, spec.random_mask_prob, spec.attn_dropout, offset_dev)
+    out = _EGTBlockFn.apply(h, e_in, flat, m8, adj, spec, layout, training, seed, offset, offset_dev)
     if spec.is_residual:
         return out
     return out, e

@@ -81,6 +81,9 @@ typedef struct egt_attn_cfg {
   float attn_dropout;
   uint64_t seed;                /* counter-based RNG (Philox4x32-10), see DESIGN.md "RNG" */
   uint64_t offset;
+  const uint64_t *offset_dev;   /* optional DEVICE pointer: the kernels add *offset_dev to offset when they run, so a step
+                                 * captured into a CUDA graph draws new noise at every replay (bump the word between replays);
+                                 * NULL: offset alone */
 } egt_attn_cfg_t;
 
 /* Hyper-parameters of GraphTransformerBase that reach the attention block

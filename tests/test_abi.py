@@ -34,8 +34,8 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_sizes_match_header():
     # mirrors of egt_attn_cfg_t / egt_block_cfg_t: field offsets must follow natural C alignment
-    assert ctypes.sizeof(L.AttnCfg) == 88
-    assert ctypes.sizeof(L.BlockCfg) == 88 + 24
+    assert ctypes.sizeof(L.AttnCfg) == 96                # ... seed, offset, offset_dev (device pointer)
+    assert ctypes.sizeof(L.BlockCfg) == 96 + 24
     assert ctypes.sizeof(L.BlockWeights) == 14 * 8
     assert ctypes.sizeof(L.BlockFwdIO) == 12 * 8
     assert ctypes.sizeof(L.BlockBwdIO) == 14 * 8

@@ -89,3 +89,51 @@ def test_full_layer_step_replays_from_a_cuda_graph():
     for got, want in zip(out, ref):
         scale = float(want.float().abs().max())
         assert float((got.float() - want.float()).abs().max()) <= 2e-3 * scale   # weight gradients: atomics, order differs
+
+
+@pytest.mark.parametrize('d,de,nh,N', [(64, 8, 8, 100), (128, 32, 16, 70)])
+def test_training_step_with_random_masks_replays_from_a_cuda_graph(d, de, nh, N):
+    """random_mask_prob > 0 in a captured step: the kernels add a device counter to their Philox offset and the captured
+    step bumps it, so replay r draws the mask of eager call (offset at capture + r) -- bit-exactly, forward and backward --
+    and consecutive replays differ (reference: fresh noise every step, egt_layers.py:103-108)."""
+    import egt_b200
+    torch.manual_seed(1)
+    B = 3
+    blk = egt_b200.EGTBlock(model_width=d, edge_width=de, num_heads=nh, random_mask_prob=0.3, seed=77).to(DEV)
+    blk.train(True)
+    h = torch.randn(B, N, d, device=DEV).bfloat16()
+    e = torch.randn(B, N, N, de, device=DEV).bfloat16()
+    m = torch.ones(B, N, dtype=torch.bool, device=DEV)
+    dh, de_ = torch.randn_like(h), torch.randn_like(e)
+
+    def step():
+        hh, ee = h.detach().requires_grad_(True), e.detach().requires_grad_(True)
+        blk.flat.grad = None
+        h2, e2 = blk(hh, ee, m)
+        torch.autograd.backward([h2, e2], [dh, de_])
+        return h2.detach(), e2.detach(), hh.grad, ee.grad
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        step()                                               # eager warm-up (host offset 1)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = step()                                         # host offset 2 is frozen into the graph
+    base = blk.rng.offset
+    c0 = int(blk._rng_counter.item())
+    replays = []
+    for r in range(3):
+        g.replay()
+        torch.cuda.synchronize()
+        replays.append([t.clone() for t in out])
+    assert int(blk._rng_counter.item()) == c0 + 3
+    # the mask acts on the attention weights: h' (and the gradients) change from replay to replay, e' does not depend on it
+    assert not torch.equal(replays[0][0], replays[1][0]) and not torch.equal(replays[1][0], replays[2][0])
+    for r in range(3):
+        blk.rng.offset = base + c0 + r - 1                   # the eager call then uses offset base + c0 + r
+        want = step()
+        for got, ref in zip(replays[r], want):
+            assert torch.equal(got, ref)
