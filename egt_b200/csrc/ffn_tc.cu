@@ -81,7 +81,7 @@ __device__ __forceinline__ void act_fd(int act, float x, float &f, float &d) {
 // sb1[j] = b1[j'] + sum_c beta[c] W1[c][j'] ;  sb2[c] = b2[c'].
 template <int W>
 __device__ __forceinline__ void build_images(uint8_t *img1, uint8_t *img2, float *sb1, float *sb2, const FfnTcArgs &a,
-                                             int tid, int nthr, float sc1 = 1.f) {
+                                             int tid, int nthr, float sc1 = 1.f, float sc2 = 1.f) {
   constexpr int H = 2 * W;
   for (int i = tid; i < 128 * 8; i += nthr) {
     const int j = i >> 3, c0 = (i & 7) << 3;
@@ -92,7 +92,7 @@ __device__ __forceinline__ void build_images(uint8_t *img1, uint8_t *img2, float
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         y1[u] = a.gamma[cw0 + u] * a.W1[(size_t)(cw0 + u) * H + jh] * sc1;
-        y2[u] = a.W2[(size_t)jh * W + cw0 + u];
+        y2[u] = a.W2[(size_t)jh * W + cw0 + u] * sc2;
       }
       v1 = pack8(y1); v2 = pack8(y2);
     }
@@ -401,8 +401,8 @@ struct BwdBars {
   uint64_t full[B_NS], readyA, doneA, readyB, doneB, doneC, out_ready, out_free;
   uint32_t tmem_base, pad;
 };
-// stages [dy | x] | out | hid (2 atoms) | dpre (2 atoms) | img1 | img2 | ones 4 KB | sb1 | xch[4][128][4] | sdg, sdb | bars
-constexpr int B_SMEM = 1024 + B_NS * 2 * TILE + TILE + 2 * TILE + 2 * TILE + 2 * TILE + 4096 + 128 * 4 + B_NQ * 128 * 4 * 4 +
+// stages [dy | x] | out | hid (2 atoms) | dpre (2 atoms) | img1 | img2 | ones 4 KB | bias-1 image 4 KB | xch[4][128][4] | sdg, sdb | bars
+constexpr int B_SMEM = 1024 + B_NS * 2 * TILE + TILE + 2 * TILE + 2 * TILE + 2 * TILE + 4096 + 4096 + B_NQ * 128 * 4 * 4 +
                        2 * 64 * 4 + sizeof(BwdBars);
 
 template <int W, int ACT>
@@ -415,8 +415,8 @@ __global__ void __launch_bounds__(B_THREADS, 1) ffn_tc_bwd_kernel(const __grid_c
   uint8_t *sOut = sStage + B_NS * 2 * TILE;
   uint8_t *sHid = sOut + TILE, *sDpre = sHid + 2 * TILE;
   uint8_t *sImg1 = sDpre + 2 * TILE, *sImg2 = sImg1 + TILE, *sOnes = sImg2 + TILE;
-  float *sb1 = (float *)(sOnes + 4096);
-  float *xch = sb1 + 128;                                   // [B_NQ][128][4]
+  uint8_t *sBb1 = sOnes + 4096;                             // bias of the first layer as an MN-major B image (k-row 0 = hi, 1 = lo)
+  float *xch = (float *)(sBb1 + 4096);                      // [B_NQ][128][4]
   float *sdg = xch + B_NQ * 128 * 4, *sdb = sdg + 64;
   BwdBars *bars = (BwdBars *)(sdb + 64);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -436,11 +436,27 @@ __global__ void __launch_bounds__(B_THREADS, 1) ffn_tc_bwd_kernel(const __grid_c
     __syncwarp();
     tmem_alloc(smem_u32(&bars->tmem_base), 512);
   }
+  // For elu the first layer is pre-multiplied by log2(e) (the exponential is one ex2 of the accumulator) and the second by
+  // ln 2, so that dpre' = ln2 dpre and dx^ = dpre' (log2e W1')^T stays exact; the accumulated dW1 / db1 are ln2 times the
+  // true sums and are scaled back when they are flushed.
+  constexpr float SC1 = ACT == EGT_ACT_ELU ? kLog2e : 1.f, SC2 = ACT == EGT_ACT_ELU ? 1.f / kLog2e : 1.f;
   {
-    float *dummy_b2 = sdg;      // build_images writes 64 floats of b2 here; zeroed below (the backward does not need b2)
-    build_images<W>(sImg1, sImg2, sb1, dummy_b2, a, tid, B_THREADS);
+    float *sb1 = xch, *dummy_b2 = xch + 128;   // bias vectors, staged in the exchange buffer until the image is built
+    build_images<W>(sImg1, sImg2, sb1, dummy_b2, a, tid, B_THREADS, SC1, SC2);
+    for (int i = tid; i < 4096 / 16; i += B_THREADS) ((uint4 *)sOnes)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    __syncthreads();
+    for (int i = tid; i < 16 * 16; i += B_THREADS) {          // 16 k-rows x 16 chunks of 8 hidden columns
+      const int k = i >> 4, n0 = (i & 15) << 3;
+      float y[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float b = sb1[n0 + u] * SC1, hi = __bfloat162float(__float2bfloat16_rn(b));
+        y[u] = k == 0 ? hi : k == 1 ? b - hi : 0.f;
+      }
+      *(uint4 *)(sBb1 + (uint32_t)(n0 >> 6) * 2048u + (uint32_t)(k >> 3) * 1024u + (uint32_t)(k & 7) * 128u +
+                 ((uint32_t)((((n0 & 63) >> 3) ^ k) & 7) << 4)) = pack8(y);
+    }
   }
-  for (int i = tid; i < 4096 / 16; i += B_THREADS) ((uint4 *)sOnes)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
   __syncthreads();
   if (tid < 128) sdg[tid] = 0.f;                            // sdg | sdb
   fence_proxy_async_smem();
@@ -517,17 +533,17 @@ __global__ void __launch_bounds__(B_THREADS, 1) ffn_tc_bwd_kernel(const __grid_c
         tmem_ld_wait();
         float hv[16], dv[16];
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          const float4 b = *(const float4 *)(sb1 + col0 + 4 * c4);
-          const float bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int c = 4 * c4 + u;
-            float f, d;
-            act_fd<ACT>(a.act, __uint_as_float(r1[c]) + bb[u], f, d);
-            hv[c] = f;
-            dv[c] = __uint_as_float(r2[c]) * d;
+        for (int c = 0; c < 16; ++c) {
+          const float p = __uint_as_float(r1[c]);            // pre-activation, bias included (elu: times log2 e)
+          float f, d;
+          if (ACT == EGT_ACT_ELU) {
+            d = ex2_approx(fminf(p, 0.f));                   // e^min(pre, 0): the derivative, 1 for pre >= 0
+            f = fmaf(fmaxf(p, 0.f), 1.f / kLog2e, d - 1.f);
+          } else {
+            act_fd<ACT>(a.act, p, f, d);
           }
+          hv[c] = f;
+          dv[c] = __uint_as_float(r2[c]) * d;
         }
         hq[2 * k] = pack8(hv); hq[2 * k + 1] = pack8(hv + 8);
         dq[2 * k] = pack8(dv); dq[2 * k + 1] = pack8(dv + 8);
@@ -616,10 +632,10 @@ __global__ void __launch_bounds__(B_THREADS, 1) ffn_tc_bwd_kernel(const __grid_c
         tmem_ld_wait();
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
-          M1[t * LD + CH * qq + c] = __uint_as_float(rw1[c]);     // sum_rows dpre[:, j = t] x^[:, c]
+          M1[t * LD + CH * qq + c] = __uint_as_float(rw1[c]) * (1.f / SC2);   // sum_rows dpre[:, j = t] x^[:, c]
           M2[t * LD + CH * qq + c] = __uint_as_float(rw2[c]);     // sum_rows hid[:, j = t] dy[:, c]
         }
-        if (qq == 0) v1s[t] = __uint_as_float(rb[0]);             // sum_rows dpre[:, j = t]
+        if (qq == 0) v1s[t] = __uint_as_float(rb[0]) * (1.f / SC2);   // sum_rows dpre[:, j = t]
         if (qq == 1 && t < 64) vb2[t] = __uint_as_float(rb2[0]);  // sum_rows dy[:, c = t]
       }
       named_bar_sync(1, NCT);
@@ -702,8 +718,9 @@ __global__ void __launch_bounds__(B_THREADS, 1) ffn_tc_bwd_kernel(const __grid_c
     const uint32_t loI1 = desc_lo(smem_u32(sImg1), TILE), loI2 = desc_lo(smem_u32(sImg2), 16);
     const uint32_t loHid = desc_lo(smem_u32(sHid), TILE), loDpre_k = desc_lo(smem_u32(sDpre), 16),
                    loDpre_mn = desc_lo(smem_u32(sDpre), TILE);
-    const uint32_t loOnes = desc_lo(smem_u32(sOnes), 128);
+    const uint32_t loOnes = desc_lo(smem_u32(sOnes), 128), loOnesA = loOnes, loBb1 = desc_lo(smem_u32(sBb1), 2048);
     constexpr uint32_t HI_ONES = desc_hi(256, LAYOUT_NONE);
+    constexpr uint32_t ID_BIAS = idesc_bf16(128, 128, 0, 1);
     constexpr uint32_t ID_A = idesc_bf16(128, 128, 0, 0), ID_D3 = idesc_bf16(128, 64, 0, 1), ID_T = idesc_bf16(128, 64, 1, 1),
                        ID_B = idesc_bf16(128, 16, 1, 0);
     auto issue_A = [&](int i) {          // pre = x^ W1blk ; dhid = dy W2blk^T
@@ -711,6 +728,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) ffn_tc_bwd_kernel(const __grid_c
       mbar_wait(smem_u32(&bars->readyA), i & 1);
       tc_fence_after();
       MmaChain<4>::ss(tmem + C_D1, desc_lo(x_addr, 16), HI_SW, desc_lo(smem_u32(sImg1), 16), HI_SW, ID_A, 0, 2, 2);
+      MmaChain<1>::ss(tmem + C_D1, loOnesA, HI_ONES, loBb1, HI_SW, ID_BIAS, 1, 0, 0);      // + 1 b1'  (all-ones A: sum of the k-rows)
       MmaChain<4>::ss(tmem + C_DH, desc_lo(dy_addr, 16), HI_SW, loI2, HI_SW, ID_A, 0, 2, 2);
       mma_commit_w(smem_u32(&bars->doneA));
     };

@@ -96,14 +96,16 @@ __device__ __forceinline__ void fused_bwd_finalize_body(const float *partials, i
                                                         const egt_block_grads_t &g, const int tid, const int nthr) {
   __shared__ float s[FPART];
   for (int col = tid; col < FPART; col += nthr) {
-    float acc[8];
+    float acc[16];                           // 16 independent loads in flight: the loop is pure L2 latency
 #pragma unroll
-    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+    for (int q = 0; q < 16; ++q) acc[q] = 0.f;
     int i = 0;
-    for (; i + 8 <= nparts; i += 8)
+    for (; i + 16 <= nparts; i += 16)
 #pragma unroll
-      for (int q = 0; q < 8; ++q) acc[q] += partials[(size_t)(i + q) * FPART + col];
+      for (int q = 0; q < 16; ++q) acc[q] += partials[(size_t)(i + q) * FPART + col];
     for (; i < nparts; ++i) acc[0] += partials[(size_t)i * FPART + col];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] += acc[q + 8];
     s[col] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
   }
   __syncthreads();
