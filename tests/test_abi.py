@@ -163,3 +163,25 @@ def test_ffn_host_side_mirrors_reference_names(golden_dir):
     assert layer.ffn_edge is not None and layer.ffn_node.width == c['cfg'].model_width
     with pytest.raises(RuntimeError):                      # no CPU fallback
         layer.ffn_node(torch.zeros(2, 3, c['cfg'].model_width))
+
+
+def test_ffn_workspace_and_allreduce_sizes_are_host_functions():
+    """egt_ffn_workspace_bytes / egt_peer_allreduce_push_floats are pure host arithmetic (callable without a GPU): which
+    feed-forward shapes ask for a workspace (the cuBLAS path of csrc/node_blas.cu) and how large the symmetric buffer of
+    the push all-reduce must be."""
+    lib = L.load()
+
+    def ws(rows, width, hidden, act=L.EGT_ACT_ELU, dtype=L.EGT_BF16):
+        c = L.FfnCfg()
+        c.rows, c.width, c.hidden, c.dtype, c.activation, c.ln_eps = rows, width, hidden, dtype, act, 1e-3
+        return int(lib.egt_ffn_workspace_bytes(ctypes.byref(c)))
+
+    assert ws(128 * 128 * 128, 8, 16) == 0                   # tcgen05 kernels: no workspace
+    assert ws(128 * 128, 64, 128) == 0
+    assert ws(32 * 512, 128, 256) > 32 * 512 * 256 * 2       # node channel at d = 128: cuBLAS path
+    assert ws(64 * 190, 96, 192) > 0
+    assert ws(64 * 190, 64, 96) > 0                          # hidden != 2 w: not a tcgen05 shape
+    assert ws(100, 128, 256) == 0                            # too few rows for a GEMM to pay: CUDA-core kernels
+    assert ws(32 * 512, 128, 256, act=L.EGT_ACT_RELU) == 0   # relu stays on the float32 kernels
+    assert ws(32 * 512, 128, 256, dtype=L.EGT_F32) == 0
+    assert int(lib.egt_peer_allreduce_push_floats(17000, 8)) == 4 * 17000 * 8
